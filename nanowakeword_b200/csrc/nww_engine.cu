@@ -1,0 +1,492 @@
+// nww_engine.cu — engine object and the C ABI of libnwwb200.so (see include/nww_b200.h).
+//
+// Host-side responsibilities: parse the weight blob, build the front-end tables, keep
+// weights/tables/workspaces resident in HBM, size grids from the SM count, and enqueue
+// stage A (per-window fused kernels) + stage B (dense tail) in L2-sized chunks.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <algorithm>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/nww_b200.h"
+#include "nww_blob.h"
+#include "nww_cnn.cuh"
+#include "nww_heads.cuh"
+#include "nww_stage.cuh"
+#include "nww_tables.h"
+#include "nww_tail.cuh"
+
+using namespace nww;
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+#define NWW_CUDA(call)                                                                                 \
+    do {                                                                                               \
+        cudaError_t _e = (call);                                                                       \
+        if (_e != cudaSuccess)                                                                         \
+            return fail(NWW_ECUDA, std::string(#call) + ": " + cudaGetErrorString(_e));                \
+    } while (0)
+
+namespace {
+
+constexpr int kStageNT = 512;       // threads per stage-A CTA
+constexpr int kNfb64 = 7;           // FFTs per batch, double
+constexpr int kNfb32 = 13;          // FFTs per batch, float
+
+template <typename T> struct DevTables {
+    FrontendTables<T> tab{};
+};
+
+struct DeviceArena {                // one allocation for all small constant tables
+    std::vector<unsigned char> host;
+    unsigned char* dev = nullptr;
+    size_t add(const void* p, size_t bytes) {
+        size_t off = (host.size() + 255) & ~(size_t)255;
+        host.resize(off + bytes);
+        memcpy(host.data() + off, p, bytes);
+        return off;
+    }
+};
+
+}  // namespace
+
+struct nww_engine {
+    int device = 0;
+    int sm_count = 0;
+    nww_spec spec{};
+    std::mutex mu;
+
+    Blob blob;                       // parsed view over host copy
+    std::vector<unsigned char> blob_host;
+    unsigned char* d_blob = nullptr;
+    DeviceArena arena;
+    FrontendTables<float> tab32{};
+    FrontendTables<double> tab64{};
+
+    int n_mels = 0, n_frames = 0, clip = 0;
+    int feat_dim = 0, emb_dim = 0;
+    TailParams tail{};
+    CnnWeights cnn{};
+    HeadWeights heads{};
+
+    int chunk = 0;
+    float* d_feat = nullptr;         // [chunk][feat_dim]
+    float* d_scratch = nullptr;      // per-head scratch (e.g. CRNN sequence), may be null
+    size_t scratch_per_window = 0;
+
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    int16_t* d_pcm[2] = {nullptr, nullptr};
+    float* d_scores = nullptr;
+    int64_t host_chunk = 0, scores_cap = 0;
+
+    int64_t launches = 0, windows = 0;
+
+    const float* dptr(const std::string& name) const {
+        const BlobTensor* t = blob.find(name);
+        return t ? reinterpret_cast<const float*>(d_blob + t->offset) : nullptr;
+    }
+};
+
+// ------------------------------------------------------------------------------ helpers
+template <typename T>
+static void fill_tables(nww_engine* e, const HostFrontendTables& h, FrontendTables<T>* out_offsets_as_ptrs) {
+    std::vector<T> ws(h.window_scaled.begin(), h.window_scaled.end());
+    std::vector<T> wu(h.window_unscaled.begin(), h.window_unscaled.end());
+    std::vector<cplx<T>> tw(h.n_fft);
+    for (int i = 0; i < h.n_fft; ++i) tw[i] = {(T)h.tw_re[i], (T)h.tw_im[i]};
+    FrontendTables<T>& t = *out_offsets_as_ptrs;
+    // store offsets in the pointer fields first; rebased after the arena is uploaded
+    t.window = reinterpret_cast<const T*>(e->arena.add(ws.data(), ws.size() * sizeof(T)));
+    t.window_unscaled = reinterpret_cast<const T*>(e->arena.add(wu.data(), wu.size() * sizeof(T)));
+    t.twiddle = reinterpret_cast<const cplx<T>*>(e->arena.add(tw.data(), tw.size() * sizeof(cplx<T>)));
+    t.binpos = reinterpret_cast<const uint16_t*>(e->arena.add(h.binpos.data(), h.binpos.size() * sizeof(uint16_t)));
+    t.mel_start = reinterpret_cast<const int*>(e->arena.add(h.mel_start.data(), h.mel_start.size() * sizeof(int)));
+    t.mel_count = reinterpret_cast<const int*>(e->arena.add(h.mel_count.data(), h.mel_count.size() * sizeof(int)));
+    t.mel_woff = reinterpret_cast<const int*>(e->arena.add(h.mel_woff.data(), h.mel_woff.size() * sizeof(int)));
+    t.mel_w = reinterpret_cast<const float*>(e->arena.add(h.mel_w.data(), h.mel_w.size() * sizeof(float)));
+    t.amin = 1e-10f;
+    t.floor_db = -100.0f;            // 10*log10(1e-10)
+}
+
+template <typename T> static void rebase_tables(FrontendTables<T>* t, unsigned char* base) {
+    auto fix = [&](auto& p) {
+        using P = std::remove_reference_t<decltype(p)>;
+        p = reinterpret_cast<P>(base + reinterpret_cast<size_t>(p));
+    };
+    fix(t->window);
+    fix(t->window_unscaled);
+    fix(t->twiddle);
+    fix(t->binpos);
+    fix(t->mel_start);
+    fix(t->mel_count);
+    fix(t->mel_woff);
+    fix(t->mel_w);
+}
+
+template <typename K> static cudaError_t set_smem(K kernel, size_t bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+static int build_tail(nww_engine* e) {
+    const BlobTensor* nl = e->blob.find("tail.n_layers");
+    if (!nl) return fail(NWW_EINVAL, "weight blob: tail.n_layers missing");
+    const int n = *reinterpret_cast<const int*>(e->blob.base + nl->offset);
+    if (n < 2 || n > kMaxTailLayers) return fail(NWW_EINVAL, "weight blob: bad tail.n_layers");
+    TailParams& P = e->tail;
+    P.n_layers = n;
+    P.act = e->spec.activation;
+    P.max_width = 1;
+    int prev_n = e->feat_dim;
+    for (int i = 0; i < n; ++i) {
+        const std::string p = "tail." + std::to_string(i);
+        const BlobTensor* w = e->blob.find(p + ".W");
+        const BlobTensor* b = e->blob.find(p + ".b");
+        const BlobTensor* post = e->blob.find(p + ".post");
+        if (!w || !b || !post || w->dims.size() != 2) return fail(NWW_EINVAL, "weight blob: " + p + " incomplete");
+        TailLayer& L = P.layers[i];
+        L.N = (int)w->dims[0];
+        L.K = (int)w->dims[1];
+        if (L.K != prev_n)
+            return fail(NWW_EINVAL, p + ": input width " + std::to_string(L.K) + " does not match producer width " +
+                                        std::to_string(prev_n));
+        if (b->numel() != (size_t)L.N) return fail(NWW_EINVAL, p + ": bias size mismatch");
+        L.W = e->dptr(p + ".W");
+        L.b = e->dptr(p + ".b");
+        L.ln_g = e->dptr(p + ".ln_g");
+        L.ln_b = e->dptr(p + ".ln_b");
+        L.post = *reinterpret_cast<const int*>(e->blob.base + post->offset);
+        if (L.post == POST_LN_ACT && (!L.ln_g || !L.ln_b)) return fail(NWW_EINVAL, p + ": LayerNorm terms missing");
+        P.max_width = std::max(P.max_width, L.N);
+        if (i > 0) P.max_width = std::max(P.max_width, L.K);
+        prev_n = L.N;
+    }
+    if (P.layers[n - 1].N != 1) return fail(NWW_EINVAL, "tail: last layer must have one output");
+    e->emb_dim = P.layers[n - 3 >= 0 ? n - 3 : 0].N;
+    if (tail_smem_bytes(P.max_width) > 200 * 1024) return fail(NWW_EUNSUPPORTED, "tail: layer too wide for shared memory");
+    return NWW_OK;
+}
+
+template <typename G> static int check_geometry(const nww_spec& s) {
+    if (s.n_fft != G::N_FFT || s.win_length != G::WIN || s.hop_length != G::HOP || s.n_mels != G::N_MELS ||
+        (s.center != 0) != (G::CENTER != 0) || s.clip_samples != G::CLIP)
+        return fail(NWW_EUNSUPPORTED,
+                    "front-end parameters do not match a built-in geometry (NS40x98: 400/512/160/40 not centred; "
+                    "REF64x101: 400/400/160/64 centred; clip 16000)");
+    return NWW_OK;
+}
+
+template <typename G> static int setup_frontend(nww_engine* e) {
+    int rc = check_geometry<G>(e->spec);
+    if (rc) return rc;
+    const BlobTensor* win = e->blob.find("frontend.window");
+    const BlobTensor* fb = e->blob.find("frontend.fb");
+    if (!win || !fb || win->numel() != (size_t)G::WIN || fb->numel() != (size_t)G::N_FREQS * G::N_MELS)
+        return fail(NWW_EINVAL, "weight blob: frontend.window / frontend.fb missing or wrong shape");
+    HostFrontendTables h;
+    std::string err;
+    const int rad[4] = {G::R0, G::R1, G::R2, G::R3};
+    if (!build_frontend_tables(G::N_FFT, G::WIN, G::N_MELS, rad, G::N_PASS, e->blob.f32("frontend.window"),
+                               e->blob.f32("frontend.fb"), &h, &err))
+        return fail(NWW_EINVAL, err);
+    fill_tables<float>(e, h, &e->tab32);
+    fill_tables<double>(e, h, &e->tab64);
+    e->n_mels = G::N_MELS;
+    e->n_frames = G::N_FRAMES;
+    e->clip = G::CLIP;
+    return NWW_OK;
+}
+
+// ------------------------------------------------------------------------------ launches
+static int grid_for(const nww_engine* e, int64_t n, int per_sm = 1) {
+    return (int)std::min<int64_t>(n, (int64_t)e->sm_count * per_sm);
+}
+
+template <typename G>
+static int launch_frontend(nww_engine* e, const int16_t* pcm, int64_t n, float* mel, int time_major, cudaStream_t st) {
+    if (e->spec.frontend_precision == NWW_FRONTEND_FP32) {
+        auto k = frontend_kernel<float, G, kNfb32, kStageNT>;
+        NWW_CUDA(set_smem(k, FrontendSmem<float, G, kNfb32>::kTotal));
+        k<<<grid_for(e, n), kStageNT, FrontendSmem<float, G, kNfb32>::kTotal, st>>>(pcm, n, e->tab32, mel, time_major);
+    } else {
+        auto k = frontend_kernel<double, G, kNfb64, kStageNT>;
+        NWW_CUDA(set_smem(k, FrontendSmem<double, G, kNfb64>::kTotal));
+        k<<<grid_for(e, n), kStageNT, FrontendSmem<double, G, kNfb64>::kTotal, st>>>(pcm, n, e->tab64, mel, time_major);
+    }
+    e->launches++;
+    NWW_CUDA(cudaGetLastError());
+    return NWW_OK;
+}
+
+static int launch_tail(nww_engine* e, const float* feat, int64_t n, float* scores, float* logits, float* emb,
+                       cudaStream_t st) {
+    const size_t smem = tail_smem_bytes(e->tail.max_width);
+    NWW_CUDA(set_smem(tail_kernel, smem));
+    const int64_t tiles = (n + kTailTM - 1) / kTailTM;
+    tail_kernel<<<grid_for(e, tiles, 2), kTailNT, smem, st>>>(feat, n, e->tail, scores, logits, emb);
+    e->launches++;
+    NWW_CUDA(cudaGetLastError());
+    return NWW_OK;
+}
+
+// Stage A for one chunk: PCM (int16, device) -> feature rows in e->d_feat.
+static int launch_stage_a(nww_engine* e, const int16_t* pcm, int64_t n, float* mel, cudaStream_t st) {
+    switch (e->spec.arch) {
+        case NWW_ARCH_DNN: {
+            // the DNN body is the identity on the (T, F) log-mel: features = flattened mel
+            int rc = launch_frontend<GeoNS40x98>(e, pcm, n, e->d_feat, /*time_major=*/1, st);
+            if (rc) return rc;
+            if (mel) return launch_frontend<GeoNS40x98>(e, pcm, n, mel, 0, st);
+            return NWW_OK;
+        }
+        case NWW_ARCH_CNN: {
+            using G = GeoNS40x98;
+            auto k = cnn_stage_kernel<double, G, kNfb64, kStageNT>;
+            const size_t smem = CnnSmem<double, G, kNfb64>::kTotal;
+            NWW_CUDA(set_smem(k, smem));
+            k<<<grid_for(e, n), kStageNT, smem, st>>>(pcm, n, e->tab64, e->cnn, e->spec.activation, e->d_feat, mel);
+            e->launches++;
+            NWW_CUDA(cudaGetLastError());
+            return NWW_OK;
+        }
+        default:
+            return launch_head_stage_a(e->spec.arch, e->heads, e->tab64, e->spec.activation, e->sm_count, pcm, n, e->d_feat,
+                                       e->d_scratch, mel, st, &e->launches, &g_last_error);
+    }
+}
+
+static int run_device(nww_engine* e, const int16_t* pcm, int64_t n, float* scores, float* mel, float* logits, float* emb,
+                      cudaStream_t st) {
+    const int64_t mel_stride = (int64_t)e->n_mels * e->n_frames;
+    for (int64_t w0 = 0; w0 < n; w0 += e->chunk) {
+        const int64_t m = std::min<int64_t>(e->chunk, n - w0);
+        int rc = launch_stage_a(e, pcm + w0 * e->clip, m, mel ? mel + w0 * mel_stride : nullptr, st);
+        if (rc) return rc;
+        rc = launch_tail(e, e->d_feat, m, scores + w0, logits ? logits + w0 : nullptr,
+                         emb ? emb + w0 * e->emb_dim : nullptr, st);
+        if (rc) return rc;
+    }
+    e->windows += n;
+    return NWW_OK;
+}
+
+// ------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char* nww_last_error(void) { return g_last_error.c_str(); }
+
+int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, int device, nww_engine** out) {
+    if (!spec || !weights || !out) return fail(NWW_EINVAL, "nww_create: null argument");
+    if (spec->struct_size != sizeof(nww_spec)) return fail(NWW_EINVAL, "nww_create: nww_spec size mismatch");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(NWW_ECUDA, std::string("no CUDA device available (this engine has no CPU fallback): ") +
+                                   cudaGetErrorString(ce));
+    if (device < 0 || device >= ndev) return fail(NWW_EINVAL, "nww_create: bad device index");
+    NWW_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    NWW_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(NWW_EUNSUPPORTED, "this library is built for sm_100a (B200) only; found sm_" +
+                                          std::to_string(prop.major) + std::to_string(prop.minor));
+
+    std::unique_ptr<nww_engine> e(new nww_engine);
+    e->device = device;
+    e->sm_count = prop.multiProcessorCount;
+    e->spec = *spec;
+    e->blob_host.assign(static_cast<const unsigned char*>(weights), static_cast<const unsigned char*>(weights) + weights_size);
+    std::string err;
+    if (!parse_blob(e->blob_host.data(), e->blob_host.size(), &e->blob, &err)) return fail(NWW_EINVAL, err);
+    if (spec->frontend_precision != NWW_FRONTEND_FP64 && spec->frontend_precision != NWW_FRONTEND_FP32)
+        return fail(NWW_EINVAL, "bad frontend_precision");
+
+    int rc = (spec->geometry == NWW_GEOM_NS40X98)    ? setup_frontend<GeoNS40x98>(e.get())
+             : (spec->geometry == NWW_GEOM_REF64X101) ? setup_frontend<GeoREF64x101>(e.get())
+                                                      : fail(NWW_EUNSUPPORTED, "unknown geometry id");
+    if (rc) return rc;
+
+    NWW_CUDA(cudaMalloc(&e->d_blob, e->blob_host.size()));
+    NWW_CUDA(cudaMemcpy(e->d_blob, e->blob_host.data(), e->blob_host.size(), cudaMemcpyHostToDevice));
+    NWW_CUDA(cudaMalloc(&e->arena.dev, e->arena.host.size()));
+    NWW_CUDA(cudaMemcpy(e->arena.dev, e->arena.host.data(), e->arena.host.size(), cudaMemcpyHostToDevice));
+    rebase_tables(&e->tab32, e->arena.dev);
+    rebase_tables(&e->tab64, e->arena.dev);
+
+    const bool ns = spec->geometry == NWW_GEOM_NS40X98;
+    switch (spec->arch) {
+        case NWW_ARCH_DNN:
+            if (!ns) return fail(NWW_EUNSUPPORTED, "dnn head is built for the NS40x98 geometry");
+            e->feat_dim = e->n_mels * e->n_frames;
+            break;
+        case NWW_ARCH_CNN: {
+            if (!ns) return fail(NWW_EUNSUPPORTED, "cnn head is built for the NS40x98 geometry");
+            e->feat_dim = CnnDims<GeoNS40x98>::FEAT;
+            e->cnn = CnnWeights{e->dptr("cnn.w1"), e->dptr("cnn.b1"), e->dptr("cnn.w2"), e->dptr("cnn.b2")};
+            if (!e->cnn.w1 || !e->cnn.b1 || !e->cnn.w2 || !e->cnn.b2) return fail(NWW_EINVAL, "weight blob: cnn.* missing");
+            break;
+        }
+        default: {
+            auto lookup = [&](const char* name, size_t expect) -> const float* {
+                const BlobTensor* t = e->blob.find(name);
+                if (!t || (expect && t->numel() != expect)) return nullptr;
+                return e->dptr(name);
+            };
+            rc = setup_head_weights(spec->arch, spec->geometry, lookup, &e->heads, &e->feat_dim, &e->scratch_per_window,
+                                    &g_last_error);
+            if (rc) return rc;
+        }
+    }
+    rc = build_tail(e.get());
+    if (rc) return rc;
+
+    e->chunk = spec->chunk_windows > 0 ? spec->chunk_windows : e->sm_count * 8;
+    NWW_CUDA(cudaMalloc(&e->d_feat, (size_t)e->chunk * e->feat_dim * sizeof(float)));
+    if (e->scratch_per_window) NWW_CUDA(cudaMalloc(&e->d_scratch, (size_t)e->chunk * e->scratch_per_window));
+    NWW_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    NWW_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        NWW_CUDA(cudaEventCreateWithFlags(&e->ev_copy[i], cudaEventDisableTiming));
+        NWW_CUDA(cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming));
+    }
+    *out = e.release();
+    return NWW_OK;
+}
+
+void nww_destroy(nww_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    cudaFree(e->d_blob);
+    cudaFree(e->arena.dev);
+    cudaFree(e->d_feat);
+    cudaFree(e->d_scratch);
+    cudaFree(e->d_pcm[0]);
+    cudaFree(e->d_pcm[1]);
+    cudaFree(e->d_scores);
+    for (int i = 0; i < 2; ++i) {
+        if (e->ev_copy[i]) cudaEventDestroy(e->ev_copy[i]);
+        if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
+    }
+    if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    delete e;
+}
+
+int nww_get_info(nww_engine* e, nww_info_t* info) {
+    if (!e || !info) return fail(NWW_EINVAL, "nww_get_info: null argument");
+    info->device = e->device;
+    info->sm_count = e->sm_count;
+    info->n_mels = e->n_mels;
+    info->n_frames = e->n_frames;
+    info->clip_samples = e->clip;
+    info->feature_dim = e->feat_dim;
+    info->embedding_dim = e->emb_dim;
+    info->chunk_windows = e->chunk;
+    info->kernel_launches = e->launches;
+    info->windows_scored = e->windows;
+    return NWW_OK;
+}
+
+int nww_run_windows(nww_engine* e, const int16_t* pcm_dev, int64_t n, float* scores_dev, float* mel_dev, float* logits_dev,
+                    float* emb_dev, void* stream) {
+    if (!e || (n > 0 && (!pcm_dev || !scores_dev))) return fail(NWW_EINVAL, "nww_run_windows: null argument");
+    if (n < 0) return fail(NWW_EINVAL, "nww_run_windows: negative window count");
+    if (n == 0) return NWW_OK;
+    if (reinterpret_cast<uintptr_t>(pcm_dev) & 15) return fail(NWW_EINVAL, "nww_run_windows: pcm_dev must be 16-byte aligned");
+    std::lock_guard<std::mutex> lock(e->mu);
+    NWW_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : e->stream;
+    return run_device(e, pcm_dev, n, scores_dev, mel_dev, logits_dev, emb_dev, st);
+}
+
+int nww_logmel(nww_engine* e, const int16_t* pcm_dev, int64_t n, float* mel_dev, int time_major, void* stream) {
+    if (!e || (n > 0 && (!pcm_dev || !mel_dev))) return fail(NWW_EINVAL, "nww_logmel: null argument");
+    if (n <= 0) return n == 0 ? NWW_OK : fail(NWW_EINVAL, "nww_logmel: negative window count");
+    if (reinterpret_cast<uintptr_t>(pcm_dev) & 15) return fail(NWW_EINVAL, "nww_logmel: pcm_dev must be 16-byte aligned");
+    std::lock_guard<std::mutex> lock(e->mu);
+    NWW_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : e->stream;
+    return e->spec.geometry == NWW_GEOM_NS40X98 ? launch_frontend<GeoNS40x98>(e, pcm_dev, n, mel_dev, time_major, st)
+                                                : launch_frontend<GeoREF64x101>(e, pcm_dev, n, mel_dev, time_major, st);
+}
+
+int nww_run_windows_f32(nww_engine* e, const float* pcm_dev, int64_t n, float* scores_dev, float* mel_dev, float* logits_dev,
+                        float* emb_dev, void* stream) {
+    // Float PCM is quantised back to the int16 grid it came from (x * 32768 is exact for the
+    // reference's x = int16 / 32768, nanointerpreter.py:750) and takes the int16 path, chunk by chunk.
+    if (!e || (n > 0 && (!pcm_dev || !scores_dev))) return fail(NWW_EINVAL, "nww_run_windows_f32: null argument");
+    if (n <= 0) return n == 0 ? NWW_OK : fail(NWW_EINVAL, "nww_run_windows_f32: negative window count");
+    std::lock_guard<std::mutex> lock(e->mu);
+    NWW_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : e->stream;
+    if (!e->d_pcm[0]) {
+        e->host_chunk = e->chunk;
+        for (int i = 0; i < 2; ++i) NWW_CUDA(cudaMalloc(&e->d_pcm[i], (size_t)e->host_chunk * e->clip * sizeof(int16_t)));
+    }
+    const int64_t mel_stride = (int64_t)e->n_mels * e->n_frames;
+    for (int64_t w0 = 0; w0 < n; w0 += e->host_chunk) {
+        const int64_t m = std::min<int64_t>(e->host_chunk, n - w0);
+        const int64_t total = m * e->clip;
+        f32_to_i16_kernel<<<(int)std::min<int64_t>((total + 255) / 256, (int64_t)e->sm_count * 16), 256, 0, st>>>(
+            pcm_dev + w0 * e->clip, e->d_pcm[0], total);
+        e->launches++;
+        NWW_CUDA(cudaGetLastError());
+        int rc = run_device(e, e->d_pcm[0], m, scores_dev + w0, mel_dev ? mel_dev + w0 * mel_stride : nullptr,
+                            logits_dev ? logits_dev + w0 : nullptr, emb_dev ? emb_dev + w0 * e->emb_dim : nullptr, st);
+        if (rc) return rc;
+    }
+    return NWW_OK;
+}
+
+int nww_run_windows_host(nww_engine* e, const int16_t* pcm_host, int64_t n, float* scores_host) {
+    if (!e || (n > 0 && (!pcm_host || !scores_host))) return fail(NWW_EINVAL, "nww_run_windows_host: null argument");
+    if (n <= 0) return n == 0 ? NWW_OK : fail(NWW_EINVAL, "nww_run_windows_host: negative window count");
+    std::lock_guard<std::mutex> lock(e->mu);
+    NWW_CUDA(cudaSetDevice(e->device));
+    if (!e->d_pcm[0]) {
+        e->host_chunk = e->chunk;
+        for (int i = 0; i < 2; ++i) NWW_CUDA(cudaMalloc(&e->d_pcm[i], (size_t)e->host_chunk * e->clip * sizeof(int16_t)));
+    }
+    if (e->scores_cap < n) {
+        cudaFree(e->d_scores);
+        e->d_scores = nullptr;
+        NWW_CUDA(cudaMalloc(&e->d_scores, (size_t)n * sizeof(float)));
+        e->scores_cap = n;
+    }
+    // copy(c) on copy_stream -> ev_copy[slot]; compute(c) on stream waits for it and records
+    // ev_done[slot], which copy(c + 2) waits for before overwriting the slot.
+    int64_t c = 0;
+    for (int64_t w0 = 0; w0 < n; w0 += e->host_chunk, ++c) {
+        const int slot = (int)(c & 1);
+        const int64_t m = std::min<int64_t>(e->host_chunk, n - w0);
+        if (c >= 2) NWW_CUDA(cudaStreamWaitEvent(e->copy_stream, e->ev_done[slot], 0));
+        NWW_CUDA(cudaMemcpyAsync(e->d_pcm[slot], pcm_host + w0 * e->clip, (size_t)m * e->clip * sizeof(int16_t),
+                                 cudaMemcpyHostToDevice, e->copy_stream));
+        NWW_CUDA(cudaEventRecord(e->ev_copy[slot], e->copy_stream));
+        NWW_CUDA(cudaStreamWaitEvent(e->stream, e->ev_copy[slot], 0));
+        int rc = run_device(e, e->d_pcm[slot], m, e->d_scores + w0, nullptr, nullptr, nullptr, e->stream);
+        if (rc) return rc;
+        NWW_CUDA(cudaEventRecord(e->ev_done[slot], e->stream));
+    }
+    NWW_CUDA(cudaMemcpyAsync(scores_host, e->d_scores, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    NWW_CUDA(cudaStreamSynchronize(e->stream));
+    return NWW_OK;
+}
+
+int nww_synchronize(nww_engine* e) {
+    if (!e) return fail(NWW_EINVAL, "nww_synchronize: null engine");
+    NWW_CUDA(cudaSetDevice(e->device));
+    NWW_CUDA(cudaStreamSynchronize(e->copy_stream));
+    NWW_CUDA(cudaStreamSynchronize(e->stream));
+    return NWW_OK;
+}
+
+}  // extern "C"

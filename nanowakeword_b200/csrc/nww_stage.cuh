@@ -1,0 +1,94 @@
+// nww_stage.cuh — persistent per-window "stage A" kernels: PCM staging + front end (+ the
+// convolutional body of a head), one window per CTA iteration, grid = a multiple of the SM count.
+#pragma once
+
+#include "nww_frontend.cuh"
+
+#ifndef NWW_CPUSIM
+#define NWW_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
+#endif
+
+namespace nww {
+
+__host__ __device__ constexpr size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Double-buffered TMA bulk staging of int16 windows (global -> shared), one mbarrier per slot.
+template <int CLIP> struct PcmStager {
+    int16_t* buf;      // [2][CLIP]
+    uint64_t* bars;    // [2]
+    static constexpr size_t kBytes = align_up(2 * CLIP * sizeof(int16_t), 128) + 128;
+    __device__ __forceinline__ void carve(unsigned char* p) {
+        buf = reinterpret_cast<int16_t*>(p);
+        bars = reinterpret_cast<uint64_t*>(p + align_up(2 * CLIP * sizeof(int16_t), 128));
+    }
+    __device__ __forceinline__ void init(int tid) {
+        if (tid == 0) {
+            mbar_init(&bars[0], 1);
+            mbar_init(&bars[1], 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+    }
+    __device__ __forceinline__ void issue(int slot, const int16_t* src, int tid) {
+        if (tid == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(&bars[slot], CLIP * (uint32_t)sizeof(int16_t));
+            bulk_g2s(buf + (size_t)slot * CLIP, src, CLIP * (uint32_t)sizeof(int16_t), &bars[slot]);
+        }
+    }
+    __device__ __forceinline__ const int16_t* wait(int slot, uint32_t parity) {
+        mbar_wait(&bars[slot], parity);
+        return buf + (size_t)slot * CLIP;
+    }
+};
+
+// ----------------------------------------------------------------------------------------
+// Front end only: log-mel to global memory, either (F, T) or (T, F) per window.
+// Used for the DNN head (whose "body" is the identity), for parity dumps and for streaming.
+// ----------------------------------------------------------------------------------------
+template <typename T, typename G, int NFB> struct FrontendSmem {
+    static constexpr size_t kWork = align_up(sizeof(cplx<T>) * G::N_FFT * NFB, 128);
+    static constexpr size_t kTotal = kWork + PcmStager<G::CLIP>::kBytes;
+};
+
+template <typename T, typename G, int NFB, int NT>
+__global__ void __launch_bounds__(NT, 1)
+frontend_kernel(const int16_t* __restrict__ pcm, long long n_windows, FrontendTables<T> tab, float* __restrict__ mel_out,
+                int time_major) {
+    NWW_DYN_SMEM(smem);
+    const int tid = threadIdx.x;
+    cplx<T>* work = reinterpret_cast<cplx<T>*>(smem);
+    PcmStager<G::CLIP> stager;
+    stager.carve(smem + FrontendSmem<T, G, NFB>::kWork);
+    stager.init(tid);
+
+    const int stride_m = time_major ? 1 : G::N_FRAMES;
+    const int stride_t = time_major ? G::N_MELS : 1;
+    long long w = blockIdx.x;
+    if (w < n_windows) stager.issue(0, pcm + w * G::CLIP, tid);
+    for (int it = 0; w < n_windows; w += gridDim.x, ++it) {
+        const long long wn = w + gridDim.x;
+        if (wn < n_windows) stager.issue((it + 1) & 1, pcm + wn * G::CLIP, tid);
+        const int16_t* x = stager.wait(it & 1, (it >> 1) & 1);
+        logmel_window<T, G, NFB, int16_t>(x, work, tab, mel_out + w * (long long)(G::N_MELS * G::N_FRAMES), stride_m,
+                                          stride_t, tid, NT);
+    }
+}
+
+// Same, for float32 PCM already scaled to [-1, 1) (what the reference feeds its session,
+// nanointerpreter.py:750, 771-775): read straight from global, no staging.
+template <typename T, typename G, int NFB, int NT>
+__global__ void __launch_bounds__(NT, 1)
+frontend_f32_kernel(const float* __restrict__ pcm, long long n_windows, FrontendTables<T> tab,
+                    float* __restrict__ mel_out, int time_major) {
+    NWW_DYN_SMEM(smem);
+    const int tid = threadIdx.x;
+    cplx<T>* work = reinterpret_cast<cplx<T>*>(smem);
+    const int stride_m = time_major ? 1 : G::N_FRAMES;
+    const int stride_t = time_major ? G::N_MELS : 1;
+    for (long long w = blockIdx.x; w < n_windows; w += gridDim.x)
+        logmel_window<T, G, NFB, float>(pcm + w * G::CLIP, work, tab,
+                                        mel_out + w * (long long)(G::N_MELS * G::N_FRAMES), stride_m, stride_t, tid, NT);
+}
+
+}  // namespace nww

@@ -1,0 +1,245 @@
+"""Engine wrapper and the InferenceSession duck type over libnwwb200.so.
+
+``B200Session`` plugs into the one seam the reference has: ``NanoInterpreter`` only ever
+talks to ``self.models[name]`` through ``get_inputs()`` and ``run(None, {"input": x})``
+(reference nanowakeword/interpreter/nanointerpreter.py:165-167, 677-682, 783), the same
+seam ``_RemoteSession`` already occupies (remote_verifier.py:490-648).  PyTorch is used
+here for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from .weights import ACT_IDS, ARCH_IDS, GEOMETRY_IDS, GEOMETRY_PARAMS, geometry_for, pack_blob, pack_tensors
+
+PROVIDER = "B200ExecutionProvider"
+N_FRAMES = {"NS40x98": 98, "REF64x101": 101}
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class Engine:
+    """One model resident on one B200: weights, tables and workspaces live in HBM."""
+
+    def __init__(self, state_dict: dict, cfg: dict, device: int = 0, frontend_precision: str = "fp64",
+                 chunk_windows: int = 0):
+        self._lib = _lib.load_library()
+        self.cfg = dict(cfg)
+        self.geometry = geometry_for(cfg)
+        g = GEOMETRY_PARAMS[self.geometry]
+        mt = cfg["model_type"]
+        if mt not in ARCH_IDS:
+            raise ValueError(f"Unsupported model_type: '{mt}'.")
+        sd = {k: np.asarray(v) for k, v in state_dict.items()}
+        blob = pack_blob(pack_tensors(sd, cfg))
+        spec = _lib.NwwSpec()
+        spec.struct_size = C.sizeof(_lib.NwwSpec)
+        spec.arch = ARCH_IDS[mt]
+        spec.activation = ACT_IDS[cfg.get("activation_function", "relu").lower()]
+        spec.geometry = GEOMETRY_IDS[self.geometry]
+        spec.n_fft, spec.win_length, spec.hop_length = g["n_fft"], g["win_length"], g["hop_length"]
+        spec.n_mels, spec.center, spec.clip_samples = g["n_mels"], g["center"], g["clip_samples"]
+        spec.frontend_precision = {"fp64": 0, "fp32": 1}[frontend_precision]
+        spec.chunk_windows = int(chunk_windows)
+        self._blob = (C.c_char * len(blob)).from_buffer_copy(blob)
+        handle = C.c_void_p()
+        rc = self._lib.nww_create(C.byref(spec), C.cast(self._blob, C.c_void_p), len(blob), int(device), C.byref(handle))
+        _lib.check(self._lib, rc, "nww_create")
+        self._h = handle
+        self.device = int(device)
+        self.clip_samples = g["clip_samples"]
+        self.n_mels = g["n_mels"]
+        self.n_frames = N_FRAMES[self.geometry]
+
+    # -- lifetime -------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.nww_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def info(self) -> dict:
+        i = _lib.NwwInfo()
+        _lib.check(self._lib, self._lib.nww_get_info(self._h, C.byref(i)), "nww_get_info")
+        return {k: getattr(i, k) for k, _ in _lib.NwwInfo._fields_}
+
+    def synchronize(self):
+        _lib.check(self._lib, self._lib.nww_synchronize(self._h), "nww_synchronize")
+
+    # -- device path ------------------------------------------------------------------------
+    def _stream_ptr(self, stream):
+        torch = _torch()
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        return C.c_void_p(s.cuda_stream)
+
+    def score_device(self, pcm, out=None, want_mel=False, want_logits=False, want_emb=False, stream=None):
+        """pcm: CUDA int16 tensor (B, clip_samples), contiguous.  Returns scores (B,) float32 on
+        the device (plus a dict of the optional dumps).  Enqueues on the current torch stream."""
+        torch = _torch()
+        if pcm.dtype != torch.int16 or not pcm.is_cuda or not pcm.is_contiguous():
+            raise ValueError("pcm must be a contiguous CUDA int16 tensor")
+        if pcm.dim() != 2 or pcm.shape[1] != self.clip_samples:
+            raise ValueError(f"pcm must have shape (B, {self.clip_samples})")
+        n = pcm.shape[0]
+        dev = pcm.device
+        scores = out if out is not None else torch.empty(n, dtype=torch.float32, device=dev)
+        extra = {}
+        mel = logits = emb = None
+        if want_mel:
+            mel = extra["mel"] = torch.empty((n, self.n_mels, self.n_frames), dtype=torch.float32, device=dev)
+        if want_logits:
+            logits = extra["logits"] = torch.empty(n, dtype=torch.float32, device=dev)
+        if want_emb:
+            emb = extra["emb"] = torch.empty((n, self.info["embedding_dim"]), dtype=torch.float32, device=dev)
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        rc = self._lib.nww_run_windows(self._h, p(pcm), n, p(scores), p(mel), p(logits), p(emb), self._stream_ptr(stream))
+        _lib.check(self._lib, rc, "nww_run_windows")
+        return (scores, extra) if extra else scores
+
+    def logmel_device(self, pcm, time_major=False, stream=None):
+        torch = _torch()
+        if pcm.dtype != torch.int16 or not pcm.is_cuda or not pcm.is_contiguous():
+            raise ValueError("pcm must be a contiguous CUDA int16 tensor")
+        n = pcm.shape[0]
+        shape = (n, self.n_frames, self.n_mels) if time_major else (n, self.n_mels, self.n_frames)
+        mel = torch.empty(shape, dtype=torch.float32, device=pcm.device)
+        rc = self._lib.nww_logmel(self._h, C.c_void_p(pcm.data_ptr()), n, C.c_void_p(mel.data_ptr()), int(time_major),
+                                  self._stream_ptr(stream))
+        _lib.check(self._lib, rc, "nww_logmel")
+        return mel
+
+    # -- host path (end to end: H2D + compute + D2H inside the call) ------------------------------
+    def score_host(self, pcm: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """pcm: int16 ndarray (B, clip_samples) in host memory (pinned memory overlaps copies)."""
+        if not isinstance(pcm, np.ndarray) or pcm.dtype != np.int16:
+            raise ValueError("pcm must be an int16 numpy array")
+        pcm = np.ascontiguousarray(pcm)
+        if pcm.ndim != 2 or pcm.shape[1] != self.clip_samples:
+            raise ValueError(f"pcm must have shape (B, {self.clip_samples})")
+        n = pcm.shape[0]
+        scores = out if out is not None else np.empty(n, dtype=np.float32)
+        rc = self._lib.nww_run_windows_host(self._h, pcm.ctypes.data_as(C.c_void_p), n, scores.ctypes.data_as(C.c_void_p))
+        _lib.check(self._lib, rc, "nww_run_windows_host")
+        return scores
+
+    def score_host_ptr(self, pcm_ptr: int, n: int, scores_ptr: int):
+        """Raw-pointer form of :meth:`score_host` for pinned torch tensors."""
+        rc = self._lib.nww_run_windows_host(self._h, C.c_void_p(pcm_ptr), int(n), C.c_void_p(scores_ptr))
+        _lib.check(self._lib, rc, "nww_run_windows_host")
+
+
+# ------------------------------------------------------------------------------ artefacts
+def save_model(path: str, state_dict: dict, cfg: dict) -> str:
+    """Write ``<path>.pt`` the way the reference does (torch.save(state_dict),
+    nanowakeword/_export/pytorch.py:26-46) plus the ``<path>.json`` sidecar that carries what a
+    state_dict cannot: model_type, input_shape, activation, hyper-parameters, geometry."""
+    torch = _torch()
+    stem = os.path.splitext(path)[0]
+    torch.save({k: torch.from_numpy(np.asarray(v)) for k, v in state_dict.items()}, stem + ".pt")
+    with open(stem + ".json", "w") as f:
+        json.dump(cfg, f, indent=1)
+    return stem + ".pt"
+
+
+def load_artifacts(path: str):
+    """Resolve a model path to (state_dict as numpy, cfg).  Accepts ``x.pt`` or ``x.onnx``
+    (the reference always writes both, trainer.py:476-535); the weights are read from the
+    ``.pt`` and the architecture from the ``.json`` sidecar.  Parsing ``.onnx`` graphs is a
+    follow-up."""
+    stem, ext = os.path.splitext(path)
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"Model file not found: {path}")
+    pt, js = stem + ".pt", stem + ".json"
+    if not os.path.exists(pt) or not os.path.exists(js):
+        raise NotImplementedError(
+            f"{path}: the B200 engine needs the PyTorch state_dict '{pt}' and the spec sidecar '{js}' "
+            "next to the model (ONNX graph ingestion is not implemented)")
+    torch = _torch()
+    sd = torch.load(pt, map_location="cpu", weights_only=True)
+    with open(js) as f:
+        cfg = json.load(f)
+    return {k: v.numpy() for k, v in sd.items()}, cfg
+
+
+# ------------------------------------------------------------------------------ session duck type
+class _NodeArg:
+    """Stand-in for onnxruntime.NodeArg (only .name/.shape/.type are read, nanointerpreter.py:165-180)."""
+
+    def __init__(self, name, shape, type_="tensor(float)"):
+        self.name, self.shape, self.type = name, shape, type_
+
+    def __repr__(self):
+        return f"NodeArg(name='{self.name}', type='{self.type}', shape={self.shape})"
+
+
+class B200Session:
+    """Drop-in for ``onnxruntime.InferenceSession`` on the e2e path.
+
+    ``run(None, {"input": clip})`` takes what the reference feeds — float32 ``(B, N)`` or
+    ``(B, 1, N)`` PCM scaled by 1/32768 (nanointerpreter.py:750, 771-775) — or raw int16, and
+    returns ``[probabilities (B, 1, 1) float32]`` exactly like the exported graph
+    (_export/onnx.py:169-172).  The ``"audio"`` feed key of _RemoteSession is accepted too.
+    """
+
+    def __init__(self, path: Optional[str] = None, *, state_dict: Optional[dict] = None, cfg: Optional[dict] = None,
+                 device: int = 0, input_ndim: int = 2, **engine_kwargs):
+        if path is not None:
+            state_dict, cfg = load_artifacts(path)
+        if state_dict is None or cfg is None:
+            raise ValueError("B200Session needs a model path or (state_dict, cfg)")
+        self._model_filename = path or "<memory>"
+        self.engine = Engine(state_dict, cfg, device=device, **engine_kwargs)
+        self.cfg = cfg
+        n = self.engine.clip_samples
+        shape = ["batch_size", n] if input_ndim == 2 else ["batch_size", 1, n]
+        self._inputs = [_NodeArg("input", shape)]
+        self._outputs = [_NodeArg("output", ["batch_size", 1, 1])]
+
+    def get_inputs(self):
+        return self._inputs
+
+    def get_outputs(self):
+        return self._outputs
+
+    def get_providers(self):
+        return [PROVIDER]
+
+    def get_modelmeta(self):
+        class _Meta:
+            custom_metadata_map = {"mode": "e2e"}        # what _export/onnx.py:212-221 records
+        return _Meta()
+
+    def run(self, output_names, input_feed, run_options=None):
+        if "input" in input_feed:
+            x = input_feed["input"]
+        elif "audio" in input_feed:
+            x = input_feed["audio"]
+        else:
+            raise ValueError("input_feed must contain 'input'")
+        x = np.asarray(x)
+        n = self.engine.clip_samples
+        if x.ndim == 3 and x.shape[1] == 1:
+            x = x[:, 0, :]
+        if x.ndim == 1:
+            x = x[None, :]
+        if x.ndim != 2 or x.shape[1] != n:
+            raise ValueError(f"Got invalid dimensions for input: expected (batch, {n}), got {tuple(x.shape)}")
+        if x.dtype != np.int16:
+            x = np.clip(np.rint(x.astype(np.float64) * 32768.0), -32768, 32767).astype(np.int16)
+        scores = self.engine.score_host(x)
+        return [scores.reshape(-1, 1, 1)]

@@ -1,0 +1,144 @@
+"""GPU parity: the CUDA engine (through the C ABI) against the oracle and the golden vectors.
+
+Tolerances (BASELINE.json north_star): final sigmoid score within 1e-3, log-mel within 1e-4 dB,
+both measured against the float64 oracle, which is itself pinned to the reference's modules.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden_head
+from nanowakeword_b200.synth import default_config, make_state_dict, synth_pcm
+
+pytestmark = pytest.mark.gpu
+
+SCORE_TOL = 1e-3
+MEL_TOL = 1e-4
+
+HEADS = ["dnn", "cnn", "tcn", "bcresnet", "crnn", "e2e_dnn"]
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+def _engine(mt, **kw):
+    from nanowakeword_b200 import Engine
+    cfg = default_config(mt)
+    sd = make_state_dict(cfg, seed=0)
+    return Engine(sd, cfg, device=0, **kw), sd, cfg
+
+
+@pytest.mark.parametrize("geom,mt", [("NS40x98", "cnn"), ("REF64x101", "e2e_dnn")])
+def test_logmel_matches_golden_and_oracle(torch_cuda, golden_frontend, geom, mt):
+    from oracle.frontend import GEOMETRIES, log_mel
+    eng, _, _ = _engine(mt)
+    pcm = golden_frontend["pcm"]
+    dev = torch_cuda.from_numpy(pcm).cuda()
+    mel = eng.logmel_device(dev).cpu().numpy()
+    ref64 = golden_frontend[f"{geom}.mel_ta64"]               # torchaudio float64 (the reference's transform)
+    assert mel.shape == ref64.shape
+    assert np.abs(mel - ref64).max() < MEL_TOL
+    assert np.abs(mel - log_mel(pcm, GEOMETRIES[geom])).max() < MEL_TOL
+    mel_t = eng.logmel_device(dev, time_major=True).cpu().numpy()
+    assert np.array_equal(mel_t, np.swapaxes(mel, 1, 2))
+    # digital silence hits the amin clamp exactly
+    zeros = list(golden_frontend["names"]).index("zeros")
+    assert np.all(mel[zeros] == -100.0)
+
+
+@pytest.mark.parametrize("mt", HEADS)
+def test_scores_match_golden(torch_cuda, golden_frontend, mt):
+    eng, sd, cfg = _engine(mt)
+    g = load_golden_head(mt)
+    pcm = golden_frontend["pcm"]
+    scores, extra = eng.score_device(torch_cuda.from_numpy(pcm).cuda(), want_logits=True, want_emb=True)
+    scores = scores.cpu().numpy()
+    assert np.abs(scores - g["scores64"].ravel()).max() < SCORE_TOL
+    logit_scale = np.abs(sd["classifier.3.weight"]).sum() + 1.0
+    assert np.abs(extra["logits"].cpu().numpy() - g["logits64"].ravel()).max() < 2e-4 * logit_scale
+    if "emb64" in g:
+        emb = extra["emb"].cpu().numpy()
+        assert np.abs(emb - g["emb64"]).max() < 1e-4 * max(1.0, np.abs(g["emb64"]).max())
+
+
+@pytest.mark.parametrize("mt", HEADS)
+def test_scores_match_oracle_on_seeded_batch(torch_cuda, mt):
+    from oracle.heads import forward_scores
+    eng, sd, cfg = _engine(mt)
+    pcm = np.concatenate([synth_pcm(40, seed=11, kind="uniform"), synth_pcm(40, seed=12, kind="gauss"),
+                          (synth_pcm(20, seed=13, kind="gauss") // 64).astype(np.int16)])
+    ref, mel_ref = forward_scores(pcm, sd, cfg, return_mel=True)
+    scores, extra = eng.score_device(torch_cuda.from_numpy(pcm).cuda(), want_mel=True)
+    assert np.abs(scores.cpu().numpy() - ref.ravel()).max() < SCORE_TOL
+    assert np.abs(extra["mel"].cpu().numpy() - mel_ref).max() < MEL_TOL
+    # host (end-to-end) path gives the same numbers as the device path
+    host = eng.score_host(pcm)
+    assert np.array_equal(host, scores.cpu().numpy())
+
+
+def test_ragged_and_empty_batches(torch_cuda):
+    from oracle.heads import forward_scores
+    eng, sd, cfg = _engine("cnn", chunk_windows=37)          # force several ragged chunks
+    assert eng.score_host(np.zeros((0, 16000), np.int16)).shape == (0,)
+    pcm = synth_pcm(101, seed=5, kind="gauss")
+    ref = forward_scores(pcm, sd, cfg).ravel()
+    got = eng.score_host(pcm)
+    assert np.abs(got - ref).max() < SCORE_TOL
+    one = eng.score_host(pcm[:1])
+    assert np.abs(one - ref[:1]).max() < SCORE_TOL
+    with pytest.raises(ValueError):
+        eng.score_host(pcm[:, :15999])
+    with pytest.raises(ValueError):
+        eng.score_host(pcm.astype(np.float32))
+
+
+def test_full_size_properties(torch_cuda):
+    """BASELINE config #2 size (4096 windows, CNN): batch-order independence and agreement
+    between a window scored alone and inside the batch (the size-independent properties of a
+    per-window map)."""
+    eng, sd, cfg = _engine("cnn")
+    pcm = synth_pcm(4096, seed=1234, kind="uniform")
+    dev = torch_cuda.from_numpy(pcm).cuda()
+    s = eng.score_device(dev).cpu().numpy()
+    assert np.isfinite(s).all() and (s >= 0).all() and (s <= 1).all()
+    perm = np.random.default_rng(0).permutation(4096)
+    s_perm = eng.score_device(torch_cuda.from_numpy(pcm[perm]).cuda()).cpu().numpy()
+    assert np.array_equal(s_perm, s[perm])
+    idx = [0, 1, 147, 148, 1183, 1184, 4095]
+    s_sub = eng.score_device(torch_cuda.from_numpy(pcm[idx]).cuda()).cpu().numpy()
+    assert np.array_equal(s_sub, s[idx])
+    from oracle.heads import forward_scores
+    ref = forward_scores(pcm[idx], sd, cfg).ravel()
+    assert np.abs(s_sub - ref).max() < SCORE_TOL
+
+
+def test_session_duck_type_and_interpreter(torch_cuda, tmp_path, golden_frontend):
+    """The reference-facing path: save artefacts like the reference's exporter, load_model(),
+    predict() in 1280-sample chunks, and compare with the oracle's streaming restatement."""
+    from nanowakeword_b200 import NanoInterpreter, save_model
+    from oracle.interp import OracleInterpreter
+    cfg = default_config("cnn")
+    sd = make_state_dict(cfg, seed=0)
+    path = save_model(str(tmp_path / "hey_b200.pt"), sd, cfg)
+    interp = NanoInterpreter.load_model(path)
+    sess = interp.models["hey_b200"]
+    assert sess.get_providers() == ["B200ExecutionProvider"]
+    assert sess.get_inputs()[0].name == "input" and sess.get_inputs()[0].shape[-1] == 16000
+    x = golden_frontend["pcm"][0]
+    out = sess.run(None, {"input": (x.astype(np.float32) / 32768.0).reshape(1, -1)})
+    assert out[0].shape == (1, 1, 1) and out[0].dtype == np.float32
+    stream = np.concatenate([golden_frontend["pcm"][0], golden_frontend["pcm"][1], golden_frontend["pcm"][6]])
+    oracle = OracleInterpreter(sd, cfg, name="hey_b200")
+    for i in range(0, len(stream), 1280):
+        chunk = stream[i:i + 1280]
+        r = interp.predict(chunk)
+        o = oracle.predict(chunk)
+        assert abs(r.score - o["hey_b200"]) < SCORE_TOL
+        assert abs(interp.raw_scores["hey_b200"] - oracle.raw_scores["hey_b200"]) < SCORE_TOL
+    assert interp.detected(0.0)
+    interp.reset()
+    assert interp.score == 0.0 and interp.e2e_buffer_samples["hey_b200"] == 0
