@@ -79,7 +79,8 @@ int nww_get_info(nww_engine* e, nww_info_t* info);
 
 /* Score n_windows windows of clip_samples int16 samples each, resident in device memory
  * (16-byte aligned), writing one float32 probability per window.  `stream` is a
- * cudaStream_t (NULL = the engine's own stream; the call returns after enqueueing).
+ * cudaStream_t (NULL = the legacy default stream, as everywhere in CUDA); the call returns
+ * after enqueueing and the outputs are ordered on that stream.
  * Optional outputs (NULL to skip): mel_dev (n, n_mels, n_frames) log-mel in dB,
  * logits_dev (n), emb_dev (n, embedding_dim).
  * Replaces session.run(None, {"input": clip}) on the exported graph

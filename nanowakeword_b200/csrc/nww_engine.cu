@@ -36,14 +36,6 @@ static int fail(int code, const std::string& msg) {
 
 namespace {
 
-constexpr int kStageNT = 512;       // threads per stage-A CTA
-constexpr int kNfb64 = 7;           // FFTs per batch, double
-constexpr int kNfb32 = 13;          // FFTs per batch, float
-
-template <typename T> struct DevTables {
-    FrontendTables<T> tab{};
-};
-
 struct DeviceArena {                // one allocation for all small constant tables
     std::vector<unsigned char> host;
     unsigned char* dev = nullptr;
@@ -129,10 +121,6 @@ template <typename T> static void rebase_tables(FrontendTables<T>* t, unsigned c
     fix(t->mel_count);
     fix(t->mel_woff);
     fix(t->mel_w);
-}
-
-template <typename K> static cudaError_t set_smem(K kernel, size_t bytes) {
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
 static int build_tail(nww_engine* e) {
@@ -257,8 +245,8 @@ static int launch_stage_a(nww_engine* e, const int16_t* pcm, int64_t n, float* m
             return NWW_OK;
         }
         default:
-            return launch_head_stage_a(e->spec.arch, e->heads, e->tab64, e->spec.activation, e->sm_count, pcm, n, e->d_feat,
-                                       e->d_scratch, mel, st, &e->launches, &g_last_error);
+            return launch_head_stage_a(e->heads, e->tab64, e->spec.activation, e->sm_count, pcm, n, e->d_feat, e->d_scratch,
+                                       mel, st, &e->launches, &g_last_error);
     }
 }
 
@@ -339,15 +327,24 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
                 if (!t || (expect && t->numel() != expect)) return nullptr;
                 return e->dptr(name);
             };
-            rc = setup_head_weights(spec->arch, spec->geometry, lookup, &e->heads, &e->feat_dim, &e->scratch_per_window,
-                                    &g_last_error);
+            auto dims = [&](const char* name) -> std::vector<uint32_t> {
+                const BlobTensor* t = e->blob.find(name);
+                return t ? t->dims : std::vector<uint32_t>();
+            };
+            rc = setup_head_weights(spec->arch, spec->geometry, lookup, dims, &e->heads, &e->feat_dim, &g_last_error);
             if (rc) return rc;
+            e->scratch_per_window = e->heads.scratch_floats * sizeof(float);
         }
     }
     rc = build_tail(e.get());
     if (rc) return rc;
 
-    e->chunk = spec->chunk_windows > 0 ? spec->chunk_windows : e->sm_count * 8;
+    // chunk: a multiple of the SM count whose intermediates (feature rows + scratch) stay around L2 size
+    {
+        const size_t per_window = (size_t)e->feat_dim * sizeof(float) + e->scratch_per_window;
+        int mult = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)64 << 20) / (per_window * e->sm_count)));
+        e->chunk = spec->chunk_windows > 0 ? spec->chunk_windows : e->sm_count * mult;
+    }
     NWW_CUDA(cudaMalloc(&e->d_feat, (size_t)e->chunk * e->feat_dim * sizeof(float)));
     if (e->scratch_per_window) NWW_CUDA(cudaMalloc(&e->d_scratch, (size_t)e->chunk * e->scratch_per_window));
     NWW_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
@@ -403,7 +400,7 @@ int nww_run_windows(nww_engine* e, const int16_t* pcm_dev, int64_t n, float* sco
     if (reinterpret_cast<uintptr_t>(pcm_dev) & 15) return fail(NWW_EINVAL, "nww_run_windows: pcm_dev must be 16-byte aligned");
     std::lock_guard<std::mutex> lock(e->mu);
     NWW_CUDA(cudaSetDevice(e->device));
-    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : e->stream;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);   // NULL = the legacy default stream, as in CUDA
     return run_device(e, pcm_dev, n, scores_dev, mel_dev, logits_dev, emb_dev, st);
 }
 
@@ -413,7 +410,7 @@ int nww_logmel(nww_engine* e, const int16_t* pcm_dev, int64_t n, float* mel_dev,
     if (reinterpret_cast<uintptr_t>(pcm_dev) & 15) return fail(NWW_EINVAL, "nww_logmel: pcm_dev must be 16-byte aligned");
     std::lock_guard<std::mutex> lock(e->mu);
     NWW_CUDA(cudaSetDevice(e->device));
-    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : e->stream;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);   // NULL = the legacy default stream, as in CUDA
     return e->spec.geometry == NWW_GEOM_NS40X98 ? launch_frontend<GeoNS40x98>(e, pcm_dev, n, mel_dev, time_major, st)
                                                 : launch_frontend<GeoREF64x101>(e, pcm_dev, n, mel_dev, time_major, st);
 }
@@ -426,7 +423,7 @@ int nww_run_windows_f32(nww_engine* e, const float* pcm_dev, int64_t n, float* s
     if (n <= 0) return n == 0 ? NWW_OK : fail(NWW_EINVAL, "nww_run_windows_f32: negative window count");
     std::lock_guard<std::mutex> lock(e->mu);
     NWW_CUDA(cudaSetDevice(e->device));
-    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : e->stream;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);   // NULL = the legacy default stream, as in CUDA
     if (!e->d_pcm[0]) {
         e->host_chunk = e->chunk;
         for (int i = 0; i < 2; ++i) NWW_CUDA(cudaMalloc(&e->d_pcm[i], (size_t)e->host_chunk * e->clip * sizeof(int16_t)));

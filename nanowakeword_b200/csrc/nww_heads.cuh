@@ -1,17 +1,48 @@
-// nww_heads.cuh — stage A of the remaining heads (TCN, BcResNet, CRNN-GRU, E2E mel-CNN).
+// nww_heads.cuh — host-side orchestration of stage A for the layer-kernel heads
+// (TCN, BcResNet, CRNN-GRU, E2E mel-CNN): front end -> log-mel in the scratch arena ->
+// the head's layers (nww_layers.cuh) -> one feature row per window for the dense tail.
 #pragma once
 
+#include <algorithm>
 #include <functional>
 #include <string>
 
 #include "../../include/nww_b200.h"
+#include "nww_layers.cuh"
 #include "nww_stage.cuh"
+#include "nww_tail.cuh"
 
 namespace nww {
 
+constexpr int kStageNT = 512;       // threads per stage-A CTA
+constexpr int kNfb64 = 7;           // FFTs per batch, double
+constexpr int kNfb32 = 13;          // FFTs per batch, float
+
+struct ConvW { const float* w = nullptr; const float* b = nullptr; };
+
 struct HeadWeights {
-    int dummy = 0;
+    int arch = -1;
+    // TCN (default channels [64, 64, 128], k = 3)
+    int tcn_levels = 0, tcn_k = 3, tcn_in = 0;
+    int tcn_ch[8] = {0};
+    ConvW tcn_c1[8], tcn_c2[8], tcn_down[8];
+    // BcResNet
+    ConvW bc_init, bc_pw[3], bc_sc[3];
+    const float* bc_dw[3] = {nullptr, nullptr, nullptr};
+    // CRNN
+    int crnn_levels = 0, crnn_ch[4] = {0}, gru_hidden = 0, gru_in = 0;
+    ConvW crnn_conv[4];
+    const float *gru_wih_f = nullptr, *gru_whh_f = nullptr, *gru_bih_f = nullptr, *gru_bhh_f = nullptr;
+    const float *gru_wih_b = nullptr, *gru_bih_b = nullptr, *gru_bhh_b = nullptr;
+    const float *gru_wih_f_nk = nullptr, *gru_wih_b_nk = nullptr;    // [3H][In] copies for the dense kernel
+    // E2E mel-CNN
+    ConvW e2e_conv[3];
+    // scratch layout (floats per window)
+    size_t scratch_floats = 0;
 };
+
+using BlobLookup = std::function<const float*(const char*, size_t)>;
+using BlobDims = std::function<std::vector<uint32_t>(const char*)>;
 
 // int16 grid recovery for float PCM that was produced as int16 / 32768 (nanointerpreter.py:750).
 __global__ void f32_to_i16_kernel(const float* __restrict__ x, int16_t* __restrict__ y, long long n) {
@@ -22,18 +53,265 @@ __global__ void f32_to_i16_kernel(const float* __restrict__ x, int16_t* __restri
     }
 }
 
-inline int setup_head_weights(int arch, int geometry, const std::function<const float*(const char*, size_t)>& lookup,
-                              HeadWeights* hw, int* feat_dim, size_t* scratch_per_window, std::string* err) {
-    (void)geometry; (void)lookup; (void)hw; (void)feat_dim; (void)scratch_per_window;
-    *err = "architecture id " + std::to_string(arch) + " is not built into this library yet";
-    return NWW_EUNSUPPORTED;
+template <typename K> static cudaError_t set_smem(K kernel, size_t bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-inline int launch_head_stage_a(int arch, const HeadWeights& hw, const FrontendTables<double>& tab, int act, int sm_count,
-                               const int16_t* pcm, long long n, float* feat, float* scratch, float* mel, cudaStream_t st,
-                               int64_t* launches, std::string* err) {
-    (void)hw; (void)tab; (void)act; (void)sm_count; (void)pcm; (void)n; (void)feat; (void)scratch; (void)mel; (void)st; (void)launches;
-    *err = "architecture id " + std::to_string(arch) + " is not built into this library yet";
+#define NWW_HCUDA(call)                                                               \
+    do {                                                                              \
+        cudaError_t _e = (call);                                                      \
+        if (_e != cudaSuccess) {                                                      \
+            *err = std::string(#call) + ": " + cudaGetErrorString(_e);                \
+            return NWW_ECUDA;                                                         \
+        }                                                                             \
+    } while (0)
+
+template <typename G>
+static int launch_frontend_f64(const FrontendTables<double>& tab, int sm_count, const int16_t* pcm, long long n, float* mel,
+                               int time_major, cudaStream_t st, int64_t* launches, std::string* err) {
+    auto k = frontend_kernel<double, G, kNfb64, kStageNT>;
+    NWW_HCUDA(set_smem(k, FrontendSmem<double, G, kNfb64>::kTotal));
+    const int grid = (int)std::min<long long>(n, sm_count);
+    k<<<grid, kStageNT, FrontendSmem<double, G, kNfb64>::kTotal, st>>>(pcm, n, tab, mel, time_major);
+    (*launches)++;
+    NWW_HCUDA(cudaGetLastError());
+    return NWW_OK;
+}
+
+static inline int ew_grid(long long total, int sm_count) {
+    return (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)sm_count * 8));
+}
+
+// ------------------------------------------------------------------------------ setup
+inline int setup_head_weights(int arch, int geometry, const BlobLookup& get, const BlobDims& dims, HeadWeights* hw,
+                              int* feat_dim, std::string* err) {
+    hw->arch = arch;
+    auto need = [&](const std::string& name, size_t numel) -> const float* {
+        const float* p = get(name.c_str(), numel);
+        if (!p && err->empty()) *err = "weight blob: tensor '" + name + "' missing or of unexpected size";
+        return p;
+    };
+    err->clear();
+    if (arch == NWW_ARCH_TCN) {
+        if (geometry != NWW_GEOM_NS40X98) { *err = "tcn head is built for the NS40x98 geometry"; return NWW_EUNSUPPORTED; }
+        int cin = GeoNS40x98::N_MELS;
+        hw->tcn_in = cin;
+        int lv = 0;
+        for (; lv < 8; ++lv) {
+            const std::string p = "tcn." + std::to_string(lv);
+            auto d = dims((p + ".conv1.w").c_str());
+            if (d.size() != 3) break;
+            const int k = (int)d[0], c = (int)d[2];
+            if ((int)d[1] != cin) { *err = p + ".conv1.w: input channels do not chain"; return NWW_EINVAL; }
+            hw->tcn_k = k;
+            hw->tcn_ch[lv] = c;
+            hw->tcn_c1[lv] = {need(p + ".conv1.w", (size_t)k * cin * c), need(p + ".conv1.b", c)};
+            hw->tcn_c2[lv] = {need(p + ".conv2.w", (size_t)k * c * c), need(p + ".conv2.b", c)};
+            if (cin != c) hw->tcn_down[lv] = {need(p + ".down.w", (size_t)cin * c), need(p + ".down.b", c)};
+            cin = c;
+        }
+        if (lv == 0) { *err = "weight blob: tcn.* missing"; return NWW_EINVAL; }
+        hw->tcn_levels = lv;
+        *feat_dim = cin;
+        size_t maxc = hw->tcn_in;
+        for (int i = 0; i < lv; ++i) maxc = std::max<size_t>(maxc, hw->tcn_ch[i]);
+        hw->scratch_floats = (size_t)GeoNS40x98::N_FRAMES * (hw->tcn_in + 3 * maxc);     // mel + 3 rotating planes
+    } else if (arch == NWW_ARCH_BCRESNET) {
+        if (geometry != NWW_GEOM_NS40X98) { *err = "bcresnet head is built for the NS40x98 geometry"; return NWW_EUNSUPPORTED; }
+        hw->bc_init = {need("bc.init.w", 32 * 9), need("bc.init.b", 32)};
+        const int ch[4] = {32, 64, 128, 256};
+        for (int j = 0; j < 3; ++j) {
+            const std::string p = "bc." + std::to_string(j);
+            hw->bc_dw[j] = need(p + ".dw", (size_t)ch[j] * 9);
+            hw->bc_pw[j] = {need(p + ".pw.w", (size_t)ch[j] * ch[j + 1]), need(p + ".pw.b", ch[j + 1])};
+            hw->bc_sc[j] = {need(p + ".sc.w", (size_t)ch[j] * ch[j + 1]), need(p + ".sc.b", ch[j + 1])};
+        }
+        *feat_dim = 256;
+        // mel 40*98, init 32*20*49, then per block: dw + out
+        hw->scratch_floats = 3920 + 31360 + (32 * 250 + 64 * 250) + (64 * 65 + 128 * 65) + (128 * 39 + 256 * 39);
+    } else if (arch == NWW_ARCH_CRNN_GRU) {
+        if (geometry != NWW_GEOM_NS40X98) { *err = "crnn head is built for the NS40x98 geometry"; return NWW_EUNSUPPORTED; }
+        int cin = 1, lv = 0, h = 40, w = 98;
+        size_t act_floats = 0;
+        for (; lv < 4; ++lv) {
+            const std::string p = "crnn.conv" + std::to_string(lv);
+            auto d = dims((p + ".w").c_str());
+            if (d.size() != 3) break;
+            const int c = (int)d[2];
+            if ((int)d[0] != cin || c % kOCT) { *err = p + ".w: unsupported channel counts"; return NWW_EINVAL; }
+            hw->crnn_ch[lv] = c;
+            hw->crnn_conv[lv] = {need(p + ".w", (size_t)cin * 9 * c), need(p + ".b", c)};
+            cin = c; h /= 2; w /= 2;
+            act_floats += (size_t)c * h * w;
+        }
+        if (lv == 0) { *err = "weight blob: crnn.conv* missing"; return NWW_EINVAL; }
+        hw->crnn_levels = lv;
+        hw->gru_in = cin * h;
+        auto dh = dims("crnn.gru.fwd.w_hh");
+        if (dh.size() != 2) { *err = "weight blob: crnn.gru.fwd.w_hh missing"; return NWW_EINVAL; }
+        const int H = (int)dh[0];
+        hw->gru_hidden = H;
+        hw->gru_whh_f = need("crnn.gru.fwd.w_hh", (size_t)H * 3 * H);
+        hw->gru_bhh_f = need("crnn.gru.fwd.b_hh", 3 * H);
+        hw->gru_bih_f = need("crnn.gru.fwd.b_ih", 3 * H);
+        hw->gru_bih_b = need("crnn.gru.bwd.b_ih", 3 * H);
+        hw->gru_bhh_b = need("crnn.gru.bwd.b_hh", 3 * H);
+        hw->gru_wih_f_nk = need("crnn.gru.fwd.w_ih_nk", (size_t)3 * H * hw->gru_in);
+        hw->gru_wih_b_nk = need("crnn.gru.bwd.w_ih_nk", (size_t)3 * H * hw->gru_in);
+        *feat_dim = 2 * H;
+        // mel + conv activations + seq [w][gru_in] + gi_f [w][3H] + gi_b [3H]
+        hw->scratch_floats = 3920 + act_floats + (size_t)w * hw->gru_in + (size_t)w * 3 * H + 3 * H;
+        if (gru_smem_bytes(H) > 200 * 1024) { *err = "GRU hidden size too large for shared memory"; return NWW_EUNSUPPORTED; }
+    } else if (arch == NWW_ARCH_E2E_MELCNN) {
+        if (geometry != NWW_GEOM_REF64X101) { *err = "e2e mel-CNN is built for the REF64x101 geometry"; return NWW_EUNSUPPORTED; }
+        const int ch[4] = {1, 16, 32, 64};
+        for (int j = 0; j < 3; ++j) {
+            const std::string p = "e2e.conv" + std::to_string(j);
+            hw->e2e_conv[j] = {need(p + ".w", (size_t)ch[j] * 9 * ch[j + 1]), need(p + ".b", ch[j + 1])};
+        }
+        *feat_dim = 256;
+        hw->scratch_floats = 64 * 101 + 16 * 32 * 50 + 32 * 16 * 25 + 64 * 16 * 25;
+    } else {
+        *err = "architecture id " + std::to_string(arch) + " is not built into this library";
+        return NWW_EUNSUPPORTED;
+    }
+    return err->empty() ? NWW_OK : NWW_EINVAL;
+}
+
+// ------------------------------------------------------------------------------ launches
+inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<double>& tab, int act, int sm_count,
+                               const int16_t* pcm, long long n, float* feat, float* scratch, float* mel_dump,
+                               cudaStream_t st, int64_t* launches, std::string* err) {
+    float* p = scratch;
+    auto take = [&](size_t floats_per_window) {
+        float* r = p;
+        p += floats_per_window * (size_t)n;
+        return r;
+    };
+    auto done = [&]() -> int {
+        (*launches)++;
+        NWW_HCUDA(cudaGetLastError());
+        return NWW_OK;
+    };
+    int rc;
+    if (hw.arch == NWW_ARCH_E2E_MELCNN) {
+        using G = GeoREF64x101;
+        float* mel = take(64 * 101);
+        float* a1 = take(16 * 32 * 50);
+        float* a2 = take(32 * 16 * 25);
+        float* a3 = take(64 * 16 * 25);
+        if ((rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel, 0, st, launches, err))) return rc;
+        conv3x3_kernel<true><<<ew_grid(n * 2 * 32 * 50, sm_count), 256, 0, st>>>(mel, hw.e2e_conv[0].w, hw.e2e_conv[0].b, a1, n, 1, 16, 64, 101, act);
+        if ((rc = done())) return rc;
+        conv3x3_kernel<true><<<ew_grid(n * 4 * 16 * 25, sm_count), 256, 0, st>>>(a1, hw.e2e_conv[1].w, hw.e2e_conv[1].b, a2, n, 16, 32, 32, 50, act);
+        if ((rc = done())) return rc;
+        conv3x3_kernel<false><<<ew_grid(n * 8 * 16 * 25, sm_count), 256, 0, st>>>(a2, hw.e2e_conv[2].w, hw.e2e_conv[2].b, a3, n, 32, 64, 16, 25, act);
+        if ((rc = done())) return rc;
+        avgpool_row_kernel<<<ew_grid(n * 256, sm_count), 256, 0, st>>>(a3, feat, n, 64, 16, 25, 4);
+        if ((rc = done())) return rc;
+        if (mel_dump) NWW_HCUDA(cudaMemcpyAsync(mel_dump, mel, (size_t)n * 64 * 101 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        return NWW_OK;
+    }
+    using G = GeoNS40x98;
+    constexpr int F = G::N_MELS, T = G::N_FRAMES;
+    float* mel = take((size_t)F * T);
+    if ((rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel, 0, st, launches, err))) return rc;
+    if (mel_dump) NWW_HCUDA(cudaMemcpyAsync(mel_dump, mel, (size_t)n * F * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
+
+    if (hw.arch == NWW_ARCH_TCN) {
+        // positions each layer output must cover so that the final step (T-1) is exact
+        const int L = hw.tcn_levels, k = hw.tcn_k;
+        int lo_out[8], lo_mid[8];
+        int need_lo = T - 1;
+        for (int i = L - 1; i >= 0; --i) {
+            const int d = 1 << i;
+            lo_out[i] = need_lo;                                  // block output (conv2 + residual)
+            lo_mid[i] = std::max(0, lo_out[i] - (k - 1) * d);     // conv1 output
+            need_lo = std::max(0, lo_mid[i] - (k - 1) * d);       // block input
+        }
+        size_t maxc = hw.tcn_in;
+        for (int i = 0; i < L; ++i) maxc = std::max<size_t>(maxc, hw.tcn_ch[i]);
+        float* buf[3] = {take(maxc * T), take(maxc * T), take(maxc * T)};
+        const float* x = mel;                                     // (B, F, T) == permute(0, 2, 1) of the (T, F) input
+        int cin = hw.tcn_in, cur = 0;
+        for (int i = 0; i < L; ++i) {
+            const int c = hw.tcn_ch[i], d = 1 << i;
+            float* mid = buf[cur];
+            float* out = buf[(cur + 1) % 3];
+            tcn_conv_kernel<<<ew_grid(n * (T - lo_mid[i]) * c, sm_count), 256, 0, st>>>(
+                x, hw.tcn_c1[i].w, hw.tcn_c1[i].b, nullptr, nullptr, nullptr, mid, n, cin, c, 0, T, k, d, lo_mid[i], 0);
+            if ((rc = done())) return rc;
+            tcn_conv_kernel<<<ew_grid(n * (T - lo_out[i]) * c, sm_count), 256, 0, st>>>(
+                mid, hw.tcn_c2[i].w, hw.tcn_c2[i].b, x, hw.tcn_down[i].w, hw.tcn_down[i].b, out, n, c, c, cin, T, k, d, lo_out[i], 1);
+            if ((rc = done())) return rc;
+            x = out;
+            cin = c;
+            cur = (cur + 2) % 3;       // next block must not overwrite its own input (= out)
+        }
+        last_step_kernel<<<ew_grid(n * cin, sm_count), 256, 0, st>>>(x, feat, n, cin, T);
+        return done();
+    }
+    if (hw.arch == NWW_ARCH_BCRESNET) {
+        float* a0 = take(32 * 20 * 49);
+        conv3x3_kernel<true><<<ew_grid(n * 4 * 20 * 49, sm_count), 256, 0, st>>>(mel, hw.bc_init.w, hw.bc_init.b, a0, n, 1, 32, F, T, act);
+        if ((rc = done())) return rc;
+        const int ch[4] = {32, 64, 128, 256};
+        const int sh[3] = {2, 2, 2}, sw[3] = {2, 2, 1};
+        int H = 20, W = 49;
+        const float* x = a0;
+        for (int j = 0; j < 3; ++j) {
+            const int Ho = (H - 1) / sh[j] + 1, Wo = (W - 1) / sw[j] + 1;
+            float* dwo = take((size_t)ch[j] * Ho * Wo);
+            float* out = take((size_t)ch[j + 1] * Ho * Wo);
+            dw3x3_kernel<<<ew_grid(n * ch[j] * Ho * Wo, sm_count), 256, 0, st>>>(x, hw.bc_dw[j], dwo, n, ch[j], H, W, sh[j], sw[j]);
+            if ((rc = done())) return rc;
+            bc_pw_res_kernel<<<ew_grid(n * (ch[j + 1] / kOCT) * Ho * Wo, sm_count), 256, 0, st>>>(
+                dwo, x, hw.bc_pw[j].w, hw.bc_pw[j].b, hw.bc_sc[j].w, hw.bc_sc[j].b, out, n, ch[j], ch[j + 1], H, W, sh[j], sw[j], act);
+            if ((rc = done())) return rc;
+            x = out; H = Ho; W = Wo;
+        }
+        gap_kernel<<<ew_grid(n * 256 * 32, sm_count), 256, 0, st>>>(x, feat, n * 256, H * W);
+        return done();
+    }
+    if (hw.arch == NWW_ARCH_CRNN_GRU) {
+        int cin = 1, H = F, W = T;
+        const float* x = mel;
+        for (int i = 0; i < hw.crnn_levels; ++i) {
+            const int c = hw.crnn_ch[i];
+            float* out = take((size_t)c * (H / 2) * (W / 2));
+            conv3x3_kernel<true><<<ew_grid(n * (c / kOCT) * (H / 2) * (W / 2), sm_count), 256, 0, st>>>(
+                x, hw.crnn_conv[i].w, hw.crnn_conv[i].b, out, n, cin, c, H, W, act);
+            if ((rc = done())) return rc;
+            x = out; cin = c; H /= 2; W /= 2;
+        }
+        const int S = W, In = hw.gru_in, Hd = hw.gru_hidden, G3 = 3 * Hd;
+        float* seq = take((size_t)S * In);
+        float* gi_f = take((size_t)S * G3);
+        float* gi_b = take((size_t)G3);
+        seq_pack_kernel<<<ew_grid(n * S * In, sm_count), 256, 0, st>>>(x, seq, n, cin, H, S);
+        if ((rc = done())) return rc;
+        // input projections as dense layers over rows: all S steps forward, the last step only backward
+        TailParams P{};
+        P.n_layers = 1; P.act = act; P.max_width = G3; P.raw_out = 1;
+        P.layers[0] = TailLayer{hw.gru_wih_f_nk, hw.gru_bih_f, nullptr, nullptr, In, G3, POST_NONE};
+        const size_t smem = tail_smem_bytes(G3);
+        NWW_HCUDA(set_smem(tail_kernel, smem));
+        const long long rows = n * S;
+        tail_kernel<<<(int)std::min<long long>((rows + kTailTM - 1) / kTailTM, (long long)sm_count * 2), kTailNT, smem, st>>>(
+            seq, rows, P, gi_f, nullptr, nullptr);
+        if ((rc = done())) return rc;
+        P.layers[0] = TailLayer{hw.gru_wih_b_nk, hw.gru_bih_b, nullptr, nullptr, In, G3, POST_NONE};
+        P.x_row_mul = S; P.x_row_off = S - 1;
+        tail_kernel<<<(int)std::min<long long>((n + kTailTM - 1) / kTailTM, (long long)sm_count * 2), kTailNT, smem, st>>>(
+            seq, n, P, gi_b, nullptr, nullptr);
+        if ((rc = done())) return rc;
+        const size_t gsmem = gru_smem_bytes(Hd);
+        NWW_HCUDA(set_smem(gru_kernel, gsmem));
+        gru_kernel<<<(int)std::min<long long>((n + kGruTM - 1) / kGruTM, (long long)sm_count), kGruNT, gsmem, st>>>(
+            gi_f, gi_b, hw.gru_whh_f, hw.gru_bhh_f, hw.gru_bhh_b, feat, n, S, Hd);
+        return done();
+    }
+    *err = "architecture id " + std::to_string(hw.arch) + " is not built into this library";
     return NWW_EUNSUPPORTED;
 }
 

@@ -33,6 +33,9 @@ struct TailParams {
     int n_layers;
     int act;
     int max_width;       // max over layers of N and of K for layers >= 1 (shared-memory row pitch)
+    int raw_out;         // 1: write the last layer's [rows][N] output instead of sigmoid scores
+    int x_row_mul;       // input row r of the first layer lives at feat[(r * x_row_mul + x_row_off) * K]
+    int x_row_off;       //   (0 is read as 1: plain row-major input)
 };
 
 constexpr int kTailTM = 32;      // windows per CTA
@@ -55,6 +58,7 @@ tail_kernel(const float* __restrict__ feat, long long n_windows, TailParams P, f
     const int lane_n = tid & 127;
     const int half = tid >> 7;                       // 0/1 -> windows [0,16) / [16,32)
     constexpr int MH = kTailTM / 2;
+    const long long xmul = P.x_row_mul > 0 ? P.x_row_mul : 1;
 
     for (long long w0 = (long long)blockIdx.x * kTailTM; w0 < n_windows; w0 += (long long)gridDim.x * kTailTM) {
         const int mt = (n_windows - w0 < kTailTM) ? (int)(n_windows - w0) : kTailTM;
@@ -78,7 +82,7 @@ tail_kernel(const float* __restrict__ feat, long long n_windows, TailParams P, f
                         __syncthreads();             // previous chunk fully consumed
                         for (int i = tid; i < kTailTM * kTailKC; i += kTailNT) {
                             const int m = i / kTailKC, k = i - m * kTailKC;
-                            xch[i] = (m < mt && k < kc) ? feat[(w0 + m) * (long long)L.K + k0 + k] : 0.0f;
+                            xch[i] = (m < mt && k < kc) ? feat[((w0 + m) * xmul + P.x_row_off) * (long long)L.K + k0 + k] : 0.0f;
                         }
                         __syncthreads();
                         xs = xch;
@@ -152,6 +156,13 @@ tail_kernel(const float* __restrict__ feat, long long n_windows, TailParams P, f
                     emb_dump[(w0 + i / L.N) * (long long)L.N + i % L.N] = nxt[(size_t)(i / L.N) * P.max_width + i % L.N];
             }
             float* t = cur; cur = nxt; nxt = t;
+        }
+        if (P.raw_out) {
+            const int NL = P.layers[P.n_layers - 1].N;
+            for (int i = tid; i < mt * NL; i += kTailNT)
+                scores[(w0 + i / NL) * (long long)NL + i % NL] = cur[(size_t)(i / NL) * P.max_width + i % NL];
+            __syncthreads();
+            continue;
         }
         // last layer has N == 1: logit in cur[m * max_width]
         for (int m = tid; m < mt; m += kTailNT) {

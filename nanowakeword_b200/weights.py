@@ -124,7 +124,7 @@ def pack_tensors(sd: dict, cfg: dict) -> dict[str, np.ndarray]:
         layers.append((_f64(sd, "model.fc.weight"), _f64(sd, "model.fc.bias"), POST_NONE, None))
     elif mt == "bcresnet":
         w, b = fold_bn(_f64(sd, "model.init_conv.0.weight"), None, sd, "model.init_conv.1")
-        out["bc.init.w"] = w.reshape(32, 9).astype(np.float32)
+        out["bc.init.w"] = _conv3x3_ic_tap_oc(w).astype(np.float32)               # (1, 9, 32)
         out["bc.init.b"] = b.astype(np.float32)
         for j, name in enumerate(("block1", "block2", "block3")):
             p = "model." + name
@@ -146,7 +146,7 @@ def pack_tensors(sd: dict, cfg: dict) -> dict[str, np.ndarray]:
             out[f"crnn.conv{i}.b"] = b.astype(np.float32)
             i += 1
         for sfx, tag in (("", "fwd"), ("_reverse", "bwd")):
-            out[f"crnn.gru.{tag}.w_ih"] = np.ascontiguousarray(_f64(sd, "model.rnn.weight_ih_l0" + sfx).T).astype(np.float32)  # (In, 3H)
+            out[f"crnn.gru.{tag}.w_ih_nk"] = _f64(sd, "model.rnn.weight_ih_l0" + sfx).astype(np.float32)  # (3H, In), dense-kernel layout
             out[f"crnn.gru.{tag}.w_hh"] = np.ascontiguousarray(_f64(sd, "model.rnn.weight_hh_l0" + sfx).T).astype(np.float32)  # (H, 3H)
             out[f"crnn.gru.{tag}.b_ih"] = _f64(sd, "model.rnn.bias_ih_l0" + sfx).astype(np.float32)
             out[f"crnn.gru.{tag}.b_hh"] = _f64(sd, "model.rnn.bias_hh_l0" + sfx).astype(np.float32)

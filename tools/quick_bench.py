@@ -32,6 +32,7 @@ for mt in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["cnn", "dnn"]):
             print(f"{mt:9s} {prec} full path      {ms:8.3f} ms  {B / ms * 1e3 / 1e6:7.3f} Mwin/s  launches={eng.info['kernel_launches']}")
             host = torch.from_numpy(synth_pcm(B, seed=1234)).pin_memory()
             hs = torch.empty(B, dtype=torch.float32).pin_memory()
+            eng.score_host_ptr(host.data_ptr(), B, hs.data_ptr())
             t0 = time.perf_counter()
             for _ in range(5): eng.score_host_ptr(host.data_ptr(), B, hs.data_ptr())
             dt = (time.perf_counter() - t0) / 5
