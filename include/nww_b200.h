@@ -104,6 +104,18 @@ int nww_run_windows_host(nww_engine* e, const int16_t* pcm_host, int64_t n_windo
  * _export/onnx.py:66-83. */
 int nww_logmel(nww_engine* e, const int16_t* pcm_dev, int64_t n_windows, float* mel_dev, int time_major, void* stream);
 
+/* Per-stage device timing with CUDA events recorded on the launching stream (used by bench.py
+ * for the roofline of the dominant kernel).  Stage A = the per-window kernels (front end +
+ * head body), stage B = the dense tail.  nww_get_profile() synchronises the recorded events,
+ * returns the totals since the last call and clears them. */
+typedef struct nww_profile_t {
+    double stage_a_ms, stage_b_ms;
+    int64_t stage_a_spans, stage_b_spans;   /* timed launch groups (one per chunk)   */
+    int64_t stage_a_windows, stage_b_windows;
+} nww_profile_t;
+int nww_set_profiling(nww_engine* e, int enable);
+int nww_get_profile(nww_engine* e, nww_profile_t* out);
+
 /* Block until everything enqueued on the engine's own streams has finished. */
 int nww_synchronize(nww_engine* e);
 

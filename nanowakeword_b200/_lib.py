@@ -37,6 +37,14 @@ class NwwInfo(C.Structure):
     ]
 
 
+class NwwProfile(C.Structure):
+    _fields_ = [
+        ("stage_a_ms", C.c_double), ("stage_b_ms", C.c_double),
+        ("stage_a_spans", C.c_int64), ("stage_b_spans", C.c_int64),
+        ("stage_a_windows", C.c_int64), ("stage_b_windows", C.c_int64),
+    ]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check every symbol the header declares
 _P = C.c_void_p
 SIGNATURES = {
@@ -48,6 +56,8 @@ SIGNATURES = {
     "nww_run_windows_f32": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, _P]),
     "nww_run_windows_host": (C.c_int, [_P, _P, C.c_int64, _P]),
     "nww_logmel": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int, _P]),
+    "nww_set_profiling": (C.c_int, [_P, C.c_int]),
+    "nww_get_profile": (C.c_int, [_P, C.POINTER(NwwProfile)]),
     "nww_synchronize": (C.c_int, [_P]),
 }
 

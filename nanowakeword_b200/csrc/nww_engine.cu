@@ -14,6 +14,7 @@
 #include "../../include/nww_b200.h"
 #include "nww_blob.h"
 #include "nww_cnn.cuh"
+#include "nww_gemm_tc.cuh"
 #include "nww_heads.cuh"
 #include "nww_stage.cuh"
 #include "nww_tables.h"
@@ -68,6 +69,14 @@ struct nww_engine {
     CnnWeights cnn{};
     HeadWeights heads{};
 
+    // tensor-core path for the first (wide) dense layer
+    bool tc_enabled = false;
+    float *d_w_hi = nullptr, *d_w_lo = nullptr;      // [N][K] split weights
+    float *d_feat_hi = nullptr, *d_feat_lo = nullptr; // [chunk][K] split feature rows
+    float* d_fc1 = nullptr;                           // [chunk][N] output of the tensor-core layer
+    CUtensorMap tm_xhi{}, tm_xlo{}, tm_whi{}, tm_wlo{};
+    TailParams tail_rest{};                           // layers 1.. (after the tensor-core layer)
+
     int chunk = 0;
     float* d_feat = nullptr;         // [chunk][feat_dim]
     float* d_scratch = nullptr;      // per-head scratch (e.g. CRNN sequence), may be null
@@ -80,6 +89,18 @@ struct nww_engine {
     int64_t host_chunk = 0, scores_cap = 0;
 
     int64_t launches = 0, windows = 0;
+
+    // optional per-stage event timing
+    bool profiling = false;
+    struct Span { cudaEvent_t a, b; int stage; int64_t windows; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> event_pool;
+    cudaEvent_t get_event() {
+        if (!event_pool.empty()) { cudaEvent_t ev = event_pool.back(); event_pool.pop_back(); return ev; }
+        cudaEvent_t ev = nullptr;
+        cudaEventCreate(&ev);
+        return ev;
+    }
 
     const float* dptr(const std::string& name) const {
         const BlobTensor* t = blob.find(name);
@@ -213,8 +234,31 @@ static int launch_frontend(nww_engine* e, const int16_t* pcm, int64_t n, float* 
     return NWW_OK;
 }
 
+static int launch_tail_tc(nww_engine* e, int64_t n, float* scores, float* logits, float* emb, cudaStream_t st) {
+    const TailLayer& L0 = e->tail.layers[0];
+    const long long n4 = n * (long long)L0.K / 4;
+    split_tf32_kernel<<<(int)std::min<long long>((n4 + 255) / 256, (long long)e->sm_count * 8), 256, 0, st>>>(
+        e->d_feat, e->d_feat_hi, e->d_feat_lo, n4);
+    e->launches++;
+    NWW_CUDA(cudaGetLastError());
+    GemmTcArgs a{L0.b, L0.ln_g, L0.ln_b, e->d_fc1, (int)n, L0.N, L0.K, L0.post, e->spec.activation};
+    const size_t smem_tc = tc_smem_bytes(L0.N);
+    NWW_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+    gemm_tf32x3_kernel<<<(int)((n + kTcBM - 1) / kTcBM), kTcThreads, smem_tc, st>>>(e->tm_xhi, e->tm_xlo, e->tm_whi, e->tm_wlo, a);
+    e->launches++;
+    NWW_CUDA(cudaGetLastError());
+    const size_t smem = tail_smem_bytes(e->tail_rest.max_width);
+    NWW_CUDA(set_smem(tail_kernel, smem));
+    const int64_t tiles = (n + kTailTM - 1) / kTailTM;
+    tail_kernel<<<grid_for(e, tiles, 2), kTailNT, smem, st>>>(e->d_fc1, n, e->tail_rest, scores, logits, emb);
+    e->launches++;
+    NWW_CUDA(cudaGetLastError());
+    return NWW_OK;
+}
+
 static int launch_tail(nww_engine* e, const float* feat, int64_t n, float* scores, float* logits, float* emb,
                        cudaStream_t st) {
+    if (e->tc_enabled) return launch_tail_tc(e, n, scores, logits, emb, st);
     const size_t smem = tail_smem_bytes(e->tail.max_width);
     NWW_CUDA(set_smem(tail_kernel, smem));
     const int64_t tiles = (n + kTailTM - 1) / kTailTM;
@@ -255,11 +299,22 @@ static int run_device(nww_engine* e, const int16_t* pcm, int64_t n, float* score
     const int64_t mel_stride = (int64_t)e->n_mels * e->n_frames;
     for (int64_t w0 = 0; w0 < n; w0 += e->chunk) {
         const int64_t m = std::min<int64_t>(e->chunk, n - w0);
+        cudaEvent_t ea = nullptr, eb = nullptr, ec = nullptr;
+        if (e->profiling) {
+            ea = e->get_event(); eb = e->get_event(); ec = e->get_event();
+            cudaEventRecord(ea, st);
+        }
         int rc = launch_stage_a(e, pcm + w0 * e->clip, m, mel ? mel + w0 * mel_stride : nullptr, st);
         if (rc) return rc;
+        if (e->profiling) cudaEventRecord(eb, st);
         rc = launch_tail(e, e->d_feat, m, scores + w0, logits ? logits + w0 : nullptr,
                          emb ? emb + w0 * e->emb_dim : nullptr, st);
         if (rc) return rc;
+        if (e->profiling) {
+            cudaEventRecord(ec, st);
+            e->spans.push_back({ea, eb, 0, m});
+            e->spans.push_back({eb, ec, 1, m});
+        }
     }
     e->windows += n;
     return NWW_OK;
@@ -347,6 +402,50 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
     }
     NWW_CUDA(cudaMalloc(&e->d_feat, (size_t)e->chunk * e->feat_dim * sizeof(float)));
     if (e->scratch_per_window) NWW_CUDA(cudaMalloc(&e->d_scratch, (size_t)e->chunk * e->scratch_per_window));
+    {
+        // First dense layer on tcgen05 (3xTF32) when its shape fits the tile constraints.
+        const TailLayer& L0 = e->tail.layers[0];
+        const bool want_tc = !(spec->reserved[0] & 1);          // reserved[0] bit 0: force the CUDA-core tail
+        if (want_tc && e->tail.n_layers >= 3 && tc_layer_eligible(L0.N, L0.K) && get_tmap_encoder() != nullptr) {
+            const size_t wn = (size_t)L0.N * L0.K;
+            std::vector<float> whi(wn), wlo(wn);
+            const float* w = e->blob.f32("tail.0.W");
+            auto rn_tf32 = [](float x) {
+                uint32_t u;
+                memcpy(&u, &x, 4);
+                u = (u + 0x1000u) & 0xFFFFE000u;                // round to nearest (ties away), like cvt.rna.tf32
+                float y;
+                memcpy(&y, &u, 4);
+                return y;
+            };
+            for (size_t i = 0; i < wn; ++i) {
+                whi[i] = rn_tf32(w[i]);
+                wlo[i] = rn_tf32(w[i] - whi[i]);
+            }
+            NWW_CUDA(cudaMalloc(&e->d_w_hi, wn * sizeof(float)));
+            NWW_CUDA(cudaMalloc(&e->d_w_lo, wn * sizeof(float)));
+            NWW_CUDA(cudaMemcpy(e->d_w_hi, whi.data(), wn * sizeof(float), cudaMemcpyHostToDevice));
+            NWW_CUDA(cudaMemcpy(e->d_w_lo, wlo.data(), wn * sizeof(float), cudaMemcpyHostToDevice));
+            const size_t rows = ((size_t)e->chunk + kTcBM - 1) / kTcBM * kTcBM;
+            NWW_CUDA(cudaMalloc(&e->d_feat_hi, rows * L0.K * sizeof(float)));
+            NWW_CUDA(cudaMalloc(&e->d_feat_lo, rows * L0.K * sizeof(float)));
+            NWW_CUDA(cudaMemset(e->d_feat_hi, 0, rows * L0.K * sizeof(float)));
+            NWW_CUDA(cudaMemset(e->d_feat_lo, 0, rows * L0.K * sizeof(float)));
+            NWW_CUDA(cudaMalloc(&e->d_fc1, rows * L0.N * sizeof(float)));
+            const bool ok = make_tmap_2d(&e->tm_xhi, e->d_feat_hi, rows, L0.K, kTcBM) &&
+                            make_tmap_2d(&e->tm_xlo, e->d_feat_lo, rows, L0.K, kTcBM) &&
+                            make_tmap_2d(&e->tm_whi, e->d_w_hi, L0.N, L0.K, L0.N) &&
+                            make_tmap_2d(&e->tm_wlo, e->d_w_lo, L0.N, L0.K, L0.N);
+            if (!ok) return fail(NWW_ECUDA, "cuTensorMapEncodeTiled failed for the dense-layer operands");
+            e->tail_rest = e->tail;
+            e->tail_rest.n_layers = e->tail.n_layers - 1;
+            for (int i = 0; i < e->tail_rest.n_layers; ++i) e->tail_rest.layers[i] = e->tail.layers[i + 1];
+            e->tail_rest.max_width = 1;
+            for (int i = 0; i < e->tail_rest.n_layers; ++i)
+                e->tail_rest.max_width = std::max(e->tail_rest.max_width, std::max(e->tail_rest.layers[i].N, e->tail_rest.layers[i].K));
+            e->tc_enabled = true;
+        }
+    }
     NWW_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     NWW_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
@@ -365,9 +464,16 @@ void nww_destroy(nww_engine* e) {
     cudaFree(e->arena.dev);
     cudaFree(e->d_feat);
     cudaFree(e->d_scratch);
+    cudaFree(e->d_w_hi);
+    cudaFree(e->d_w_lo);
+    cudaFree(e->d_feat_hi);
+    cudaFree(e->d_feat_lo);
+    cudaFree(e->d_fc1);
     cudaFree(e->d_pcm[0]);
     cudaFree(e->d_pcm[1]);
     cudaFree(e->d_scores);
+    for (auto& sp : e->spans) { if (sp.stage == 0) cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto ev : e->event_pool) cudaEventDestroy(ev);
     for (int i = 0; i < 2; ++i) {
         if (e->ev_copy[i]) cudaEventDestroy(e->ev_copy[i]);
         if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
@@ -475,6 +581,35 @@ int nww_run_windows_host(nww_engine* e, const int16_t* pcm_host, int64_t n, floa
     }
     NWW_CUDA(cudaMemcpyAsync(scores_host, e->d_scores, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     NWW_CUDA(cudaStreamSynchronize(e->stream));
+    return NWW_OK;
+}
+
+int nww_set_profiling(nww_engine* e, int enable) {
+    if (!e) return fail(NWW_EINVAL, "nww_set_profiling: null engine");
+    std::lock_guard<std::mutex> lock(e->mu);
+    e->profiling = enable != 0;
+    return NWW_OK;
+}
+
+int nww_get_profile(nww_engine* e, nww_profile_t* out) {
+    if (!e || !out) return fail(NWW_EINVAL, "nww_get_profile: null argument");
+    std::lock_guard<std::mutex> lock(e->mu);
+    NWW_CUDA(cudaSetDevice(e->device));
+    *out = nww_profile_t{};
+    // spans come in (a, b) pairs that share the middle event: release each event once
+    for (size_t i = 0; i < e->spans.size(); ++i) {
+        const auto& sp = e->spans[i];
+        NWW_CUDA(cudaEventSynchronize(sp.b));
+        float ms = 0.f;
+        NWW_CUDA(cudaEventElapsedTime(&ms, sp.a, sp.b));
+        if (sp.stage == 0) { out->stage_a_ms += ms; out->stage_a_spans++; out->stage_a_windows += sp.windows; }
+        else { out->stage_b_ms += ms; out->stage_b_spans++; out->stage_b_windows += sp.windows; }
+    }
+    for (size_t i = 0; i < e->spans.size(); ++i) {
+        if (e->spans[i].stage == 0) e->event_pool.push_back(e->spans[i].a);
+        e->event_pool.push_back(e->spans[i].b);
+    }
+    e->spans.clear();
     return NWW_OK;
 }
 

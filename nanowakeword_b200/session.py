@@ -31,7 +31,7 @@ class Engine:
     """One model resident on one B200: weights, tables and workspaces live in HBM."""
 
     def __init__(self, state_dict: dict, cfg: dict, device: int = 0, frontend_precision: str = "fp64",
-                 chunk_windows: int = 0):
+                 chunk_windows: int = 0, tensor_cores: bool = True):
         self._lib = _lib.load_library()
         self.cfg = dict(cfg)
         self.geometry = geometry_for(cfg)
@@ -50,6 +50,7 @@ class Engine:
         spec.n_mels, spec.center, spec.clip_samples = g["n_mels"], g["center"], g["clip_samples"]
         spec.frontend_precision = {"fp64": 0, "fp32": 1}[frontend_precision]
         spec.chunk_windows = int(chunk_windows)
+        spec.reserved[0] = 0 if tensor_cores else 1      # bit 0: keep the first dense layer on CUDA cores
         self._blob = (C.c_char * len(blob)).from_buffer_copy(blob)
         handle = C.c_void_p()
         rc = self._lib.nww_create(C.byref(spec), C.cast(self._blob, C.c_void_p), len(blob), int(device), C.byref(handle))
@@ -77,6 +78,14 @@ class Engine:
         i = _lib.NwwInfo()
         _lib.check(self._lib, self._lib.nww_get_info(self._h, C.byref(i)), "nww_get_info")
         return {k: getattr(i, k) for k, _ in _lib.NwwInfo._fields_}
+
+    def set_profiling(self, enable: bool):
+        _lib.check(self._lib, self._lib.nww_set_profiling(self._h, int(enable)), "nww_set_profiling")
+
+    def get_profile(self) -> dict:
+        p = _lib.NwwProfile()
+        _lib.check(self._lib, self._lib.nww_get_profile(self._h, C.byref(p)), "nww_get_profile")
+        return {k: getattr(p, k) for k, _ in _lib.NwwProfile._fields_}
 
     def synchronize(self):
         _lib.check(self._lib, self._lib.nww_synchronize(self._h), "nww_synchronize")

@@ -78,14 +78,15 @@ def batchnorm(x, sd, prefix, axis=1):
 
 
 def conv2d(x, w, b=None, stride=(1, 1), pad=(1, 1), groups=1):
-    """NCHW cross-correlation, zero padding, as torch.nn.Conv2d."""
+    """NCHW cross-correlation, zero padding, as torch.nn.Conv2d (im2col + one matmul)."""
     bsz, cin, _, _ = x.shape
     cout, cin_g, kh, kw = w.shape
     xp = np.pad(x, ((0, 0), (0, 0), (pad[0], pad[0]), (pad[1], pad[1])))
     win = sliding_window_view(xp, (kh, kw), axis=(2, 3))[:, :, ::stride[0], ::stride[1]]
-    # win: (B, Cin, Ho, Wo, kh, kw)
+    ho, wo = win.shape[2], win.shape[3]                  # win: (B, Cin, Ho, Wo, kh, kw)
     if groups == 1:
-        y = np.einsum("bchwij,ocij->bohw", win, w, optimize=True)
+        cols = np.ascontiguousarray(win.transpose(0, 2, 3, 1, 4, 5)).reshape(bsz * ho * wo, cin * kh * kw)
+        y = (cols @ w.reshape(cout, cin * kh * kw).T).reshape(bsz, ho, wo, cout).transpose(0, 3, 1, 2)
     else:
         assert groups == cin and cin_g == 1 and cout == cin, "only depthwise grouping is used"
         y = np.einsum("bchwij,cij->bchw", win, w[:, 0], optimize=True)
