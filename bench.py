@@ -40,6 +40,8 @@ FLOP_FRONTEND = 1.3e6             # 98 x rFFT-512 + power + sparse-triangular me
 FLOP_CNN_CONV = 1.13e6 + 9.03e6   # conv1 + conv2 (stage A together with the front end)
 FLOP_CNN_TAIL = 1.97e6 + 0.02e6   # fc1, fc2, classifier (stage B)
 BYTES_IN, BYTES_OUT = CLIP * 2, 4
+# FP64 thread-instructions per window of the v2 front end: 49 packed FFT-512 x (64 x (pass 1 + pass 2) + 32 x pass 3)
+FP64_OPS_PER_WINDOW = 49 * (64 * (118 + 88) + 32 * 190)
 
 
 def workload_config(n_gpus):
@@ -50,7 +52,7 @@ def workload_config(n_gpus):
         "clip_samples": CLIP,
         "geometry": GEOMETRY,
         "head": MODEL,
-        "frontend_precision": "fp64 FFT/power/mel, fp32 log + head",
+        "frontend_precision": "fp64 FFT/power, fp32 mel/log; conv2 bf16x3 split + fc1 tf32x3 split on tcgen05, fp32 accumulate",
         "weights": "random init, numpy default_rng(0) (nanowakeword_b200.synth)",
         "l2_policy": f"{N_ROTATE} distinct {WINDOWS_PER_GPU * CLIP * 2 / 1e6:.0f} MB input batches per GPU cycled between steps (each > 126 MB L2)",
         "parallelism": f"dp{n_gpus} (windows sharded, weights replicated, NCCL gather of scores)",
@@ -283,20 +285,25 @@ def run_gpu_arm(args, rank, world, local_rank):
     a_ms = prof["stage_a_ms"] / max(1, prof["stage_a_spans"])            # average launch of the dominant kernel
     a_win = prof["stage_a_windows"] / max(1, prof["stage_a_spans"])
     share = prof["stage_a_ms"] / max(1e-9, prof["stage_a_ms"] + prof["stage_b_ms"])
-    ach_gbs = a_win * (BYTES_IN + 4 * 7680) / (a_ms * 1e-3) / 1e9      # PCM in + 7680-float feature row out
-    fp32_peak_tflops = 148 * 128 * 2 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e12 if clocks else None
+    alg_bytes = BYTES_IN + BYTES_OUT                                     # 32 000 B PCM in + 4 B score out
+    ach_gbs = a_win * alg_bytes / (a_ms * 1e-3) / 1e9
+    sm_mhz = (clocks.get("sm_mhz") if clocks else None) or 1965.0
+    cyc_per_window = a_ms * 1e-3 * sm_mhz * 1e6 * 148 / max(1.0, a_win)  # SM-cycles one window occupies one SM
     roofline = {
-        "kernel": "cnn_stage_kernel (PCM staging + FFT front end + conv1 + conv2, one window per CTA iteration)",
+        "kernel": "cnn2_stage_kernel (TMA PCM staging + FP64 FFT front end + conv1 + tcgen05 conv2, one window per CTA iteration)",
         "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
         "peak_source": peak_src, "traffic": None,
         "avg_launch_ms": a_ms, "windows_per_launch": a_win, "share_of_step": share,
-        "algorithmic_bytes_per_window": BYTES_IN + 4 * 7680,
-        "compute": {"pipe": "fp32/fp64 CUDA cores (no tensor-core tiles yet)",
+        "algorithmic_bytes_per_window": alg_bytes,
+        "intermediate_bytes_per_window": 2 * 4 * 7680,                   # TF32 hi/lo feature row handed to the fc1 GEMM (L2-resident)
+        "compute": {"pipe": "FP64 CUDA cores (FFT + power, 64 DFMA/clk/SM) and tcgen05 (conv2, fc1); conv1 + mel on FP32",
                     "flop_per_window": FLOP_FRONTEND + FLOP_CNN_CONV,
                     "achieved_tflops": a_win * (FLOP_FRONTEND + FLOP_CNN_CONV) / (a_ms * 1e-3) / 1e12,
-                    "fp32_peak_tflops_at_clock": fp32_peak_tflops},
+                    "sm_cycles_per_window": cyc_per_window,
+                    "fp64_issue_cycles_per_window": FP64_OPS_PER_WINDOW / 64.0,
+                    "fp64_pipe_frac": FP64_OPS_PER_WINDOW / 64.0 / cyc_per_window},
         "note": "the path is compute-bound (SURVEY.md §8(d): HBM roof ~204 M windows/s/GPU); HBM fraction is reported "
-                "because the contract asks for it, the compute block is what limits the kernel",
+                "because the contract asks for it; the binding on-chip roof is FP64 issue (fp64_pipe_frac)",
     }
 
     cores = os.cpu_count() or 1

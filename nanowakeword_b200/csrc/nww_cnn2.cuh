@@ -1,0 +1,258 @@
+// nww_cnn2.cuh — stage A of the CNN head, v2: PCM -> log-mel -> conv1+act+pool -> conv2+act+pool,
+// one window per CTA iteration, persistent one CTA per SM; conv2 (81 % of the head's MACs) runs on
+// the 5th-generation tensor cores as an implicit GEMM with no im2col.
+//
+// Reference: CNNModel, nanowakeword/modules/architectures.py:51-80
+//   conv1 = Conv2d(1, 16, 3, pad 1) -> act -> MaxPool2d(2)      (40,98) -> (16,20,49)
+//   conv2 = Conv2d(16, 32, 3, pad 1) -> act -> MaxPool2d(2)     -> (32,10,24)   [49 -> 24: floor]
+//   flatten (c, h, w) row-major -> 7680 -> fc1 (nww_gemm_tc.cuh)
+//
+// conv2 as tcgen05 tiles.  Let a1[ic][y][x] be the pooled conv1 output (y < 20, x < 49) with a
+// zero border.  The conv2 output needed by pooled position (ph, pw) and pooling quad (dy, dx) is
+//   sum_{r,c,ic} w2[oc][ic][r][c] * a1[ic][2 ph + dy + r - 1][2 pw + dx + c - 1].
+// a1 is stored as four PARITY PLANES (y & 1, x & 1), each a flat list of positions
+//   s = ((y >> 1) + 1) * 25 + (x >> 1) + 1          (pitch 25: column 25 of a row is column 0 of the next)
+// with the 16 input channels of a position as two 16-byte rows (8 bf16 each) in two K groups.  With
+// m = ph * 25 + pw as the GEMM row, the operand of (quad, tap) is the plane
+// ((dy + r - 1) & 1, (dx + c - 1) & 1) starting at position  m + 26 + 25 * ((dy + r - 1) >> 1) +
+// ((dx + c - 1) >> 1): a K-major, un-swizzled UMMA operand whose core matrices are 8 consecutive
+// positions (128 contiguous bytes, SBO = 128) and whose second K half is the other K group
+// (LBO = plane stride) — every tap is the same buffer behind a different descriptor start address.
+// The four quads accumulate into four TMEM column groups with identical row <-> (ph, pw) mapping, so
+// the 2x2 max pool is an element-wise max of four tcgen05.ld results in registers.
+// M = 250 rows = 2 tiles of 128; per tile 4 quads x 9 taps x 3 bf16 split products
+// (a_hi w_hi + a_lo w_hi + a_hi w_lo, ~2^-16 relative) of 128 x 32 x 16.
+//
+// The epilogue writes the 7680 features directly as the TF32 hi / lo pair the fc1 tensor-core GEMM
+// consumes, in the K order (ph, pw, oc) (fc1's weight columns are permuted to match at create time).
+#pragma once
+
+#include "nww_fe2.cuh"
+
+namespace nww {
+
+struct Cnn2 {
+    using G = GeoNS40x98;
+    static constexpr int NT = 512;
+    static constexpr int F = 40, TT = 98, C1 = 16, H1 = 20, W1 = 49, C2 = 32, H2 = 10, W2 = 24;
+    static constexpr int FEAT = C2 * H2 * W2;                     // 7680
+    static constexpr int MEL_P = 100, MEL_ROWS = 42;              // zero-bordered log-mel plane
+    static constexpr int PITCH = 25;                              // GEMM row m = ph * 25 + pw
+    static constexpr int NPOS = 308;                              // positions per parity plane (max read 307)
+    static constexpr int KG_BYTES = NPOS * 16;                    // one K group of one plane (LBO)
+    static constexpr int PLANE_BYTES = 2 * KG_BYTES;              // [kg][pos] x 16 B
+    static constexpr int A1_BYTES = 4 * 2 * PLANE_BYTES;          // [plane][hi|lo] = 78848
+    static constexpr int W2_TAP_BYTES = 1024;                     // [kg 2][oc 32] x 16 B per (tap, hi|lo)
+    static constexpr int W2_BYTES = 9 * 2 * W2_TAP_BYTES;         // 18432
+    static constexpr int CONV1_TASKS = H1 * W1 * 2;               // (position, channel group of 8) = 1960
+    static constexpr int CONV1_SPLIT_ROUNDS = 3;                  // after 3 rounds of 512 tasks a1 rows 0..14 are complete
+    static constexpr int TMEM_COLS = 256;                         // 2 tiles x 4 quads x 32 columns
+
+    static constexpr size_t kUnion = align_up(Fe2::kScratchBytes > (size_t)A1_BYTES ? Fe2::kScratchBytes : (size_t)A1_BYTES, 1024);
+    static constexpr size_t kTw = align_up(Fe2::kTwBytes, 128);
+    static constexpr size_t kMel = align_up(sizeof(float) * MEL_ROWS * MEL_P, 128);
+    static constexpr size_t kW2 = W2_BYTES;
+    static constexpr size_t kSmall = align_up(sizeof(float) * (16 * 9 + 16 + 32), 128);
+    static constexpr size_t kBars = 128;                          // 2 mbarriers + TMEM base slot
+    static constexpr size_t oTw = kUnion, oMel = oTw + kTw, oW2 = oMel + kMel, oSmall = oW2 + kW2, oBars = oSmall + kSmall,
+                            oPcm = oBars + kBars;
+    static constexpr size_t kTotal = oPcm + PcmStager<G::CLIP>::kBytes;
+};
+
+struct Cnn2Weights {
+    const float* w1;          // [16][9]
+    const float* b1;          // [16]
+    const uint4* w2_umma;     // Cnn2::W2_BYTES: [tap][hi|lo][kg][oc][8 ic] bf16, built by the engine
+    const float* b2;          // [32]
+};
+
+__device__ __forceinline__ uint32_t cnn2_pack_bf16(uint32_t lo16, uint32_t hi16) { return lo16 | (hi16 << 16); }
+
+__global__ void __launch_bounds__(Cnn2::NT, 1)
+cnn2_stage_kernel(const int16_t* __restrict__ pcm, long long n_windows, FrontendTables<double> tab, Cnn2Weights wt, int act,
+                  float* __restrict__ feat_hi, float* __restrict__ feat_lo /* [n][7680], K order (ph, pw, oc) */,
+                  float* __restrict__ mel_dump /* nullable, (F,T) */) {
+    using D = Cnn2;
+    NWW_DYN_SMEM(smem);
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    unsigned char* a1b = smem;                                                   // overlays the FFT scratch
+    cplx<double>* tw = reinterpret_cast<cplx<double>*>(smem + D::oTw);
+    float* melp = reinterpret_cast<float*>(smem + D::oMel);
+    unsigned char* w2s = smem + D::oW2;
+    float* w1s = reinterpret_cast<float*>(smem + D::oSmall);
+    float* b1s = w1s + 16 * 9;
+    float* b2s = b1s + 16;
+    uint64_t* mma_bar = reinterpret_cast<uint64_t*>(smem + D::oBars);            // [2], one per M tile
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + D::oBars + 64);
+    PcmStager<D::G::CLIP> stager;
+    stager.carve(smem + D::oPcm);
+    stager.init(tid);
+
+    if (tid == 0) {
+        mbar_init(&mma_bar[0], 1);
+        mbar_init(&mma_bar[1], 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, D::TMEM_COLS);
+    fe2_build_twiddles(tw, tab.twiddle, tid, D::NT);
+    for (int i = tid; i < 16 * 9; i += D::NT) w1s[i] = wt.w1[i];
+    for (int i = tid; i < 16; i += D::NT) b1s[i] = wt.b1[i];
+    for (int i = tid; i < 32; i += D::NT) b2s[i] = wt.b2[i];
+    for (int i = tid; i < D::W2_BYTES / 16; i += D::NT) reinterpret_cast<uint4*>(w2s)[i] = wt.w2_umma[i];
+    for (int i = tid; i < D::MEL_ROWS * D::MEL_P; i += D::NT) melp[i] = 0.0f;    // zero border, written once
+    fence_proxy_async();                                                         // w2s is read by the tensor core (async proxy)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t a1_addr = smem_u32(a1b), w2_addr = smem_u32(w2s);
+    constexpr uint32_t kIdesc = umma_idesc_bf16(128, 32);
+
+    // One elected thread issues the 108 MMAs of M tile `tile` (4 quads x 9 taps x 3 split products).
+    auto issue_tile = [&](int tile) {
+        tc_fence_after();
+#pragma unroll 1
+        for (int quad = 0; quad < 4; ++quad) {
+            const int dy = quad >> 1, dx = quad & 1;
+            const uint32_t d_tmem = tmem_base + (uint32_t)((tile * 4 + quad) * 32);
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const int ry = dy + r - 1, cx = dx + c - 1;
+                    const int plane = ((ry & 1) << 1) | (cx & 1);
+                    const int s0 = tile * 128 + 26 + 25 * (ry >> 1) + (cx >> 1);
+                    const uint32_t a_hi = a1_addr + (uint32_t)(plane * 2 * D::PLANE_BYTES + s0 * 16);
+                    const uint32_t a_lo = a_hi + D::PLANE_BYTES;
+                    const uint32_t b_hi = w2_addr + (uint32_t)((r * 3 + c) * 2 * D::W2_TAP_BYTES);
+                    const uint32_t b_lo = b_hi + D::W2_TAP_BYTES;
+                    const uint64_t da_hi = umma_desc_noswz(a_hi, D::KG_BYTES, 128);
+                    const uint64_t da_lo = umma_desc_noswz(a_lo, D::KG_BYTES, 128);
+                    const uint64_t db_hi = umma_desc_noswz(b_hi, 512, 128);
+                    const uint64_t db_lo = umma_desc_noswz(b_lo, 512, 128);
+                    umma_bf16(d_tmem, da_hi, db_hi, kIdesc, (r | c) != 0);
+                    umma_bf16(d_tmem, da_lo, db_hi, kIdesc, 1);
+                    umma_bf16(d_tmem, da_hi, db_lo, kIdesc, 1);
+                }
+        }
+        umma_commit(&mma_bar[tile]);
+    };
+
+    // conv1 + act + 2x2 max pool for task T = (position, channel group): 8 channels of one pooled pixel
+    // -> bf16 hi / lo rows of the parity planes.
+    auto conv1_task = [&](int T) {
+        const int pos = T >> 1, cg = T & 1;
+        const int y = pos / D::W1, x = pos - y * D::W1;
+        float in[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float2 lo = *reinterpret_cast<const float2*>(melp + (2 * y + r) * D::MEL_P + 2 * x);
+            const float2 hi = *reinterpret_cast<const float2*>(melp + (2 * y + r) * D::MEL_P + 2 * x + 2);
+            in[r][0] = lo.x; in[r][1] = lo.y; in[r][2] = hi.x; in[r][3] = hi.y;
+        }
+        uint32_t hb[8], lb[8];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            const float* k = w1s + (cg * 8 + o) * 9;
+            const float bias = b1s[cg * 8 + o];
+            float best = -3.4e38f;
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    float s = bias;
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) s = fmaf(in[dy + r][dx + c], k[r * 3 + c], s);
+                    best = fmaxf(best, apply_act(s, act));
+                }
+            hb[o] = float_to_bf16_bits(best);
+            lb[o] = float_to_bf16_bits(best - bf16_bits_to_float(hb[o]));
+        }
+        const int plane = ((y & 1) << 1) | (x & 1);
+        const int s = ((y >> 1) + 1) * D::PITCH + (x >> 1) + 1;
+        unsigned char* dst = a1b + plane * 2 * D::PLANE_BYTES + cg * D::KG_BYTES + s * 16;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(cnn2_pack_bf16(hb[0], hb[1]), cnn2_pack_bf16(hb[2], hb[3]),
+                                                    cnn2_pack_bf16(hb[4], hb[5]), cnn2_pack_bf16(hb[6], hb[7]));
+        *reinterpret_cast<uint4*>(dst + D::PLANE_BYTES) = make_uint4(cnn2_pack_bf16(lb[0], lb[1]), cnn2_pack_bf16(lb[2], lb[3]),
+                                                                     cnn2_pack_bf16(lb[4], lb[5]), cnn2_pack_bf16(lb[6], lb[7]));
+    };
+
+    long long w = blockIdx.x;
+    if (w < n_windows) stager.issue(0, pcm + w * D::G::CLIP, tid);
+    for (int it = 0; w < n_windows; w += gridDim.x, ++it) {
+        const long long wn = w + gridDim.x;
+        if (wn < n_windows) stager.issue((it + 1) & 1, pcm + wn * D::G::CLIP, tid);
+        const int16_t* x = stager.wait(it & 1, (it >> 1) & 1);
+
+        // ---- log-mel into the zero-bordered (F+2, T+2) plane (ends with a CTA barrier) ----------------
+        fe2_logmel_window(x, smem, tw, tab, melp + D::MEL_P + 1, D::MEL_P, 1, tid);
+        if (mel_dump != nullptr) {
+            float* md = mel_dump + w * (long long)(D::F * D::TT);
+            for (int i = tid; i < D::F * D::TT; i += D::NT) md[i] = melp[(i / D::TT + 1) * D::MEL_P + (i % D::TT) + 1];
+        }
+
+        // ---- the FFT scratch becomes the parity planes: clear (borders must read as zero) ---------------
+        for (int i = tid; i < D::A1_BYTES / 16; i += D::NT) reinterpret_cast<uint4*>(a1b)[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+
+        // ---- conv1, first three rounds; then M tile 0 of conv2 can start on the tensor core ----------------
+#pragma unroll 1
+        for (int rd = 0; rd < D::CONV1_SPLIT_ROUNDS; ++rd) conv1_task(rd * D::NT + tid);
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == D::NT - 32) issue_tile(0);                        // warp 15 has no conv1 work in the last round
+        if (D::CONV1_SPLIT_ROUNDS * D::NT + tid < D::CONV1_TASKS) conv1_task(D::CONV1_SPLIT_ROUNDS * D::NT + tid);
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == D::NT - 32) issue_tile(1);
+
+        // ---- epilogue: warp -> (TMEM lane quarter, M tile, channel half) ------------------------------------
+        {
+            const int q = warp & 3, tile = (warp >> 2) & 1, half = warp >> 3;
+            mbar_wait(&mma_bar[tile], it & 1);
+            tc_fence_after();
+            uint32_t r[4][16];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tile * 4 * 32 + half * 16);
+#pragma unroll
+            for (int quad = 0; quad < 4; ++quad) tmem_ld_32x32b_x16_nowait(taddr + quad * 32, r[quad]);
+            tmem_ld_wait();
+            tc_fence_before();
+            const int m = tile * 128 + q * 32 + lane;
+            const int ph = m / D::PITCH, pw = m - ph * D::PITCH;
+            if (m < D::H2 * D::PITCH && pw < D::W2) {
+                float hi[16], lo[16];
+#pragma unroll
+                for (int o = 0; o < 16; ++o) {
+                    const float bias = b2s[half * 16 + o];
+                    float v = apply_act(__uint_as_float(r[0][o]) + bias, act);
+                    v = fmaxf(v, apply_act(__uint_as_float(r[1][o]) + bias, act));
+                    v = fmaxf(v, apply_act(__uint_as_float(r[2][o]) + bias, act));
+                    v = fmaxf(v, apply_act(__uint_as_float(r[3][o]) + bias, act));
+                    hi[o] = round_tf32(v);
+                    lo[o] = round_tf32(v - hi[o]);
+                }
+                const long long off = w * (long long)D::FEAT + (ph * D::W2 + pw) * 32 + half * 16;
+                float4* dh = reinterpret_cast<float4*>(feat_hi + off);
+                float4* dl = reinterpret_cast<float4*>(feat_lo + off);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    dh[j] = make_float4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                    dl[j] = make_float4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                }
+            }
+        }
+        __syncthreads();      // planes (= FFT scratch) and TMEM are free again
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, D::TMEM_COLS);
+    }
+}
+
+}  // namespace nww

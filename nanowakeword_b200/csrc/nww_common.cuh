@@ -78,6 +78,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 #else
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)((const unsigned char*)p - cudasim::g_dyn_smem); }
 __device__ __forceinline__ void mbar_init(uint64_t*, uint32_t) {}
 __device__ __forceinline__ void fence_mbar_init() {}
 __device__ __forceinline__ void fence_proxy_async() {}

@@ -9,11 +9,13 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/nww_b200.h"
 #include "nww_blob.h"
 #include "nww_cnn.cuh"
+#include "nww_cnn2.cuh"
 #include "nww_gemm_tc.cuh"
 #include "nww_heads.cuh"
 #include "nww_stage.cuh"
@@ -73,7 +75,12 @@ struct nww_engine {
     bool tc_enabled = false;
     float *d_w_hi = nullptr, *d_w_lo = nullptr;      // [N][K] split weights
     float *d_feat_hi = nullptr, *d_feat_lo = nullptr; // [chunk][K] split feature rows
-    float* d_fc1 = nullptr;                           // [chunk][N] output of the tensor-core layer
+    float* d_part = nullptr;                          // [kTcMaxSplits][rows][N] split-K partial sums of that layer
+    int tc_rows = 0;                                  // rows allocated per operand / partial slab (multiple of 128)
+    // CNN stage v2 (tcgen05 conv2): conv2 weights as UMMA operands; features written pre-split by the stage kernel
+    bool cnn2_enabled = false;
+    uint4* d_w2_umma = nullptr;
+    Cnn2Weights cnn2{};
     CUtensorMap tm_xhi{}, tm_xlo{}, tm_whi{}, tm_wlo{};
     TailParams tail_rest{};                           // layers 1.. (after the tensor-core layer)
 
@@ -224,6 +231,9 @@ static int launch_frontend(nww_engine* e, const int16_t* pcm, int64_t n, float* 
         auto k = frontend_kernel<float, G, kNfb32, kStageNT>;
         NWW_CUDA(set_smem(k, FrontendSmem<float, G, kNfb32>::kTotal));
         k<<<grid_for(e, n), kStageNT, FrontendSmem<float, G, kNfb32>::kTotal, st>>>(pcm, n, e->tab32, mel, time_major);
+    } else if constexpr (std::is_same<G, GeoNS40x98>::value) {
+        NWW_CUDA(set_smem(frontend2_kernel, Fe2KernelSmem::kTotal));
+        frontend2_kernel<<<grid_for(e, n), Fe2::NT, Fe2KernelSmem::kTotal, st>>>(pcm, n, e->tab64, mel, time_major);
     } else {
         auto k = frontend_kernel<double, G, kNfb64, kStageNT>;
         NWW_CUDA(set_smem(k, FrontendSmem<double, G, kNfb64>::kTotal));
@@ -236,21 +246,38 @@ static int launch_frontend(nww_engine* e, const int16_t* pcm, int64_t n, float* 
 
 static int launch_tail_tc(nww_engine* e, int64_t n, float* scores, float* logits, float* emb, cudaStream_t st) {
     const TailLayer& L0 = e->tail.layers[0];
-    const long long n4 = n * (long long)L0.K / 4;
-    split_tf32_kernel<<<(int)std::min<long long>((n4 + 255) / 256, (long long)e->sm_count * 8), 256, 0, st>>>(
-        e->d_feat, e->d_feat_hi, e->d_feat_lo, n4);
-    e->launches++;
-    NWW_CUDA(cudaGetLastError());
-    GemmTcArgs a{L0.b, L0.ln_g, L0.ln_b, e->d_fc1, (int)n, L0.N, L0.K, L0.post, e->spec.activation};
+    if (!e->cnn2_enabled) {                                     // the v2 CNN stage writes the hi / lo pair itself
+        const long long n4 = n * (long long)L0.K / 4;
+        split_tf32_kernel<<<(int)std::min<long long>((n4 + 255) / 256, (long long)e->sm_count * 8), 256, 0, st>>>(
+            e->d_feat, e->d_feat_hi, e->d_feat_lo, n4);
+        e->launches++;
+        NWW_CUDA(cudaGetLastError());
+    }
+    // split-K so that (row tiles x splits) fills the SMs; partial sums are reduced in a fixed order by the tail
+    const int m_tiles = (int)((n + kTcBM - 1) / kTcBM);
+    const int nkb = L0.K / kTcBK;
+    int splits = std::max(1, std::min(std::min(kTcMaxSplits, nkb), e->sm_count / m_tiles));
+    const int kbps = (nkb + splits - 1) / splits;
+    splits = (nkb + kbps - 1) / kbps;
+    GemmTcArgs a{L0.b, L0.ln_g, L0.ln_b, nullptr, (int)n, L0.N, L0.K, L0.post, e->spec.activation, e->d_part, kbps, e->tc_rows};
     const size_t smem_tc = tc_smem_bytes(L0.N);
     NWW_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
-    gemm_tf32x3_kernel<<<(int)((n + kTcBM - 1) / kTcBM), kTcThreads, smem_tc, st>>>(e->tm_xhi, e->tm_xlo, e->tm_whi, e->tm_wlo, a);
+    gemm_tf32x3_kernel<<<dim3(m_tiles, splits), kTcThreads, smem_tc, st>>>(e->tm_xhi, e->tm_xlo, e->tm_whi, e->tm_wlo, a);
     e->launches++;
     NWW_CUDA(cudaGetLastError());
-    const size_t smem = tail_smem_bytes(e->tail_rest.max_width);
+    TailParams P = e->tail_rest;
+    P.pre_part = e->d_part;
+    P.pre_b = L0.b;
+    P.pre_g = L0.ln_g;
+    P.pre_beta = L0.ln_b;
+    P.pre_splits = splits;
+    P.pre_mpad = e->tc_rows;
+    P.pre_N = L0.N;
+    P.pre_post = L0.post;
+    const size_t smem = tail_smem_bytes(P.max_width);
     NWW_CUDA(set_smem(tail_kernel, smem));
     const int64_t tiles = (n + kTailTM - 1) / kTailTM;
-    tail_kernel<<<grid_for(e, tiles, 2), kTailNT, smem, st>>>(e->d_fc1, n, e->tail_rest, scores, logits, emb);
+    tail_kernel<<<grid_for(e, tiles, 2), kTailNT, smem, st>>>(nullptr, n, P, scores, logits, emb);
     e->launches++;
     NWW_CUDA(cudaGetLastError());
     return NWW_OK;
@@ -280,6 +307,14 @@ static int launch_stage_a(nww_engine* e, const int16_t* pcm, int64_t n, float* m
         }
         case NWW_ARCH_CNN: {
             using G = GeoNS40x98;
+            if (e->cnn2_enabled) {
+                NWW_CUDA(set_smem(cnn2_stage_kernel, Cnn2::kTotal));
+                cnn2_stage_kernel<<<grid_for(e, n), Cnn2::NT, Cnn2::kTotal, st>>>(pcm, n, e->tab64, e->cnn2, e->spec.activation,
+                                                                                 e->d_feat_hi, e->d_feat_lo, mel);
+                e->launches++;
+                NWW_CUDA(cudaGetLastError());
+                return NWW_OK;
+            }
             auto k = cnn_stage_kernel<double, G, kNfb64, kStageNT>;
             const size_t smem = CnnSmem<double, G, kNfb64>::kTotal;
             NWW_CUDA(set_smem(k, smem));
@@ -408,8 +443,20 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
         const bool want_tc = !(spec->reserved[0] & 1);          // reserved[0] bit 0: force the CUDA-core tail
         if (want_tc && e->tail.n_layers >= 3 && tc_layer_eligible(L0.N, L0.K) && get_tmap_encoder() != nullptr) {
             const size_t wn = (size_t)L0.N * L0.K;
-            std::vector<float> whi(wn), wlo(wn);
+            std::vector<float> whi(wn), wlo(wn), wperm;
             const float* w = e->blob.f32("tail.0.W");
+            // CNN stage v2 (tcgen05 conv2) emits features in the K order (ph, pw, oc): permute fc1's columns to match
+            const bool want_cnn2 = spec->arch == NWW_ARCH_CNN && !(spec->reserved[0] & 2) && L0.K == Cnn2::FEAT;
+            if (want_cnn2) {
+                wperm.resize(wn);
+                for (int nn = 0; nn < L0.N; ++nn)
+                    for (int oc = 0; oc < Cnn2::C2; ++oc)
+                        for (int ph = 0; ph < Cnn2::H2; ++ph)
+                            for (int pw = 0; pw < Cnn2::W2; ++pw)
+                                wperm[(size_t)nn * L0.K + (ph * Cnn2::W2 + pw) * Cnn2::C2 + oc] =
+                                    w[(size_t)nn * L0.K + (oc * Cnn2::H2 + ph) * Cnn2::W2 + pw];
+                w = wperm.data();
+            }
             auto rn_tf32 = [](float x) {
                 uint32_t u;
                 memcpy(&u, &x, 4);
@@ -427,16 +474,47 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
             NWW_CUDA(cudaMemcpy(e->d_w_hi, whi.data(), wn * sizeof(float), cudaMemcpyHostToDevice));
             NWW_CUDA(cudaMemcpy(e->d_w_lo, wlo.data(), wn * sizeof(float), cudaMemcpyHostToDevice));
             const size_t rows = ((size_t)e->chunk + kTcBM - 1) / kTcBM * kTcBM;
+            e->tc_rows = (int)rows;
             NWW_CUDA(cudaMalloc(&e->d_feat_hi, rows * L0.K * sizeof(float)));
             NWW_CUDA(cudaMalloc(&e->d_feat_lo, rows * L0.K * sizeof(float)));
             NWW_CUDA(cudaMemset(e->d_feat_hi, 0, rows * L0.K * sizeof(float)));
             NWW_CUDA(cudaMemset(e->d_feat_lo, 0, rows * L0.K * sizeof(float)));
-            NWW_CUDA(cudaMalloc(&e->d_fc1, rows * L0.N * sizeof(float)));
+            NWW_CUDA(cudaMalloc(&e->d_part, (size_t)kTcMaxSplits * rows * L0.N * sizeof(float)));
             const bool ok = make_tmap_2d(&e->tm_xhi, e->d_feat_hi, rows, L0.K, kTcBM) &&
                             make_tmap_2d(&e->tm_xlo, e->d_feat_lo, rows, L0.K, kTcBM) &&
                             make_tmap_2d(&e->tm_whi, e->d_w_hi, L0.N, L0.K, L0.N) &&
                             make_tmap_2d(&e->tm_wlo, e->d_w_lo, L0.N, L0.K, L0.N);
             if (!ok) return fail(NWW_ECUDA, "cuTensorMapEncodeTiled failed for the dense-layer operands");
+            if (want_cnn2) {
+                // conv2 weights as un-swizzled K-major UMMA operands: [tap][hi|lo][kg][oc][8 ic] bf16
+                const float* w2 = e->blob.f32("cnn.w2");          // [ic 16][tap 9][oc 32]
+                auto bf16_rn = [](float x) {
+                    uint32_t u;
+                    memcpy(&u, &x, 4);
+                    u += 0x7FFFu + ((u >> 16) & 1u);
+                    return (uint16_t)(u >> 16);
+                };
+                auto bf16_f = [](uint16_t b) {
+                    uint32_t u = (uint32_t)b << 16;
+                    float f;
+                    memcpy(&f, &u, 4);
+                    return f;
+                };
+                std::vector<uint16_t> wb(Cnn2::W2_BYTES / 2);
+                for (int tap = 0; tap < 9; ++tap)
+                    for (int ic = 0; ic < 16; ++ic)
+                        for (int oc = 0; oc < 32; ++oc) {
+                            const float v = w2[(ic * 9 + tap) * 32 + oc];
+                            const uint16_t hi = bf16_rn(v), lo = bf16_rn(v - bf16_f(hi));
+                            const size_t base = (size_t)tap * 2 * (Cnn2::W2_TAP_BYTES / 2) + (size_t)(ic >> 3) * 256 + oc * 8 + (ic & 7);
+                            wb[base] = hi;
+                            wb[base + Cnn2::W2_TAP_BYTES / 2] = lo;
+                        }
+                NWW_CUDA(cudaMalloc(&e->d_w2_umma, Cnn2::W2_BYTES));
+                NWW_CUDA(cudaMemcpy(e->d_w2_umma, wb.data(), Cnn2::W2_BYTES, cudaMemcpyHostToDevice));
+                e->cnn2 = Cnn2Weights{e->cnn.w1, e->cnn.b1, e->d_w2_umma, e->cnn.b2};
+                e->cnn2_enabled = true;
+            }
             e->tail_rest = e->tail;
             e->tail_rest.n_layers = e->tail.n_layers - 1;
             for (int i = 0; i < e->tail_rest.n_layers; ++i) e->tail_rest.layers[i] = e->tail.layers[i + 1];
@@ -468,7 +546,8 @@ void nww_destroy(nww_engine* e) {
     cudaFree(e->d_w_lo);
     cudaFree(e->d_feat_hi);
     cudaFree(e->d_feat_lo);
-    cudaFree(e->d_fc1);
+    cudaFree(e->d_part);
+    cudaFree(e->d_w2_umma);
     cudaFree(e->d_pcm[0]);
     cudaFree(e->d_pcm[1]);
     cudaFree(e->d_scores);

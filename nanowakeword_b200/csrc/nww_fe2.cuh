@@ -1,0 +1,225 @@
+// nww_fe2.cuh — front end v2 for the NS40x98 geometry (frame 400 -> FFT 512, hop 160, 40 mels):
+// int16 PCM window in shared memory -> log-mel (dB), by one 512-thread CTA.
+//
+// Same arithmetic contract as nww_frontend.cuh (reference MelSpectrogram + AmplitudeToDB,
+// nanowakeword/modules/architectures.py:830-837, 869-878; _export/onnx.py:27-83; int16 scaling of
+// nanowakeword/interpreter/nanointerpreter.py:750) — FFT and power spectrum in FP64 — but organised
+// for the SM instead of for generality:
+//
+//   * the CTA is four independent groups of 128 threads; a group transforms two packed complex
+//     FFT-512 at a time (frames 4b .. 4b+3 of batch b) and synchronises only with itself through a
+//     named barrier (bar.sync id, 128), so one group's barrier wait is another group's issue slot;
+//   * radix 8 x 8 x 8 decimation in frequency; every thread owns one radix-8 butterfly in passes 1
+//     and 2, so its Hann weights (pass 1) are registers and its twiddles come from two small
+//     pre-arranged shared tables (conflict-free rows);
+//   * the work buffer index is p + (p >> 6): with 16-byte complex elements every quarter-warp of
+//     every pass touches 8 distinct 16-byte bank groups;
+//   * pass 3 is one warp per FFT: lane c (1..31) owns the two final butterflies that hold bins
+//     {64 i + c} and {64 i + 64 - c}, i.e. every (k, N-k) pair needed to split the two packed
+//     real frames lives in one thread's registers; lane 0 owns the two self-paired butterflies
+//     (bins 64 i and 64 i + 32).  The spectrum is never written back: the power of both frames
+//     goes straight to a small FP32 table;
+//   * the sparse triangular mel filters run in FP32 from that table, then 10*log10.
+#pragma once
+
+#include "nww_stage.cuh"
+#include "nww_tc.cuh"
+
+namespace nww {
+
+struct Fe2 {
+    static constexpr int NT = 512, NGROUP = 4, GT = 128, NFB = 2;
+    static constexpr int N = 512, NPAD = 520;                  // idx(p) = p + (p >> 6)
+    static constexpr int PW_PITCH = 264;                       // 257 power bins per frame, padded
+    static constexpr int N_FFT_TOTAL = 49, N_BATCH = 25;       // 98 frames = 49 packed FFTs = 24.5 batches of two
+    static constexpr size_t kWorkBytes = (size_t)NGROUP * NFB * NPAD * sizeof(cplx<double>);   // 66560
+    static constexpr size_t kPowBytes = (size_t)NGROUP * NFB * 2 * PW_PITCH * sizeof(float);   // 16896
+    static constexpr size_t kTwBytes = (size_t)(7 * 64 + 7 * 8) * sizeof(cplx<double>);        // 8064
+    static constexpr size_t kScratchBytes = kWorkBytes + kPowBytes;                            // reusable between windows
+};
+
+__device__ __forceinline__ int fe2_idx(int p) { return p + (p >> 6); }
+
+// int16 -> double through the 2^52 trick: one integer op + one DADD instead of a 64-bit I2F.
+__device__ __forceinline__ double fe2_i16_to_f64(int16_t v) {
+#ifndef NWW_CPUSIM
+    const uint32_t lo = (uint32_t)((int)v + 32768);
+    return __hiloint2double(0x43300000, (int)lo) - 4503599627403264.0;     // 2^52 + 2^15
+#else
+    return (double)v;
+#endif
+}
+
+// Twiddle tables in shared memory, built once per CTA from the engine's exp(-2 pi i k / 512) table:
+//   tw1[(q-1) * 64 + j]  = W512^(j q)      (pass 1, j = 0..63)
+//   tw2[(q-1) * 8 + j2]  = W512^(8 j2 q)   (pass 2, j2 = 0..7)
+__device__ __forceinline__ void fe2_build_twiddles(cplx<double>* tw_smem, const cplx<double>* __restrict__ tw512, int tid,
+                                                   int nthreads) {
+    for (int i = tid; i < 7 * 64; i += nthreads) tw_smem[i] = tw512[((i & 63) * ((i >> 6) + 1)) & 511];
+    for (int i = tid; i < 7 * 8; i += nthreads) tw_smem[7 * 64 + i] = tw512[(8 * (i & 7) * ((i >> 3) + 1)) & 511];
+}
+
+// One window.  pcm: 16000 int16 in shared memory; scratch: Fe2::kScratchBytes of shared memory;
+// tw_smem: the tables above.  Writes mel[m * stride_m + t * stride_t] (shared or global).
+// Must be called by all 512 threads; ends with __syncthreads().
+__device__ __forceinline__ void fe2_logmel_window(const int16_t* __restrict__ pcm, unsigned char* __restrict__ scratch,
+                                                  const cplx<double>* __restrict__ tw_smem,
+                                                  const FrontendTables<double>& tab, float* __restrict__ mel,
+                                                  int stride_m, int stride_t, int tid) {
+    const int g = tid >> 7;                   // group
+    const int t = tid & 127;                  // thread in group
+    const int wg = t >> 5, lane = t & 31;
+    cplx<double>* work = reinterpret_cast<cplx<double>*>(scratch) + (size_t)g * Fe2::NFB * Fe2::NPAD;
+    float* pw = reinterpret_cast<float*>(scratch + Fe2::kWorkBytes) + (size_t)g * Fe2::NFB * 2 * Fe2::PW_PITCH;
+    const cplx<double>* tw1 = tw_smem;
+    const cplx<double>* tw2 = tw_smem + 7 * 64;
+
+    // passes 1 and 2: FFT slot f, butterfly jj
+    const int f = wg >> 1;
+    const int jj = ((wg & 1) << 5) | lane;
+    cplx<double>* wf = work + f * Fe2::NPAD;
+    // Hann * 2^-15 (int16 scaling) * 1/2 (so that |Z_k +- conj Z_{N-k}|^2 needs no final /4), zero beyond the frame
+    double wreg[7];
+#pragma unroll
+    for (int m = 0; m < 7; ++m) {
+        const int n = jj + 64 * m;
+        wreg[m] = (n < GeoNS40x98::WIN) ? 0.5 * tab.window[n] : 0.0;
+    }
+    const int b2 = jj >> 3, j2 = jj & 7;
+
+    for (int b = g; b < Fe2::N_BATCH; b += Fe2::NGROUP) {
+        const bool fvalid = (2 * b + f) < Fe2::N_FFT_TOTAL;
+        // ---- pass 1: L = 512, inputs straight from PCM (frames 4b + 2f and 4b + 2f + 1) -------------
+        if (fvalid) {
+            const int16_t* xa = pcm + (4 * b + 2 * f) * GeoNS40x98::HOP + jj;
+            cplx<double> v[8];
+#pragma unroll
+            for (int m = 0; m < 7; ++m) {
+                const double sa = fe2_i16_to_f64(xa[64 * m]);
+                const double sb = fe2_i16_to_f64(xa[64 * m + GeoNS40x98::HOP]);
+                v[m] = {wreg[m] * sa, wreg[m] * sb};
+            }
+            v[7] = {0.0, 0.0};
+            SmallDft<double, 8>::run(v);
+            wf[jj] = v[0];
+#pragma unroll
+            for (int q = 1; q < 8; ++q) wf[jj + 65 * q] = cmul(v[q], tw1[(q - 1) * 64 + jj]);    // idx(jj + 64 q)
+        }
+        named_bar_sync(1 + g, Fe2::GT);
+        // ---- pass 2: L = 64 inside block b2 -------------------------------------------------------------
+        if (fvalid) {
+            cplx<double>* blk = wf + 65 * b2 + j2;                 // idx(64 b2 + j2 + 8 m) = 65 b2 + j2 + 8 m
+            cplx<double> v[8];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) v[m] = blk[8 * m];
+            SmallDft<double, 8>::run(v);
+            blk[0] = v[0];
+#pragma unroll
+            for (int q = 1; q < 8; ++q) blk[8 * q] = cmul(v[q], tw2[(q - 1) * 8 + j2]);
+        }
+        named_bar_sync(1 + g, Fe2::GT);
+        // ---- pass 3 + power: one warp per FFT, lane c ------------------------------------------------------
+        if (wg < Fe2::NFB && (2 * b + wg) < Fe2::N_FFT_TOTAL) {
+            const int c = lane;
+            const int cb = (c == 0) ? 32 : 64 - c;
+            // butterfly with residue r = 8 q2 + b holds positions 64 b + 8 q2 + m -> idx = 65 (r & 7) + 8 (r >> 3) + m
+            const cplx<double>* pa = work + wg * Fe2::NPAD + 65 * (c & 7) + 8 * (c >> 3);
+            const cplx<double>* pb = work + wg * Fe2::NPAD + 65 * (cb & 7) + 8 * (cb >> 3);
+            cplx<double> A[8], B[8];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) A[m] = pa[m];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) B[m] = pb[m];
+            SmallDft<double, 8>::run(A);      // A[i] = Z[64 i + c]
+            SmallDft<double, 8>::run(B);      // B[i] = Z[64 i + cb]
+            cplx<double> U[8], W[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                U[i] = A[i];
+                W[i] = B[7 - i];              // N - (64 i + c) = 64 (7 - i) + (64 - c)
+            }
+            const bool special = (c == 0);
+            if (special) {
+                // lane 0: bins 0, 64, 128, 192 pair inside A (i <-> 8 - i), bins 32 .. 224 inside B (i <-> 7 - i)
+                W[0] = A[0]; W[1] = A[7]; W[2] = A[6]; W[3] = A[5];
+                U[4] = B[0]; U[5] = B[1]; U[6] = B[2]; U[7] = B[3];
+                W[4] = B[7]; W[5] = B[6]; W[6] = B[5]; W[7] = B[4];
+            }
+            float* pwa = pw + (wg * 2 + 0) * Fe2::PW_PITCH;
+            float* pwb = pw + (wg * 2 + 1) * Fe2::PW_PITCH;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                // X_A = Z_k + conj(Z_{N-k}),  X_B = (Z_k - conj(Z_{N-k})) / i   (the 1/2 is in the window)
+                const double ar = U[i].x + W[i].x, ai = U[i].y - W[i].y;
+                const double br = U[i].y + W[i].y, bi = U[i].x - W[i].x;
+                const int bin = (i < 4) ? (64 * i + c) : (special ? (64 * (i - 4) + 32) : (64 * (7 - i) + 64 - c));
+                pwa[bin] = (float)(ar * ar + ai * ai);
+                pwb[bin] = (float)(br * br + bi * bi);
+            }
+            if (special) {                     // bin 256 pairs with itself
+                const double ar = 2.0 * A[4].x, br = 2.0 * A[4].y;
+                pwa[256] = (float)(ar * ar);
+                pwb[256] = (float)(br * br);
+            }
+        }
+        named_bar_sync(1 + g, Fe2::GT);
+        // ---- mel + dB: 4 frames x 40 filters per batch ------------------------------------------------------
+        for (int task = t; task < 4 * GeoNS40x98::N_MELS; task += Fe2::GT) {
+            const int fr = task & 3;                       // FFT slot fr >> 1, packed frame fr & 1
+            const int m = task >> 2;
+            const int frame = 4 * b + fr;
+            if (frame >= GeoNS40x98::N_FRAMES) continue;
+            const int ks = __ldg(tab.mel_start + m);
+            const int cnt = __ldg(tab.mel_count + m);
+            const float* __restrict__ w = tab.mel_w + __ldg(tab.mel_woff + m);
+            const float* __restrict__ p = pw + fr * Fe2::PW_PITCH + ks;
+            float acc0 = 0.0f, acc1 = 0.0f;
+            int i = 0;
+            for (; i + 1 < cnt; i += 2) {
+                acc0 = fmaf(__ldg(w + i), p[i], acc0);
+                acc1 = fmaf(__ldg(w + i + 1), p[i + 1], acc1);
+            }
+            if (i < cnt) acc0 = fmaf(__ldg(w + i), p[i], acc0);
+            const float pm = acc0 + acc1;
+            mel[m * stride_m + frame * stride_t] = (pm <= tab.amin) ? tab.floor_db : 10.0f * log10f(pm);
+        }
+        // no barrier here: the next batch's pass-3 writes to pw are two group barriers away
+    }
+    __syncthreads();
+}
+
+// ----------------------------------------------------------------------------------------
+// Front end only (NS40x98): log-mel to global memory, (F, T) or (T, F) per window.
+// ----------------------------------------------------------------------------------------
+struct Fe2KernelSmem {
+    static constexpr size_t kScratch = (Fe2::kScratchBytes + 127) / 128 * 128;
+    static constexpr size_t kTw = (Fe2::kTwBytes + 127) / 128 * 128;
+    static constexpr size_t kTotal = kScratch + kTw + PcmStager<GeoNS40x98::CLIP>::kBytes;
+};
+
+__global__ void __launch_bounds__(Fe2::NT, 1)
+frontend2_kernel(const int16_t* __restrict__ pcm, long long n_windows, FrontendTables<double> tab,
+                 float* __restrict__ mel_out, int time_major) {
+    using G = GeoNS40x98;
+    NWW_DYN_SMEM(smem);
+    const int tid = threadIdx.x;
+    cplx<double>* tw = reinterpret_cast<cplx<double>*>(smem + Fe2KernelSmem::kScratch);
+    PcmStager<G::CLIP> stager;
+    stager.carve(smem + Fe2KernelSmem::kScratch + Fe2KernelSmem::kTw);
+    stager.init(tid);
+    fe2_build_twiddles(tw, tab.twiddle, tid, Fe2::NT);
+    __syncthreads();
+
+    const int stride_m = time_major ? 1 : G::N_FRAMES;
+    const int stride_t = time_major ? G::N_MELS : 1;
+    long long w = blockIdx.x;
+    if (w < n_windows) stager.issue(0, pcm + w * G::CLIP, tid);
+    for (int it = 0; w < n_windows; w += gridDim.x, ++it) {
+        const long long wn = w + gridDim.x;
+        if (wn < n_windows) stager.issue((it + 1) & 1, pcm + wn * G::CLIP, tid);
+        const int16_t* x = stager.wait(it & 1, (it >> 1) & 1);
+        fe2_logmel_window(x, smem, tw, tab, mel_out + w * (long long)(G::N_MELS * G::N_FRAMES), stride_m, stride_t, tid);
+    }
+}
+
+}  // namespace nww

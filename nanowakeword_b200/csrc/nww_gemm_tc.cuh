@@ -22,6 +22,7 @@
 
 #include "nww_common.cuh"
 #include "nww_tail.cuh"
+#include "nww_tc.cuh"
 
 namespace nww {
 
@@ -30,6 +31,7 @@ constexpr int kTcBK = 32;           // floats per K tile = one 128-byte swizzle 
 constexpr int kTcStages = 3;
 constexpr int kTcThreads = 192;
 constexpr int kTcMaxN = 128;
+constexpr int kTcMaxSplits = 16;    // split-K slabs of the partial-sum buffer
 
 __host__ __device__ constexpr size_t tc_stage_bytes(int n) { return (size_t)(2 * kTcBM + 2 * n) * kTcBK * sizeof(float); }
 __host__ __device__ constexpr size_t tc_smem_bytes(int n) { return kTcStages * tc_stage_bytes(n) + 1024 /*align*/ + 256 /*barriers*/; }
@@ -44,54 +46,6 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, in
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, float* v) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-// start address >> 4 | LBO (unused for swizzled K-major) | SBO = 8 rows * 128 B | version 1 | layout 2
-__device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem_tile) {
-    const uint64_t addr = (uint64_t)(smem_u32(smem_tile) >> 4) & 0x3FFF;
-    return addr | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-// kind::tf32 instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-
 struct GemmTcArgs {
     const float* bias;      // [N]
     const float* ln_g;      // [N] or null
@@ -99,6 +53,12 @@ struct GemmTcArgs {
     float* out;             // [M][N]
     int M, N, K;
     int post, act;
+    // split-K: gridDim.y CTAs share one row tile; CTA y reduces K blocks [y * kb_per_split, ...) and
+    // writes its raw FP32 partial sums to partial[y][M_pad][N]; bias / post-op then happen in the
+    // consumer (tail_kernel's pre-stage), which adds the partials in a fixed order (deterministic).
+    float* partial;         // null: single-pass GEMM with the fused epilogue
+    int kb_per_split;
+    int m_pad;              // rows per split slab of `partial`
 };
 
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -114,7 +74,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * kTcBM;
-    const int nkb = a.K / kTcBK;
+    const int nkb_total = a.K / kTcBK;
+    const int kb0 = a.partial ? (int)blockIdx.y * a.kb_per_split : 0;
+    const int nkb = a.partial ? min(a.kb_per_split, nkb_total - kb0) : nkb_total;   // K blocks of this CTA
     const uint32_t tmem_cols = a.N <= 32 ? 32 : a.N <= 64 ? 64 : 128;
 
     if (warp == 0 && lane == 0) {
@@ -148,10 +110,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_cons
                 float* whi = xlo + kTcBM * kTcBK;
                 float* wlo = whi + a.N * kTcBK;
                 mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
-                tma_load_2d(xhi, &tm_xhi, kb * kTcBK, m0, &full[s]);
-                tma_load_2d(xlo, &tm_xlo, kb * kTcBK, m0, &full[s]);
-                tma_load_2d(whi, &tm_whi, kb * kTcBK, 0, &full[s]);
-                tma_load_2d(wlo, &tm_wlo, kb * kTcBK, 0, &full[s]);
+                tma_load_2d(xhi, &tm_xhi, (kb0 + kb) * kTcBK, m0, &full[s]);
+                tma_load_2d(xlo, &tm_xlo, (kb0 + kb) * kTcBK, m0, &full[s]);
+                tma_load_2d(whi, &tm_whi, (kb0 + kb) * kTcBK, 0, &full[s]);
+                tma_load_2d(wlo, &tm_wlo, (kb0 + kb) * kTcBK, 0, &full[s]);
             }
         }
     } else if (warp == 1) {
@@ -164,10 +126,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_cons
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
                 unsigned char* st = smem + (size_t)s * stage_bytes;
-                const uint64_t d_xhi = umma_desc_sw128(st);
-                const uint64_t d_xlo = umma_desc_sw128(st + (size_t)kTcBM * kTcBK * 4);
-                const uint64_t d_whi = umma_desc_sw128(st + (size_t)2 * kTcBM * kTcBK * 4);
-                const uint64_t d_wlo = umma_desc_sw128(st + (size_t)(2 * kTcBM + a.N) * kTcBK * 4);
+                const uint64_t d_xhi = umma_desc_sw128_addr(smem_u32(st));
+                const uint64_t d_xlo = umma_desc_sw128_addr(smem_u32(st + (size_t)kTcBM * kTcBK * 4));
+                const uint64_t d_whi = umma_desc_sw128_addr(smem_u32(st + (size_t)2 * kTcBM * kTcBK * 4));
+                const uint64_t d_wlo = umma_desc_sw128_addr(smem_u32(st + (size_t)(2 * kTcBM + a.N) * kTcBK * 4));
 #pragma unroll
                 for (int k = 0; k < kTcBK / 8; ++k) {          // one MMA = K 8 floats = 32 bytes = 2 x 16 B
                     const uint64_t off = (uint64_t)(k * 2);
@@ -191,7 +153,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_cons
             if (c * 32 < a.N) tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v + c * 32);
         }
         const int m = m0 + row;
-        if (m < a.M) {
+        if (a.partial != nullptr) {
+            if (m < a.M) {
+                float4* dst = reinterpret_cast<float4*>(a.partial + ((size_t)blockIdx.y * a.m_pad + m) * a.N);
+#pragma unroll
+                for (int n4 = 0; n4 < kTcMaxN / 4; ++n4)
+                    if (n4 * 4 < a.N) dst[n4] = make_float4(v[4 * n4], v[4 * n4 + 1], v[4 * n4 + 2], v[4 * n4 + 3]);
+            }
+        } else if (m < a.M) {
             const int N = a.N;
 #pragma unroll
             for (int n = 0; n < kTcMaxN; ++n)

@@ -6,9 +6,11 @@
 #include <algorithm>
 #include <functional>
 #include <string>
+#include <type_traits>
 
 #include "../../include/nww_b200.h"
 #include "nww_layers.cuh"
+#include "nww_fe2.cuh"
 #include "nww_stage.cuh"
 #include "nww_tail.cuh"
 
@@ -69,10 +71,15 @@ template <typename K> static cudaError_t set_smem(K kernel, size_t bytes) {
 template <typename G>
 static int launch_frontend_f64(const FrontendTables<double>& tab, int sm_count, const int16_t* pcm, long long n, float* mel,
                                int time_major, cudaStream_t st, int64_t* launches, std::string* err) {
-    auto k = frontend_kernel<double, G, kNfb64, kStageNT>;
-    NWW_HCUDA(set_smem(k, FrontendSmem<double, G, kNfb64>::kTotal));
     const int grid = (int)std::min<long long>(n, sm_count);
-    k<<<grid, kStageNT, FrontendSmem<double, G, kNfb64>::kTotal, st>>>(pcm, n, tab, mel, time_major);
+    if constexpr (std::is_same<G, GeoNS40x98>::value) {
+        NWW_HCUDA(set_smem(frontend2_kernel, Fe2KernelSmem::kTotal));
+        frontend2_kernel<<<grid, Fe2::NT, Fe2KernelSmem::kTotal, st>>>(pcm, n, tab, mel, time_major);
+    } else {
+        auto k = frontend_kernel<double, G, kNfb64, kStageNT>;
+        NWW_HCUDA(set_smem(k, FrontendSmem<double, G, kNfb64>::kTotal));
+        k<<<grid, kStageNT, FrontendSmem<double, G, kNfb64>::kTotal, st>>>(pcm, n, tab, mel, time_major);
+    }
     (*launches)++;
     NWW_HCUDA(cudaGetLastError());
     return NWW_OK;

@@ -36,7 +36,38 @@ struct TailParams {
     int raw_out;         // 1: write the last layer's [rows][N] output instead of sigmoid scores
     int x_row_mul;       // input row r of the first layer lives at feat[(r * x_row_mul + x_row_off) * K]
     int x_row_off;       //   (0 is read as 1: plain row-major input)
+    // Optional pre-stage: the first activations are not read from `feat` but rebuilt from the
+    // split-K partial sums of the tensor-core GEMM (nww_gemm_tc.cuh):
+    //   x[m][n] = post( sum_{s < pre_splits} pre_part[s][m][n] + pre_b[n] ),  s in increasing order.
+    const float* pre_part;   // [pre_splits][pre_mpad][pre_N] or null
+    const float* pre_b;
+    const float* pre_g;      // LayerNorm terms when pre_post == POST_LN_ACT
+    const float* pre_beta;
+    int pre_splits, pre_mpad, pre_N, pre_post;
 };
+
+// LayerNorm over N (biased variance, eps 1e-5) then activation on a [TM][pitch] tile: one warp per row.
+__device__ __forceinline__ void tail_layernorm_act(float* tile, int pitch, int rows, int N, const float* g,
+                                                   const float* b, int act, int tid, int nthreads) {
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int m = warp; m < rows; m += nthreads / 32) {
+        float* row = tile + (size_t)m * pitch;
+        float s = 0.0f;
+        for (int n = lane; n < N; n += 32) s += row[n];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mu = s / (float)N;
+        float v = 0.0f;
+        for (int n = lane; n < N; n += 32) {
+            const float d = row[n] - mu;
+            v = fmaf(d, d, v);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const float rstd = 1.0f / sqrtf(v / (float)N + 1e-5f);
+        for (int n = lane; n < N; n += 32) row[n] = apply_act((row[n] - mu) * rstd * g[n] + b[n], act);
+    }
+}
 
 constexpr int kTailTM = 32;      // windows per CTA
 constexpr int kTailKC = 32;      // K chunk staged in shared memory
@@ -64,9 +95,29 @@ tail_kernel(const float* __restrict__ feat, long long n_windows, TailParams P, f
         const int mt = (n_windows - w0 < kTailTM) ? (int)(n_windows - w0) : kTailTM;
         float* cur = actA;
         float* nxt = actB;
+        const bool pre = P.pre_part != nullptr;
+        if (pre) {
+            for (int i = tid; i < kTailTM * P.pre_N; i += kTailNT) {
+                const int m = i / P.pre_N, n = i - m * P.pre_N;
+                float v = 0.0f;
+                if (m < mt) {
+                    const float* src = P.pre_part + (size_t)(w0 + m) * P.pre_N + n;
+                    for (int sidx = 0; sidx < P.pre_splits; ++sidx) v += src[(size_t)sidx * P.pre_mpad * P.pre_N];
+                    v += P.pre_b[n];
+                    if (P.pre_post == POST_ACT) v = apply_act(v, P.act);
+                }
+                cur[(size_t)m * P.max_width + n] = v;
+            }
+            __syncthreads();
+            if (P.pre_post == POST_LN_ACT) {
+                tail_layernorm_act(cur, P.max_width, kTailTM, P.pre_N, P.pre_g, P.pre_beta, P.act, tid, kTailNT);
+                __syncthreads();
+            }
+        }
         for (int li = 0; li < P.n_layers; ++li) {
             const TailLayer L = P.layers[li];
-            const int pitch_in = (li == 0) ? 0 : P.max_width;
+            const bool from_feat = (li == 0) && !pre;
+            const int pitch_in = from_feat ? 0 : P.max_width;
             for (int nb = 0; nb < L.N; nb += 128) {
                 const int n = nb + lane_n;
                 const bool nvalid = n < L.N;
@@ -78,7 +129,7 @@ tail_kernel(const float* __restrict__ feat, long long n_windows, TailParams P, f
                     const int kc = (L.K - k0 < kTailKC) ? (L.K - k0) : kTailKC;
                     const float* xs;
                     int xpitch;
-                    if (li == 0) {
+                    if (from_feat) {
                         __syncthreads();             // previous chunk fully consumed
                         for (int i = tid; i < kTailTM * kTailKC; i += kTailNT) {
                             const int m = i / kTailKC, k = i - m * kTailKC;
@@ -129,26 +180,7 @@ tail_kernel(const float* __restrict__ feat, long long n_windows, TailParams P, f
             }
             __syncthreads();
             if (L.post == POST_LN_ACT) {
-                // LayerNorm over N (biased variance, eps 1e-5) then activation: one warp per window.
-                const int warp = tid >> 5, lane = tid & 31;
-                for (int m = warp; m < kTailTM; m += kTailNT / 32) {
-                    float* row = nxt + (size_t)m * P.max_width;
-                    float s = 0.0f;
-                    for (int n = lane; n < L.N; n += 32) s += row[n];
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                    const float mu = s / (float)L.N;
-                    float v = 0.0f;
-                    for (int n = lane; n < L.N; n += 32) {
-                        const float d = row[n] - mu;
-                        v = fmaf(d, d, v);
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                    const float rstd = 1.0f / sqrtf(v / (float)L.N + 1e-5f);
-                    for (int n = lane; n < L.N; n += 32)
-                        row[n] = apply_act((row[n] - mu) * rstd * L.ln_g[n] + L.ln_b[n], P.act);
-                }
+                tail_layernorm_act(nxt, P.max_width, kTailTM, L.N, L.ln_g, L.ln_b, P.act, tid, kTailNT);
                 __syncthreads();
             }
             if (emb_dump != nullptr && li == P.n_layers - 3) {      // output of the backbone's last layer

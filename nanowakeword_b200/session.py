@@ -31,7 +31,7 @@ class Engine:
     """One model resident on one B200: weights, tables and workspaces live in HBM."""
 
     def __init__(self, state_dict: dict, cfg: dict, device: int = 0, frontend_precision: str = "fp64",
-                 chunk_windows: int = 0, tensor_cores: bool = True):
+                 chunk_windows: int = 0, tensor_cores: bool = True, cnn_stage: str = "v2"):
         self._lib = _lib.load_library()
         self.cfg = dict(cfg)
         self.geometry = geometry_for(cfg)
@@ -50,7 +50,11 @@ class Engine:
         spec.n_mels, spec.center, spec.clip_samples = g["n_mels"], g["center"], g["clip_samples"]
         spec.frontend_precision = {"fp64": 0, "fp32": 1}[frontend_precision]
         spec.chunk_windows = int(chunk_windows)
-        spec.reserved[0] = 0 if tensor_cores else 1      # bit 0: keep the first dense layer on CUDA cores
+        # reserved[0] bit 0: keep the first dense layer on CUDA cores; bit 1: CNN head on the v1
+        # (CUDA-core conv2) stage kernel instead of the tcgen05 one (A/B measurements)
+        if cnn_stage not in ("v1", "v2"):
+            raise ValueError("cnn_stage must be 'v1' or 'v2'")
+        spec.reserved[0] = (0 if tensor_cores else 1) | (2 if cnn_stage == "v1" else 0)
         self._blob = (C.c_char * len(blob)).from_buffer_copy(blob)
         handle = C.c_void_p()
         rc = self._lib.nww_create(C.byref(spec), C.cast(self._blob, C.c_void_p), len(blob), int(device), C.byref(handle))

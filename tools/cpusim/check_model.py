@@ -7,13 +7,14 @@ from nanowakeword_b200.synth import default_config, make_state_dict
 from nanowakeword_b200.weights import pack_blob, pack_tensors
 from oracle.heads import forward_logits, embedding_from_features, head_input_from_mel
 from oracle.frontend import GEOMETRIES, log_mel
-arch = sys.argv[1]
+sim = sys.argv[1]
+arch = "cnn" if sim == "cnn2" else sim
 pcm = np.load(os.path.join(ROOT, "tests/golden/frontend.npz"))["pcm"]
 cfg = default_config(arch); sd = make_state_dict(cfg, 0)
 d = tempfile.mkdtemp()
 open(d + "/blob.bin", "wb").write(pack_blob(pack_tensors(sd, cfg)))
 pcm.tofile(d + "/pcm.i16")
-subprocess.check_call(["/tmp/sim_model", arch, d])
+subprocess.check_call(["/tmp/sim_cnn2", d] if sim == "cnn2" else ["/tmp/sim_model", arch, d])
 logits, mel = forward_logits(pcm, sd, cfg, return_mel=True)
 got = np.fromfile(d + "/logits.f32", np.float32)
 gmel = np.fromfile(d + "/mel.f32", np.float32).reshape(mel.shape)

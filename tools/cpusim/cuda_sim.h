@@ -33,6 +33,9 @@ struct int4 { int x, y, z, w; };
 struct uint4 { unsigned x, y, z, w; };
 struct int2 { int x, y; };
 inline float4 make_float4(float a, float b, float c, float d) { return {a, b, c, d}; }
+inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return {a, b, c, d}; }
+inline float __uint_as_float(unsigned v) { float f; memcpy(&f, &v, 4); return f; }
+inline unsigned __float_as_uint(float v) { unsigned f; memcpy(&f, &v, 4); return f; }
 inline float2 make_float2(float a, float b) { return {a, b}; }
 
 namespace cudasim {
@@ -42,6 +45,11 @@ inline std::barrier<>* g_block_barrier = nullptr;
 inline std::vector<std::unique_ptr<std::barrier<>>> g_warp_barriers;
 inline std::vector<uint64_t> g_shfl;     // one slot per thread
 inline unsigned char* g_dyn_smem = nullptr;
+inline std::vector<std::unique_ptr<std::barrier<>>> g_named_barriers;   // id -> barrier (fixed participant count)
+inline void named_barrier(int id, int count) {
+    (void)count;
+    g_named_barriers[id]->arrive_and_wait();
+}
 inline int linear_tid() { return (int)(t_threadIdx.x + g_blockDim.x * (t_threadIdx.y + g_blockDim.y * t_threadIdx.z)); }
 }  // namespace cudasim
 
@@ -101,6 +109,8 @@ template <typename F> void launch(dim3 grid, dim3 block, size_t dyn_smem, F&& bo
                 std::barrier<> bar(nthreads);
                 g_block_barrier = &bar;
                 g_warp_barriers.clear();
+                g_named_barriers.clear();
+                for (int i = 0; i < 16; ++i) g_named_barriers.emplace_back(new std::barrier<>(128));
                 for (int w = 0; w < (nthreads + 31) / 32; ++w)
                     g_warp_barriers.emplace_back(new std::barrier<>(std::min(32, nthreads - 32 * w)));
                 std::vector<std::thread> ts;

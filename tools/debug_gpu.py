@@ -7,7 +7,9 @@ from oracle.heads import forward_scores, forward_logits
 mt = sys.argv[1]; B = int(sys.argv[2])
 cfg = default_config(mt); sd = make_state_dict(cfg, 0)
 pcm = synth_pcm(B, seed=5, kind="gauss")
-eng = Engine(sd, cfg)
+kw = dict(a.split("=") for a in sys.argv[3:])
+eng = Engine(sd, cfg, **kw)
+print("engine", mt, kw, eng.info)
 dev = torch.from_numpy(pcm).cuda()
 scores, ex = eng.score_device(dev, want_mel=True, want_logits=True, want_emb=True)
 torch.cuda.synchronize()

@@ -19,14 +19,14 @@ pcm = torch.from_numpy(synth_pcm(B, seed=1234)).cuda()
 print(torch.cuda.get_device_name(0), "B =", B)
 for mt in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["cnn", "dnn"]):
     cfg = default_config(mt); sd = make_state_dict(cfg, 0)
-    for prec in ("fp64", "fp32"):
+    for prec in ("fp64", "v1", "fp32"):
         try:
-            eng = Engine(sd, cfg, frontend_precision=prec)
+            eng = Engine(sd, cfg, cnn_stage="v1") if prec == "v1" else Engine(sd, cfg, frontend_precision=prec)
         except Exception as ex:
             print(mt, prec, "engine:", ex); continue
         ms = timeit(lambda: eng.logmel_device(pcm))
         print(f"{mt:9s} {prec} frontend-only  {ms:8.3f} ms  {B / ms * 1e3 / 1e6:7.3f} Mwin/s")
-        if prec == "fp64":
+        if prec in ("fp64", "v1"):
             out = torch.empty(B, dtype=torch.float32, device="cuda")
             ms = timeit(lambda: eng.score_device(pcm, out=out))
             print(f"{mt:9s} {prec} full path      {ms:8.3f} ms  {B / ms * 1e3 / 1e6:7.3f} Mwin/s  launches={eng.info['kernel_launches']}")
