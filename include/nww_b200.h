@@ -99,6 +99,29 @@ int nww_run_windows_f32(nww_engine* e, const float* pcm_dev, int64_t n_windows, 
  * This is what B200Session.run() (the session duck type) calls. */
 int nww_run_windows_host(nww_engine* e, const int16_t* pcm_host, int64_t n_windows, float* scores_host);
 
+/* ---- many independent audio streams ---------------------------------------------------------
+ * The reference keeps, per model, a deque(maxlen=clip_samples) of the most recent samples and a
+ * cumulative sample counter, and on every predict(chunk) re-scores the last clip_samples once the
+ * counter has reached clip_samples (nanointerpreter.py:176-183 create, :750-756 append + window,
+ * :785-786 score 0.0 before that, :719-733 reset).  These entry points hold that state for
+ * n_streams streams in device memory (one int16 ring per stream) and advance all of them by one
+ * chunk per call.  Warm-up zeroing of the first five predictions and the patience / debounce
+ * filters (:789-790, :1034-1064) stay on the host side (nanowakeword_b200/streams.py).
+ *
+ * nww_stream_open    allocate and zero the rings (re-opening discards the previous set).
+ * nww_stream_push    chunks_dev is (n_streams, chunk_len) int16 on the device: every stream gets
+ *                    chunk_len new samples (any positive length); scores_dev (n_streams) receives the
+ *                    probability of each stream's last clip_samples, or 0 while a stream has received
+ *                    fewer than clip_samples since it was opened / reset.  Ordered on `stream`.
+ * nww_stream_push_host  same with host buffers (H2D of the chunks, D2H of the scores; synchronous).
+ * nww_stream_reset   ids_host == NULL resets every stream, else the n_ids listed streams.
+ */
+int nww_stream_open(nww_engine* e, int64_t n_streams);
+int nww_stream_push(nww_engine* e, const int16_t* chunks_dev, int32_t chunk_len, float* scores_dev, void* stream);
+int nww_stream_push_host(nww_engine* e, const int16_t* chunks_host, int32_t chunk_len, float* scores_host);
+int nww_stream_reset(nww_engine* e, const int64_t* ids_host, int64_t n_ids);
+int nww_stream_close(nww_engine* e);
+
 /* Front end only: log-mel in dB, (n, n_mels, n_frames) or, if time_major, (n, n_frames, n_mels).
  * Replaces MelSpectrogram + AmplitudeToDB — architectures.py:830-837, 873-875;
  * _export/onnx.py:66-83. */

@@ -56,6 +56,11 @@ SIGNATURES = {
     "nww_run_windows_f32": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, _P]),
     "nww_run_windows_host": (C.c_int, [_P, _P, C.c_int64, _P]),
     "nww_logmel": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int, _P]),
+    "nww_stream_open": (C.c_int, [_P, C.c_int64]),
+    "nww_stream_push": (C.c_int, [_P, _P, C.c_int32, _P, _P]),
+    "nww_stream_push_host": (C.c_int, [_P, _P, C.c_int32, _P]),
+    "nww_stream_reset": (C.c_int, [_P, _P, C.c_int64]),
+    "nww_stream_close": (C.c_int, [_P]),
     "nww_set_profiling": (C.c_int, [_P, C.c_int]),
     "nww_get_profile": (C.c_int, [_P, C.POINTER(NwwProfile)]),
     "nww_synchronize": (C.c_int, [_P]),

@@ -41,7 +41,7 @@ template <typename T, typename G, int NFB> struct CnnSmem {
 
 template <typename T, typename G, int NFB, int NT>
 __global__ void __launch_bounds__(NT, 1)
-cnn_stage_kernel(const int16_t* __restrict__ pcm, long long n_windows, FrontendTables<T> tab, CnnWeights wt, int act,
+cnn_stage_kernel(WindowSource src, long long n_windows, FrontendTables<T> tab, CnnWeights wt, int act,
                  float* __restrict__ feat_out, float* __restrict__ mel_dump /* nullable, (F,T) */) {
     using D = CnnDims<G>;
     NWW_DYN_SMEM(smem);
@@ -65,11 +65,11 @@ cnn_stage_kernel(const int16_t* __restrict__ pcm, long long n_windows, FrontendT
     __syncthreads();
 
     long long w = blockIdx.x;
-    if (w < n_windows) stager.issue(0, pcm + w * G::CLIP, tid);
+    if (w < n_windows) stager.issue(0, src.at(w), tid);
     for (int it = 0; w < n_windows; w += gridDim.x, ++it) {
         const long long wn = w + gridDim.x;
-        if (wn < n_windows) stager.issue((it + 1) & 1, pcm + wn * G::CLIP, tid);
-        const int16_t* x = stager.wait(it & 1, (it >> 1) & 1);
+        if (wn < n_windows) stager.issue((it + 1) & 1, src.at(wn), tid);
+        const int16_t* x = stager.wait(it & 1, (it >> 1) & 1, src.at(w));
 
         // ---- K1: log-mel into the padded (F+2, T+2) plane --------------------------------
         logmel_window<T, G, NFB, int16_t>(x, work, tab, melp + D::MEL_P + 1, D::MEL_P, 1, tid, NT);

@@ -69,7 +69,7 @@ struct Cnn2Weights {
 __device__ __forceinline__ uint32_t cnn2_pack_bf16(uint32_t lo16, uint32_t hi16) { return lo16 | (hi16 << 16); }
 
 __global__ void __launch_bounds__(Cnn2::NT, 1)
-cnn2_stage_kernel(const int16_t* __restrict__ pcm, long long n_windows, FrontendTables<double> tab, Cnn2Weights wt, int act,
+cnn2_stage_kernel(WindowSource src, long long n_windows, FrontendTables<double> tab, Cnn2Weights wt, int act,
                   float* __restrict__ feat_hi, float* __restrict__ feat_lo /* [n][7680], K order (ph, pw, oc) */,
                   float* __restrict__ mel_dump /* nullable, (F,T) */) {
     using D = Cnn2;
@@ -181,11 +181,11 @@ cnn2_stage_kernel(const int16_t* __restrict__ pcm, long long n_windows, Frontend
     };
 
     long long w = blockIdx.x;
-    if (w < n_windows) stager.issue(0, pcm + w * D::G::CLIP, tid);
+    if (w < n_windows) stager.issue(0, src.at(w), tid);
     for (int it = 0; w < n_windows; w += gridDim.x, ++it) {
         const long long wn = w + gridDim.x;
-        if (wn < n_windows) stager.issue((it + 1) & 1, pcm + wn * D::G::CLIP, tid);
-        const int16_t* x = stager.wait(it & 1, (it >> 1) & 1);
+        if (wn < n_windows) stager.issue((it + 1) & 1, src.at(wn), tid);
+        const int16_t* x = stager.wait(it & 1, (it >> 1) & 1, src.at(w));
 
         // ---- log-mel into the zero-bordered (F+2, T+2) plane (ends with a CTA barrier) ----------------
         fe2_logmel_window(x, smem, tw, tab, melp + D::MEL_P + 1, D::MEL_P, 1, tid);

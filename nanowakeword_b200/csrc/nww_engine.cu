@@ -19,6 +19,7 @@
 #include "nww_gemm_tc.cuh"
 #include "nww_heads.cuh"
 #include "nww_stage.cuh"
+#include "nww_stream.cuh"
 #include "nww_tables.h"
 #include "nww_tail.cuh"
 
@@ -96,6 +97,13 @@ struct nww_engine {
     int64_t host_chunk = 0, scores_cap = 0;
 
     int64_t launches = 0, windows = 0;
+
+    // multi-stream mode (nww_stream_*): mirrored int16 rings in HBM
+    StreamState streams{};
+    int16_t* d_chunk = nullptr;          // staging for nww_stream_push_host
+    size_t chunk_cap = 0;
+    long long* d_ids = nullptr;
+    int64_t ids_cap = 0;
 
     // optional per-stage event timing
     bool profiling = false;
@@ -226,7 +234,7 @@ static int grid_for(const nww_engine* e, int64_t n, int per_sm = 1) {
 }
 
 template <typename G>
-static int launch_frontend(nww_engine* e, const int16_t* pcm, int64_t n, float* mel, int time_major, cudaStream_t st) {
+static int launch_frontend(nww_engine* e, WindowSource pcm, int64_t n, float* mel, int time_major, cudaStream_t st) {
     if (e->spec.frontend_precision == NWW_FRONTEND_FP32) {
         auto k = frontend_kernel<float, G, kNfb32, kStageNT>;
         NWW_CUDA(set_smem(k, FrontendSmem<float, G, kNfb32>::kTotal));
@@ -253,12 +261,13 @@ static int launch_tail_tc(nww_engine* e, int64_t n, float* scores, float* logits
         e->launches++;
         NWW_CUDA(cudaGetLastError());
     }
-    // split-K so that (row tiles x splits) fills the SMs; partial sums are reduced in a fixed order by the tail
+    // split-K with a FIXED number of K blocks per split (so a window's result does not depend on the batch
+    // it is scored in): 7680 / 32 = 240 K blocks -> 12 splits x 10 row tiles = 120 CTAs for a full chunk;
+    // partial sums are reduced in a fixed order by the tail's pre-stage
     const int m_tiles = (int)((n + kTcBM - 1) / kTcBM);
     const int nkb = L0.K / kTcBK;
-    int splits = std::max(1, std::min(std::min(kTcMaxSplits, nkb), e->sm_count / m_tiles));
-    const int kbps = (nkb + splits - 1) / splits;
-    splits = (nkb + kbps - 1) / kbps;
+    const int kbps = std::max(kTcKbPerSplit, (nkb + kTcMaxSplits - 1) / kTcMaxSplits);
+    const int splits = (nkb + kbps - 1) / kbps;
     GemmTcArgs a{L0.b, L0.ln_g, L0.ln_b, nullptr, (int)n, L0.N, L0.K, L0.post, e->spec.activation, e->d_part, kbps, e->tc_rows};
     const size_t smem_tc = tc_smem_bytes(L0.N);
     NWW_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
@@ -296,7 +305,7 @@ static int launch_tail(nww_engine* e, const float* feat, int64_t n, float* score
 }
 
 // Stage A for one chunk: PCM (int16, device) -> feature rows in e->d_feat.
-static int launch_stage_a(nww_engine* e, const int16_t* pcm, int64_t n, float* mel, cudaStream_t st) {
+static int launch_stage_a(nww_engine* e, WindowSource pcm, int64_t n, float* mel, cudaStream_t st) {
     switch (e->spec.arch) {
         case NWW_ARCH_DNN: {
             // the DNN body is the identity on the (T, F) log-mel: features = flattened mel
@@ -330,7 +339,7 @@ static int launch_stage_a(nww_engine* e, const int16_t* pcm, int64_t n, float* m
 }
 
 static int run_device(nww_engine* e, const int16_t* pcm, int64_t n, float* scores, float* mel, float* logits, float* emb,
-                      cudaStream_t st) {
+                      cudaStream_t st, const long long* win_off = nullptr) {
     const int64_t mel_stride = (int64_t)e->n_mels * e->n_frames;
     for (int64_t w0 = 0; w0 < n; w0 += e->chunk) {
         const int64_t m = std::min<int64_t>(e->chunk, n - w0);
@@ -339,7 +348,9 @@ static int run_device(nww_engine* e, const int16_t* pcm, int64_t n, float* score
             ea = e->get_event(); eb = e->get_event(); ec = e->get_event();
             cudaEventRecord(ea, st);
         }
-        int rc = launch_stage_a(e, pcm + w0 * e->clip, m, mel ? mel + w0 * mel_stride : nullptr, st);
+        const WindowSource src = win_off ? WindowSource{pcm, win_off + w0, e->clip}
+                                         : WindowSource{pcm + w0 * e->clip, nullptr, e->clip};
+        int rc = launch_stage_a(e, src, m, mel ? mel + w0 * mel_stride : nullptr, st);
         if (rc) return rc;
         if (e->profiling) cudaEventRecord(eb, st);
         rc = launch_tail(e, e->d_feat, m, scores + w0, logits ? logits + w0 : nullptr,
@@ -353,6 +364,14 @@ static int run_device(nww_engine* e, const int16_t* pcm, int64_t n, float* score
     }
     e->windows += n;
     return NWW_OK;
+}
+
+static void stream_free(nww_engine* e) {
+    cudaFree(e->streams.ring);
+    cudaFree(e->streams.wpos);
+    cudaFree(e->streams.count);
+    cudaFree(e->streams.win_off);
+    e->streams = StreamState{};
 }
 
 // ------------------------------------------------------------------------------ C ABI
@@ -551,6 +570,9 @@ void nww_destroy(nww_engine* e) {
     cudaFree(e->d_pcm[0]);
     cudaFree(e->d_pcm[1]);
     cudaFree(e->d_scores);
+    cudaFree(e->d_chunk);
+    cudaFree(e->d_ids);
+    stream_free(e);
     for (auto& sp : e->spans) { if (sp.stage == 0) cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto ev : e->event_pool) cudaEventDestroy(ev);
     for (int i = 0; i < 2; ++i) {
@@ -596,8 +618,9 @@ int nww_logmel(nww_engine* e, const int16_t* pcm_dev, int64_t n, float* mel_dev,
     std::lock_guard<std::mutex> lock(e->mu);
     NWW_CUDA(cudaSetDevice(e->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);   // NULL = the legacy default stream, as in CUDA
-    return e->spec.geometry == NWW_GEOM_NS40X98 ? launch_frontend<GeoNS40x98>(e, pcm_dev, n, mel_dev, time_major, st)
-                                                : launch_frontend<GeoREF64x101>(e, pcm_dev, n, mel_dev, time_major, st);
+    const WindowSource src{pcm_dev, nullptr, e->clip};
+    return e->spec.geometry == NWW_GEOM_NS40X98 ? launch_frontend<GeoNS40x98>(e, src, n, mel_dev, time_major, st)
+                                                : launch_frontend<GeoREF64x101>(e, src, n, mel_dev, time_major, st);
 }
 
 int nww_run_windows_f32(nww_engine* e, const float* pcm_dev, int64_t n, float* scores_dev, float* mel_dev, float* logits_dev,
@@ -659,6 +682,117 @@ int nww_run_windows_host(nww_engine* e, const int16_t* pcm_host, int64_t n, floa
         NWW_CUDA(cudaEventRecord(e->ev_done[slot], e->stream));
     }
     NWW_CUDA(cudaMemcpyAsync(scores_host, e->d_scores, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    NWW_CUDA(cudaStreamSynchronize(e->stream));
+    return NWW_OK;
+}
+
+// ------------------------------------------------------------------------------ streams
+
+int nww_stream_open(nww_engine* e, int64_t n_streams) {
+    if (!e || n_streams <= 0) return fail(NWW_EINVAL, "nww_stream_open: need an engine and n_streams > 0");
+    std::lock_guard<std::mutex> lock(e->mu);
+    NWW_CUDA(cudaSetDevice(e->device));
+    NWW_CUDA(cudaStreamSynchronize(e->stream));
+    stream_free(e);
+    StreamState st{};
+    st.n_streams = n_streams;
+    st.R = e->clip;
+    const size_t ring_bytes = (size_t)n_streams * st.pitch() * sizeof(int16_t);
+    NWW_CUDA(cudaMalloc(&st.ring, ring_bytes));
+    NWW_CUDA(cudaMalloc(&st.wpos, (size_t)n_streams * sizeof(int)));
+    NWW_CUDA(cudaMalloc(&st.count, (size_t)n_streams * sizeof(long long)));
+    NWW_CUDA(cudaMalloc(&st.win_off, (size_t)n_streams * sizeof(long long)));
+    e->streams = st;
+    stream_reset_kernel<<<(unsigned)n_streams, 256, 0, e->stream>>>(st, nullptr, n_streams);
+    e->launches++;
+    NWW_CUDA(cudaGetLastError());
+    NWW_CUDA(cudaStreamSynchronize(e->stream));
+    return NWW_OK;
+}
+
+int nww_stream_close(nww_engine* e) {
+    if (!e) return fail(NWW_EINVAL, "nww_stream_close: null engine");
+    std::lock_guard<std::mutex> lock(e->mu);
+    NWW_CUDA(cudaSetDevice(e->device));
+    NWW_CUDA(cudaDeviceSynchronize());
+    stream_free(e);
+    return NWW_OK;
+}
+
+static int stream_push_locked(nww_engine* e, const int16_t* chunks_dev, int chunk_len, float* scores_dev, cudaStream_t st) {
+    const StreamState& S = e->streams;
+    stream_append_kernel<<<(unsigned)S.n_streams, 256, 0, st>>>(S, chunks_dev, chunk_len);
+    e->launches++;
+    NWW_CUDA(cudaGetLastError());
+    int rc = run_device(e, S.ring, S.n_streams, scores_dev, nullptr, nullptr, nullptr, st, S.win_off);
+    if (rc) return rc;
+    stream_mask_kernel<<<(unsigned)((S.n_streams + 255) / 256), 256, 0, st>>>(S, scores_dev);
+    e->launches++;
+    NWW_CUDA(cudaGetLastError());
+    return NWW_OK;
+}
+
+int nww_stream_push(nww_engine* e, const int16_t* chunks_dev, int32_t chunk_len, float* scores_dev, void* stream) {
+    if (!e || !chunks_dev || !scores_dev) return fail(NWW_EINVAL, "nww_stream_push: null argument");
+    if (chunk_len <= 0) return fail(NWW_EINVAL, "nww_stream_push: chunk_len must be positive");
+    std::lock_guard<std::mutex> lock(e->mu);
+    if (!e->streams.ring) return fail(NWW_EINVAL, "nww_stream_push: no streams are open (call nww_stream_open)");
+    NWW_CUDA(cudaSetDevice(e->device));
+    return stream_push_locked(e, chunks_dev, chunk_len, scores_dev, static_cast<cudaStream_t>(stream));
+}
+
+int nww_stream_push_host(nww_engine* e, const int16_t* chunks_host, int32_t chunk_len, float* scores_host) {
+    if (!e || !chunks_host || !scores_host) return fail(NWW_EINVAL, "nww_stream_push_host: null argument");
+    if (chunk_len <= 0) return fail(NWW_EINVAL, "nww_stream_push_host: chunk_len must be positive");
+    std::lock_guard<std::mutex> lock(e->mu);
+    if (!e->streams.ring) return fail(NWW_EINVAL, "nww_stream_push_host: no streams are open (call nww_stream_open)");
+    NWW_CUDA(cudaSetDevice(e->device));
+    const int64_t n = e->streams.n_streams;
+    const size_t bytes = (size_t)n * chunk_len * sizeof(int16_t);
+    if (e->chunk_cap < bytes) {
+        cudaFree(e->d_chunk);
+        e->d_chunk = nullptr;
+        NWW_CUDA(cudaMalloc(&e->d_chunk, bytes));
+        e->chunk_cap = bytes;
+    }
+    if (e->scores_cap < n) {
+        cudaFree(e->d_scores);
+        e->d_scores = nullptr;
+        NWW_CUDA(cudaMalloc(&e->d_scores, (size_t)n * sizeof(float)));
+        e->scores_cap = n;
+    }
+    NWW_CUDA(cudaMemcpyAsync(e->d_chunk, chunks_host, bytes, cudaMemcpyHostToDevice, e->stream));
+    int rc = stream_push_locked(e, e->d_chunk, chunk_len, e->d_scores, e->stream);
+    if (rc) return rc;
+    NWW_CUDA(cudaMemcpyAsync(scores_host, e->d_scores, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    NWW_CUDA(cudaStreamSynchronize(e->stream));
+    return NWW_OK;
+}
+
+int nww_stream_reset(nww_engine* e, const int64_t* ids_host, int64_t n_ids) {
+    if (!e) return fail(NWW_EINVAL, "nww_stream_reset: null engine");
+    std::lock_guard<std::mutex> lock(e->mu);
+    if (!e->streams.ring) return fail(NWW_EINVAL, "nww_stream_reset: no streams are open");
+    NWW_CUDA(cudaSetDevice(e->device));
+    const StreamState& S = e->streams;
+    if (!ids_host) {
+        stream_reset_kernel<<<(unsigned)S.n_streams, 256, 0, e->stream>>>(S, nullptr, S.n_streams);
+    } else {
+        if (n_ids <= 0) return NWW_OK;
+        for (int64_t i = 0; i < n_ids; ++i)
+            if (ids_host[i] < 0 || ids_host[i] >= S.n_streams) return fail(NWW_EINVAL, "nww_stream_reset: stream id out of range");
+        if (e->ids_cap < n_ids) {
+            cudaFree(e->d_ids);
+            e->d_ids = nullptr;
+            NWW_CUDA(cudaMalloc(&e->d_ids, (size_t)n_ids * sizeof(long long)));
+            e->ids_cap = n_ids;
+        }
+        static_assert(sizeof(long long) == sizeof(int64_t), "id width");
+        NWW_CUDA(cudaMemcpyAsync(e->d_ids, ids_host, (size_t)n_ids * sizeof(int64_t), cudaMemcpyHostToDevice, e->stream));
+        stream_reset_kernel<<<(unsigned)n_ids, 256, 0, e->stream>>>(S, e->d_ids, n_ids);
+    }
+    e->launches++;
+    NWW_CUDA(cudaGetLastError());
     NWW_CUDA(cudaStreamSynchronize(e->stream));
     return NWW_OK;
 }

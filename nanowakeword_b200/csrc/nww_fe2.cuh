@@ -198,7 +198,7 @@ struct Fe2KernelSmem {
 };
 
 __global__ void __launch_bounds__(Fe2::NT, 1)
-frontend2_kernel(const int16_t* __restrict__ pcm, long long n_windows, FrontendTables<double> tab,
+frontend2_kernel(WindowSource src, long long n_windows, FrontendTables<double> tab,
                  float* __restrict__ mel_out, int time_major) {
     using G = GeoNS40x98;
     NWW_DYN_SMEM(smem);
@@ -213,11 +213,11 @@ frontend2_kernel(const int16_t* __restrict__ pcm, long long n_windows, FrontendT
     const int stride_m = time_major ? 1 : G::N_FRAMES;
     const int stride_t = time_major ? G::N_MELS : 1;
     long long w = blockIdx.x;
-    if (w < n_windows) stager.issue(0, pcm + w * G::CLIP, tid);
+    if (w < n_windows) stager.issue(0, src.at(w), tid);
     for (int it = 0; w < n_windows; w += gridDim.x, ++it) {
         const long long wn = w + gridDim.x;
-        if (wn < n_windows) stager.issue((it + 1) & 1, pcm + wn * G::CLIP, tid);
-        const int16_t* x = stager.wait(it & 1, (it >> 1) & 1);
+        if (wn < n_windows) stager.issue((it + 1) & 1, src.at(wn), tid);
+        const int16_t* x = stager.wait(it & 1, (it >> 1) & 1, src.at(w));
         fe2_logmel_window(x, smem, tw, tab, mel_out + w * (long long)(G::N_MELS * G::N_FRAMES), stride_m, stride_t, tid);
     }
 }

@@ -32,6 +32,7 @@ constexpr int kTcStages = 3;
 constexpr int kTcThreads = 192;
 constexpr int kTcMaxN = 128;
 constexpr int kTcMaxSplits = 16;    // split-K slabs of the partial-sum buffer
+constexpr int kTcKbPerSplit = 20;   // K blocks (of 32 floats) per split
 
 __host__ __device__ constexpr size_t tc_stage_bytes(int n) { return (size_t)(2 * kTcBM + 2 * n) * kTcBK * sizeof(float); }
 __host__ __device__ constexpr size_t tc_smem_bytes(int n) { return kTcStages * tc_stage_bytes(n) + 1024 /*align*/ + 256 /*barriers*/; }

@@ -69,7 +69,7 @@ template <typename K> static cudaError_t set_smem(K kernel, size_t bytes) {
     } while (0)
 
 template <typename G>
-static int launch_frontend_f64(const FrontendTables<double>& tab, int sm_count, const int16_t* pcm, long long n, float* mel,
+static int launch_frontend_f64(const FrontendTables<double>& tab, int sm_count, WindowSource pcm, long long n, float* mel,
                                int time_major, cudaStream_t st, int64_t* launches, std::string* err) {
     const int grid = (int)std::min<long long>(n, sm_count);
     if constexpr (std::is_same<G, GeoNS40x98>::value) {
@@ -187,7 +187,7 @@ inline int setup_head_weights(int arch, int geometry, const BlobLookup& get, con
 
 // ------------------------------------------------------------------------------ launches
 inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<double>& tab, int act, int sm_count,
-                               const int16_t* pcm, long long n, float* feat, float* scratch, float* mel_dump,
+                               WindowSource pcm, long long n, float* feat, float* scratch, float* mel_dump,
                                cudaStream_t st, int64_t* launches, std::string* err) {
     float* p = scratch;
     auto take = [&](size_t floats_per_window) {

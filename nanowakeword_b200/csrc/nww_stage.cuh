@@ -13,13 +13,17 @@ namespace nww {
 __host__ __device__ constexpr size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Double-buffered TMA bulk staging of int16 windows (global -> shared), one mbarrier per slot.
+// A window may start at any int16 boundary (the stream rings of nww_stream.cuh hand out
+// windows that begin wherever the stream's write position is): the bulk copy starts at the
+// enclosing 16-byte boundary, moves 16 extra bytes, and wait() returns the skewed pointer.
 template <int CLIP> struct PcmStager {
-    int16_t* buf;      // [2][CLIP]
+    int16_t* buf;      // [2][SLOT]
     uint64_t* bars;    // [2]
-    static constexpr size_t kBytes = align_up(2 * CLIP * sizeof(int16_t), 128) + 128;
+    static constexpr int SLOT = CLIP + 8;
+    static constexpr size_t kBytes = align_up(2 * SLOT * sizeof(int16_t), 128) + 128;
     __device__ __forceinline__ void carve(unsigned char* p) {
         buf = reinterpret_cast<int16_t*>(p);
-        bars = reinterpret_cast<uint64_t*>(p + align_up(2 * CLIP * sizeof(int16_t), 128));
+        bars = reinterpret_cast<uint64_t*>(p + align_up(2 * SLOT * sizeof(int16_t), 128));
     }
     __device__ __forceinline__ void init(int tid) {
         if (tid == 0) {
@@ -29,16 +33,30 @@ template <int CLIP> struct PcmStager {
         }
         __syncthreads();
     }
+    static __device__ __forceinline__ int skew_of(const int16_t* src) { return (int)((reinterpret_cast<uintptr_t>(src) & 15) >> 1); }
     __device__ __forceinline__ void issue(int slot, const int16_t* src, int tid) {
         if (tid == 0) {
+            const int skew = skew_of(src);
+            const uint32_t bytes = CLIP * (uint32_t)sizeof(int16_t) + (skew ? 16u : 0u);
             fence_proxy_async();
-            mbar_expect_tx(&bars[slot], CLIP * (uint32_t)sizeof(int16_t));
-            bulk_g2s(buf + (size_t)slot * CLIP, src, CLIP * (uint32_t)sizeof(int16_t), &bars[slot]);
+            mbar_expect_tx(&bars[slot], bytes);
+            bulk_g2s(buf + (size_t)slot * SLOT, src - skew, bytes, &bars[slot]);
         }
     }
-    __device__ __forceinline__ const int16_t* wait(int slot, uint32_t parity) {
+    __device__ __forceinline__ const int16_t* wait(int slot, uint32_t parity, const int16_t* src) {
         mbar_wait(&bars[slot], parity);
-        return buf + (size_t)slot * CLIP;
+        return buf + (size_t)slot * SLOT + skew_of(src);
+    }
+};
+
+// Where window w of a launch starts: densely packed windows, or (stream mode) an explicit
+// element offset per window into the ring arena.
+struct WindowSource {
+    const int16_t* base;
+    const long long* offsets;     // nullable
+    int clip;
+    __device__ __forceinline__ const int16_t* at(long long w) const {
+        return base + (offsets ? offsets[w] : w * (long long)clip);
     }
 };
 
@@ -53,7 +71,7 @@ template <typename T, typename G, int NFB> struct FrontendSmem {
 
 template <typename T, typename G, int NFB, int NT>
 __global__ void __launch_bounds__(NT, 1)
-frontend_kernel(const int16_t* __restrict__ pcm, long long n_windows, FrontendTables<T> tab, float* __restrict__ mel_out,
+frontend_kernel(WindowSource src, long long n_windows, FrontendTables<T> tab, float* __restrict__ mel_out,
                 int time_major) {
     NWW_DYN_SMEM(smem);
     const int tid = threadIdx.x;
@@ -65,11 +83,11 @@ frontend_kernel(const int16_t* __restrict__ pcm, long long n_windows, FrontendTa
     const int stride_m = time_major ? 1 : G::N_FRAMES;
     const int stride_t = time_major ? G::N_MELS : 1;
     long long w = blockIdx.x;
-    if (w < n_windows) stager.issue(0, pcm + w * G::CLIP, tid);
+    if (w < n_windows) stager.issue(0, src.at(w), tid);
     for (int it = 0; w < n_windows; w += gridDim.x, ++it) {
         const long long wn = w + gridDim.x;
-        if (wn < n_windows) stager.issue((it + 1) & 1, pcm + wn * G::CLIP, tid);
-        const int16_t* x = stager.wait(it & 1, (it >> 1) & 1);
+        if (wn < n_windows) stager.issue((it + 1) & 1, src.at(wn), tid);
+        const int16_t* x = stager.wait(it & 1, (it >> 1) & 1, src.at(w));
         logmel_window<T, G, NFB, int16_t>(x, work, tab, mel_out + w * (long long)(G::N_MELS * G::N_FRAMES), stride_m,
                                           stride_t, tid, NT);
     }

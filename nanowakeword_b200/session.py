@@ -156,6 +156,50 @@ class Engine:
         _lib.check(self._lib, rc, "nww_run_windows_host")
 
 
+    # -- many streams (device-resident rings; reference semantics of nanointerpreter.py:750-756) ------
+    def stream_open(self, n_streams: int):
+        _lib.check(self._lib, self._lib.nww_stream_open(self._h, int(n_streams)), "nww_stream_open")
+        self.n_streams = int(n_streams)
+
+    def stream_close(self):
+        _lib.check(self._lib, self._lib.nww_stream_close(self._h), "nww_stream_close")
+        self.n_streams = 0
+
+    def stream_reset(self, ids=None):
+        if ids is None:
+            rc = self._lib.nww_stream_reset(self._h, None, 0)
+        else:
+            a = np.ascontiguousarray(np.asarray(ids, dtype=np.int64).ravel())
+            rc = self._lib.nww_stream_reset(self._h, a.ctypes.data_as(C.c_void_p), a.size)
+        _lib.check(self._lib, rc, "nww_stream_reset")
+
+    def stream_push_device(self, chunks, out=None, stream=None):
+        """chunks: contiguous CUDA int16 tensor (n_streams, chunk_len).  Returns raw scores (n_streams,)
+        float32 on the device (0 for streams that have not yet received clip_samples)."""
+        torch = _torch()
+        if chunks.dtype != torch.int16 or not chunks.is_cuda or not chunks.is_contiguous() or chunks.dim() != 2:
+            raise ValueError("chunks must be a contiguous CUDA int16 tensor (n_streams, chunk_len)")
+        if chunks.shape[0] != getattr(self, "n_streams", 0):
+            raise ValueError(f"chunks must have one row per open stream ({getattr(self, 'n_streams', 0)})")
+        scores = out if out is not None else torch.empty(chunks.shape[0], dtype=torch.float32, device=chunks.device)
+        rc = self._lib.nww_stream_push(self._h, C.c_void_p(chunks.data_ptr()), int(chunks.shape[1]),
+                                       C.c_void_p(scores.data_ptr()), self._stream_ptr(stream))
+        _lib.check(self._lib, rc, "nww_stream_push")
+        return scores
+
+    def stream_push_host(self, chunks: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if not isinstance(chunks, np.ndarray) or chunks.dtype != np.int16 or chunks.ndim != 2:
+            raise ValueError("chunks must be an int16 numpy array (n_streams, chunk_len)")
+        if chunks.shape[0] != getattr(self, "n_streams", 0):
+            raise ValueError(f"chunks must have one row per open stream ({getattr(self, 'n_streams', 0)})")
+        chunks = np.ascontiguousarray(chunks)
+        scores = out if out is not None else np.empty(chunks.shape[0], dtype=np.float32)
+        rc = self._lib.nww_stream_push_host(self._h, chunks.ctypes.data_as(C.c_void_p), int(chunks.shape[1]),
+                                            scores.ctypes.data_as(C.c_void_p))
+        _lib.check(self._lib, rc, "nww_stream_push_host")
+        return scores
+
+
 # ------------------------------------------------------------------------------ artefacts
 def save_model(path: str, state_dict: dict, cfg: dict) -> str:
     """Write ``<path>.pt`` the way the reference does (torch.save(state_dict),

@@ -1,0 +1,98 @@
+"""``StreamBank`` — the reference's per-stream interpreter state for MANY streams at once.
+
+One ``NanoInterpreter`` of the reference serves one audio stream: a ring of the last
+``clip_samples`` samples, a cumulative counter, five warm-up predictions reported as 0, a
+30-deep prediction history and the patience / debounce filters
+(reference nanowakeword/interpreter/nanointerpreter.py:176-183, 735-814, 1002, 1034-1064).
+``StreamBank`` keeps exactly that state for ``n_streams`` independent streams: the audio rings
+live on the GPU (``nww_stream_*`` in include/nww_b200.h), the O(1)-per-call bookkeeping is
+vectorised numpy on the host.  Stream ``i`` of a bank behaves like its own reference
+interpreter fed the same chunks.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+HISTORY = 30          # prediction_buffer depth (nanointerpreter.py:1002)
+WARMUP = 5            # predictions forced to 0.0 after (re)start (:789-790)
+
+
+class StreamBank:
+    def __init__(self, engine, n_streams: int):
+        self.engine = engine
+        self.n = int(n_streams)
+        engine.stream_open(self.n)
+        self.raw_scores = np.zeros(self.n, np.float32)
+        self.post_processed_scores = np.zeros(self.n, np.float32)
+        self._hist = np.zeros((self.n, HISTORY), np.float32)   # column HISTORY-1 is the most recent
+        self._hist_len = np.zeros(self.n, np.int64)
+
+    def close(self):
+        self.engine.stream_close()
+
+    # ------------------------------------------------------------------ predict for every stream
+    def push(self, chunks: np.ndarray, patience: int = 0, threshold: float = 0.0, debounce_time: float = 0.0) -> np.ndarray:
+        """Give every stream ``chunks[i]`` (int16, any common length) and return the (n_streams,)
+        post-processed scores, as ``predict()`` would stream by stream.  ``patience`` /
+        ``threshold`` / ``debounce_time`` apply to all streams (the reference keys them by model
+        name; a bank holds one model)."""
+        if not isinstance(chunks, np.ndarray):
+            raise ValueError("Input audio `chunks` must be a Numpy array.")
+        if chunks.dtype != np.int16:
+            chunks = chunks.astype(np.int16)
+        raw = self.engine.stream_push_host(chunks)
+        return self._finish(raw, chunks.shape[1], patience, threshold, debounce_time)
+
+    def _finish(self, raw: np.ndarray, n_samples: int, patience, threshold, debounce_time) -> np.ndarray:
+        self.raw_scores = raw.astype(np.float32, copy=True)
+        final = raw.astype(np.float32, copy=True)
+        final[self._hist_len < WARMUP] = 0.0
+        self._post(final, patience, threshold, debounce_time, n_samples)
+        self._hist[:, :-1] = self._hist[:, 1:]
+        self._hist[:, -1] = final
+        self._hist_len = np.minimum(self._hist_len + 1, HISTORY)
+        self.post_processed_scores = final
+        return final.copy()
+
+    def _post(self, final, patience, threshold, debounce_time, n_samples):
+        """Vectorised ``_apply_post_processing`` (nanointerpreter.py:1034-1064)."""
+        if not patience and debounce_time <= 0:
+            return
+        if not threshold:
+            raise ValueError("`threshold` must be provided when using `patience` or `debounce_time`.")
+        if patience and debounce_time > 0:
+            raise ValueError("`patience` and `debounce_time` cannot be used together.")
+        live = final != 0.0
+        cols = np.arange(HISTORY)[None, :]
+        valid = cols >= (HISTORY - self._hist_len)[:, None]            # entries that exist in each history
+        if patience:
+            need = int(patience)
+            short = self._hist_len < need
+            # the reference slices [-(need-1):], which for need == 1 is the whole buffer (:1054)
+            depth = HISTORY if need == 1 else need - 1
+            recent = valid & (cols >= HISTORY - depth)
+            hits = ((self._hist >= threshold) & recent).sum(1) + (final >= threshold)
+            final[live & (short | (hits < need))] = 0.0
+        else:
+            frame_s = n_samples / 16000.0
+            if frame_s <= 0:
+                return
+            k = int(np.ceil(debounce_time / frame_s))
+            recent = valid & (cols >= HISTORY - k)
+            fired = ((self._hist >= threshold) & recent).any(1)
+            final[live & (final >= threshold) & fired] = 0.0
+
+    def detected(self, threshold: float) -> np.ndarray:
+        return self.post_processed_scores >= threshold
+
+    def reset(self, ids: Optional[np.ndarray] = None):
+        """``reset()`` of the listed streams (all when ``ids`` is None): audio ring, counters,
+        scores and prediction history (nanointerpreter.py:719-733)."""
+        self.engine.stream_reset(ids)
+        sel = slice(None) if ids is None else np.asarray(ids, dtype=np.int64)
+        self.raw_scores[sel] = 0.0
+        self.post_processed_scores[sel] = 0.0
+        self._hist[sel] = 0.0
+        self._hist_len[sel] = 0

@@ -142,3 +142,53 @@ def test_session_duck_type_and_interpreter(torch_cuda, tmp_path, golden_frontend
     assert interp.detected(0.0)
     interp.reset()
     assert interp.score == 0.0 and interp.e2e_buffer_samples["hey_b200"] == 0
+
+
+@pytest.mark.parametrize("mt,chunk_len", [("cnn", 1280), ("cnn", 1000), ("dnn", 1280), ("tcn", 777)])
+def test_stream_rings_match_oracle_interpreters(torch_cuda, golden_frontend, mt, chunk_len):
+    """Multi-stream mode (nww_stream_*): every stream of a StreamBank must behave like its own
+    reference interpreter (oracle/interp.py restates nanointerpreter.py:735-814) fed the same
+    chunks — including chunk lengths that leave the ring's window on an odd int16 boundary."""
+    from nanowakeword_b200 import StreamBank
+    from oracle.heads import forward_scores
+    from oracle.interp import OracleInterpreter
+    eng, sd, cfg = _engine(mt)
+    n = 5
+    g = golden_frontend["pcm"]
+    audio = np.stack([np.concatenate([g[(i + k) % len(g)] for k in range(3)]) for i in range(n)])   # (n, 48000)
+    bank = StreamBank(eng, n)
+    oracles = [OracleInterpreter(sd, cfg, name="m") for _ in range(n)]
+    n_steps = audio.shape[1] // chunk_len
+    windows, where = [], []
+    for s in range(n_steps):
+        chunks = np.ascontiguousarray(audio[:, s * chunk_len:(s + 1) * chunk_len])
+        if s == n_steps // 2:
+            bank.reset([2])
+            oracles[2].reset()
+        got = bank.push(chunks)
+        for i, o in enumerate(oracles):
+            want = o.predict(chunks[i])["m"]
+            assert abs(got[i] - want) < SCORE_TOL, (s, i, got[i], want)
+            assert abs(bank.raw_scores[i] - o.raw_scores["m"]) < SCORE_TOL
+    bank.reset()
+    assert np.all(bank.push(np.zeros((n, chunk_len), np.int16)) == 0.0)
+    bank.close()
+
+
+def test_stream_push_device_equals_batch_scoring(torch_cuda):
+    """After each stream has received exactly one window's worth of audio, the ring path and the
+    batch path see the same 16000 samples and must return bit-identical scores."""
+    eng, sd, cfg = _engine("cnn")
+    n = 300
+    pcm = synth_pcm(n, seed=21, kind="gauss")
+    batch = eng.score_device(torch_cuda.from_numpy(pcm).cuda()).cpu().numpy()
+    eng.stream_open(n)
+    dev = torch_cuda.from_numpy(pcm).cuda()
+    for s in range(0, 16000, 3200):
+        scores = eng.stream_push_device(dev[:, s:s + 3200].contiguous())
+        if s + 3200 < 16000:
+            assert float(scores.abs().max()) == 0.0            # not enough audio yet
+    assert np.array_equal(scores.cpu().numpy(), batch)
+    eng.stream_close()
+    with pytest.raises(ValueError):
+        eng.stream_push_host(np.zeros((n, 100), np.int16))      # closed: no streams are open

@@ -177,3 +177,72 @@ def test_cascade_gating_order(tmp_path):
     for _ in range(8):
         r = it.predict(x)
     assert ver.calls == 0 and r.score == 0.0 and it.model_name == "wake" and it.gate_name == "wake_lite"
+
+
+class _FakeStreamEngine:
+    """Host-only stand-in for Engine's stream calls: per-stream rings in numpy and a toy score
+    function, so StreamBank's bookkeeping can be compared with the oracle interpreter on CPU."""
+
+    def __init__(self, clip, score_fn):
+        self.clip, self.score_fn = clip, score_fn
+
+    def stream_open(self, n):
+        self.n = n
+        self.rings = np.zeros((n, self.clip), np.int16)
+        self.count = np.zeros(n, np.int64)
+
+    def stream_close(self):
+        pass
+
+    def stream_reset(self, ids=None):
+        sel = slice(None) if ids is None else np.asarray(ids)
+        self.rings[sel] = 0
+        self.count[sel] = 0
+
+    def stream_push_host(self, chunks):
+        L = chunks.shape[1]
+        self.rings = np.concatenate([self.rings, chunks], axis=1)[:, -self.clip:]
+        self.count += L
+        out = np.array([self.score_fn(r) for r in self.rings], np.float32)
+        out[self.count < self.clip] = 0.0
+        return out
+
+
+@pytest.mark.parametrize("mode", ["plain", "patience", "patience1", "debounce"])
+def test_stream_bank_matches_per_stream_oracle_interpreters(mode):
+    from nanowakeword_b200.streams import StreamBank
+    clip, n, L = 4000, 6, 500
+
+    def score_i16(win):                      # toy "model": a smooth function of the window, in (0, 1)
+        return float(1.0 / (1.0 + np.exp(-(np.abs(win.astype(np.float64)).mean() / 2000.0 - 1.5) * 3.0)))
+
+    bank = StreamBank(_FakeStreamEngine(clip, score_i16), n)
+    oracles = [OracleInterpreter(name="m", clip_samples=clip,
+                                 score_fn=lambda c: score_i16(np.rint(c.astype(np.float64) * 32768.0).astype(np.int16)))
+               for _ in range(n)]
+    kw_bank = {"plain": {}, "patience": dict(patience=3, threshold=0.5), "patience1": dict(patience=1, threshold=0.5),
+               "debounce": dict(debounce_time=0.1, threshold=0.5)}[mode]
+    kw_or = {"plain": {}, "patience": dict(patience={"m": 3}, threshold={"m": 0.5}),
+             "patience1": dict(patience={"m": 1}, threshold={"m": 0.5}),
+             "debounce": dict(debounce_time=0.1, threshold={"m": 0.5})}[mode]
+    rng = np.random.default_rng(3)
+    for step in range(40):
+        amp = rng.uniform(500, 9000, size=(n, 1))
+        chunks = np.clip(rng.normal(0, 1, (n, L)) * amp, -32768, 32767).astype(np.int16)
+        if step == 17:
+            bank.reset([1, 4])
+            oracles[1].reset()
+            oracles[4].reset()
+        if step == 29:
+            bank.reset()
+            for o in oracles:
+                o.reset()
+        got = bank.push(chunks, **kw_bank)
+        for i, o in enumerate(oracles):
+            want = o.predict(chunks[i], **kw_or)["m"]
+            assert abs(got[i] - want) < 1e-6, (mode, step, i)
+            assert abs(bank.raw_scores[i] - o.raw_scores["m"]) < 1e-6
+    with pytest.raises(ValueError):
+        bank.push(chunks, patience=2)                       # threshold missing
+    with pytest.raises(ValueError):
+        bank.push(chunks, patience=2, debounce_time=0.5, threshold=0.5)
