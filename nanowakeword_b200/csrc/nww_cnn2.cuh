@@ -47,6 +47,7 @@ struct Cnn2 {
     static constexpr int CONV1_TASKS = H1 * W1 * 2;               // (position, channel group of 8) = 1960
     static constexpr int CONV1_SPLIT_ROUNDS = 3;                  // after 3 rounds of 512 tasks a1 rows 0..14 are complete
     static constexpr int TMEM_COLS = 256;                         // 2 tiles x 4 quads x 32 columns
+    static constexpr int ZSLOTS = 62;                             // border positions per (plane, hi|lo, K group) copy
 
     static constexpr size_t kUnion = align_up(Fe2::kScratchBytes > (size_t)A1_BYTES ? Fe2::kScratchBytes : (size_t)A1_BYTES, 1024);
     static constexpr size_t kTw = align_up(Fe2::kTwBytes, 128);
@@ -60,7 +61,7 @@ struct Cnn2 {
 };
 
 struct Cnn2Weights {
-    const float* w1;          // [16][9]
+    const float* w1;          // [cg 2][tap 9][8 oc]: conv1 weights, 8 output channels of a tap contiguous
     const float* b1;          // [16]
     const uint4* w2_umma;     // Cnn2::W2_BYTES: [tap][hi|lo][kg][oc][8 ic] bf16, built by the engine
     const float* b2;          // [32]
@@ -68,8 +69,14 @@ struct Cnn2Weights {
 
 __device__ __forceinline__ uint32_t cnn2_pack_bf16(uint32_t lo16, uint32_t hi16) { return lo16 | (hi16 << 16); }
 
+template <int ACT> __device__ __forceinline__ float cnn2_act(float x) {
+    if (ACT == ACT_RELU) return fmaxf(x, 0.0f);
+    return apply_act(x, ACT);
+}
+
+template <int ACT>
 __global__ void __launch_bounds__(Cnn2::NT, 1)
-cnn2_stage_kernel(WindowSource src, long long n_windows, FrontendTables<double> tab, Cnn2Weights wt, int act,
+cnn2_stage_kernel(WindowSource src, long long n_windows, FrontendTables<double> tab, Cnn2Weights wt,
                   float* __restrict__ feat_hi, float* __restrict__ feat_lo /* [n][7680], K order (ph, pw, oc) */,
                   float* __restrict__ mel_dump /* nullable, (F,T) */) {
     using D = Cnn2;
@@ -140,7 +147,7 @@ cnn2_stage_kernel(WindowSource src, long long n_windows, FrontendTables<double> 
     };
 
     // conv1 + act + 2x2 max pool for task T = (position, channel group): 8 channels of one pooled pixel
-    // -> bf16 hi / lo rows of the parity planes.
+    // -> bf16 hi / lo rows of the parity planes.  Weights come as two 128-bit shared loads per tap.
     auto conv1_task = [&](int T) {
         const int pos = T >> 1, cg = T & 1;
         const int y = pos / D::W1, x = pos - y * D::W1;
@@ -151,23 +158,37 @@ cnn2_stage_kernel(WindowSource src, long long n_windows, FrontendTables<double> 
             const float2 hi = *reinterpret_cast<const float2*>(melp + (2 * y + r) * D::MEL_P + 2 * x + 2);
             in[r][0] = lo.x; in[r][1] = lo.y; in[r][2] = hi.x; in[r][3] = hi.y;
         }
+        float acc[8][4];
+        {
+            const float4 ba = *reinterpret_cast<const float4*>(b1s + cg * 8);
+            const float4 bb = *reinterpret_cast<const float4*>(b1s + cg * 8 + 4);
+            const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+            for (int o = 0; o < 8; ++o)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[o][q] = bv[o];
+        }
+        const float* wk = w1s + cg * 72;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float4 wa = *reinterpret_cast<const float4*>(wk + (r * 3 + c) * 8);
+                const float4 wb = *reinterpret_cast<const float4*>(wk + (r * 3 + c) * 8 + 4);
+                const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                for (int o = 0; o < 8; ++o) {
+                    acc[o][0] = fmaf(in[r][c], wv[o], acc[o][0]);
+                    acc[o][1] = fmaf(in[r][c + 1], wv[o], acc[o][1]);
+                    acc[o][2] = fmaf(in[r + 1][c], wv[o], acc[o][2]);
+                    acc[o][3] = fmaf(in[r + 1][c + 1], wv[o], acc[o][3]);
+                }
+            }
         uint32_t hb[8], lb[8];
 #pragma unroll
         for (int o = 0; o < 8; ++o) {
-            const float* k = w1s + (cg * 8 + o) * 9;
-            const float bias = b1s[cg * 8 + o];
-            float best = -3.4e38f;
-#pragma unroll
-            for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-                for (int dx = 0; dx < 2; ++dx) {
-                    float s = bias;
-#pragma unroll
-                    for (int r = 0; r < 3; ++r)
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) s = fmaf(in[dy + r][dx + c], k[r * 3 + c], s);
-                    best = fmaxf(best, apply_act(s, act));
-                }
+            const float best = fmaxf(fmaxf(cnn2_act<ACT>(acc[o][0]), cnn2_act<ACT>(acc[o][1])),
+                                     fmaxf(cnn2_act<ACT>(acc[o][2]), cnn2_act<ACT>(acc[o][3])));
             hb[o] = float_to_bf16_bits(best);
             lb[o] = float_to_bf16_bits(best - bf16_bits_to_float(hb[o]));
         }
@@ -194,9 +215,20 @@ cnn2_stage_kernel(WindowSource src, long long n_windows, FrontendTables<double> 
             for (int i = tid; i < D::F * D::TT; i += D::NT) md[i] = melp[(i / D::TT + 1) * D::MEL_P + (i % D::TT) + 1];
         }
 
-        // ---- the FFT scratch becomes the parity planes: clear (borders must read as zero) ---------------
-        for (int i = tid; i < D::A1_BYTES / 16; i += D::NT) reinterpret_cast<uint4*>(a1b)[i] = make_uint4(0, 0, 0, 0);
-        __syncthreads();
+        // ---- the FFT scratch becomes the parity planes.  conv1 writes every position that holds a real
+        // pixel; the positions that stand for the zero border are cleared here (disjoint from conv1's, so no
+        // barrier in between): position rows 0 and 11, and in the odd-x planes the column shared by x = -1
+        // and x = 49 (s = 25 r).
+        for (int i = tid; i < 16 * D::ZSLOTS; i += D::NT) {
+            const int copy = i / D::ZSLOTS, z = i - copy * D::ZSLOTS;      // copy = (plane, hi|lo, kg)
+            const int plane = copy >> 2;
+            int s;
+            if (z < 26) s = z;
+            else if (z < 52) s = 250 + z;                                   // 276 .. 301
+            else if (plane & 1) s = 25 * (z - 50);                          // 50, 75, .., 275
+            else continue;
+            *reinterpret_cast<uint4*>(a1b + copy * D::KG_BYTES + s * 16) = make_uint4(0, 0, 0, 0);
+        }
 
         // ---- conv1, first three rounds; then M tile 0 of conv2 can start on the tensor core ----------------
 #pragma unroll 1
@@ -227,10 +259,10 @@ cnn2_stage_kernel(WindowSource src, long long n_windows, FrontendTables<double> 
 #pragma unroll
                 for (int o = 0; o < 16; ++o) {
                     const float bias = b2s[half * 16 + o];
-                    float v = apply_act(__uint_as_float(r[0][o]) + bias, act);
-                    v = fmaxf(v, apply_act(__uint_as_float(r[1][o]) + bias, act));
-                    v = fmaxf(v, apply_act(__uint_as_float(r[2][o]) + bias, act));
-                    v = fmaxf(v, apply_act(__uint_as_float(r[3][o]) + bias, act));
+                    float v = cnn2_act<ACT>(__uint_as_float(r[0][o]) + bias);
+                    v = fmaxf(v, cnn2_act<ACT>(__uint_as_float(r[1][o]) + bias));
+                    v = fmaxf(v, cnn2_act<ACT>(__uint_as_float(r[2][o]) + bias));
+                    v = fmaxf(v, cnn2_act<ACT>(__uint_as_float(r[3][o]) + bias));
                     hi[o] = round_tf32(v);
                     lo[o] = round_tf32(v - hi[o]);
                 }

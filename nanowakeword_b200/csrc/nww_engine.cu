@@ -283,10 +283,11 @@ static int launch_tail_tc(nww_engine* e, int64_t n, float* scores, float* logits
     P.pre_mpad = e->tc_rows;
     P.pre_N = L0.N;
     P.pre_post = L0.post;
-    const size_t smem = tail_smem_bytes(P.max_width);
-    NWW_CUDA(set_smem(tail_kernel, smem));
-    const int64_t tiles = (n + kTailTM - 1) / kTailTM;
-    tail_kernel<<<grid_for(e, tiles, 2), kTailNT, smem, st>>>(nullptr, n, P, scores, logits, emb);
+    // what is left is a chain of small layers: 8-window tiles give one CTA per SM at chunk size
+    const size_t smem = tail_smem_bytes(P.max_width, kTailTMSmall);
+    NWW_CUDA(set_smem(tail_kernel_t<kTailTMSmall>, smem));
+    const int64_t tiles = (n + kTailTMSmall - 1) / kTailTMSmall;
+    tail_kernel_t<kTailTMSmall><<<grid_for(e, tiles, 2), kTailNT, smem, st>>>(nullptr, n, P, scores, logits, emb);
     e->launches++;
     NWW_CUDA(cudaGetLastError());
     return NWW_OK;
@@ -295,6 +296,15 @@ static int launch_tail_tc(nww_engine* e, int64_t n, float* scores, float* logits
 static int launch_tail(nww_engine* e, const float* feat, int64_t n, float* scores, float* logits, float* emb,
                        cudaStream_t st) {
     if (e->tc_enabled) return launch_tail_tc(e, n, scores, logits, emb, st);
+    if ((size_t)e->tail.layers[0].K * e->tail.layers[0].N <= 65536) {      // small layers only: favour CTA count
+        const size_t smem = tail_smem_bytes(e->tail.max_width, kTailTMSmall);
+        NWW_CUDA(set_smem(tail_kernel_t<kTailTMSmall>, smem));
+        const int64_t tiles = (n + kTailTMSmall - 1) / kTailTMSmall;
+        tail_kernel_t<kTailTMSmall><<<grid_for(e, tiles, 2), kTailNT, smem, st>>>(feat, n, e->tail, scores, logits, emb);
+        e->launches++;
+        NWW_CUDA(cudaGetLastError());
+        return NWW_OK;
+    }
     const size_t smem = tail_smem_bytes(e->tail.max_width);
     NWW_CUDA(set_smem(tail_kernel, smem));
     const int64_t tiles = (n + kTailTM - 1) / kTailTM;
@@ -317,9 +327,11 @@ static int launch_stage_a(nww_engine* e, WindowSource pcm, int64_t n, float* mel
         case NWW_ARCH_CNN: {
             using G = GeoNS40x98;
             if (e->cnn2_enabled) {
-                NWW_CUDA(set_smem(cnn2_stage_kernel, Cnn2::kTotal));
-                cnn2_stage_kernel<<<grid_for(e, n), Cnn2::NT, Cnn2::kTotal, st>>>(pcm, n, e->tab64, e->cnn2, e->spec.activation,
-                                                                                 e->d_feat_hi, e->d_feat_lo, mel);
+                auto k = e->spec.activation == NWW_ACT_RELU   ? cnn2_stage_kernel<ACT_RELU>
+                         : e->spec.activation == NWW_ACT_GELU ? cnn2_stage_kernel<ACT_GELU>
+                                                              : cnn2_stage_kernel<ACT_SILU>;
+                NWW_CUDA(set_smem(k, Cnn2::kTotal));
+                k<<<grid_for(e, n), Cnn2::NT, Cnn2::kTotal, st>>>(pcm, n, e->tab64, e->cnn2, e->d_feat_hi, e->d_feat_lo, mel);
                 e->launches++;
                 NWW_CUDA(cudaGetLastError());
                 return NWW_OK;
@@ -529,9 +541,16 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
                             wb[base] = hi;
                             wb[base + Cnn2::W2_TAP_BYTES / 2] = lo;
                         }
-                NWW_CUDA(cudaMalloc(&e->d_w2_umma, Cnn2::W2_BYTES));
+                // conv1 weights with the 8 output channels of a tap contiguous: [cg][tap][8 oc]
+                const float* w1 = e->blob.f32("cnn.w1");          // [oc 16][tap 9]
+                std::vector<float> w1v(144);
+                for (int oc = 0; oc < 16; ++oc)
+                    for (int tap = 0; tap < 9; ++tap) w1v[(oc >> 3) * 72 + tap * 8 + (oc & 7)] = w1[oc * 9 + tap];
+                NWW_CUDA(cudaMalloc(&e->d_w2_umma, Cnn2::W2_BYTES + 144 * sizeof(float)));
                 NWW_CUDA(cudaMemcpy(e->d_w2_umma, wb.data(), Cnn2::W2_BYTES, cudaMemcpyHostToDevice));
-                e->cnn2 = Cnn2Weights{e->cnn.w1, e->cnn.b1, e->d_w2_umma, e->cnn.b2};
+                float* d_w1v = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(e->d_w2_umma) + Cnn2::W2_BYTES);
+                NWW_CUDA(cudaMemcpy(d_w1v, w1v.data(), 144 * sizeof(float), cudaMemcpyHostToDevice));
+                e->cnn2 = Cnn2Weights{d_w1v, e->cnn.b1, e->d_w2_umma, e->cnn.b2};
                 e->cnn2_enabled = true;
             }
             e->tail_rest = e->tail;

@@ -19,7 +19,11 @@
 //     real frames lives in one thread's registers; lane 0 owns the two self-paired butterflies
 //     (bins 64 i and 64 i + 32).  The spectrum is never written back: the power of both frames
 //     goes straight to a small FP32 table;
-//   * the sparse triangular mel filters run in FP32 from that table, then 10*log10.
+//   * the sparse triangular mel filters run in FP32 from that table, then 10*log10 — by the two
+//     warps of the group that are NOT in pass 3, one batch behind (the power table is double-
+//     buffered), so the filterbank costs no time on the critical path; the pass-3 pair alternates
+//     between warps {0,1} and {2,3} every batch so that all four SM sub-partitions see the same
+//     FP64 load.
 #pragma once
 
 #include "nww_stage.cuh"
@@ -33,7 +37,7 @@ struct Fe2 {
     static constexpr int PW_PITCH = 264;                       // 257 power bins per frame, padded
     static constexpr int N_FFT_TOTAL = 49, N_BATCH = 25;       // 98 frames = 49 packed FFTs = 24.5 batches of two
     static constexpr size_t kWorkBytes = (size_t)NGROUP * NFB * NPAD * sizeof(cplx<double>);   // 66560
-    static constexpr size_t kPowBytes = (size_t)NGROUP * NFB * 2 * PW_PITCH * sizeof(float);   // 16896
+    static constexpr size_t kPowBytes = (size_t)2 * NGROUP * NFB * 2 * PW_PITCH * sizeof(float);   // 33792 (double-buffered)
     static constexpr size_t kTwBytes = (size_t)(7 * 64 + 7 * 8) * sizeof(cplx<double>);        // 8064
     static constexpr size_t kScratchBytes = kWorkBytes + kPowBytes;                            // reusable between windows
 };
@@ -70,7 +74,9 @@ __device__ __forceinline__ void fe2_logmel_window(const int16_t* __restrict__ pc
     const int t = tid & 127;                  // thread in group
     const int wg = t >> 5, lane = t & 31;
     cplx<double>* work = reinterpret_cast<cplx<double>*>(scratch) + (size_t)g * Fe2::NFB * Fe2::NPAD;
-    float* pw = reinterpret_cast<float*>(scratch + Fe2::kWorkBytes) + (size_t)g * Fe2::NFB * 2 * Fe2::PW_PITCH;
+    // power tables: [buffer 2][group][fft 2][frame 2][PW_PITCH]
+    float* pw_base = reinterpret_cast<float*>(scratch + Fe2::kWorkBytes) + (size_t)g * Fe2::NFB * 2 * Fe2::PW_PITCH;
+    constexpr int kPwBuf = Fe2::NGROUP * Fe2::NFB * 2 * Fe2::PW_PITCH;       // floats per buffer
     const cplx<double>* tw1 = tw_smem;
     const cplx<double>* tw2 = tw_smem + 7 * 64;
 
@@ -87,7 +93,36 @@ __device__ __forceinline__ void fe2_logmel_window(const int16_t* __restrict__ pc
     }
     const int b2 = jj >> 3, j2 = jj & 7;
 
-    for (int b = g; b < Fe2::N_BATCH; b += Fe2::NGROUP) {
+    // mel + dB of batch `mb` (4 frames x 40 filters = 160 tasks) from power table `p0`, by `nth` threads
+    // of which this is number `t2`.  Filters are dealt in octets ordered long, short, ... so that the two
+    // warps of a pair get about the same number of filter taps (the triangles widen with frequency).
+    auto mel_batch2 = [&](int mb, const float* __restrict__ p0, int t2, int nth) {
+        for (int task = t2; task < 4 * GeoNS40x98::N_MELS; task += nth) {
+            const int fr = task & 3;                       // FFT slot fr >> 1, packed frame fr & 1
+            const int slot = task >> 2;                    // 0..39 -> filter octets in the order 4, 3, 0, 2, 1
+            const int oct = slot >> 3;
+            const int m = ((oct == 0) ? 32 : (oct == 1) ? 24 : (oct == 2) ? 0 : (oct == 3) ? 16 : 8) + (slot & 7);
+            const int frame = 4 * mb + fr;
+            if (frame >= GeoNS40x98::N_FRAMES) continue;
+            const int ks = __ldg(tab.mel_start + m);
+            const int cnt = __ldg(tab.mel_count + m);
+            const float* __restrict__ w = tab.mel_w + __ldg(tab.mel_woff + m);
+            const float* __restrict__ p = p0 + fr * Fe2::PW_PITCH + ks;
+            float acc0 = 0.0f, acc1 = 0.0f;
+            int i = 0;
+            for (; i + 1 < cnt; i += 2) {
+                acc0 = fmaf(__ldg(w + i), p[i], acc0);
+                acc1 = fmaf(__ldg(w + i + 1), p[i + 1], acc1);
+            }
+            if (i < cnt) acc0 = fmaf(__ldg(w + i), p[i], acc0);
+            const float pm = acc0 + acc1;
+            mel[m * stride_m + frame * stride_t] = (pm <= tab.amin) ? tab.floor_db : 10.0f * log10f(pm);
+        }
+    };
+
+    int it = 0, b_prev = -1;
+    for (int b = g; b < Fe2::N_BATCH; b += Fe2::NGROUP, ++it) {
+        float* pw = pw_base + (it & 1) * kPwBuf;
         const bool fvalid = (2 * b + f) < Fe2::N_FFT_TOTAL;
         // ---- pass 1: L = 512, inputs straight from PCM (frames 4b + 2f and 4b + 2f + 1) -------------
         if (fvalid) {
@@ -118,13 +153,16 @@ __device__ __forceinline__ void fe2_logmel_window(const int16_t* __restrict__ pc
             for (int q = 1; q < 8; ++q) blk[8 * q] = cmul(v[q], tw2[(q - 1) * 8 + j2]);
         }
         named_bar_sync(1 + g, Fe2::GT);
-        // ---- pass 3 + power: one warp per FFT, lane c ------------------------------------------------------
-        if (wg < Fe2::NFB && (2 * b + wg) < Fe2::N_FFT_TOTAL) {
+        // ---- pass 3 + power (one warp per FFT, lane c)  ||  mel + dB of the previous batch -----------------
+        const int p3_first = (it & 1) << 1;                    // warps {0,1} on even batches, {2,3} on odd ones
+        const int fs = wg - p3_first;                          // FFT slot for a pass-3 warp
+        if (fs >= 0 && fs < Fe2::NFB) {
+          if ((2 * b + fs) < Fe2::N_FFT_TOTAL) {
             const int c = lane;
             const int cb = (c == 0) ? 32 : 64 - c;
             // butterfly with residue r = 8 q2 + b holds positions 64 b + 8 q2 + m -> idx = 65 (r & 7) + 8 (r >> 3) + m
-            const cplx<double>* pa = work + wg * Fe2::NPAD + 65 * (c & 7) + 8 * (c >> 3);
-            const cplx<double>* pb = work + wg * Fe2::NPAD + 65 * (cb & 7) + 8 * (cb >> 3);
+            const cplx<double>* pa = work + fs * Fe2::NPAD + 65 * (c & 7) + 8 * (c >> 3);
+            const cplx<double>* pb = work + fs * Fe2::NPAD + 65 * (cb & 7) + 8 * (cb >> 3);
             cplx<double> A[8], B[8];
 #pragma unroll
             for (int m = 0; m < 8; ++m) A[m] = pa[m];
@@ -145,8 +183,8 @@ __device__ __forceinline__ void fe2_logmel_window(const int16_t* __restrict__ pc
                 U[4] = B[0]; U[5] = B[1]; U[6] = B[2]; U[7] = B[3];
                 W[4] = B[7]; W[5] = B[6]; W[6] = B[5]; W[7] = B[4];
             }
-            float* pwa = pw + (wg * 2 + 0) * Fe2::PW_PITCH;
-            float* pwb = pw + (wg * 2 + 1) * Fe2::PW_PITCH;
+            float* pwa = pw + (fs * 2 + 0) * Fe2::PW_PITCH;
+            float* pwb = pw + (fs * 2 + 1) * Fe2::PW_PITCH;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 // X_A = Z_k + conj(Z_{N-k}),  X_B = (Z_k - conj(Z_{N-k})) / i   (the 1/2 is in the window)
@@ -161,30 +199,16 @@ __device__ __forceinline__ void fe2_logmel_window(const int16_t* __restrict__ pc
                 pwa[256] = (float)(ar * ar);
                 pwb[256] = (float)(br * br);
             }
+          }
+        } else if (b_prev >= 0) {
+            const int wm = (wg - p3_first) & 3;                // 2 or 3 -> mel warp 0 / 1
+            mel_batch2(b_prev, pw_base + ((it - 1) & 1) * kPwBuf, ((wm - 2) << 5) | lane, 64);
         }
         named_bar_sync(1 + g, Fe2::GT);
-        // ---- mel + dB: 4 frames x 40 filters per batch ------------------------------------------------------
-        for (int task = t; task < 4 * GeoNS40x98::N_MELS; task += Fe2::GT) {
-            const int fr = task & 3;                       // FFT slot fr >> 1, packed frame fr & 1
-            const int m = task >> 2;
-            const int frame = 4 * b + fr;
-            if (frame >= GeoNS40x98::N_FRAMES) continue;
-            const int ks = __ldg(tab.mel_start + m);
-            const int cnt = __ldg(tab.mel_count + m);
-            const float* __restrict__ w = tab.mel_w + __ldg(tab.mel_woff + m);
-            const float* __restrict__ p = pw + fr * Fe2::PW_PITCH + ks;
-            float acc0 = 0.0f, acc1 = 0.0f;
-            int i = 0;
-            for (; i + 1 < cnt; i += 2) {
-                acc0 = fmaf(__ldg(w + i), p[i], acc0);
-                acc1 = fmaf(__ldg(w + i + 1), p[i + 1], acc1);
-            }
-            if (i < cnt) acc0 = fmaf(__ldg(w + i), p[i], acc0);
-            const float pm = acc0 + acc1;
-            mel[m * stride_m + frame * stride_t] = (pm <= tab.amin) ? tab.floor_db : 10.0f * log10f(pm);
-        }
-        // no barrier here: the next batch's pass-3 writes to pw are two group barriers away
+        b_prev = b;
     }
+    // the group's last batch: all four warps
+    if (b_prev >= 0) mel_batch2(b_prev, pw_base + ((it - 1) & 1) * kPwBuf, t, Fe2::GT);
     __syncthreads();
 }
 

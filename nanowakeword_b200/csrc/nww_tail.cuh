@@ -69,35 +69,37 @@ __device__ __forceinline__ void tail_layernorm_act(float* tile, int pitch, int r
     }
 }
 
-constexpr int kTailTM = 32;      // windows per CTA
+constexpr int kTailTM = 32;      // windows per CTA (wide first layers: weight rows are re-used by 16 windows per thread)
+constexpr int kTailTMSmall = 8;  // windows per CTA for chains of small layers (more CTAs, less latency)
 constexpr int kTailKC = 32;      // K chunk staged in shared memory
 constexpr int kTailNT = 256;
 
-__host__ __device__ inline size_t tail_smem_bytes(int max_width) {
+__host__ __device__ inline size_t tail_smem_bytes(int max_width, int tm = kTailTM) {
     // two ping-pong activation tiles [TM][max_width] + one K chunk [TM][KC]
-    return sizeof(float) * ((size_t)2 * kTailTM * max_width + (size_t)kTailTM * kTailKC);
+    return sizeof(float) * ((size_t)2 * tm * max_width + (size_t)tm * kTailKC);
 }
 
+template <int TM>
 __global__ void __launch_bounds__(kTailNT, 2)
-tail_kernel(const float* __restrict__ feat, long long n_windows, TailParams P, float* __restrict__ scores,
+tail_kernel_t(const float* __restrict__ feat, long long n_windows, TailParams P, float* __restrict__ scores,
             float* __restrict__ logits /* nullable */, float* __restrict__ emb_dump /* nullable: input of classifier */) {
     NWW_DYN_SMEM(smem);
     float* actA = reinterpret_cast<float*>(smem);
-    float* actB = actA + (size_t)kTailTM * P.max_width;
-    float* xch = actB + (size_t)kTailTM * P.max_width;
+    float* actB = actA + (size_t)TM * P.max_width;
+    float* xch = actB + (size_t)TM * P.max_width;
     const int tid = threadIdx.x;
     const int lane_n = tid & 127;
     const int half = tid >> 7;                       // 0/1 -> windows [0,16) / [16,32)
-    constexpr int MH = kTailTM / 2;
+    constexpr int MH = TM / 2;
     const long long xmul = P.x_row_mul > 0 ? P.x_row_mul : 1;
 
-    for (long long w0 = (long long)blockIdx.x * kTailTM; w0 < n_windows; w0 += (long long)gridDim.x * kTailTM) {
-        const int mt = (n_windows - w0 < kTailTM) ? (int)(n_windows - w0) : kTailTM;
+    for (long long w0 = (long long)blockIdx.x * TM; w0 < n_windows; w0 += (long long)gridDim.x * TM) {
+        const int mt = (n_windows - w0 < TM) ? (int)(n_windows - w0) : TM;
         float* cur = actA;
         float* nxt = actB;
         const bool pre = P.pre_part != nullptr;
         if (pre) {
-            for (int i = tid; i < kTailTM * P.pre_N; i += kTailNT) {
+            for (int i = tid; i < TM * P.pre_N; i += kTailNT) {
                 const int m = i / P.pre_N, n = i - m * P.pre_N;
                 float v = 0.0f;
                 if (m < mt) {
@@ -110,7 +112,7 @@ tail_kernel(const float* __restrict__ feat, long long n_windows, TailParams P, f
             }
             __syncthreads();
             if (P.pre_post == POST_LN_ACT) {
-                tail_layernorm_act(cur, P.max_width, kTailTM, P.pre_N, P.pre_g, P.pre_beta, P.act, tid, kTailNT);
+                tail_layernorm_act(cur, P.max_width, TM, P.pre_N, P.pre_g, P.pre_beta, P.act, tid, kTailNT);
                 __syncthreads();
             }
         }
@@ -131,7 +133,7 @@ tail_kernel(const float* __restrict__ feat, long long n_windows, TailParams P, f
                     int xpitch;
                     if (from_feat) {
                         __syncthreads();             // previous chunk fully consumed
-                        for (int i = tid; i < kTailTM * kTailKC; i += kTailNT) {
+                        for (int i = tid; i < TM * kTailKC; i += kTailNT) {
                             const int m = i / kTailKC, k = i - m * kTailKC;
                             xch[i] = (m < mt && k < kc) ? feat[((w0 + m) * xmul + P.x_row_off) * (long long)L.K + k0 + k] : 0.0f;
                         }
@@ -180,7 +182,7 @@ tail_kernel(const float* __restrict__ feat, long long n_windows, TailParams P, f
             }
             __syncthreads();
             if (L.post == POST_LN_ACT) {
-                tail_layernorm_act(nxt, P.max_width, kTailTM, L.N, L.ln_g, L.ln_b, P.act, tid, kTailNT);
+                tail_layernorm_act(nxt, P.max_width, TM, L.N, L.ln_g, L.ln_b, P.act, tid, kTailNT);
                 __syncthreads();
             }
             if (emb_dump != nullptr && li == P.n_layers - 3) {      // output of the backbone's last layer
@@ -205,5 +207,8 @@ tail_kernel(const float* __restrict__ feat, long long n_windows, TailParams P, f
         __syncthreads();
     }
 }
+
+// the historical name: 32 windows per CTA
+#define tail_kernel tail_kernel_t<kTailTM>
 
 }  // namespace nww

@@ -52,10 +52,14 @@ int main(int argc, char** argv) {
                 const size_t base = (size_t)tap * 2 * (Cnn2::W2_TAP_BYTES / 2) + (size_t)(ic >> 3) * 256 + oc * 8 + (ic & 7);
                 wb[base] = hi; wb[base + Cnn2::W2_TAP_BYTES / 2] = lo;
             }
-    Cnn2Weights wt{b.f32("cnn.w1"), b.f32("cnn.b1"), reinterpret_cast<const uint4*>(wb.data()), b.f32("cnn.b2")};
+    const float* w1 = b.f32("cnn.w1");
+    std::vector<float> w1v(144);
+    for (int oc = 0; oc < 16; ++oc)
+        for (int tap = 0; tap < 9; ++tap) w1v[(oc >> 3) * 72 + tap * 8 + (oc & 7)] = w1[oc * 9 + tap];
+    Cnn2Weights wt{w1v.data(), b.f32("cnn.b1"), reinterpret_cast<const uint4*>(wb.data()), b.f32("cnn.b2")};
     std::vector<float> fhi(nw * 7680, -7777.f), flo(nw * 7680, -7777.f), mel(nw * 40 * 98, -7777.f);
     cudasim::launch(dim3(3), dim3(Cnn2::NT), Cnn2::kTotal, [&] {
-        cnn2_stage_kernel(pcm.data(), nw, tab, wt, 0, fhi.data(), flo.data(), mel.data());
+        cnn2_stage_kernel<ACT_RELU>(WindowSource{pcm.data(), nullptr, 16000}, nw, tab, wt, fhi.data(), flo.data(), mel.data());
     });
     // back to the reference's (oc, ph, pw) flatten order
     std::vector<float> feat(nw * 7680);

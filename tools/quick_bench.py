@@ -17,6 +17,9 @@ def timeit(fn, iters=10, warm=3):
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 pcm = torch.from_numpy(synth_pcm(B, seed=1234)).cuda()
 print(torch.cuda.get_device_name(0), "B =", B)
+_h = torch.from_numpy(synth_pcm(B, seed=1)).pin_memory(); _d = torch.empty_like(_h, device="cuda")
+ms = timeit(lambda: _d.copy_(_h, non_blocking=True))
+print(f"H2D pinned {_h.numel() * 2 / 1e6:.0f} MB: {ms:.3f} ms = {_h.numel() * 2 / ms / 1e6:.1f} GB/s")
 for mt in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["cnn", "dnn"]):
     cfg = default_config(mt); sd = make_state_dict(cfg, 0)
     for prec in ("fp64", "v1", "fp32"):
