@@ -28,6 +28,7 @@
 #pragma once
 
 #include "nww_fe2.cuh"
+#include "nww_stream_mel.cuh"
 
 namespace nww {
 
@@ -67,6 +68,14 @@ struct Cnn2Weights {
     const float* b2;          // [32]
 };
 
+// Stream mode: the log-mel of window w is read from the streams' mel ring (nww_stream_mel.cuh)
+// instead of being computed from PCM.  ring == nullptr selects the PCM path.
+struct Cnn2MelSource {
+    const float* ring;
+    const long long* count;     // per-stream sample counters (position of the window in the ring)
+    long long s0;               // stream index of window 0 of this launch
+};
+
 __device__ __forceinline__ uint32_t cnn2_pack_bf16(uint32_t lo16, uint32_t hi16) { return lo16 | (hi16 << 16); }
 
 template <int ACT> __device__ __forceinline__ float cnn2_act(float x) {
@@ -76,7 +85,7 @@ template <int ACT> __device__ __forceinline__ float cnn2_act(float x) {
 
 template <int ACT>
 __global__ void __launch_bounds__(Cnn2::NT, 1)
-cnn2_stage_kernel(WindowSource src, long long n_windows, FrontendTables<double> tab, Cnn2Weights wt,
+cnn2_stage_kernel(WindowSource src, Cnn2MelSource msrc, long long n_windows, FrontendTables<double> tab, Cnn2Weights wt,
                   float* __restrict__ feat_hi, float* __restrict__ feat_lo /* [n][7680], K order (ph, pw, oc) */,
                   float* __restrict__ mel_dump /* nullable, (F,T) */) {
     using D = Cnn2;
@@ -201,15 +210,27 @@ cnn2_stage_kernel(WindowSource src, long long n_windows, FrontendTables<double> 
                                                                      cnn2_pack_bf16(lb[4], lb[5]), cnn2_pack_bf16(lb[6], lb[7]));
     };
 
+    const bool from_mel = msrc.ring != nullptr;
     long long w = blockIdx.x;
-    if (w < n_windows) stager.issue(0, src.at(w), tid);
+    if (!from_mel && w < n_windows) stager.issue(0, src.at(w), tid);
     for (int it = 0; w < n_windows; w += gridDim.x, ++it) {
-        const long long wn = w + gridDim.x;
-        if (wn < n_windows) stager.issue((it + 1) & 1, src.at(wn), tid);
-        const int16_t* x = stager.wait(it & 1, (it >> 1) & 1, src.at(w));
-
-        // ---- log-mel into the zero-bordered (F+2, T+2) plane (ends with a CTA barrier) ----------------
-        fe2_logmel_window(x, smem, tw, tab, melp + D::MEL_P + 1, D::MEL_P, 1, tid);
+        if (from_mel) {
+            // ---- stream mode: the window's 98 frames are contiguous per mel row in the mirrored ring ---------
+            const long long s = msrc.s0 + w;
+            const int head = smel_slot(msrc.count[s] / SMel::HOP - 3 + 1);
+            const float* ring = msrc.ring + s * SMel::STREAM_FLOATS + head;
+            for (int i = tid; i < D::F * D::TT; i += D::NT) {
+                const int m = i / D::TT, t = i - m * D::TT;
+                melp[(m + 1) * D::MEL_P + t + 1] = ring[m * SMel::ROW + t];
+            }
+            __syncthreads();
+        } else {
+            const long long wn = w + gridDim.x;
+            if (wn < n_windows) stager.issue((it + 1) & 1, src.at(wn), tid);
+            const int16_t* x = stager.wait(it & 1, (it >> 1) & 1, src.at(w));
+            // ---- log-mel into the zero-bordered (F+2, T+2) plane (ends with a CTA barrier) ----------------
+            fe2_logmel_window(x, smem, tw, tab, melp + D::MEL_P + 1, D::MEL_P, 1, tid);
+        }
         if (mel_dump != nullptr) {
             float* md = mel_dump + w * (long long)(D::F * D::TT);
             for (int i = tid; i < D::F * D::TT; i += D::NT) md[i] = melp[(i / D::TT + 1) * D::MEL_P + (i % D::TT) + 1];

@@ -20,6 +20,7 @@
 #include "nww_heads.cuh"
 #include "nww_stage.cuh"
 #include "nww_stream.cuh"
+#include "nww_stream_mel.cuh"
 #include "nww_tables.h"
 #include "nww_tail.cuh"
 
@@ -100,6 +101,8 @@ struct nww_engine {
 
     // multi-stream mode (nww_stream_*): mirrored int16 rings in HBM
     StreamState streams{};
+    float* d_mel_ring = nullptr;         // [n_streams][40][2 x 98] incremental log-mel (NS40x98 only)
+    bool mel_inc = false;                // every chunk since open / full reset was a multiple of the hop
     int16_t* d_chunk = nullptr;          // staging for nww_stream_push_host
     size_t chunk_cap = 0;
     long long* d_ids = nullptr;
@@ -315,9 +318,23 @@ static int launch_tail(nww_engine* e, const float* feat, int64_t n, float* score
 }
 
 // Stage A for one chunk: PCM (int16, device) -> feature rows in e->d_feat.
-static int launch_stage_a(nww_engine* e, WindowSource pcm, int64_t n, float* mel, cudaStream_t st) {
+// stream_s0 >= 0: stream mode, the log-mel of window i is that of stream stream_s0 + i in the mel ring.
+static int launch_stage_a(nww_engine* e, WindowSource pcm, int64_t n, float* mel, cudaStream_t st, int64_t stream_s0 = -1) {
+    const bool from_ring = stream_s0 >= 0;
+    StreamState sub = e->streams;                 // view of streams [stream_s0, stream_s0 + n) for the gather kernel
+    if (from_ring) {
+        sub.count += stream_s0;
+        sub.n_streams = n;
+    }
+    const float* ring0 = from_ring ? e->d_mel_ring + stream_s0 * (int64_t)SMel::STREAM_FLOATS : nullptr;
     switch (e->spec.arch) {
         case NWW_ARCH_DNN: {
+            if (from_ring) {
+                stream_mel_gather_kernel<<<ew_grid(n * 3920, e->sm_count), 256, 0, st>>>(sub, ring0, e->d_feat, 1);
+                e->launches++;
+                NWW_CUDA(cudaGetLastError());
+                return NWW_OK;
+            }
             // the DNN body is the identity on the (T, F) log-mel: features = flattened mel
             int rc = launch_frontend<GeoNS40x98>(e, pcm, n, e->d_feat, /*time_major=*/1, st);
             if (rc) return rc;
@@ -331,7 +348,8 @@ static int launch_stage_a(nww_engine* e, WindowSource pcm, int64_t n, float* mel
                          : e->spec.activation == NWW_ACT_GELU ? cnn2_stage_kernel<ACT_GELU>
                                                               : cnn2_stage_kernel<ACT_SILU>;
                 NWW_CUDA(set_smem(k, Cnn2::kTotal));
-                k<<<grid_for(e, n), Cnn2::NT, Cnn2::kTotal, st>>>(pcm, n, e->tab64, e->cnn2, e->d_feat_hi, e->d_feat_lo, mel);
+                const Cnn2MelSource ms{from_ring ? e->d_mel_ring : nullptr, e->streams.count, from_ring ? stream_s0 : 0};
+                k<<<grid_for(e, n), Cnn2::NT, Cnn2::kTotal, st>>>(pcm, ms, n, e->tab64, e->cnn2, e->d_feat_hi, e->d_feat_lo, mel);
                 e->launches++;
                 NWW_CUDA(cudaGetLastError());
                 return NWW_OK;
@@ -345,13 +363,18 @@ static int launch_stage_a(nww_engine* e, WindowSource pcm, int64_t n, float* mel
             return NWW_OK;
         }
         default:
+            if (from_ring) {
+                stream_mel_gather_kernel<<<ew_grid(n * 3920, e->sm_count), 256, 0, st>>>(sub, ring0, e->d_scratch, 0);
+                e->launches++;
+                NWW_CUDA(cudaGetLastError());
+            }
             return launch_head_stage_a(e->heads, e->tab64, e->spec.activation, e->sm_count, pcm, n, e->d_feat, e->d_scratch,
-                                       mel, st, &e->launches, &g_last_error);
+                                       mel, st, &e->launches, &g_last_error, from_ring);
     }
 }
 
 static int run_device(nww_engine* e, const int16_t* pcm, int64_t n, float* scores, float* mel, float* logits, float* emb,
-                      cudaStream_t st, const long long* win_off = nullptr) {
+                      cudaStream_t st, const long long* win_off = nullptr, bool from_mel_ring = false) {
     const int64_t mel_stride = (int64_t)e->n_mels * e->n_frames;
     for (int64_t w0 = 0; w0 < n; w0 += e->chunk) {
         const int64_t m = std::min<int64_t>(e->chunk, n - w0);
@@ -362,7 +385,7 @@ static int run_device(nww_engine* e, const int16_t* pcm, int64_t n, float* score
         }
         const WindowSource src = win_off ? WindowSource{pcm, win_off + w0, e->clip}
                                          : WindowSource{pcm + w0 * e->clip, nullptr, e->clip};
-        int rc = launch_stage_a(e, src, m, mel ? mel + w0 * mel_stride : nullptr, st);
+        int rc = launch_stage_a(e, src, m, mel ? mel + w0 * mel_stride : nullptr, st, from_mel_ring ? w0 : -1);
         if (rc) return rc;
         if (e->profiling) cudaEventRecord(eb, st);
         rc = launch_tail(e, e->d_feat, m, scores + w0, logits ? logits + w0 : nullptr,
@@ -383,6 +406,9 @@ static void stream_free(nww_engine* e) {
     cudaFree(e->streams.wpos);
     cudaFree(e->streams.count);
     cudaFree(e->streams.win_off);
+    cudaFree(e->d_mel_ring);
+    e->d_mel_ring = nullptr;
+    e->mel_inc = false;
     e->streams = StreamState{};
 }
 
@@ -722,6 +748,14 @@ int nww_stream_open(nww_engine* e, int64_t n_streams) {
     NWW_CUDA(cudaMalloc(&st.count, (size_t)n_streams * sizeof(long long)));
     NWW_CUDA(cudaMalloc(&st.win_off, (size_t)n_streams * sizeof(long long)));
     e->streams = st;
+    // incremental log-mel (nww_stream_mel.cuh): un-centred geometry, and a stage A that can start from mel
+    const bool v1_cnn = e->spec.arch == NWW_ARCH_CNN && !e->cnn2_enabled;
+    if (e->spec.geometry == NWW_GEOM_NS40X98 && e->spec.frontend_precision == NWW_FRONTEND_FP64 && !v1_cnn &&
+        !(e->spec.reserved[0] & 4)) {
+        NWW_CUDA(cudaMalloc(&e->d_mel_ring, (size_t)n_streams * SMel::STREAM_FLOATS * sizeof(float)));
+        NWW_CUDA(cudaMemsetAsync(e->d_mel_ring, 0, (size_t)n_streams * SMel::STREAM_FLOATS * sizeof(float), e->stream));
+        e->mel_inc = true;
+    }
     stream_reset_kernel<<<(unsigned)n_streams, 256, 0, e->stream>>>(st, nullptr, n_streams);
     e->launches++;
     NWW_CUDA(cudaGetLastError());
@@ -743,7 +777,19 @@ static int stream_push_locked(nww_engine* e, const int16_t* chunks_dev, int chun
     stream_append_kernel<<<(unsigned)S.n_streams, 256, 0, st>>>(S, chunks_dev, chunk_len);
     e->launches++;
     NWW_CUDA(cudaGetLastError());
-    int rc = run_device(e, S.ring, S.n_streams, scores_dev, nullptr, nullptr, nullptr, st, S.win_off);
+    const int n_new = chunk_len / SMel::HOP;
+    if (e->mel_inc && (chunk_len % SMel::HOP != 0 || n_new > SMel::MAX_NEW)) e->mel_inc = false;   // until the next full reset
+    int rc;
+    if (e->mel_inc) {
+        NWW_CUDA(set_smem(stream_mel_update_kernel, SMel::kTotal));
+        const int64_t groups = (S.n_streams + SMel::SPB - 1) / SMel::SPB;
+        stream_mel_update_kernel<<<grid_for(e, groups), Fe2::NT, SMel::kTotal, st>>>(S, e->d_mel_ring, e->tab64, n_new);
+        e->launches++;
+        NWW_CUDA(cudaGetLastError());
+        rc = run_device(e, S.ring, S.n_streams, scores_dev, nullptr, nullptr, nullptr, st, S.win_off, true);
+    } else {
+        rc = run_device(e, S.ring, S.n_streams, scores_dev, nullptr, nullptr, nullptr, st, S.win_off);
+    }
     if (rc) return rc;
     stream_mask_kernel<<<(unsigned)((S.n_streams + 255) / 256), 256, 0, st>>>(S, scores_dev);
     e->launches++;
@@ -795,6 +841,7 @@ int nww_stream_reset(nww_engine* e, const int64_t* ids_host, int64_t n_ids) {
     NWW_CUDA(cudaSetDevice(e->device));
     const StreamState& S = e->streams;
     if (!ids_host) {
+        if (e->d_mel_ring) e->mel_inc = true;      // all counters return to 0: frame numbering restarts
         stream_reset_kernel<<<(unsigned)S.n_streams, 256, 0, e->stream>>>(S, nullptr, S.n_streams);
     } else {
         if (n_ids <= 0) return NWW_OK;

@@ -63,13 +63,21 @@ __device__ __forceinline__ void fe2_build_twiddles(cplx<double>* tw_smem, const 
     for (int i = tid; i < 7 * 8; i += nthreads) tw_smem[7 * 64 + i] = tw512[(8 * (i & 7) * ((i >> 3) + 1)) & 511];
 }
 
-// One window.  pcm: 16000 int16 in shared memory; scratch: Fe2::kScratchBytes of shared memory;
-// tw_smem: the tables above.  Writes mel[m * stride_m + t * stride_t] (shared or global).
-// Must be called by all 512 threads; ends with __syncthreads().
-__device__ __forceinline__ void fe2_logmel_window(const int16_t* __restrict__ pcm, unsigned char* __restrict__ scratch,
-                                                  const cplx<double>* __restrict__ tw_smem,
-                                                  const FrontendTables<double>& tab, float* __restrict__ mel,
-                                                  int stride_m, int stride_t, int tid) {
+// A batch = up to four consecutive frames (hop 160) = two packed FFTs.  `x` points at sample 0 of the
+// batch's first frame in shared memory; frames beyond `nframes` are computed on whatever follows in
+// shared memory (it must be readable up to x + 3 * 160 + 448) and dropped.
+struct Fe2Batch {
+    const int16_t* x;
+    int nframes;
+};
+
+// The front-end core: `n_batches` batches dealt round-robin to the four groups.  batch_of(b) -> Fe2Batch,
+// store(b, frame_in_batch, mel_bin, dB).  scratch: Fe2::kScratchBytes of shared memory; tw_smem: the
+// tables above.  Must be called by all 512 threads; ends with __syncthreads().
+template <typename BatchFn, typename StoreFn>
+__device__ __forceinline__ void fe2_run(int n_batches, BatchFn batch_of, StoreFn store, unsigned char* __restrict__ scratch,
+                                        const cplx<double>* __restrict__ tw_smem, const FrontendTables<double>& tab,
+                                        int tid) {
     const int g = tid >> 7;                   // group
     const int t = tid & 127;                  // thread in group
     const int wg = t >> 5, lane = t & 31;
@@ -96,14 +104,13 @@ __device__ __forceinline__ void fe2_logmel_window(const int16_t* __restrict__ pc
     // mel + dB of batch `mb` (4 frames x 40 filters = 160 tasks) from power table `p0`, by `nth` threads
     // of which this is number `t2`.  Filters are dealt in octets ordered long, short, ... so that the two
     // warps of a pair get about the same number of filter taps (the triangles widen with frequency).
-    auto mel_batch2 = [&](int mb, const float* __restrict__ p0, int t2, int nth) {
+    auto mel_batch2 = [&](int mb, int mb_frames, const float* __restrict__ p0, int t2, int nth) {
         for (int task = t2; task < 4 * GeoNS40x98::N_MELS; task += nth) {
             const int fr = task & 3;                       // FFT slot fr >> 1, packed frame fr & 1
             const int slot = task >> 2;                    // 0..39 -> filter octets in the order 4, 3, 0, 2, 1
             const int oct = slot >> 3;
             const int m = ((oct == 0) ? 32 : (oct == 1) ? 24 : (oct == 2) ? 0 : (oct == 3) ? 16 : 8) + (slot & 7);
-            const int frame = 4 * mb + fr;
-            if (frame >= GeoNS40x98::N_FRAMES) continue;
+            if (fr >= mb_frames) continue;
             const int ks = __ldg(tab.mel_start + m);
             const int cnt = __ldg(tab.mel_count + m);
             const float* __restrict__ w = tab.mel_w + __ldg(tab.mel_woff + m);
@@ -116,17 +123,18 @@ __device__ __forceinline__ void fe2_logmel_window(const int16_t* __restrict__ pc
             }
             if (i < cnt) acc0 = fmaf(__ldg(w + i), p[i], acc0);
             const float pm = acc0 + acc1;
-            mel[m * stride_m + frame * stride_t] = (pm <= tab.amin) ? tab.floor_db : 10.0f * log10f(pm);
+            store(mb, fr, m, (pm <= tab.amin) ? tab.floor_db : 10.0f * log10f(pm));
         }
     };
 
-    int it = 0, b_prev = -1;
-    for (int b = g; b < Fe2::N_BATCH; b += Fe2::NGROUP, ++it) {
+    int it = 0, b_prev = -1, nf_prev = 0;
+    for (int b = g; b < n_batches; b += Fe2::NGROUP, ++it) {
         float* pw = pw_base + (it & 1) * kPwBuf;
-        const bool fvalid = (2 * b + f) < Fe2::N_FFT_TOTAL;
+        const Fe2Batch bt = batch_of(b);
+        const bool fvalid = 2 * f < bt.nframes;
         // ---- pass 1: L = 512, inputs straight from PCM (frames 4b + 2f and 4b + 2f + 1) -------------
         if (fvalid) {
-            const int16_t* xa = pcm + (4 * b + 2 * f) * GeoNS40x98::HOP + jj;
+            const int16_t* xa = bt.x + 2 * f * GeoNS40x98::HOP + jj;
             cplx<double> v[8];
 #pragma unroll
             for (int m = 0; m < 7; ++m) {
@@ -157,7 +165,7 @@ __device__ __forceinline__ void fe2_logmel_window(const int16_t* __restrict__ pc
         const int p3_first = (it & 1) << 1;                    // warps {0,1} on even batches, {2,3} on odd ones
         const int fs = wg - p3_first;                          // FFT slot for a pass-3 warp
         if (fs >= 0 && fs < Fe2::NFB) {
-          if ((2 * b + fs) < Fe2::N_FFT_TOTAL) {
+          if (2 * fs < bt.nframes) {
             const int c = lane;
             const int cb = (c == 0) ? 32 : 64 - c;
             // butterfly with residue r = 8 q2 + b holds positions 64 b + 8 q2 + m -> idx = 65 (r & 7) + 8 (r >> 3) + m
@@ -202,14 +210,29 @@ __device__ __forceinline__ void fe2_logmel_window(const int16_t* __restrict__ pc
           }
         } else if (b_prev >= 0) {
             const int wm = (wg - p3_first) & 3;                // 2 or 3 -> mel warp 0 / 1
-            mel_batch2(b_prev, pw_base + ((it - 1) & 1) * kPwBuf, ((wm - 2) << 5) | lane, 64);
+            mel_batch2(b_prev, nf_prev, pw_base + ((it - 1) & 1) * kPwBuf, ((wm - 2) << 5) | lane, 64);
         }
         named_bar_sync(1 + g, Fe2::GT);
         b_prev = b;
+        nf_prev = bt.nframes;
     }
     // the group's last batch: all four warps
-    if (b_prev >= 0) mel_batch2(b_prev, pw_base + ((it - 1) & 1) * kPwBuf, t, Fe2::GT);
+    if (b_prev >= 0) mel_batch2(b_prev, nf_prev, pw_base + ((it - 1) & 1) * kPwBuf, t, Fe2::GT);
     __syncthreads();
+}
+
+// One window.  pcm: 16000 int16 in shared memory.  Writes mel[m * stride_m + t * stride_t] (shared or global).
+__device__ __forceinline__ void fe2_logmel_window(const int16_t* __restrict__ pcm, unsigned char* __restrict__ scratch,
+                                                  const cplx<double>* __restrict__ tw_smem,
+                                                  const FrontendTables<double>& tab, float* __restrict__ mel,
+                                                  int stride_m, int stride_t, int tid) {
+    fe2_run(
+        Fe2::N_BATCH,
+        [&](int b) {
+            const int left = GeoNS40x98::N_FRAMES - 4 * b;
+            return Fe2Batch{pcm + 4 * b * GeoNS40x98::HOP, left < 4 ? left : 4};
+        },
+        [&](int b, int fr, int m, float db) { mel[m * stride_m + (4 * b + fr) * stride_t] = db; }, scratch, tw_smem, tab, tid);
 }
 
 // ----------------------------------------------------------------------------------------

@@ -188,7 +188,8 @@ inline int setup_head_weights(int arch, int geometry, const BlobLookup& get, con
 // ------------------------------------------------------------------------------ launches
 inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<double>& tab, int act, int sm_count,
                                WindowSource pcm, long long n, float* feat, float* scratch, float* mel_dump,
-                               cudaStream_t st, int64_t* launches, std::string* err) {
+                               cudaStream_t st, int64_t* launches, std::string* err, bool mel_ready = false) {
+    // mel_ready: the caller already placed the (n, F, T) log-mel at the start of `scratch` (stream mode)
     float* p = scratch;
     auto take = [&](size_t floats_per_window) {
         float* r = p;
@@ -222,7 +223,7 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
     using G = GeoNS40x98;
     constexpr int F = G::N_MELS, T = G::N_FRAMES;
     float* mel = take((size_t)F * T);
-    if ((rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel, 0, st, launches, err))) return rc;
+    if (!mel_ready && (rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel, 0, st, launches, err))) return rc;
     if (mel_dump) NWW_HCUDA(cudaMemcpyAsync(mel_dump, mel, (size_t)n * F * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
 
     if (hw.arch == NWW_ARCH_TCN) {

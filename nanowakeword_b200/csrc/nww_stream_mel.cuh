@@ -1,0 +1,93 @@
+// nww_stream_mel.cuh — incremental log-mel for streams (NS40x98 geometry): the K9 "ring-buffer kernel".
+//
+// The reference re-runs its whole graph on the last clip_samples at every predict(chunk)
+// (nanointerpreter.py:755-756, 783): with 1280-sample chunks, 90 of the 98 STFT frames of a window are
+// the same samples, windowed the same way, as 90 frames of the previous window.  Without centring
+// (NS40x98) frame t of a window is exactly frame t + 8 of the previous one, so the engine keeps, per
+// stream, a ring of log-mel frames indexed by ABSOLUTE frame number a (frame a covers stream samples
+// [160 a, 160 a + 400)) and computes only the frames a chunk completes — bit-identical to recomputing
+// the window, 12x less front-end work at the reference's 80 ms hop.
+//
+// Layout: mel ring [n_streams][40][2 x 98] float, mirrored along time like the PCM ring, so the 98
+// frames of the current window are contiguous per mel row starting at slot (a_new + 1) mod 98, where
+// a_new = count / 160 - 3 is the newest complete frame.
+// Requires every chunk since open/reset to be a multiple of the hop (160); the engine falls back to the
+// full-window path otherwise.
+#pragma once
+
+#include "nww_fe2.cuh"
+#include "nww_stream.cuh"
+
+namespace nww {
+
+struct SMel {
+    static constexpr int T = GeoNS40x98::N_FRAMES, F = GeoNS40x98::N_MELS, HOP = GeoNS40x98::HOP;
+    static constexpr int ROW = 2 * T;                              // mirrored row pitch
+    static constexpr int STREAM_FLOATS = F * ROW;                  // 7840 floats = 31 360 B per stream
+    static constexpr int SPB = 8;                                  // streams per CTA iteration
+    static constexpr int MAX_NEW = 16;                             // frames per push handled incrementally
+    static constexpr int PCM_SLOT = 160 * (MAX_NEW - 1) + 400 + 160 * 3 + 64;   // samples per stream in shared memory (+ slack for dropped frames)
+    static constexpr size_t kScratch = (Fe2::kScratchBytes + 127) / 128 * 128;
+    static constexpr size_t kTw = (Fe2::kTwBytes + 127) / 128 * 128;
+    static constexpr size_t kPcm = ((size_t)SPB * PCM_SLOT * sizeof(int16_t) + 127) / 128 * 128;
+    static constexpr size_t kTotal = kScratch + kTw + kPcm;
+};
+
+__device__ __forceinline__ int smel_slot(long long a) {
+    int r = (int)(a % SMel::T);
+    return r < 0 ? r + SMel::T : r;
+}
+
+// After stream_append_kernel: compute the n_new = chunk_len / 160 frames the chunk completed, for every stream.
+__global__ void __launch_bounds__(Fe2::NT, 1)
+stream_mel_update_kernel(StreamState st, float* __restrict__ mel_ring, FrontendTables<double> tab, int n_new) {
+    NWW_DYN_SMEM(smem);
+    const int tid = threadIdx.x;
+    cplx<double>* tw = reinterpret_cast<cplx<double>*>(smem + SMel::kScratch);
+    int16_t* pcm_s = reinterpret_cast<int16_t*>(smem + SMel::kScratch + SMel::kTw);
+    fe2_build_twiddles(tw, tab.twiddle, tid, Fe2::NT);
+    const int nbps = (n_new + 3) >> 2;                              // batches per stream
+    const int n_samp = SMel::HOP * (n_new - 1) + GeoNS40x98::WIN;   // samples the new frames span
+    const int w_off = st.R - SMel::HOP * (n_new + 2);               // their offset inside the stream's current window
+    for (long long s0 = (long long)blockIdx.x * SMel::SPB; s0 < st.n_streams; s0 += (long long)gridDim.x * SMel::SPB) {
+        const int ns = (int)((st.n_streams - s0 < SMel::SPB) ? (st.n_streams - s0) : SMel::SPB);
+        __syncthreads();                                            // previous iteration done with pcm_s (and tw built)
+        for (int i = tid; i < ns * SMel::PCM_SLOT; i += Fe2::NT) {
+            const int sl = i / SMel::PCM_SLOT, j = i - sl * SMel::PCM_SLOT;
+            pcm_s[i] = (j < n_samp) ? st.ring[st.win_off[s0 + sl] + w_off + j] : (int16_t)0;
+        }
+        __syncthreads();
+        fe2_run(
+            ns * nbps,
+            [&](int b) {
+                const int sl = b / nbps, q = b - sl * nbps;
+                const int left = n_new - 4 * q;
+                return Fe2Batch{pcm_s + sl * SMel::PCM_SLOT + 4 * q * SMel::HOP, left < 4 ? left : 4};
+            },
+            [&](int b, int fr, int m, float db) {
+                const int sl = b / nbps, q = b - sl * nbps;
+                const long long s = s0 + sl;
+                const long long a = st.count[s] / SMel::HOP - 3 - (n_new - 1) + 4 * q + fr;   // absolute frame number
+                float* row = mel_ring + s * SMel::STREAM_FLOATS + m * SMel::ROW + smel_slot(a);
+                row[0] = db;
+                row[SMel::T] = db;
+            },
+            smem, tw, tab, tid);
+    }
+}
+
+// Current window of every stream out of the mel ring: (n, F, T) or, time_major, (n, T, F).
+__global__ void __launch_bounds__(256)
+stream_mel_gather_kernel(StreamState st, const float* __restrict__ mel_ring, float* __restrict__ out, int time_major) {
+    const long long total = st.n_streams * (long long)(SMel::F * SMel::T);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long s = i / (SMel::F * SMel::T);
+        const int r = (int)(i - s * (SMel::F * SMel::T));
+        const int m = r / SMel::T, t = r - m * SMel::T;             // reads are contiguous along t
+        const int head = smel_slot(st.count[s] / SMel::HOP - 3 + 1);
+        const float v = mel_ring[s * SMel::STREAM_FLOATS + m * SMel::ROW + head + t];
+        out[s * (long long)(SMel::F * SMel::T) + (time_major ? t * SMel::F + m : r)] = v;
+    }
+}
+
+}  // namespace nww

@@ -31,7 +31,8 @@ class Engine:
     """One model resident on one B200: weights, tables and workspaces live in HBM."""
 
     def __init__(self, state_dict: dict, cfg: dict, device: int = 0, frontend_precision: str = "fp64",
-                 chunk_windows: int = 0, tensor_cores: bool = True, cnn_stage: str = "v2"):
+                 chunk_windows: int = 0, tensor_cores: bool = True, cnn_stage: str = "v2",
+                 stream_incremental: bool = True):
         self._lib = _lib.load_library()
         self.cfg = dict(cfg)
         self.geometry = geometry_for(cfg)
@@ -54,7 +55,8 @@ class Engine:
         # (CUDA-core conv2) stage kernel instead of the tcgen05 one (A/B measurements)
         if cnn_stage not in ("v1", "v2"):
             raise ValueError("cnn_stage must be 'v1' or 'v2'")
-        spec.reserved[0] = (0 if tensor_cores else 1) | (2 if cnn_stage == "v1" else 0)
+        # bit 2: streams always re-run the front end on the whole window (no incremental mel ring)
+        spec.reserved[0] = (0 if tensor_cores else 1) | (2 if cnn_stage == "v1" else 0) | (0 if stream_incremental else 4)
         self._blob = (C.c_char * len(blob)).from_buffer_copy(blob)
         handle = C.c_void_p()
         rc = self._lib.nww_create(C.byref(spec), C.cast(self._blob, C.c_void_p), len(blob), int(device), C.byref(handle))

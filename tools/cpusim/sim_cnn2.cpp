@@ -59,7 +59,7 @@ int main(int argc, char** argv) {
     Cnn2Weights wt{w1v.data(), b.f32("cnn.b1"), reinterpret_cast<const uint4*>(wb.data()), b.f32("cnn.b2")};
     std::vector<float> fhi(nw * 7680, -7777.f), flo(nw * 7680, -7777.f), mel(nw * 40 * 98, -7777.f);
     cudasim::launch(dim3(3), dim3(Cnn2::NT), Cnn2::kTotal, [&] {
-        cnn2_stage_kernel<ACT_RELU>(WindowSource{pcm.data(), nullptr, 16000}, nw, tab, wt, fhi.data(), flo.data(), mel.data());
+        cnn2_stage_kernel<ACT_RELU>(WindowSource{pcm.data(), nullptr, 16000}, Cnn2MelSource{nullptr, nullptr, 0}, nw, tab, wt, fhi.data(), flo.data(), mel.data());
     });
     // back to the reference's (oc, ph, pw) flatten order
     std::vector<float> feat(nw * 7680);
