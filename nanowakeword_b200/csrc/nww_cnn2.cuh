@@ -27,7 +27,7 @@
 // consumes, in the K order (ph, pw, oc) (fc1's weight columns are permuted to match at create time).
 #pragma once
 
-#include "nww_fe2.cuh"
+#include "nww_fe3.cuh"
 #include "nww_stream_mel.cuh"
 
 namespace nww {
@@ -50,15 +50,17 @@ struct Cnn2 {
     static constexpr int TMEM_COLS = 256;                         // 2 tiles x 4 quads x 32 columns
     static constexpr int ZSLOTS = 62;                             // border positions per (plane, hi|lo, K group) copy
 
-    static constexpr size_t kUnion = align_up(Fe2::kScratchBytes > (size_t)A1_BYTES ? Fe2::kScratchBytes : (size_t)A1_BYTES, 1024);
-    static constexpr size_t kTw = align_up(Fe2::kTwBytes, 128);
+    static constexpr size_t kUnion = align_up(Fe3::kWorkBytes > (size_t)A1_BYTES ? Fe3::kWorkBytes : (size_t)A1_BYTES, 1024);
+    static constexpr size_t kTw = Fe3::kTwBytes + Fe3::kWinBytes;     // twiddles, then the Hann table
     static constexpr size_t kMel = align_up(sizeof(float) * MEL_ROWS * MEL_P, 128);
     static constexpr size_t kW2 = W2_BYTES;
     static constexpr size_t kSmall = align_up(sizeof(float) * (16 * 9 + 16 + 32), 128);
     static constexpr size_t kBars = 128;                          // 2 mbarriers + TMEM base slot
     static constexpr size_t oTw = kUnion, oMel = oTw + kTw, oW2 = oMel + kMel, oSmall = oW2 + kW2, oBars = oSmall + kSmall,
                             oPcm = oBars + kBars;
-    static constexpr size_t kTotal = oPcm + PcmStager<G::CLIP>::kBytes;
+    using Stager = PcmStager<G::CLIP, 1>;                          // one PCM slot: the next window is fetched as soon as
+                                                                  // the FFT phase has consumed this one
+    static constexpr size_t kTotal = oPcm + Stager::kBytes;
 };
 
 struct Cnn2Weights {
@@ -94,6 +96,7 @@ cnn2_stage_kernel(WindowSource src, Cnn2MelSource msrc, long long n_windows, Fro
     const int warp = tid >> 5, lane = tid & 31;
     unsigned char* a1b = smem;                                                   // overlays the FFT scratch
     cplx<double>* tw = reinterpret_cast<cplx<double>*>(smem + D::oTw);
+    double* win_s = reinterpret_cast<double*>(smem + D::oTw + Fe3::kTwBytes);
     float* melp = reinterpret_cast<float*>(smem + D::oMel);
     unsigned char* w2s = smem + D::oW2;
     float* w1s = reinterpret_cast<float*>(smem + D::oSmall);
@@ -101,7 +104,7 @@ cnn2_stage_kernel(WindowSource src, Cnn2MelSource msrc, long long n_windows, Fro
     float* b2s = b1s + 16;
     uint64_t* mma_bar = reinterpret_cast<uint64_t*>(smem + D::oBars);            // [2], one per M tile
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + D::oBars + 64);
-    PcmStager<D::G::CLIP> stager;
+    typename D::Stager stager;
     stager.carve(smem + D::oPcm);
     stager.init(tid);
 
@@ -112,6 +115,7 @@ cnn2_stage_kernel(WindowSource src, Cnn2MelSource msrc, long long n_windows, Fro
     }
     if (warp == 0) tmem_alloc(tmem_slot, D::TMEM_COLS);
     fe2_build_twiddles(tw, tab.twiddle, tid, D::NT);
+    fe3_build_window(win_s, tab.window, tid, D::NT);
     for (int i = tid; i < 16 * 9; i += D::NT) w1s[i] = wt.w1[i];
     for (int i = tid; i < 16; i += D::NT) b1s[i] = wt.b1[i];
     for (int i = tid; i < 32; i += D::NT) b2s[i] = wt.b2[i];
@@ -225,11 +229,12 @@ cnn2_stage_kernel(WindowSource src, Cnn2MelSource msrc, long long n_windows, Fro
             }
             __syncthreads();
         } else {
-            const long long wn = w + gridDim.x;
-            if (wn < n_windows) stager.issue((it + 1) & 1, src.at(wn), tid);
-            const int16_t* x = stager.wait(it & 1, (it >> 1) & 1, src.at(w));
+            const int16_t* x = stager.wait(0, it & 1, src.at(w));
             // ---- log-mel into the zero-bordered (F+2, T+2) plane (ends with a CTA barrier) ----------------
-            fe2_logmel_window(x, smem, tw, tab, melp + D::MEL_P + 1, D::MEL_P, 1, tid);
+            fe3_logmel_window(x, smem, win_s, tw, tab, melp + D::MEL_P + 1, D::MEL_P, 1, tid);
+            // the PCM slot is free: fetch the next window behind conv1 / conv2 / the epilogue
+            const long long wn = w + gridDim.x;
+            if (wn < n_windows) stager.issue(0, src.at(wn), tid);
         }
         if (mel_dump != nullptr) {
             float* md = mel_dump + w * (long long)(D::F * D::TT);

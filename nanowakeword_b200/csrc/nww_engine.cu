@@ -243,8 +243,8 @@ static int launch_frontend(nww_engine* e, WindowSource pcm, int64_t n, float* me
         NWW_CUDA(set_smem(k, FrontendSmem<float, G, kNfb32>::kTotal));
         k<<<grid_for(e, n), kStageNT, FrontendSmem<float, G, kNfb32>::kTotal, st>>>(pcm, n, e->tab32, mel, time_major);
     } else if constexpr (std::is_same<G, GeoNS40x98>::value) {
-        NWW_CUDA(set_smem(frontend2_kernel, Fe2KernelSmem::kTotal));
-        frontend2_kernel<<<grid_for(e, n), Fe2::NT, Fe2KernelSmem::kTotal, st>>>(pcm, n, e->tab64, mel, time_major);
+        NWW_CUDA(set_smem(frontend3_kernel, Fe3KernelSmem::kTotal));
+        frontend3_kernel<<<grid_for(e, n), Fe3::NT, Fe3KernelSmem::kTotal, st>>>(pcm, n, e->tab64, mel, time_major);
     } else {
         auto k = frontend_kernel<double, G, kNfb64, kStageNT>;
         NWW_CUDA(set_smem(k, FrontendSmem<double, G, kNfb64>::kTotal));

@@ -10,7 +10,7 @@
 
 #include "../../include/nww_b200.h"
 #include "nww_layers.cuh"
-#include "nww_fe2.cuh"
+#include "nww_fe3.cuh"
 #include "nww_stage.cuh"
 #include "nww_tail.cuh"
 
@@ -73,8 +73,8 @@ static int launch_frontend_f64(const FrontendTables<double>& tab, int sm_count, 
                                int time_major, cudaStream_t st, int64_t* launches, std::string* err) {
     const int grid = (int)std::min<long long>(n, sm_count);
     if constexpr (std::is_same<G, GeoNS40x98>::value) {
-        NWW_HCUDA(set_smem(frontend2_kernel, Fe2KernelSmem::kTotal));
-        frontend2_kernel<<<grid, Fe2::NT, Fe2KernelSmem::kTotal, st>>>(pcm, n, tab, mel, time_major);
+        NWW_HCUDA(set_smem(frontend3_kernel, Fe3KernelSmem::kTotal));
+        frontend3_kernel<<<grid, Fe3::NT, Fe3KernelSmem::kTotal, st>>>(pcm, n, tab, mel, time_major);
     } else {
         auto k = frontend_kernel<double, G, kNfb64, kStageNT>;
         NWW_HCUDA(set_smem(k, FrontendSmem<double, G, kNfb64>::kTotal));

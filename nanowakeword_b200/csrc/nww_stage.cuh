@@ -16,19 +16,18 @@ __host__ __device__ constexpr size_t align_up(size_t v, size_t a) { return (v + 
 // A window may start at any int16 boundary (the stream rings of nww_stream.cuh hand out
 // windows that begin wherever the stream's write position is): the bulk copy starts at the
 // enclosing 16-byte boundary, moves 16 extra bytes, and wait() returns the skewed pointer.
-template <int CLIP> struct PcmStager {
-    int16_t* buf;      // [2][SLOT]
-    uint64_t* bars;    // [2]
+template <int CLIP, int NSLOT = 2> struct PcmStager {
+    int16_t* buf;      // [NSLOT][SLOT]
+    uint64_t* bars;    // [NSLOT]
     static constexpr int SLOT = CLIP + 8;
-    static constexpr size_t kBytes = align_up(2 * SLOT * sizeof(int16_t), 128) + 128;
+    static constexpr size_t kBytes = align_up(NSLOT * SLOT * sizeof(int16_t), 128) + 128;
     __device__ __forceinline__ void carve(unsigned char* p) {
         buf = reinterpret_cast<int16_t*>(p);
-        bars = reinterpret_cast<uint64_t*>(p + align_up(2 * SLOT * sizeof(int16_t), 128));
+        bars = reinterpret_cast<uint64_t*>(p + align_up(NSLOT * SLOT * sizeof(int16_t), 128));
     }
     __device__ __forceinline__ void init(int tid) {
         if (tid == 0) {
-            mbar_init(&bars[0], 1);
-            mbar_init(&bars[1], 1);
+            for (int i = 0; i < NSLOT; ++i) mbar_init(&bars[i], 1);
             fence_mbar_init();
         }
         __syncthreads();
