@@ -79,6 +79,7 @@ struct nww_engine {
     float *d_feat_hi = nullptr, *d_feat_lo = nullptr; // [chunk][K] split feature rows
     float* d_part = nullptr;                          // [kTcMaxSplits][rows][N] split-K partial sums of that layer
     int tc_rows = 0;                                  // rows allocated per operand / partial slab (multiple of 128)
+    int tc_kp = 0;                                    // K of that layer padded to a multiple of the 32-float K tile
     // CNN stage v2 (tcgen05 conv2): conv2 weights as UMMA operands; features written pre-split by the stage kernel
     bool cnn2_enabled = false;
     uint4* d_w2_umma = nullptr;
@@ -244,7 +245,7 @@ static int launch_frontend(nww_engine* e, WindowSource pcm, int64_t n, float* me
         k<<<grid_for(e, n), kStageNT, FrontendSmem<float, G, kNfb32>::kTotal, st>>>(pcm, n, e->tab32, mel, time_major);
     } else if constexpr (std::is_same<G, GeoNS40x98>::value) {
         NWW_CUDA(set_smem(frontend3_kernel, Fe3KernelSmem::kTotal));
-        frontend3_kernel<<<grid_for(e, n), Fe3::NT, Fe3KernelSmem::kTotal, st>>>(pcm, n, e->tab64, mel, time_major);
+        frontend3_kernel<<<grid_for(e, n), Fe3::NT, Fe3KernelSmem::kTotal, st>>>(pcm, n, e->tab64, mel, time_major, 0);
     } else {
         auto k = frontend_kernel<double, G, kNfb64, kStageNT>;
         NWW_CUDA(set_smem(k, FrontendSmem<double, G, kNfb64>::kTotal));
@@ -260,7 +261,7 @@ static int launch_tail_tc(nww_engine* e, int64_t n, float* scores, float* logits
     if (!e->cnn2_enabled) {                                     // the v2 CNN stage writes the hi / lo pair itself
         const long long n4 = n * (long long)L0.K / 4;
         split_tf32_kernel<<<(int)std::min<long long>((n4 + 255) / 256, (long long)e->sm_count * 8), 256, 0, st>>>(
-            e->d_feat, e->d_feat_hi, e->d_feat_lo, n4);
+            e->d_feat, e->d_feat_hi, e->d_feat_lo, n, L0.K, e->tc_kp);
         e->launches++;
         NWW_CUDA(cudaGetLastError());
     }
@@ -268,10 +269,10 @@ static int launch_tail_tc(nww_engine* e, int64_t n, float* scores, float* logits
     // it is scored in): 7680 / 32 = 240 K blocks -> 12 splits x 10 row tiles = 120 CTAs for a full chunk;
     // partial sums are reduced in a fixed order by the tail's pre-stage
     const int m_tiles = (int)((n + kTcBM - 1) / kTcBM);
-    const int nkb = L0.K / kTcBK;
+    const int nkb = e->tc_kp / kTcBK;
     const int kbps = std::max(kTcKbPerSplit, (nkb + kTcMaxSplits - 1) / kTcMaxSplits);
     const int splits = (nkb + kbps - 1) / kbps;
-    GemmTcArgs a{L0.b, L0.ln_g, L0.ln_b, nullptr, (int)n, L0.N, L0.K, L0.post, e->spec.activation, e->d_part, kbps, e->tc_rows};
+    GemmTcArgs a{L0.b, L0.ln_g, L0.ln_b, nullptr, (int)n, L0.N, e->tc_kp, L0.post, e->spec.activation, e->d_part, kbps, e->tc_rows};
     const size_t smem_tc = tc_smem_bytes(L0.N);
     NWW_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
     gemm_tf32x3_kernel<<<dim3(m_tiles, splits), kTcThreads, smem_tc, st>>>(e->tm_xhi, e->tm_xlo, e->tm_whi, e->tm_wlo, a);
@@ -364,7 +365,8 @@ static int launch_stage_a(nww_engine* e, WindowSource pcm, int64_t n, float* mel
         }
         default:
             if (from_ring) {
-                stream_mel_gather_kernel<<<ew_grid(n * 3920, e->sm_count), 256, 0, st>>>(sub, ring0, e->d_scratch, 0);
+                const int tm = (e->spec.arch == NWW_ARCH_TCN && e->heads.tcn_cone) ? 1 : 0;   // the cone kernel reads (T, F) rows
+                stream_mel_gather_kernel<<<ew_grid(n * 3920, e->sm_count), 256, 0, st>>>(sub, ring0, e->d_scratch, tm);
                 e->launches++;
                 NWW_CUDA(cudaGetLastError());
             }
@@ -499,8 +501,10 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
         const TailLayer& L0 = e->tail.layers[0];
         const bool want_tc = !(spec->reserved[0] & 1);          // reserved[0] bit 0: force the CUDA-core tail
         if (want_tc && e->tail.n_layers >= 3 && tc_layer_eligible(L0.N, L0.K) && get_tmap_encoder() != nullptr) {
-            const size_t wn = (size_t)L0.N * L0.K;
-            std::vector<float> whi(wn), wlo(wn), wperm;
+            const int Kp = tc_padded_k(L0.K);
+            e->tc_kp = Kp;
+            const size_t wn = (size_t)L0.N * L0.K, wnp = (size_t)L0.N * Kp;
+            std::vector<float> whi(wnp, 0.0f), wlo(wnp, 0.0f), wperm;
             const float* w = e->blob.f32("tail.0.W");
             // CNN stage v2 (tcgen05 conv2) emits features in the K order (ph, pw, oc): permute fc1's columns to match
             const bool want_cnn2 = spec->arch == NWW_ARCH_CNN && !(spec->reserved[0] & 2) && L0.K == Cnn2::FEAT;
@@ -522,25 +526,29 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
                 memcpy(&y, &u, 4);
                 return y;
             };
-            for (size_t i = 0; i < wn; ++i) {
-                whi[i] = rn_tf32(w[i]);
-                wlo[i] = rn_tf32(w[i] - whi[i]);
-            }
-            NWW_CUDA(cudaMalloc(&e->d_w_hi, wn * sizeof(float)));
-            NWW_CUDA(cudaMalloc(&e->d_w_lo, wn * sizeof(float)));
-            NWW_CUDA(cudaMemcpy(e->d_w_hi, whi.data(), wn * sizeof(float), cudaMemcpyHostToDevice));
-            NWW_CUDA(cudaMemcpy(e->d_w_lo, wlo.data(), wn * sizeof(float), cudaMemcpyHostToDevice));
+            for (int nn = 0; nn < L0.N; ++nn)
+                for (int k = 0; k < L0.K; ++k) {
+                    const float v = w[(size_t)nn * L0.K + k];
+                    const float h = rn_tf32(v);
+                    whi[(size_t)nn * Kp + k] = h;
+                    wlo[(size_t)nn * Kp + k] = rn_tf32(v - h);
+                }
+            (void)wn;
+            NWW_CUDA(cudaMalloc(&e->d_w_hi, wnp * sizeof(float)));
+            NWW_CUDA(cudaMalloc(&e->d_w_lo, wnp * sizeof(float)));
+            NWW_CUDA(cudaMemcpy(e->d_w_hi, whi.data(), wnp * sizeof(float), cudaMemcpyHostToDevice));
+            NWW_CUDA(cudaMemcpy(e->d_w_lo, wlo.data(), wnp * sizeof(float), cudaMemcpyHostToDevice));
             const size_t rows = ((size_t)e->chunk + kTcBM - 1) / kTcBM * kTcBM;
             e->tc_rows = (int)rows;
-            NWW_CUDA(cudaMalloc(&e->d_feat_hi, rows * L0.K * sizeof(float)));
-            NWW_CUDA(cudaMalloc(&e->d_feat_lo, rows * L0.K * sizeof(float)));
-            NWW_CUDA(cudaMemset(e->d_feat_hi, 0, rows * L0.K * sizeof(float)));
-            NWW_CUDA(cudaMemset(e->d_feat_lo, 0, rows * L0.K * sizeof(float)));
+            NWW_CUDA(cudaMalloc(&e->d_feat_hi, rows * Kp * sizeof(float)));
+            NWW_CUDA(cudaMalloc(&e->d_feat_lo, rows * Kp * sizeof(float)));
+            NWW_CUDA(cudaMemset(e->d_feat_hi, 0, rows * Kp * sizeof(float)));
+            NWW_CUDA(cudaMemset(e->d_feat_lo, 0, rows * Kp * sizeof(float)));
             NWW_CUDA(cudaMalloc(&e->d_part, (size_t)kTcMaxSplits * rows * L0.N * sizeof(float)));
-            const bool ok = make_tmap_2d(&e->tm_xhi, e->d_feat_hi, rows, L0.K, kTcBM) &&
-                            make_tmap_2d(&e->tm_xlo, e->d_feat_lo, rows, L0.K, kTcBM) &&
-                            make_tmap_2d(&e->tm_whi, e->d_w_hi, L0.N, L0.K, L0.N) &&
-                            make_tmap_2d(&e->tm_wlo, e->d_w_lo, L0.N, L0.K, L0.N);
+            const bool ok = make_tmap_2d(&e->tm_xhi, e->d_feat_hi, rows, Kp, kTcBM) &&
+                            make_tmap_2d(&e->tm_xlo, e->d_feat_lo, rows, Kp, kTcBM) &&
+                            make_tmap_2d(&e->tm_whi, e->d_w_hi, L0.N, Kp, L0.N) &&
+                            make_tmap_2d(&e->tm_wlo, e->d_w_lo, L0.N, Kp, L0.N);
             if (!ok) return fail(NWW_ECUDA, "cuTensorMapEncodeTiled failed for the dense-layer operands");
             if (want_cnn2) {
                 // conv2 weights as un-swizzled K-major UMMA operands: [tap][hi|lo][kg][oc][8 ic] bf16

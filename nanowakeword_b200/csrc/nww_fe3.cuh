@@ -161,11 +161,11 @@ __device__ __forceinline__ void fe3_warp_fft(const int16_t* __restrict__ x, cplx
 __device__ __forceinline__ void fe3_logmel_window(const int16_t* __restrict__ pcm, unsigned char* __restrict__ scratch,
                                                   const double* __restrict__ win_s, const cplx<double>* __restrict__ tw_smem,
                                                   const FrontendTables<double>& tab, float* __restrict__ mel, int stride_m,
-                                                  int stride_t, int tid) {
+                                                  int stride_t, int tid, int f_lo = 0 /* first packed FFT = frame_lo / 2 */) {
     const int warp = tid >> 5, lane = tid & 31;
     cplx<double>* wb = reinterpret_cast<cplx<double>*>(scratch) + (size_t)warp * Fe3::NPAD;
 #pragma unroll 1
-    for (int f = warp; f < Fe3::N_PRIVATE; f += Fe3::NWARP) {
+    for (int f = f_lo + warp; f < Fe3::N_PRIVATE; f += Fe3::NWARP) {
         float* mf = mel + 2 * f * stride_t;
         fe3_warp_fft(pcm + 2 * f * GeoNS40x98::HOP, wb, win_s, tw_smem, tab,
                      [&](int fr, int m, float db) { mf[m * stride_m + fr * stride_t] = db; }, lane);
@@ -187,7 +187,7 @@ struct Fe3KernelSmem {
 
 __global__ void __launch_bounds__(Fe3::NT, 1)
 frontend3_kernel(WindowSource src, long long n_windows, FrontendTables<double> tab, float* __restrict__ mel_out,
-                 int time_major) {
+                 int time_major, int frame_lo /* even: frames below it are neither staged nor computed */) {
     using G = GeoNS40x98;
     NWW_DYN_SMEM(smem);
     const int tid = threadIdx.x;
@@ -202,13 +202,15 @@ frontend3_kernel(WindowSource src, long long n_windows, FrontendTables<double> t
 
     const int stride_m = time_major ? 1 : G::N_FRAMES;
     const int stride_t = time_major ? G::N_MELS : 1;
+    const int first_sample = frame_lo * G::HOP;
     long long w = blockIdx.x;
-    if (w < n_windows) stager.issue(0, src.at(w), tid);
+    if (w < n_windows) stager.issue(0, src.at(w), tid, first_sample);
     for (int it = 0; w < n_windows; w += gridDim.x, ++it) {
         const long long wn = w + gridDim.x;
-        if (wn < n_windows) stager.issue((it + 1) & 1, src.at(wn), tid);
+        if (wn < n_windows) stager.issue((it + 1) & 1, src.at(wn), tid, first_sample);
         const int16_t* x = stager.wait(it & 1, (it >> 1) & 1, src.at(w));
-        fe3_logmel_window(x, smem, win_s, tw, tab, mel_out + w * (long long)(G::N_MELS * G::N_FRAMES), stride_m, stride_t, tid);
+        fe3_logmel_window(x, smem, win_s, tw, tab, mel_out + w * (long long)(G::N_MELS * G::N_FRAMES), stride_m, stride_t, tid,
+                          frame_lo >> 1);
     }
 }
 

@@ -199,22 +199,22 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_cons
     }
 }
 
-// x -> (hi, lo) with hi = RN_tf32(x) (low 13 mantissa bits zero), lo = RN_tf32(x - hi)
-__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n4) {
+// x [rows][K] -> (hi, lo) [rows][Kp] with hi = RN_tf32(x) (low 13 mantissa bits zero), lo = RN_tf32(x - hi).
+// Kp >= K is the K extent padded to a multiple of the 32-float K tile; the pad columns are zeroed once at
+// allocation time and never written.  K must be a multiple of 4.
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo,
+                                                         long long rows, int K, int Kp) {
+    const int k4 = K / 4;
+    const long long n4 = rows * k4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / k4;
+        const int c = (int)(i - r * k4);
         const float4 v = reinterpret_cast<const float4*>(x)[i];
         float4 h, l;
-        uint32_t t;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); h.x = __uint_as_float(t);
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t);
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t);
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t);
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x - h.x)); l.x = __uint_as_float(t);
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y - h.y)); l.y = __uint_as_float(t);
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z - h.z)); l.z = __uint_as_float(t);
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w - h.w)); l.w = __uint_as_float(t);
-        reinterpret_cast<float4*>(hi)[i] = h;
-        reinterpret_cast<float4*>(lo)[i] = l;
+        h.x = round_tf32(v.x); h.y = round_tf32(v.y); h.z = round_tf32(v.z); h.w = round_tf32(v.w);
+        l.x = round_tf32(v.x - h.x); l.y = round_tf32(v.y - h.y); l.z = round_tf32(v.z - h.z); l.w = round_tf32(v.w - h.w);
+        reinterpret_cast<float4*>(hi + r * Kp)[c] = h;
+        reinterpret_cast<float4*>(lo + r * Kp)[c] = l;
     }
 }
 
@@ -248,6 +248,7 @@ inline bool make_tmap_2d(CUtensorMap* tm, const float* base, uint64_t rows, uint
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-inline bool tc_layer_eligible(int N, int K) { return N % 16 == 0 && N >= 16 && N <= kTcMaxN && K % kTcBK == 0 && K >= 512; }
+inline bool tc_layer_eligible(int N, int K) { return N % 16 == 0 && N >= 16 && N <= kTcMaxN && K % 4 == 0 && K >= 512; }
+inline int tc_padded_k(int K) { return (K + kTcBK - 1) / kTcBK * kTcBK; }
 
 }  // namespace nww

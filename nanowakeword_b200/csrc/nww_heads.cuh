@@ -13,6 +13,7 @@
 #include "nww_fe3.cuh"
 #include "nww_stage.cuh"
 #include "nww_tail.cuh"
+#include "nww_tcn.cuh"
 
 namespace nww {
 
@@ -28,6 +29,8 @@ struct HeadWeights {
     int tcn_levels = 0, tcn_k = 3, tcn_in = 0;
     int tcn_ch[8] = {0};
     ConvW tcn_c1[8], tcn_c2[8], tcn_down[8];
+    bool tcn_cone = false;            // fused dependency-cone kernel (nww_tcn.cuh) instead of the layer kernels
+    TcnConeParams tcn_plan{};
     // BcResNet
     ConvW bc_init, bc_pw[3], bc_sc[3];
     const float* bc_dw[3] = {nullptr, nullptr, nullptr};
@@ -70,11 +73,11 @@ template <typename K> static cudaError_t set_smem(K kernel, size_t bytes) {
 
 template <typename G>
 static int launch_frontend_f64(const FrontendTables<double>& tab, int sm_count, WindowSource pcm, long long n, float* mel,
-                               int time_major, cudaStream_t st, int64_t* launches, std::string* err) {
+                               int time_major, cudaStream_t st, int64_t* launches, std::string* err, int frame_lo = 0) {
     const int grid = (int)std::min<long long>(n, sm_count);
     if constexpr (std::is_same<G, GeoNS40x98>::value) {
         NWW_HCUDA(set_smem(frontend3_kernel, Fe3KernelSmem::kTotal));
-        frontend3_kernel<<<grid, Fe3::NT, Fe3KernelSmem::kTotal, st>>>(pcm, n, tab, mel, time_major);
+        frontend3_kernel<<<grid, Fe3::NT, Fe3KernelSmem::kTotal, st>>>(pcm, n, tab, mel, time_major, frame_lo);
     } else {
         auto k = frontend_kernel<double, G, kNfb64, kStageNT>;
         NWW_HCUDA(set_smem(k, FrontendSmem<double, G, kNfb64>::kTotal));
@@ -123,6 +126,24 @@ inline int setup_head_weights(int arch, int geometry, const BlobLookup& get, con
         size_t maxc = hw->tcn_in;
         for (int i = 0; i < lv; ++i) maxc = std::max<size_t>(maxc, hw->tcn_ch[i]);
         hw->scratch_floats = (size_t)GeoNS40x98::N_FRAMES * (hw->tcn_in + 3 * maxc);     // mel + 3 rotating planes
+        // the fused cone kernel covers the reference's default shape family: k = 3, <= 4 levels, channel counts
+        // that are multiples of 8 up to 128, and a cone that fits in the window
+        bool cone_ok = hw->tcn_k == 3 && lv <= kTcnMaxLevels && hw->tcn_in % 4 == 0;
+        for (int i = 0; i < lv; ++i) cone_ok = cone_ok && hw->tcn_ch[i] % 8 == 0 && hw->tcn_ch[i] <= 128;
+        if (cone_ok) {
+            TcnConeParams& P = hw->tcn_plan;
+            P.levels = lv;
+            P.c_in = hw->tcn_in;
+            P.T = GeoNS40x98::N_FRAMES;
+            for (int i = 0; i < lv; ++i) {
+                P.ch[i] = hw->tcn_ch[i];
+                P.w1[i] = hw->tcn_c1[i].w; P.b1[i] = hw->tcn_c1[i].b;
+                P.w2[i] = hw->tcn_c2[i].w; P.b2[i] = hw->tcn_c2[i].b;
+                P.wd[i] = hw->tcn_down[i].w; P.bd[i] = hw->tcn_down[i].b;
+            }
+            cone_ok = tcn_plan(&P) && (size_t)P.per_window * kTcnWT * sizeof(float) <= 200 * 1024;
+        }
+        hw->tcn_cone = cone_ok;
     } else if (arch == NWW_ARCH_BCRESNET) {
         if (geometry != NWW_GEOM_NS40X98) { *err = "bcresnet head is built for the NS40x98 geometry"; return NWW_EUNSUPPORTED; }
         hw->bc_init = {need("bc.init.w", 32 * 9), need("bc.init.b", 32)};
@@ -223,6 +244,18 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
     using G = GeoNS40x98;
     constexpr int F = G::N_MELS, T = G::N_FRAMES;
     float* mel = take((size_t)F * T);
+    if (hw.arch == NWW_ARCH_TCN && hw.tcn_cone) {
+        // time-major log-mel of the cone's frames only (or, in stream mode, gathered by the caller), then one kernel
+        const TcnConeParams& P = hw.tcn_plan;
+        const int frame_lo = (T - P.n_in) & ~1;
+        if (!mel_ready && (rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel, 1, st, launches, err, frame_lo))) return rc;
+        if (mel_dump && (rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel_dump, 0, st, launches, err))) return rc;
+        const size_t smem = (size_t)P.per_window * kTcnWT * sizeof(float);
+        NWW_HCUDA(set_smem(tcn_cone_kernel, smem));
+        const long long tiles = (n + kTcnWT - 1) / kTcnWT;
+        tcn_cone_kernel<<<(int)std::min<long long>(tiles, sm_count), kTcnNT, smem, st>>>(mel, (long long)F * T, n, P, feat);
+        return done();
+    }
     if (!mel_ready && (rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel, 0, st, launches, err))) return rc;
     if (mel_dump) NWW_HCUDA(cudaMemcpyAsync(mel_dump, mel, (size_t)n * F * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
 

@@ -33,13 +33,15 @@ template <int CLIP, int NSLOT = 2> struct PcmStager {
         __syncthreads();
     }
     static __device__ __forceinline__ int skew_of(const int16_t* src) { return (int)((reinterpret_cast<uintptr_t>(src) & 15) >> 1); }
-    __device__ __forceinline__ void issue(int slot, const int16_t* src, int tid) {
+    // first_sample (a multiple of 8): stage only samples [first_sample, CLIP) of the window — heads that read
+    // just the tail of the clip (the TCN's dependency cone) do not pay for the rest.  Indexing is unchanged.
+    __device__ __forceinline__ void issue(int slot, const int16_t* src, int tid, int first_sample = 0) {
         if (tid == 0) {
             const int skew = skew_of(src);
-            const uint32_t bytes = CLIP * (uint32_t)sizeof(int16_t) + (skew ? 16u : 0u);
+            const uint32_t bytes = (uint32_t)(CLIP - first_sample) * (uint32_t)sizeof(int16_t) + (skew ? 16u : 0u);
             fence_proxy_async();
             mbar_expect_tx(&bars[slot], bytes);
-            bulk_g2s(buf + (size_t)slot * SLOT, src - skew, bytes, &bars[slot]);
+            bulk_g2s(buf + (size_t)slot * SLOT + first_sample, src + first_sample - skew, bytes, &bars[slot]);
         }
     }
     __device__ __forceinline__ const int16_t* wait(int slot, uint32_t parity, const int16_t* src) {

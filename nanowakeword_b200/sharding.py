@@ -40,11 +40,12 @@ def scatter_windows(pcm_root, n_total: int, clip_samples: int, rank: int, world:
             if r == src:
                 local.copy_(pcm_root[s:s + c])
             elif c:
-                reqs.append(dist.isend(pcm_root[s:s + c].contiguous(), dst=r))
+                # NCCL has no int16: ship the rows as raw bytes
+                reqs.append(dist.isend(pcm_root[s:s + c].contiguous().view(torch.uint8), dst=r))
         for q in reqs:
             q.wait()
     elif count:
-        dist.recv(local, src=src)
+        dist.recv(local.view(torch.uint8), src=src)
     return local
 
 
