@@ -33,7 +33,6 @@ namespace nww {
 constexpr int kTcnMaxLevels = 4;
 constexpr int kTcnWT = 8;            // windows per CTA tile
 constexpr int kTcnNT = 256;
-constexpr int kTcnRM = 4;            // rows per thread tile
 
 struct TcnConeParams {
     int levels, c_in, T;                         // T = frames per window in the mel input
@@ -46,7 +45,7 @@ struct TcnConeParams {
     const float* bd[kTcnMaxLevels];
     // shared-memory plan (floats per window): input, then per level mid / out
     int n_in;                                    // input positions (2 c0 + 3 of level 0)
-    int off_in, off_mid[kTcnMaxLevels], off_out[kTcnMaxLevels], per_window;
+    int off_in, off_mid[kTcnMaxLevels], off_out[kTcnMaxLevels], off_res, per_window;
     int n_mid[kTcnMaxLevels], n_out[kTcnMaxLevels];
 };
 
@@ -73,117 +72,146 @@ inline bool tcn_plan(TcnConeParams* P) {
         P->off_out[i] = off;
         off += n_out[i] * P->ch[i];
     }
+    P->off_res = off;                            // downsampled residual of the block being computed
+    int max_res = 0;
+    for (int i = 0; i < P->levels; ++i) max_res = n_out[i] * P->ch[i] > max_res ? n_out[i] * P->ch[i] : max_res;
+    off += max_res;
     P->per_window = (off + 3) & ~3;
     return true;
 }
 
-// out[w][p][oc] = post( b[oc] + sum_{j < taps, ic} W[j][ic][oc] * in[w][in_mul * p + j][ic] )
-//   RES = 0: ReLU.   RES = 1: ReLU( ReLU(.) + in_res[w][2 p + 4][oc] )   (identity residual)
-//   RES = 2: ReLU( ReLU(.) + bd[oc] + sum_ic Wd[ic][oc] * in_res[w][2 p + 4][ic] )   (1x1 downsample)
-template <int RN>
-__device__ __forceinline__ void tcn_layer(const float* __restrict__ in, int in_pitch /*floats per window*/, int Cin, int in_mul,
-                                          const float* __restrict__ W, const float* __restrict__ bias, int taps,
-                                          float* __restrict__ out, int out_pitch, int Cout, int n_pos, int n_win, int res_mode,
-                                          const float* __restrict__ in_res, int res_pitch, int Cres,
-                                          const float* __restrict__ Wd, const float* __restrict__ bd, int tid) {
+// ---- one layer as a small GEMM with the weights streamed through shared memory -------------------------
+//   out[w][p][oc] = post( b[oc] + sum_{k < K} W[k][oc] * in[w][in_mul * p + in_off][k] )        K = taps * Cin
+// A row of the A operand is CONTIGUOUS: activations are [position][channel] rows, so the taps j = 0..2 of
+// position q are the 3 Cin floats that start at in[w][q].  W arrives in chunks of kTcnKC rows by cp.async,
+// double-buffered; thread (tn, tm) keeps RN = Cout / 16 columns of up to kTcnRows rows (r = tm + 16 i) in
+// registers across the whole K loop.
+//   post: relu ? max(., 0) : identity;  then, with res != nullptr,  max(. + res[w][p][oc], 0)
+//   (res rows have pitch res_pitch per window and Cout per position, positions res_mul * p + res_off).
+constexpr int kTcnKC = 16;            // weight rows per staged chunk
+constexpr int kTcnRows = 14;          // rows per thread at 4 columns (16 x 14 = 224 rows per pass); half of that at 8 columns
+constexpr int kTcnWBuf = kTcnKC * 128;   // floats per weight buffer (Cout <= 128)
+
+#ifndef NWW_CPUSIM
+__device__ __forceinline__ void tcn_cp_async16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void tcn_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tcn_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#else
+inline void tcn_cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
+inline void tcn_cp_commit() {}
+template <int N> inline void tcn_cp_wait() {}
+#endif
+
+struct TcnLayerArgs {
+    const float* in; int in_pitch, in_mul, in_off;      // A rows: in + w * in_pitch + (in_mul * p + in_off) * Cin
+    int Cin, K;                                         // K = taps * Cin (multiple of 4)
+    const float* W; const float* bias;                  // W [K][Cout]
+    float* out; int out_pitch;                          // out + w * out_pitch + p * Cout
+    int Cout, n_pos, n_win, relu;
+    const float* res; int res_pitch, res_mul, res_off;  // nullable
+};
+
+template <int RN, int ROWS>
+__device__ __forceinline__ void tcn_layer(const TcnLayerArgs& L, float* __restrict__ wbuf /* [2][kTcnWBuf] shared */, int tid) {
     const int tn = tid & 15, tm = tid >> 4;
     const int oc0 = tn * RN;
-    if (oc0 >= Cout) return;
-    const int rows = n_win * n_pos;
-    for (int r0 = tm * kTcnRM; r0 < rows; r0 += (kTcnNT / 16) * kTcnRM) {
-        float acc[kTcnRM][RN];
-        const float* arow[kTcnRM];
-        int rw[kTcnRM], rp[kTcnRM];
-#pragma unroll
-        for (int i = 0; i < kTcnRM; ++i) {
-            const int r = (r0 + i < rows) ? r0 + i : rows - 1;          // clamp: duplicates are computed, not stored
-            rw[i] = r / n_pos;
-            rp[i] = r - rw[i] * n_pos;
-            arow[i] = in + (size_t)rw[i] * in_pitch + (size_t)(in_mul * rp[i]) * Cin;
-#pragma unroll
-            for (int c = 0; c < RN; ++c) acc[i][c] = __ldg(bias + oc0 + c);
+    const bool col_ok = oc0 < L.Cout;
+    const int rows = L.n_win * L.n_pos;
+    const int n_chunks = (L.K + kTcnKC - 1) / kTcnKC;
+    const int row_f4 = L.Cout / 4;                       // float4 per weight row
+    auto stage = [&](int chunk, int buf) {
+        const int k0 = chunk * kTcnKC;
+        const int kc = (L.K - k0 < kTcnKC) ? (L.K - k0) : kTcnKC;
+        for (int i = tid; i < kc * row_f4; i += kTcnNT) {
+            const int kr = i / row_f4, c4 = i - kr * row_f4;
+            tcn_cp_async16(wbuf + buf * kTcnWBuf + kr * L.Cout + 4 * c4, L.W + (size_t)(k0 + kr) * L.Cout + 4 * c4);
         }
-        for (int j = 0; j < taps; ++j) {
-            const float* wj = W + (size_t)j * Cin * Cout + oc0;
-            for (int ic = 0; ic < Cin; ic += 4) {
-                float4 a[kTcnRM];
+        tcn_cp_commit();
+    };
+    for (int rbase = 0; rbase < rows; rbase += 16 * ROWS) {
+        float acc[ROWS][RN];
+        int aoff[ROWS];                                  // float offset of the row's A vector from L.in
 #pragma unroll
-                for (int i = 0; i < kTcnRM; ++i) a[i] = *reinterpret_cast<const float4*>(arow[i] + (size_t)j * Cin + ic);
+        for (int i = 0; i < ROWS; ++i) {
+            int r = rbase + tm + 16 * i;
+            if (r >= rows) r = rows - 1;                 // clamp: computed, never stored
+            const int w = r / L.n_pos, p = r - w * L.n_pos;
+            aoff[i] = w * L.in_pitch + (L.in_mul * p + L.in_off) * L.Cin;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float wv[RN];
-#pragma unroll
-                    for (int c4 = 0; c4 < RN / 4; ++c4) {
-                        const float4 t = __ldg(reinterpret_cast<const float4*>(wj + (size_t)(ic + q) * Cout) + c4);
-                        wv[4 * c4] = t.x; wv[4 * c4 + 1] = t.y; wv[4 * c4 + 2] = t.z; wv[4 * c4 + 3] = t.w;
-                    }
-#pragma unroll
-                    for (int i = 0; i < kTcnRM; ++i) {
-                        const float av = (q == 0) ? a[i].x : (q == 1) ? a[i].y : (q == 2) ? a[i].z : a[i].w;
-#pragma unroll
-                        for (int c = 0; c < RN; ++c) acc[i][c] = fmaf(av, wv[c], acc[i][c]);
-                    }
-                }
-            }
+            for (int c = 0; c < RN; ++c) acc[i][c] = col_ok ? __ldg(L.bias + oc0 + c) : 0.0f;
         }
-#pragma unroll
-        for (int i = 0; i < kTcnRM; ++i)
-#pragma unroll
-            for (int c = 0; c < RN; ++c) acc[i][c] = fmaxf(acc[i][c], 0.0f);
-        if (res_mode != 0) {
-            float rs[kTcnRM][RN];
-            if (res_mode == 1) {
-#pragma unroll
-                for (int i = 0; i < kTcnRM; ++i)
-#pragma unroll
-                    for (int c = 0; c < RN; ++c)
-                        rs[i][c] = in_res[(size_t)rw[i] * res_pitch + (size_t)(2 * rp[i] + 4) * Cres + oc0 + c];
+        __syncthreads();                                 // previous users of wbuf are done
+        stage(0, 0);
+        for (int ch = 0; ch < n_chunks; ++ch) {
+            if (ch + 1 < n_chunks) {
+                stage(ch + 1, (ch + 1) & 1);
+                tcn_cp_wait<1>();
             } else {
+                tcn_cp_wait<0>();
+            }
+            __syncthreads();                             // chunk ch is visible to everybody
+            const float* wb = wbuf + (ch & 1) * kTcnWBuf + oc0;
+            const int k0 = ch * kTcnKC;
+            const int kc = (L.K - k0 < kTcnKC) ? (L.K - k0) : kTcnKC;
+            if (col_ok) {
+                for (int kk = 0; kk < kc; kk += 4) {
+                    float wv[4][RN];
 #pragma unroll
-                for (int i = 0; i < kTcnRM; ++i)
+                    for (int q = 0; q < 4; ++q)
 #pragma unroll
-                    for (int c = 0; c < RN; ++c) rs[i][c] = __ldg(bd + oc0 + c);
-                for (int ic = 0; ic < Cres; ++ic) {
-                    float wv[RN];
+                        for (int c4 = 0; c4 < RN / 4; ++c4) {
+                            const float4 t = *reinterpret_cast<const float4*>(wb + (kk + q) * L.Cout + 4 * c4);
+                            wv[q][4 * c4] = t.x; wv[q][4 * c4 + 1] = t.y; wv[q][4 * c4 + 2] = t.z; wv[q][4 * c4 + 3] = t.w;
+                        }
 #pragma unroll
-                    for (int c4 = 0; c4 < RN / 4; ++c4) {
-                        const float4 t = __ldg(reinterpret_cast<const float4*>(Wd + (size_t)ic * Cout + oc0) + c4);
-                        wv[4 * c4] = t.x; wv[4 * c4 + 1] = t.y; wv[4 * c4 + 2] = t.z; wv[4 * c4 + 3] = t.w;
-                    }
+                    for (int i = 0; i < ROWS; ++i) {
+                        const float4 a = *reinterpret_cast<const float4*>(L.in + aoff[i] + k0 + kk);
 #pragma unroll
-                    for (int i = 0; i < kTcnRM; ++i) {
-                        const float av = in_res[(size_t)rw[i] * res_pitch + (size_t)(2 * rp[i] + 4) * Cres + ic];
-#pragma unroll
-                        for (int c = 0; c < RN; ++c) rs[i][c] = fmaf(av, wv[c], rs[i][c]);
+                        for (int c = 0; c < RN; ++c) {
+                            float s = acc[i][c];
+                            s = fmaf(a.x, wv[0][c], s);
+                            s = fmaf(a.y, wv[1][c], s);
+                            s = fmaf(a.z, wv[2][c], s);
+                            s = fmaf(a.w, wv[3][c], s);
+                            acc[i][c] = s;
+                        }
                     }
                 }
             }
-#pragma unroll
-            for (int i = 0; i < kTcnRM; ++i)
-#pragma unroll
-                for (int c = 0; c < RN; ++c) acc[i][c] = fmaxf(acc[i][c] + rs[i][c], 0.0f);
+            __syncthreads();                             // everybody is done with buffer ch & 1 before it is refilled
         }
+        if (col_ok) {
 #pragma unroll
-        for (int i = 0; i < kTcnRM; ++i) {
-            if (r0 + i >= rows) continue;
-            float* o = out + (size_t)rw[i] * out_pitch + (size_t)rp[i] * Cout + oc0;
+            for (int i = 0; i < ROWS; ++i) {
+                const int r = rbase + tm + 16 * i;
+                if (r >= rows) continue;
+                const int w = r / L.n_pos, p = r - w * L.n_pos;
+                float v[RN];
 #pragma unroll
-            for (int c4 = 0; c4 < RN / 4; ++c4)
-                reinterpret_cast<float4*>(o)[c4] = make_float4(acc[i][4 * c4], acc[i][4 * c4 + 1], acc[i][4 * c4 + 2], acc[i][4 * c4 + 3]);
+                for (int c = 0; c < RN; ++c) v[c] = L.relu ? fmaxf(acc[i][c], 0.0f) : acc[i][c];
+                if (L.res != nullptr) {
+                    const float* rr = L.res + (size_t)w * L.res_pitch + (size_t)(L.res_mul * p + L.res_off) * L.Cout + oc0;
+#pragma unroll
+                    for (int c = 0; c < RN; ++c) v[c] = fmaxf(v[c] + rr[c], 0.0f);
+                }
+                float* o = L.out + (size_t)w * L.out_pitch + (size_t)p * L.Cout + oc0;
+#pragma unroll
+                for (int c4 = 0; c4 < RN / 4; ++c4)
+                    reinterpret_cast<float4*>(o)[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+            }
         }
     }
 }
 
-__device__ __forceinline__ void tcn_layer_any(int Cout, const float* in, int in_pitch, int Cin, int in_mul, const float* W,
-                                              const float* bias, int taps, float* out, int out_pitch, int n_pos, int n_win,
-                                              int res_mode, const float* in_res, int res_pitch, int Cres, const float* Wd,
-                                              const float* bd, int tid) {
-    if (Cout <= 64)
-        tcn_layer<4>(in, in_pitch, Cin, in_mul, W, bias, taps, out, out_pitch, Cout, n_pos, n_win, res_mode, in_res, res_pitch,
-                     Cres, Wd, bd, tid);
-    else
-        tcn_layer<8>(in, in_pitch, Cin, in_mul, W, bias, taps, out, out_pitch, Cout, n_pos, n_win, res_mode, in_res, res_pitch,
-                     Cres, Wd, bd, tid);
+__device__ __forceinline__ void tcn_layer_any(const TcnLayerArgs& L, float* wbuf, int tid) {
+    if (L.Cout <= 64) tcn_layer<4, kTcnRows>(L, wbuf, tid);
+    else tcn_layer<8, kTcnRows / 2>(L, wbuf, tid);
+}
+
+inline size_t tcn_cone_smem_bytes(const TcnConeParams& P) {
+    return sizeof(float) * ((size_t)2 * kTcnWBuf + (size_t)P.per_window * kTcnWT);
 }
 
 // mel_tm: time-major log-mel, window w at mel_tm + w * mel_win_stride, frame t at + t * c_in (only the last n_in
@@ -192,7 +220,8 @@ __global__ void __launch_bounds__(kTcnNT, 1)
 tcn_cone_kernel(const float* __restrict__ mel_tm, long long mel_win_stride, long long n_windows, TcnConeParams P,
                 float* __restrict__ feat) {
     NWW_DYN_SMEM(smem);
-    float* act = reinterpret_cast<float*>(smem);
+    float* wbuf = reinterpret_cast<float*>(smem);                       // [2][kTcnWBuf]
+    float* act = wbuf + 2 * kTcnWBuf;
     const int tid = threadIdx.x;
     const int pw = P.per_window;
     const int c_last = P.ch[P.levels - 1];
@@ -212,10 +241,22 @@ tcn_cone_kernel(const float* __restrict__ mel_tm, long long mel_win_stride, long
             const int C = P.ch[l];
             float* mid = act + P.off_mid[l];
             float* out = act + P.off_out[l];
-            tcn_layer_any(C, x, pw, cin, 1, P.w1[l], P.b1[l], 3, mid, pw, P.n_mid[l], nw, 0, nullptr, 0, 0, nullptr, nullptr, tid);
-            __syncthreads();
-            tcn_layer_any(C, mid, pw, C, 2, P.w2[l], P.b2[l], 3, out, pw, P.n_out[l], nw, P.wd[l] ? 2 : 1, x, pw, cin, P.wd[l],
-                          P.bd[l], tid);
+            float* tmp = act + P.off_res;
+            // conv1: taps of position p start at input position p
+            tcn_layer_any(TcnLayerArgs{x, pw, 1, 0, cin, 3 * cin, P.w1[l], P.b1[l], mid, pw, C, P.n_mid[l], nw, 1, nullptr, 0, 0, 0},
+                          wbuf, tid);
+            const float* res = x;
+            int res_mul = 2, res_off = 4;
+            if (P.wd[l] != nullptr) {                    // 1x1 downsample of the block input at the output positions
+                tcn_layer_any(TcnLayerArgs{x, pw, 2, 4, cin, cin, P.wd[l], P.bd[l], tmp, pw, C, P.n_out[l], nw, 0, nullptr, 0, 0, 0},
+                              wbuf, tid);
+                res = tmp;
+                res_mul = 1;
+                res_off = 0;
+            }
+            // conv2 on the conv1 output (positions 2 p + j), then ReLU(ReLU(.) + res)
+            tcn_layer_any(TcnLayerArgs{mid, pw, 2, 0, C, 3 * C, P.w2[l], P.b2[l], out, pw, C, P.n_out[l], nw, 1, res, pw, res_mul, res_off},
+                          wbuf, tid);
             __syncthreads();
             x = out;
             cin = C;
