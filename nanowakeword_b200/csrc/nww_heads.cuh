@@ -141,7 +141,7 @@ inline int setup_head_weights(int arch, int geometry, const BlobLookup& get, con
                 P.w2[i] = hw->tcn_c2[i].w; P.b2[i] = hw->tcn_c2[i].b;
                 P.wd[i] = hw->tcn_down[i].w; P.bd[i] = hw->tcn_down[i].b;
             }
-            cone_ok = tcn_plan(&P) && tcn_cone_smem_bytes(P) <= 200 * 1024;
+            cone_ok = tcn_plan(&P);
         }
         hw->tcn_cone = cone_ok;
     } else if (arch == NWW_ARCH_BCRESNET) {
@@ -252,7 +252,7 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
         if (mel_dump && (rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel_dump, 0, st, launches, err))) return rc;
         const size_t smem = tcn_cone_smem_bytes(P);
         NWW_HCUDA(set_smem(tcn_cone_kernel, smem));
-        const long long tiles = (n + kTcnWT - 1) / kTcnWT;
+        const long long tiles = (n + P.wt - 1) / P.wt;
         tcn_cone_kernel<<<(int)std::min<long long>(tiles, sm_count), kTcnNT, smem, st>>>(mel, (long long)F * T, n, P, feat);
         return done();
     }

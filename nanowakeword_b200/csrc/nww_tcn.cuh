@@ -31,7 +31,7 @@
 namespace nww {
 
 constexpr int kTcnMaxLevels = 4;
-constexpr int kTcnWT = 8;            // windows per CTA tile
+constexpr int kTcnWTMax = 8;         // windows per CTA tile (upper bound; the plan picks what fits in shared memory)
 constexpr int kTcnNT = 256;
 
 struct TcnConeParams {
@@ -47,6 +47,7 @@ struct TcnConeParams {
     int n_in;                                    // input positions (2 c0 + 3 of level 0)
     int off_in, off_mid[kTcnMaxLevels], off_out[kTcnMaxLevels], off_res, per_window;
     int n_mid[kTcnMaxLevels], n_out[kTcnMaxLevels];
+    int wt;                                      // windows per CTA tile
 };
 
 // positions of the cone, host side.  Returns false when the cone does not fit in T frames.
@@ -77,7 +78,13 @@ inline bool tcn_plan(TcnConeParams* P) {
     for (int i = 0; i < P->levels; ++i) max_res = n_out[i] * P->ch[i] > max_res ? n_out[i] * P->ch[i] : max_res;
     off += max_res;
     P->per_window = (off + 3) & ~3;
-    return true;
+    P->wt = 0;
+    for (int wt = kTcnWTMax; wt >= 1; --wt)
+        if (sizeof(float) * ((size_t)2 * 16 * 128 + (size_t)P->per_window * wt) <= (size_t)200 * 1024) {
+            P->wt = wt;
+            break;
+        }
+    return P->wt > 0;
 }
 
 // ---- one layer as a small GEMM with the weights streamed through shared memory -------------------------
@@ -211,7 +218,7 @@ __device__ __forceinline__ void tcn_layer_any(const TcnLayerArgs& L, float* wbuf
 }
 
 inline size_t tcn_cone_smem_bytes(const TcnConeParams& P) {
-    return sizeof(float) * ((size_t)2 * kTcnWBuf + (size_t)P.per_window * kTcnWT);
+    return sizeof(float) * ((size_t)2 * kTcnWBuf + (size_t)P.per_window * P.wt);
 }
 
 // mel_tm: time-major log-mel, window w at mel_tm + w * mel_win_stride, frame t at + t * c_in (only the last n_in
@@ -225,8 +232,8 @@ tcn_cone_kernel(const float* __restrict__ mel_tm, long long mel_win_stride, long
     const int tid = threadIdx.x;
     const int pw = P.per_window;
     const int c_last = P.ch[P.levels - 1];
-    for (long long w0 = (long long)blockIdx.x * kTcnWT; w0 < n_windows; w0 += (long long)gridDim.x * kTcnWT) {
-        const int nw = (int)((n_windows - w0 < kTcnWT) ? (n_windows - w0) : kTcnWT);
+    for (long long w0 = (long long)blockIdx.x * P.wt; w0 < n_windows; w0 += (long long)gridDim.x * P.wt) {
+        const int nw = (int)((n_windows - w0 < P.wt) ? (n_windows - w0) : P.wt);
         __syncthreads();
         // the last n_in frames of each window, [pos][mel] rows
         const int n_in_f = P.n_in * P.c_in;
