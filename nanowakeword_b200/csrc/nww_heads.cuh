@@ -144,6 +144,7 @@ inline int setup_head_weights(int arch, int geometry, const BlobLookup& get, con
             cone_ok = tcn_plan(&P);
         }
         hw->tcn_cone = cone_ok;
+        if (cone_ok) hw->scratch_floats = (size_t)GeoNS40x98::N_FRAMES * hw->tcn_in;      // only the (T, F) log-mel goes through HBM
     } else if (arch == NWW_ARCH_BCRESNET) {
         if (geometry != NWW_GEOM_NS40X98) { *err = "bcresnet head is built for the NS40x98 geometry"; return NWW_EUNSUPPORTED; }
         hw->bc_init = {need("bc.init.w", 32 * 9), need("bc.init.b", 32)};

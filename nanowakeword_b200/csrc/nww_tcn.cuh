@@ -80,7 +80,7 @@ inline bool tcn_plan(TcnConeParams* P) {
     P->per_window = (off + 3) & ~3;
     P->wt = 0;
     for (int wt = kTcnWTMax; wt >= 1; --wt)
-        if (sizeof(float) * ((size_t)2 * 16 * 128 + (size_t)P->per_window * wt) <= (size_t)200 * 1024) {
+        if (sizeof(float) * ((size_t)2 * 16 * 128 + (size_t)P->per_window * wt) <= (size_t)220 * 1024) {
             P->wt = wt;
             break;
         }
