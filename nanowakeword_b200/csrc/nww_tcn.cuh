@@ -149,6 +149,10 @@ __device__ __forceinline__ void tcn_layer(const TcnLayerArgs& L, float* __restri
 #pragma unroll
             for (int c = 0; c < RN; ++c) acc[i][c] = col_ok ? __ldg(L.bias + oc0 + c) : 0.0f;
         }
+        // rows this warp really has (its two tm values differ by one row at most): the FMA blocks of the
+        // other register rows are skipped, which is most of them in the small late layers
+        const int left = rows - rbase - (tm & ~1);
+        const int nv = left <= 0 ? 0 : ((left + 15) >> 4) < ROWS ? ((left + 15) >> 4) : ROWS;
         __syncthreads();                                 // previous users of wbuf are done
         stage(0, 0);
         for (int ch = 0; ch < n_chunks; ++ch) {
@@ -162,7 +166,7 @@ __device__ __forceinline__ void tcn_layer(const TcnLayerArgs& L, float* __restri
             const float* wb = wbuf + (ch & 1) * kTcnWBuf + oc0;
             const int k0 = ch * kTcnKC;
             const int kc = (L.K - k0 < kTcnKC) ? (L.K - k0) : kTcnKC;
-            if (col_ok) {
+            if (col_ok && nv > 0) {
                 for (int kk = 0; kk < kc; kk += 4) {
                     float wv[4][RN];
 #pragma unroll
@@ -174,6 +178,7 @@ __device__ __forceinline__ void tcn_layer(const TcnLayerArgs& L, float* __restri
                         }
 #pragma unroll
                     for (int i = 0; i < ROWS; ++i) {
+                        if (i >= nv) break;
                         const float4 a = *reinterpret_cast<const float4*>(L.in + aoff[i] + k0 + kk);
 #pragma unroll
                         for (int c = 0; c < RN; ++c) {
