@@ -488,10 +488,12 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
     rc = build_tail(e.get());
     if (rc) return rc;
 
-    // chunk: a multiple of the SM count whose intermediates (feature rows + scratch) stay around L2 size
+    // chunk: windows per internal launch group, a multiple of the SM count.  Measured on B200
+    // (tools/chunk_bench.py): every head gains from large chunks (more CTAs / rows per launch; the
+    // intermediates need not stay L2-resident), so take up to 28 windows per SM within a 2 GB budget.
     {
-        const size_t per_window = (size_t)e->feat_dim * sizeof(float) + e->scratch_per_window;
-        int mult = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)64 << 20) / (per_window * e->sm_count)));
+        const size_t per_window = (size_t)e->feat_dim * sizeof(float) * 3 + e->scratch_per_window;
+        int mult = (int)std::max<size_t>(1, std::min<size_t>(28, ((size_t)2 << 30) / (per_window * e->sm_count)));
         e->chunk = spec->chunk_windows > 0 ? spec->chunk_windows : e->sm_count * mult;
     }
     NWW_CUDA(cudaMalloc(&e->d_feat, (size_t)e->chunk * e->feat_dim * sizeof(float)));
@@ -686,7 +688,7 @@ int nww_run_windows_f32(nww_engine* e, const float* pcm_dev, int64_t n, float* s
     NWW_CUDA(cudaSetDevice(e->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);   // NULL = the legacy default stream, as in CUDA
     if (!e->d_pcm[0]) {
-        e->host_chunk = e->chunk;
+        e->host_chunk = std::min<int64_t>(e->chunk, (int64_t)e->sm_count * 8);
         for (int i = 0; i < 2; ++i) NWW_CUDA(cudaMalloc(&e->d_pcm[i], (size_t)e->host_chunk * e->clip * sizeof(int16_t)));
     }
     const int64_t mel_stride = (int64_t)e->n_mels * e->n_frames;
@@ -710,7 +712,8 @@ int nww_run_windows_host(nww_engine* e, const int16_t* pcm_host, int64_t n, floa
     std::lock_guard<std::mutex> lock(e->mu);
     NWW_CUDA(cudaSetDevice(e->device));
     if (!e->d_pcm[0]) {
-        e->host_chunk = e->chunk;
+        // copy / compute overlap wants several chunks per call: 8 windows per SM (38 MB) per copy
+        e->host_chunk = std::min<int64_t>(e->chunk, (int64_t)e->sm_count * 8);
         for (int i = 0; i < 2; ++i) NWW_CUDA(cudaMalloc(&e->d_pcm[i], (size_t)e->host_chunk * e->clip * sizeof(int16_t)));
     }
     if (e->scores_cap < n) {
