@@ -14,6 +14,7 @@
 #include "nww_stage.cuh"
 #include "nww_tail.cuh"
 #include "nww_tcn.cuh"
+#include "nww_bc.cuh"
 
 namespace nww {
 
@@ -157,7 +158,7 @@ inline int setup_head_weights(int arch, int geometry, const BlobLookup& get, con
         }
         *feat_dim = 256;
         // mel 40*98, init 32*20*49, then per block: dw + out
-        hw->scratch_floats = 3920 + 31360 + (32 * 250 + 64 * 250) + (64 * 65 + 128 * 65) + (128 * 39 + 256 * 39);
+        hw->scratch_floats = 3920 + 31360 + (2 * 32 * 250 + 64 * 250) + (2 * 64 * 65 + 128 * 65) + (2 * 128 * 39 + 256 * 39);
     } else if (arch == NWW_ARCH_CRNN_GRU) {
         if (geometry != NWW_GEOM_NS40X98) { *err = "crnn head is built for the NS40x98 geometry"; return NWW_EUNSUPPORTED; }
         int cin = 1, lv = 0, h = 40, w = 98;
@@ -294,8 +295,9 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
         return done();
     }
     if (hw.arch == NWW_ARCH_BCRESNET) {
+        // channel-last pipeline (nww_bc.cuh): init conv -> 3 x (depthwise + centre tap, pointwise/shortcut row GEMMs) -> GAP
         float* a0 = take(32 * 20 * 49);
-        conv3x3_kernel<true><<<ew_grid(n * 4 * 20 * 49, sm_count), 256, 0, st>>>(mel, hw.bc_init.w, hw.bc_init.b, a0, n, 1, 32, F, T, act);
+        bc_init_conv_kernel<<<ew_grid(n * 4 * 20 * 49, sm_count), 256, 0, st>>>(mel, hw.bc_init.w, hw.bc_init.b, a0, n, F, T, 32, act);
         if ((rc = done())) return rc;
         const int ch[4] = {32, 64, 128, 256};
         const int sh[3] = {2, 2, 2}, sw[3] = {2, 2, 1};
@@ -304,15 +306,20 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
         for (int j = 0; j < 3; ++j) {
             const int Ho = (H - 1) / sh[j] + 1, Wo = (W - 1) / sw[j] + 1;
             float* dwo = take((size_t)ch[j] * Ho * Wo);
+            float* ctr = take((size_t)ch[j] * Ho * Wo);
             float* out = take((size_t)ch[j + 1] * Ho * Wo);
-            dw3x3_kernel<<<ew_grid(n * ch[j] * Ho * Wo, sm_count), 256, 0, st>>>(x, hw.bc_dw[j], dwo, n, ch[j], H, W, sh[j], sw[j]);
+            bc_dw_kernel<<<ew_grid(n * (ch[j] / 4) * Ho * Wo, sm_count), 256, 0, st>>>(x, hw.bc_dw[j], dwo, ctr, n, ch[j], H, W, sh[j], sw[j]);
             if ((rc = done())) return rc;
-            bc_pw_res_kernel<<<ew_grid(n * (ch[j + 1] / kOCT) * Ho * Wo, sm_count), 256, 0, st>>>(
-                dwo, x, hw.bc_pw[j].w, hw.bc_pw[j].b, hw.bc_sc[j].w, hw.bc_sc[j].b, out, n, ch[j], ch[j + 1], H, W, sh[j], sw[j], act);
+            const size_t smem = bc_block_smem_bytes(ch[j]);
+            NWW_HCUDA(set_smem(bc_block_gemm_kernel, smem));
+            const long long rows = n * Ho * Wo;
+            const long long tiles = (rows + kBcRows - 1) / kBcRows;
+            bc_block_gemm_kernel<<<(int)std::min<long long>(tiles, (long long)sm_count), kTcnNT, smem, st>>>(
+                dwo, ctr, hw.bc_pw[j].w, hw.bc_pw[j].b, hw.bc_sc[j].w, hw.bc_sc[j].b, out, rows, ch[j], ch[j + 1], act);
             if ((rc = done())) return rc;
             x = out; H = Ho; W = Wo;
         }
-        gap_kernel<<<ew_grid(n * 256 * 32, sm_count), 256, 0, st>>>(x, feat, n * 256, H * W);
+        bc_gap_kernel<<<ew_grid(n * 256, sm_count), 256, 0, st>>>(x, feat, n, H * W, 256);
         return done();
     }
     if (hw.arch == NWW_ARCH_CRNN_GRU) {

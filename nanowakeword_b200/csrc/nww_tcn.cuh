@@ -114,10 +114,12 @@ template <int N> inline void tcn_cp_wait() {}
 struct TcnLayerArgs {
     const float* in; int in_pitch, in_mul, in_off;      // A rows: in + w * in_pitch + (in_mul * p + in_off) * Cin
     int Cin, K;                                         // K = taps * Cin (multiple of 4)
-    const float* W; const float* bias;                  // W [K][Cout]
-    float* out; int out_pitch;                          // out + w * out_pitch + p * Cout
-    int Cout, n_pos, n_win, relu;
-    const float* res; int res_pitch, res_mul, res_off;  // nullable
+    const float* W; const float* bias;                  // W [K][ldw], columns [0, Cout) of it are used
+    float* out; int out_pitch;                          // out + w * out_pitch + p * ldo
+    int Cout, n_pos, n_win, relu;                       // relu: 0 none, 1 ReLU, 2 + a = activation a (nww_common.cuh)
+    const float* res; int res_pitch, res_mul, res_off;  // nullable; rows of ldr floats
+    int ldw, ldo, ldr;                                  // leading dimensions; 0 = Cout
+    int res_relu;                                       // 1: max(. + res, 0) (TCN)   0: . + res (BcResNet)
 };
 
 template <int RN, int ROWS>
@@ -128,12 +130,13 @@ __device__ __forceinline__ void tcn_layer(const TcnLayerArgs& L, float* __restri
     const int rows = L.n_win * L.n_pos;
     const int n_chunks = (L.K + kTcnKC - 1) / kTcnKC;
     const int row_f4 = L.Cout / 4;                       // float4 per weight row
+    const int ldw = L.ldw ? L.ldw : L.Cout, ldo = L.ldo ? L.ldo : L.Cout, ldr = L.ldr ? L.ldr : L.Cout;
     auto stage = [&](int chunk, int buf) {
         const int k0 = chunk * kTcnKC;
         const int kc = (L.K - k0 < kTcnKC) ? (L.K - k0) : kTcnKC;
         for (int i = tid; i < kc * row_f4; i += kTcnNT) {
             const int kr = i / row_f4, c4 = i - kr * row_f4;
-            tcn_cp_async16(wbuf + buf * kTcnWBuf + kr * L.Cout + 4 * c4, L.W + (size_t)(k0 + kr) * L.Cout + 4 * c4);
+            tcn_cp_async16(wbuf + buf * kTcnWBuf + kr * L.Cout + 4 * c4, L.W + (size_t)(k0 + kr) * ldw + 4 * c4);
         }
         tcn_cp_commit();
     };
@@ -202,13 +205,14 @@ __device__ __forceinline__ void tcn_layer(const TcnLayerArgs& L, float* __restri
                 const int w = r / L.n_pos, p = r - w * L.n_pos;
                 float v[RN];
 #pragma unroll
-                for (int c = 0; c < RN; ++c) v[c] = L.relu ? fmaxf(acc[i][c], 0.0f) : acc[i][c];
+                for (int c = 0; c < RN; ++c)
+                    v[c] = L.relu == 0 ? acc[i][c] : L.relu == 1 ? fmaxf(acc[i][c], 0.0f) : apply_act(acc[i][c], L.relu - 2);
                 if (L.res != nullptr) {
-                    const float* rr = L.res + (size_t)w * L.res_pitch + (size_t)(L.res_mul * p + L.res_off) * L.Cout + oc0;
+                    const float* rr = L.res + (size_t)w * L.res_pitch + (size_t)(L.res_mul * p + L.res_off) * ldr + oc0;
 #pragma unroll
-                    for (int c = 0; c < RN; ++c) v[c] = fmaxf(v[c] + rr[c], 0.0f);
+                    for (int c = 0; c < RN; ++c) v[c] = L.res_relu ? fmaxf(v[c] + rr[c], 0.0f) : v[c] + rr[c];
                 }
-                float* o = L.out + (size_t)w * L.out_pitch + (size_t)p * L.Cout + oc0;
+                float* o = L.out + (size_t)w * L.out_pitch + (size_t)p * ldo + oc0;
 #pragma unroll
                 for (int c4 = 0; c4 < RN / 4; ++c4)
                     reinterpret_cast<float4*>(o)[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
@@ -255,19 +259,19 @@ tcn_cone_kernel(const float* __restrict__ mel_tm, long long mel_win_stride, long
             float* out = act + P.off_out[l];
             float* tmp = act + P.off_res;
             // conv1: taps of position p start at input position p
-            tcn_layer_any(TcnLayerArgs{x, pw, 1, 0, cin, 3 * cin, P.w1[l], P.b1[l], mid, pw, C, P.n_mid[l], nw, 1, nullptr, 0, 0, 0},
+            tcn_layer_any(TcnLayerArgs{x, pw, 1, 0, cin, 3 * cin, P.w1[l], P.b1[l], mid, pw, C, P.n_mid[l], nw, 1, nullptr, 0, 0, 0, 0, 0, 0, 1},
                           wbuf, tid);
             const float* res = x;
             int res_mul = 2, res_off = 4;
             if (P.wd[l] != nullptr) {                    // 1x1 downsample of the block input at the output positions
-                tcn_layer_any(TcnLayerArgs{x, pw, 2, 4, cin, cin, P.wd[l], P.bd[l], tmp, pw, C, P.n_out[l], nw, 0, nullptr, 0, 0, 0},
+                tcn_layer_any(TcnLayerArgs{x, pw, 2, 4, cin, cin, P.wd[l], P.bd[l], tmp, pw, C, P.n_out[l], nw, 0, nullptr, 0, 0, 0, 0, 0, 0, 1},
                               wbuf, tid);
                 res = tmp;
                 res_mul = 1;
                 res_off = 0;
             }
             // conv2 on the conv1 output (positions 2 p + j), then ReLU(ReLU(.) + res)
-            tcn_layer_any(TcnLayerArgs{mid, pw, 2, 0, C, 3 * C, P.w2[l], P.b2[l], out, pw, C, P.n_out[l], nw, 1, res, pw, res_mul, res_off},
+            tcn_layer_any(TcnLayerArgs{mid, pw, 2, 0, C, 3 * C, P.w2[l], P.b2[l], out, pw, C, P.n_out[l], nw, 1, res, pw, res_mul, res_off, 0, 0, 0, 1},
                           wbuf, tid);
             __syncthreads();
             x = out;
