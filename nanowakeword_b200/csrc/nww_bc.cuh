@@ -16,6 +16,10 @@
 //     window, which IS the strided 1x1 shortcut's input pixel (stride s, pad 1: centre = (s y, s x)).
 #pragma once
 
+#include <string.h>
+#include <vector>
+
+#include "nww_tc.cuh"
 #include "nww_tcn.cuh"
 
 namespace nww {
@@ -145,6 +149,174 @@ bc_block_gemm_kernel(const float* __restrict__ dwo, const float* __restrict__ ct
                           wbuf, tid);
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The same block tail on the 5th-generation tensor cores (default).  One CTA owns tiles of 128 pixels:
+//   * the tile's depthwise output and centre-tap rows ([128][Cin] FP32 each) are converted to bf16 hi / lo
+//     and laid out as un-swizzled K-major UMMA operands  [K-group][row][8 channels]  (SBO 128 B, LBO 2 KB);
+//   * for every chunk of 64 output channels the folded weights of both 1x1 convolutions arrive from the
+//     engine's pre-split bf16 copy ([chunk][pw|sc][hi|lo][K-group][64][8], built once at create time);
+//   * 2 x (Cin / 16) x 3 tcgen05.mma (128 x 64 x 16, bf16 split products a_hi w_hi + a_lo w_hi + a_hi w_lo)
+//     accumulate the two products side by side in 128 TMEM columns;
+//   * epilogue: act(pw + b_pw) + (sc + b_sc) straight from TMEM to the channel-last output.
+constexpr int kBcuRows = 128, kBcuNC = 64, kBcuNT = 256;
+inline size_t bcu_smem_bytes(int Cin) {
+    return (size_t)4 * kBcuRows * Cin * 2 /* A: dw, ctr x hi, lo */ + (size_t)4 * kBcuNC * Cin * 2 /* B chunk */ + 128;
+}
+
+__global__ void __launch_bounds__(kBcuNT, 1)
+bc_block_umma_kernel(const float* __restrict__ dwo, const float* __restrict__ ctr, const uint4* __restrict__ wq /* see above */,
+                     const float* __restrict__ bpw, const float* __restrict__ bsc, float* __restrict__ out, long long rows,
+                     int Cin, int Cout, int act) {
+    NWW_DYN_SMEM(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int a_op = kBcuRows * Cin * 2;                 // bytes of one A operand (dw_hi, dw_lo, ct_hi, ct_lo)
+    const int b_op = kBcuNC * Cin * 2;                   // bytes of one B operand (pw_hi, pw_lo, sc_hi, sc_lo)
+    unsigned char* a_s = smem;
+    unsigned char* b_s = smem + 4 * a_op;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 4 * a_op + 4 * b_op);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t a_addr = smem_u32(a_s), b_addr = smem_u32(b_s);
+    const uint32_t idesc = umma_idesc_bf16(128, kBcuNC);
+    const int kg_n = Cin / 8;                            // 16-byte K groups
+    const int n_chunks = Cout / kBcuNC;
+    uint32_t phase = 0;
+    int b_loaded = -1;                                   // weight chunk currently in shared memory
+
+    for (long long r0 = (long long)blockIdx.x * kBcuRows; r0 < rows; r0 += (long long)gridDim.x * kBcuRows) {
+        // ---- A: FP32 rows -> bf16 hi / lo UMMA operands --------------------------------------------------------
+        for (int i = tid; i < kBcuRows * kg_n; i += kBcuNT) {
+            const int g = i / kBcuRows, r = i - g * kBcuRows;           // consecutive threads -> consecutive rows
+            uint4 dh = make_uint4(0, 0, 0, 0), dl = dh, ch = dh, cl = dh;
+            if (r0 + r < rows) {
+                const float4* pd = reinterpret_cast<const float4*>(dwo + (r0 + r) * Cin + 8 * g);
+                const float4* pc = reinterpret_cast<const float4*>(ctr + (r0 + r) * Cin + 8 * g);
+                const float4 d0 = __ldg(pd), d1 = __ldg(pd + 1), c0 = __ldg(pc), c1 = __ldg(pc + 1);
+                const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+                const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                uint32_t h[8], l[8], hc[8], lc[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    h[k] = float_to_bf16_bits(dv[k]);
+                    l[k] = float_to_bf16_bits(dv[k] - bf16_bits_to_float(h[k]));
+                    hc[k] = float_to_bf16_bits(cv[k]);
+                    lc[k] = float_to_bf16_bits(cv[k] - bf16_bits_to_float(hc[k]));
+                }
+                dh = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+                dl = make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
+                ch = make_uint4(hc[0] | (hc[1] << 16), hc[2] | (hc[3] << 16), hc[4] | (hc[5] << 16), hc[6] | (hc[7] << 16));
+                cl = make_uint4(lc[0] | (lc[1] << 16), lc[2] | (lc[3] << 16), lc[4] | (lc[5] << 16), lc[6] | (lc[7] << 16));
+            }
+            const int off = (g * kBcuRows + r) * 16;
+            *reinterpret_cast<uint4*>(a_s + 0 * a_op + off) = dh;
+            *reinterpret_cast<uint4*>(a_s + 1 * a_op + off) = dl;
+            *reinterpret_cast<uint4*>(a_s + 2 * a_op + off) = ch;
+            *reinterpret_cast<uint4*>(a_s + 3 * a_op + off) = cl;
+        }
+        for (int nc = 0; nc < n_chunks; ++nc) {
+            // ---- B: this chunk's pre-split weights (skipped when the single chunk is already resident) ---------
+            if (b_loaded != nc) {
+                const uint4* src = wq + (size_t)nc * (4 * b_op / 16);
+                for (int i = tid; i < 4 * b_op / 16; i += kBcuNT) reinterpret_cast<uint4*>(b_s)[i] = __ldg(src + i);
+                b_loaded = nc;
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                for (int gemm = 0; gemm < 2; ++gemm) {                  // 0: pointwise (A = dw), 1: shortcut (A = ctr)
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(gemm * kBcuNC);
+                    const uint32_t ah = a_addr + (uint32_t)((2 * gemm) * a_op), al = ah + (uint32_t)a_op;
+                    const uint32_t bh = b_addr + (uint32_t)((2 * gemm) * b_op), bl = bh + (uint32_t)b_op;
+                    for (int ks = 0; ks < Cin / 16; ++ks) {             // one MMA = 16 channels = 2 K groups
+                        const uint32_t ao = (uint32_t)(2 * ks * kBcuRows * 16), bo = (uint32_t)(2 * ks * kBcuNC * 16);
+                        const uint64_t dah = umma_desc_noswz(ah + ao, kBcuRows * 16, 128);
+                        const uint64_t dal = umma_desc_noswz(al + ao, kBcuRows * 16, 128);
+                        const uint64_t dbh = umma_desc_noswz(bh + bo, kBcuNC * 16, 128);
+                        const uint64_t dbl = umma_desc_noswz(bl + bo, kBcuNC * 16, 128);
+                        umma_bf16(d_tmem, dah, dbh, idesc, ks != 0);
+                        umma_bf16(d_tmem, dal, dbh, idesc, 1);
+                        umma_bf16(d_tmem, dah, dbl, idesc, 1);
+                    }
+                }
+                umma_commit(bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            tc_fence_after();
+            // ---- epilogue: warp -> (TMEM lane quarter, 32-column half) ---------------------------------------------
+            {
+                const int q = warp & 3, hcol = warp >> 2;
+                float pv[32], sv[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hcol * 32), pv);
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kBcuNC + hcol * 32), sv);
+                tc_fence_before();
+                const long long r = r0 + q * 32 + lane;
+                if (r < rows) {
+                    const int n0 = nc * kBcuNC + hcol * 32;
+                    float4* dst = reinterpret_cast<float4*>(out + r * Cout + n0);
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        float v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int n = n0 + 4 * j4 + j;
+                            v[j] = apply_act(pv[4 * j4 + j] + __ldg(bpw + n), act) + (sv[4 * j4 + j] + __ldg(bsc + n));
+                        }
+                        dst[j4] = make_float4(v[0], v[1], v[2], v[3]);
+                    }
+                }
+            }
+            __syncthreads();          // TMEM and (for multi-chunk layers) the weight buffer are free again
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 128);
+    }
+}
+
+// host: folded (Cin, Cout) FP32 weights of both 1x1 convolutions -> [chunk][pw|sc][hi|lo][K-group][64][8] bf16
+inline void bcu_pack_weights(const float* pw, const float* sc, int Cin, int Cout, std::vector<uint16_t>* out) {
+    auto bf16_rn = [](float x) {
+        uint32_t u;
+        memcpy(&u, &x, 4);
+        u += 0x7FFFu + ((u >> 16) & 1u);
+        return (uint16_t)(u >> 16);
+    };
+    auto bf16_f = [](uint16_t b) {
+        uint32_t u = (uint32_t)b << 16;
+        float f;
+        memcpy(&f, &u, 4);
+        return f;
+    };
+    const int n_chunks = Cout / kBcuNC, op = kBcuNC * Cin;          // elements per operand
+    out->assign((size_t)n_chunks * 4 * op, 0);
+    for (int nc = 0; nc < n_chunks; ++nc)
+        for (int gemm = 0; gemm < 2; ++gemm) {
+            const float* w = gemm ? sc : pw;
+            for (int k = 0; k < Cin; ++k)
+                for (int n = 0; n < kBcuNC; ++n) {
+                    const float v = w[(size_t)k * Cout + nc * kBcuNC + n];
+                    const uint16_t hi = bf16_rn(v), lo = bf16_rn(v - bf16_f(hi));
+                    const size_t base = ((size_t)nc * 4 + 2 * gemm) * op + (size_t)(k >> 3) * kBcuNC * 8 + n * 8 + (k & 7);
+                    (*out)[base] = hi;
+                    (*out)[base + op] = lo;
+                }
+        }
 }
 
 // global average pool, channel-last: in [n][P][C] -> out [n][C]

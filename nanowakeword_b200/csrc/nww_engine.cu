@@ -83,6 +83,7 @@ struct nww_engine {
     // CNN stage v2 (tcgen05 conv2): conv2 weights as UMMA operands; features written pre-split by the stage kernel
     bool cnn2_enabled = false;
     uint4* d_w2_umma = nullptr;
+    void* d_bc_wq[3] = {nullptr, nullptr, nullptr};   // BcResNet 1x1 weights as bf16 UMMA operands
     Cnn2Weights cnn2{};
     CUtensorMap tm_xhi{}, tm_xlo{}, tm_whi{}, tm_wlo{};
     TailParams tail_rest{};                           // layers 1.. (after the tensor-core layer)
@@ -482,6 +483,18 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
             };
             rc = setup_head_weights(spec->arch, spec->geometry, lookup, dims, &e->heads, &e->feat_dim, &g_last_error);
             if (rc) return rc;
+            if (spec->arch == NWW_ARCH_BCRESNET && !(spec->reserved[0] & 1)) {
+                // pointwise + shortcut weights as pre-split bf16 UMMA operands (reserved[0] bit 0 keeps the FP32 row GEMM)
+                const int ch[4] = {32, 64, 128, 256};
+                for (int j = 0; j < 3; ++j) {
+                    const std::string p = "bc." + std::to_string(j);
+                    std::vector<uint16_t> wq;
+                    bcu_pack_weights(e->blob.f32(p + ".pw.w"), e->blob.f32(p + ".sc.w"), ch[j], ch[j + 1], &wq);
+                    NWW_CUDA(cudaMalloc(&e->d_bc_wq[j], wq.size() * sizeof(uint16_t)));
+                    NWW_CUDA(cudaMemcpy(e->d_bc_wq[j], wq.data(), wq.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+                    e->heads.bc_wq[j] = reinterpret_cast<const uint4*>(e->d_bc_wq[j]);
+                }
+            }
             e->scratch_per_window = e->heads.scratch_floats * sizeof(float);
         }
     }
@@ -622,6 +635,7 @@ void nww_destroy(nww_engine* e) {
     cudaFree(e->d_feat_lo);
     cudaFree(e->d_part);
     cudaFree(e->d_w2_umma);
+    for (int j = 0; j < 3; ++j) cudaFree(e->d_bc_wq[j]);
     cudaFree(e->d_pcm[0]);
     cudaFree(e->d_pcm[1]);
     cudaFree(e->d_scores);

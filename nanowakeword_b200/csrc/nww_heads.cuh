@@ -35,6 +35,7 @@ struct HeadWeights {
     // BcResNet
     ConvW bc_init, bc_pw[3], bc_sc[3];
     const float* bc_dw[3] = {nullptr, nullptr, nullptr};
+    const uint4* bc_wq[3] = {nullptr, nullptr, nullptr};     // pre-split bf16 UMMA weights (nww_bc.cuh); null: FP32 row GEMM
     // CRNN
     int crnn_levels = 0, crnn_ch[4] = {0}, gru_hidden = 0, gru_in = 0;
     ConvW crnn_conv[4];
@@ -310,12 +311,20 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
             float* out = take((size_t)ch[j + 1] * Ho * Wo);
             bc_dw_kernel<<<ew_grid(n * (ch[j] / 4) * Ho * Wo, sm_count), 256, 0, st>>>(x, hw.bc_dw[j], dwo, ctr, n, ch[j], H, W, sh[j], sw[j]);
             if ((rc = done())) return rc;
-            const size_t smem = bc_block_smem_bytes(ch[j]);
-            NWW_HCUDA(set_smem(bc_block_gemm_kernel, smem));
             const long long rows = n * Ho * Wo;
-            const long long tiles = (rows + kBcRows - 1) / kBcRows;
-            bc_block_gemm_kernel<<<(int)std::min<long long>(tiles, (long long)sm_count), kTcnNT, smem, st>>>(
-                dwo, ctr, hw.bc_pw[j].w, hw.bc_pw[j].b, hw.bc_sc[j].w, hw.bc_sc[j].b, out, rows, ch[j], ch[j + 1], act);
+            if (hw.bc_wq[j] != nullptr) {
+                const size_t smem = bcu_smem_bytes(ch[j]);
+                NWW_HCUDA(set_smem(bc_block_umma_kernel, smem));
+                const long long tiles = (rows + kBcuRows - 1) / kBcuRows;
+                bc_block_umma_kernel<<<(int)std::min<long long>(tiles, (long long)sm_count), kBcuNT, smem, st>>>(
+                    dwo, ctr, hw.bc_wq[j], hw.bc_pw[j].b, hw.bc_sc[j].b, out, rows, ch[j], ch[j + 1], act);
+            } else {
+                const size_t smem = bc_block_smem_bytes(ch[j]);
+                NWW_HCUDA(set_smem(bc_block_gemm_kernel, smem));
+                const long long tiles = (rows + kBcRows - 1) / kBcRows;
+                bc_block_gemm_kernel<<<(int)std::min<long long>(tiles, (long long)sm_count), kTcnNT, smem, st>>>(
+                    dwo, ctr, hw.bc_pw[j].w, hw.bc_pw[j].b, hw.bc_sc[j].w, hw.bc_sc[j].b, out, rows, ch[j], ch[j + 1], act);
+            }
             if ((rc = done())) return rc;
             x = out; H = Ho; W = Wo;
         }
