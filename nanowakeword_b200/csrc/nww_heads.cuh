@@ -15,6 +15,7 @@
 #include "nww_tail.cuh"
 #include "nww_tcn.cuh"
 #include "nww_bc.cuh"
+#include "nww_rowgemm.cuh"
 
 namespace nww {
 
@@ -42,6 +43,7 @@ struct HeadWeights {
     const float *gru_wih_f = nullptr, *gru_whh_f = nullptr, *gru_bih_f = nullptr, *gru_bhh_f = nullptr;
     const float *gru_wih_b = nullptr, *gru_bih_b = nullptr, *gru_bhh_b = nullptr;
     const float *gru_wih_f_nk = nullptr, *gru_wih_b_nk = nullptr;    // [3H][In] copies for the dense kernel
+    const float *gru_wih_f_kn = nullptr, *gru_wih_b_kn = nullptr;    // [In][3H] copies for the row GEMM (preferred)
     // E2E mel-CNN
     ConvW e2e_conv[3];
     // scratch layout (floats per window)
@@ -189,6 +191,11 @@ inline int setup_head_weights(int arch, int geometry, const BlobLookup& get, con
         hw->gru_bhh_b = need("crnn.gru.bwd.b_hh", 3 * H);
         hw->gru_wih_f_nk = need("crnn.gru.fwd.w_ih_nk", (size_t)3 * H * hw->gru_in);
         hw->gru_wih_b_nk = need("crnn.gru.bwd.w_ih_nk", (size_t)3 * H * hw->gru_in);
+        // row-GEMM layout (newer blobs); eligible shapes: In, H multiples of 4, 3H a multiple of 8
+        if (hw->gru_in % 4 == 0 && H % 8 == 0 && gru2_smem_bytes(H) <= 200 * 1024 && rowgemm_smem_bytes(hw->gru_in) <= 200 * 1024) {
+            hw->gru_wih_f_kn = get("crnn.gru.fwd.w_ih_kn", (size_t)3 * H * hw->gru_in);
+            hw->gru_wih_b_kn = get("crnn.gru.bwd.w_ih_kn", (size_t)3 * H * hw->gru_in);
+        }
         *feat_dim = 2 * H;
         // mel + conv activations + seq [w][gru_in] + gi_f [w][3H] + gi_b [3H]
         hw->scratch_floats = 3920 + act_floats + (size_t)w * hw->gru_in + (size_t)w * 3 * H + 3 * H;
@@ -348,7 +355,23 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
         float* gi_b = take((size_t)G3);
         seq_pack_kernel<<<ew_grid(n * S * In, sm_count), 256, 0, st>>>(x, seq, n, cin, H, S);
         if ((rc = done())) return rc;
-        // input projections as dense layers over rows: all S steps forward, the last step only backward
+        // input projections over rows (all S steps forward, the last step only backward), then the recurrence
+        if (hw.gru_wih_f_kn && hw.gru_wih_b_kn) {
+            const size_t rsm = rowgemm_smem_bytes(In);
+            NWW_HCUDA(set_smem(rowgemm_kernel, rsm));
+            const long long rows = n * S;
+            rowgemm_kernel<<<(int)std::min<long long>((rows + kRgRows - 1) / kRgRows, sm_count), kTcnNT, rsm, st>>>(
+                seq, 1, 0, hw.gru_wih_f_kn, hw.gru_bih_f, gi_f, rows, In, G3);
+            if ((rc = done())) return rc;
+            rowgemm_kernel<<<(int)std::min<long long>((n + kRgRows - 1) / kRgRows, sm_count), kTcnNT, rsm, st>>>(
+                seq, S, S - 1, hw.gru_wih_b_kn, hw.gru_bih_b, gi_b, n, In, G3);
+            if ((rc = done())) return rc;
+            const size_t gsm = gru2_smem_bytes(Hd);
+            NWW_HCUDA(set_smem(gru2_kernel, gsm));
+            gru2_kernel<<<(int)std::min<long long>((n + kGru2TM - 1) / kGru2TM, (long long)sm_count), kTcnNT, gsm, st>>>(
+                gi_f, gi_b, hw.gru_whh_f, hw.gru_bhh_f, hw.gru_bhh_b, feat, n, S, Hd);
+            return done();
+        }
         TailParams P{};
         P.n_layers = 1; P.act = act; P.max_width = G3; P.raw_out = 1;
         P.layers[0] = TailLayer{hw.gru_wih_f_nk, hw.gru_bih_f, nullptr, nullptr, In, G3, POST_NONE};

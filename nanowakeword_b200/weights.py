@@ -147,6 +147,7 @@ def pack_tensors(sd: dict, cfg: dict) -> dict[str, np.ndarray]:
             i += 1
         for sfx, tag in (("", "fwd"), ("_reverse", "bwd")):
             out[f"crnn.gru.{tag}.w_ih_nk"] = _f64(sd, "model.rnn.weight_ih_l0" + sfx).astype(np.float32)  # (3H, In), dense-kernel layout
+            out[f"crnn.gru.{tag}.w_ih_kn"] = np.ascontiguousarray(_f64(sd, "model.rnn.weight_ih_l0" + sfx).T).astype(np.float32)  # (In, 3H), row-GEMM layout
             out[f"crnn.gru.{tag}.w_hh"] = np.ascontiguousarray(_f64(sd, "model.rnn.weight_hh_l0" + sfx).T).astype(np.float32)  # (H, 3H)
             out[f"crnn.gru.{tag}.b_ih"] = _f64(sd, "model.rnn.bias_ih_l0" + sfx).astype(np.float32)
             out[f"crnn.gru.{tag}.b_hh"] = _f64(sd, "model.rnn.bias_hh_l0" + sfx).astype(np.float32)
