@@ -88,7 +88,8 @@ template <int ACT> __device__ __forceinline__ float cnn2_act(float x) {
 template <int ACT>
 __global__ void __launch_bounds__(Cnn2::NT, 1)
 cnn2_stage_kernel(WindowSource src, Cnn2MelSource msrc, long long n_windows, FrontendTables<double> tab, Cnn2Weights wt,
-                  float* __restrict__ feat_hi, float* __restrict__ feat_lo /* [n][7680], K order (ph, pw, oc) */,
+                  float* __restrict__ feat_hi, float* __restrict__ feat_lo /* [n][7680], K order (ph, pw, oc); feat_lo ==
+                  nullptr: plain FP32 rows into feat_hi (channel-last input of the CRNN's third conv) */,
                   float* __restrict__ mel_dump /* nullable, (F,T) */) {
     using D = Cnn2;
     NWW_DYN_SMEM(smem);
@@ -289,16 +290,17 @@ cnn2_stage_kernel(WindowSource src, Cnn2MelSource msrc, long long n_windows, Fro
                     v = fmaxf(v, cnn2_act<ACT>(__uint_as_float(r[1][o]) + bias));
                     v = fmaxf(v, cnn2_act<ACT>(__uint_as_float(r[2][o]) + bias));
                     v = fmaxf(v, cnn2_act<ACT>(__uint_as_float(r[3][o]) + bias));
-                    hi[o] = round_tf32(v);
+                    hi[o] = feat_lo ? round_tf32(v) : v;
                     lo[o] = round_tf32(v - hi[o]);
                 }
                 const long long off = w * (long long)D::FEAT + (ph * D::W2 + pw) * 32 + half * 16;
                 float4* dh = reinterpret_cast<float4*>(feat_hi + off);
                 float4* dl = reinterpret_cast<float4*>(feat_lo + off);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    dh[j] = make_float4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                    dl[j] = make_float4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                for (int j = 0; j < 4; ++j) dh[j] = make_float4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                if (feat_lo != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dl[j] = make_float4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
                 }
             }
         }

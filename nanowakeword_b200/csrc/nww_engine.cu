@@ -82,6 +82,8 @@ struct nww_engine {
     int tc_kp = 0;                                    // K of that layer padded to a multiple of the 32-float K tile
     // CNN stage v2 (tcgen05 conv2): conv2 weights as UMMA operands; features written pre-split by the stage kernel
     bool cnn2_enabled = false;
+    bool crnn_cnn2 = false;                           // CRNN head: conv1 + conv2 through cnn2_stage_kernel
+    float* d_nhwc = nullptr;                          // [chunk][7680] channel-last conv2 output for that path
     uint4* d_w2_umma = nullptr;
     void* d_bc_wq[3] = {nullptr, nullptr, nullptr};   // BcResNet 1x1 weights as bf16 UMMA operands
     Cnn2Weights cnn2{};
@@ -233,6 +235,45 @@ template <typename G> static int setup_frontend(nww_engine* e) {
     return NWW_OK;
 }
 
+
+// conv weights of a (1 -> 16, 16 -> 32) 3x3 pair in the layouts cnn2_stage_kernel wants:
+//   conv1 [cg][tap][8 oc] FP32 and conv2 [tap][hi|lo][kg][oc][8 ic] bf16 (un-swizzled K-major UMMA operand).
+// w1_at(oc, tap) reads the first conv's weight; w2 is [ic 16][tap 9][oc 32].
+template <typename W1At>
+static int build_cnn2_weights(nww_engine* e, W1At w1_at, const float* w2, const float* d_b1, const float* d_b2) {
+    auto bf16_rn = [](float x) {
+        uint32_t u;
+        memcpy(&u, &x, 4);
+        u += 0x7FFFu + ((u >> 16) & 1u);
+        return (uint16_t)(u >> 16);
+    };
+    auto bf16_f = [](uint16_t b) {
+        uint32_t u = (uint32_t)b << 16;
+        float f;
+        memcpy(&f, &u, 4);
+        return f;
+    };
+    std::vector<uint16_t> wb(Cnn2::W2_BYTES / 2);
+    for (int tap = 0; tap < 9; ++tap)
+        for (int ic = 0; ic < 16; ++ic)
+            for (int oc = 0; oc < 32; ++oc) {
+                const float v = w2[(ic * 9 + tap) * 32 + oc];
+                const uint16_t hi = bf16_rn(v), lo = bf16_rn(v - bf16_f(hi));
+                const size_t base = (size_t)tap * 2 * (Cnn2::W2_TAP_BYTES / 2) + (size_t)(ic >> 3) * 256 + oc * 8 + (ic & 7);
+                wb[base] = hi;
+                wb[base + Cnn2::W2_TAP_BYTES / 2] = lo;
+            }
+    std::vector<float> w1v(144);
+    for (int oc = 0; oc < 16; ++oc)
+        for (int tap = 0; tap < 9; ++tap) w1v[(oc >> 3) * 72 + tap * 8 + (oc & 7)] = w1_at(oc, tap);
+    NWW_CUDA(cudaMalloc(&e->d_w2_umma, Cnn2::W2_BYTES + 144 * sizeof(float)));
+    NWW_CUDA(cudaMemcpy(e->d_w2_umma, wb.data(), Cnn2::W2_BYTES, cudaMemcpyHostToDevice));
+    float* d_w1v = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(e->d_w2_umma) + Cnn2::W2_BYTES);
+    NWW_CUDA(cudaMemcpy(d_w1v, w1v.data(), 144 * sizeof(float), cudaMemcpyHostToDevice));
+    e->cnn2 = Cnn2Weights{d_w1v, d_b1, e->d_w2_umma, d_b2};
+    return NWW_OK;
+}
+
 // ------------------------------------------------------------------------------ launches
 static int grid_for(const nww_engine* e, int64_t n, int per_sm = 1) {
     return (int)std::min<int64_t>(n, (int64_t)e->sm_count * per_sm);
@@ -364,6 +405,20 @@ static int launch_stage_a(nww_engine* e, WindowSource pcm, int64_t n, float* mel
             NWW_CUDA(cudaGetLastError());
             return NWW_OK;
         }
+        case NWW_ARCH_CRNN_GRU:
+            if (e->crnn_cnn2) {
+                auto k = e->spec.activation == NWW_ACT_RELU   ? cnn2_stage_kernel<ACT_RELU>
+                         : e->spec.activation == NWW_ACT_GELU ? cnn2_stage_kernel<ACT_GELU>
+                                                              : cnn2_stage_kernel<ACT_SILU>;
+                NWW_CUDA(set_smem(k, Cnn2::kTotal));
+                const Cnn2MelSource ms{from_ring ? e->d_mel_ring : nullptr, e->streams.count, from_ring ? stream_s0 : 0};
+                k<<<grid_for(e, n), Cnn2::NT, Cnn2::kTotal, st>>>(pcm, ms, n, e->tab64, e->cnn2, e->d_nhwc, nullptr, mel);
+                e->launches++;
+                NWW_CUDA(cudaGetLastError());
+                return launch_head_stage_a(e->heads, e->tab64, e->spec.activation, e->sm_count, pcm, n, e->d_feat, e->d_scratch,
+                                           nullptr, st, &e->launches, &g_last_error, true, e->d_nhwc);
+            }
+            // fall through
         default:
             if (from_ring) {
                 const int tm = (e->spec.arch == NWW_ARCH_TCN && e->heads.tcn_cone) ? 1 : 0;   // the cone kernel reads (T, F) rows
@@ -483,6 +538,14 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
             };
             rc = setup_head_weights(spec->arch, spec->geometry, lookup, dims, &e->heads, &e->feat_dim, &g_last_error);
             if (rc) return rc;
+            if (spec->arch == NWW_ARCH_CRNN_GRU && e->heads.crnn_cnn2 && !(spec->reserved[0] & 1)) {
+                // conv1 + conv2 (same shapes as the CNN head's) through cnn2_stage_kernel, channel-last FP32 output
+                const float* w0 = e->blob.f32("crnn.conv0.w");    // [1][tap 9][oc 16]
+                rc = build_cnn2_weights(e.get(), [&](int oc, int tap) { return w0[tap * 16 + oc]; }, e->blob.f32("crnn.conv1.w"),
+                                        e->heads.crnn_conv[0].b, e->heads.crnn_conv[1].b);
+                if (rc) return rc;
+                e->crnn_cnn2 = true;
+            }
             if (spec->arch == NWW_ARCH_BCRESNET && !(spec->reserved[0] & 1)) {
                 // pointwise + shortcut weights as pre-split bf16 UMMA operands (reserved[0] bit 0 keeps the FP32 row GEMM)
                 const int ch[4] = {32, 64, 128, 256};
@@ -510,6 +573,7 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
         e->chunk = spec->chunk_windows > 0 ? spec->chunk_windows : e->sm_count * mult;
     }
     NWW_CUDA(cudaMalloc(&e->d_feat, (size_t)e->chunk * e->feat_dim * sizeof(float)));
+    if (e->crnn_cnn2) NWW_CUDA(cudaMalloc(&e->d_nhwc, (size_t)e->chunk * Cnn2::FEAT * sizeof(float)));
     if (e->scratch_per_window) NWW_CUDA(cudaMalloc(&e->d_scratch, (size_t)e->chunk * e->scratch_per_window));
     {
         // First dense layer on tcgen05 (3xTF32) when its shape fits the tile constraints.
@@ -566,40 +630,10 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
                             make_tmap_2d(&e->tm_wlo, e->d_w_lo, L0.N, Kp, L0.N);
             if (!ok) return fail(NWW_ECUDA, "cuTensorMapEncodeTiled failed for the dense-layer operands");
             if (want_cnn2) {
-                // conv2 weights as un-swizzled K-major UMMA operands: [tap][hi|lo][kg][oc][8 ic] bf16
-                const float* w2 = e->blob.f32("cnn.w2");          // [ic 16][tap 9][oc 32]
-                auto bf16_rn = [](float x) {
-                    uint32_t u;
-                    memcpy(&u, &x, 4);
-                    u += 0x7FFFu + ((u >> 16) & 1u);
-                    return (uint16_t)(u >> 16);
-                };
-                auto bf16_f = [](uint16_t b) {
-                    uint32_t u = (uint32_t)b << 16;
-                    float f;
-                    memcpy(&f, &u, 4);
-                    return f;
-                };
-                std::vector<uint16_t> wb(Cnn2::W2_BYTES / 2);
-                for (int tap = 0; tap < 9; ++tap)
-                    for (int ic = 0; ic < 16; ++ic)
-                        for (int oc = 0; oc < 32; ++oc) {
-                            const float v = w2[(ic * 9 + tap) * 32 + oc];
-                            const uint16_t hi = bf16_rn(v), lo = bf16_rn(v - bf16_f(hi));
-                            const size_t base = (size_t)tap * 2 * (Cnn2::W2_TAP_BYTES / 2) + (size_t)(ic >> 3) * 256 + oc * 8 + (ic & 7);
-                            wb[base] = hi;
-                            wb[base + Cnn2::W2_TAP_BYTES / 2] = lo;
-                        }
-                // conv1 weights with the 8 output channels of a tap contiguous: [cg][tap][8 oc]
                 const float* w1 = e->blob.f32("cnn.w1");          // [oc 16][tap 9]
-                std::vector<float> w1v(144);
-                for (int oc = 0; oc < 16; ++oc)
-                    for (int tap = 0; tap < 9; ++tap) w1v[(oc >> 3) * 72 + tap * 8 + (oc & 7)] = w1[oc * 9 + tap];
-                NWW_CUDA(cudaMalloc(&e->d_w2_umma, Cnn2::W2_BYTES + 144 * sizeof(float)));
-                NWW_CUDA(cudaMemcpy(e->d_w2_umma, wb.data(), Cnn2::W2_BYTES, cudaMemcpyHostToDevice));
-                float* d_w1v = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(e->d_w2_umma) + Cnn2::W2_BYTES);
-                NWW_CUDA(cudaMemcpy(d_w1v, w1v.data(), 144 * sizeof(float), cudaMemcpyHostToDevice));
-                e->cnn2 = Cnn2Weights{d_w1v, e->cnn.b1, e->d_w2_umma, e->cnn.b2};
+                int rcw = build_cnn2_weights(e.get(), [&](int oc, int tap) { return w1[oc * 9 + tap]; }, e->blob.f32("cnn.w2"),
+                                             e->cnn.b1, e->cnn.b2);
+                if (rcw) return rcw;
                 e->cnn2_enabled = true;
             }
             e->tail_rest = e->tail;
@@ -635,6 +669,7 @@ void nww_destroy(nww_engine* e) {
     cudaFree(e->d_feat_lo);
     cudaFree(e->d_part);
     cudaFree(e->d_w2_umma);
+    cudaFree(e->d_nhwc);
     for (int j = 0; j < 3; ++j) cudaFree(e->d_bc_wq[j]);
     cudaFree(e->d_pcm[0]);
     cudaFree(e->d_pcm[1]);

@@ -31,6 +31,7 @@ struct HeadWeights {
     int tcn_levels = 0, tcn_k = 3, tcn_in = 0;
     int tcn_ch[8] = {0};
     ConvW tcn_c1[8], tcn_c2[8], tcn_down[8];
+    bool crnn_cnn2 = false;           // conv1 + conv2 through cnn2_stage_kernel (default channel counts 16, 32, 32)
     bool tcn_cone = false;            // fused dependency-cone kernel (nww_tcn.cuh) instead of the layer kernels
     TcnConeParams tcn_plan{};
     // BcResNet
@@ -180,6 +181,7 @@ inline int setup_head_weights(int arch, int geometry, const BlobLookup& get, con
         if (lv == 0) { *err = "weight blob: crnn.conv* missing"; return NWW_EINVAL; }
         hw->crnn_levels = lv;
         hw->gru_in = cin * h;
+        hw->crnn_cnn2 = lv == 3 && hw->crnn_ch[0] == 16 && hw->crnn_ch[1] == 32 && hw->crnn_ch[2] % kOCT == 0;
         auto dh = dims("crnn.gru.fwd.w_hh");
         if (dh.size() != 2) { *err = "weight blob: crnn.gru.fwd.w_hh missing"; return NWW_EINVAL; }
         const int H = (int)dh[0];
@@ -199,6 +201,7 @@ inline int setup_head_weights(int arch, int geometry, const BlobLookup& get, con
         *feat_dim = 2 * H;
         // mel + conv activations + seq [w][gru_in] + gi_f [w][3H] + gi_b [3H]
         hw->scratch_floats = 3920 + act_floats + (size_t)w * hw->gru_in + (size_t)w * 3 * H + 3 * H;
+        if (hw->crnn_cnn2) hw->scratch_floats = 3920 + 7680 + (size_t)w * hw->gru_in + (size_t)w * 3 * H + 3 * H;
         if (gru_smem_bytes(H) > 200 * 1024) { *err = "GRU hidden size too large for shared memory"; return NWW_EUNSUPPORTED; }
     } else if (arch == NWW_ARCH_E2E_MELCNN) {
         if (geometry != NWW_GEOM_REF64X101) { *err = "e2e mel-CNN is built for the REF64x101 geometry"; return NWW_EUNSUPPORTED; }
@@ -219,7 +222,8 @@ inline int setup_head_weights(int arch, int geometry, const BlobLookup& get, con
 // ------------------------------------------------------------------------------ launches
 inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<double>& tab, int act, int sm_count,
                                WindowSource pcm, long long n, float* feat, float* scratch, float* mel_dump,
-                               cudaStream_t st, int64_t* launches, std::string* err, bool mel_ready = false) {
+                               cudaStream_t st, int64_t* launches, std::string* err, bool mel_ready = false,
+                               const float* conv2_nhwc = nullptr /* CRNN: conv1 + conv2 output of cnn2_stage_kernel */) {
     // mel_ready: the caller already placed the (n, F, T) log-mel at the start of `scratch` (stream mode)
     float* p = scratch;
     auto take = [&](size_t floats_per_window) {
@@ -266,8 +270,8 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
         tcn_cone_kernel<<<(int)std::min<long long>(tiles, sm_count), kTcnNT, smem, st>>>(mel, (long long)F * T, n, P, feat);
         return done();
     }
-    if (!mel_ready && (rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel, 0, st, launches, err))) return rc;
-    if (mel_dump) NWW_HCUDA(cudaMemcpyAsync(mel_dump, mel, (size_t)n * F * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (!mel_ready && !conv2_nhwc && (rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel, 0, st, launches, err))) return rc;
+    if (mel_dump && !conv2_nhwc) NWW_HCUDA(cudaMemcpyAsync(mel_dump, mel, (size_t)n * F * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
 
     if (hw.arch == NWW_ARCH_TCN) {
         // positions each layer output must cover so that the final step (T-1) is exact
@@ -341,7 +345,17 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
     if (hw.arch == NWW_ARCH_CRNN_GRU) {
         int cin = 1, H = F, W = T;
         const float* x = mel;
-        for (int i = 0; i < hw.crnn_levels; ++i) {
+        const int S0 = 12, In0 = hw.gru_in;
+        float* seq_direct = nullptr;
+        if (conv2_nhwc != nullptr) {
+            // conv1 + conv2 already done by cnn2_stage_kernel (channel-last, 10 x 24 x 32): third conv -> sequence
+            seq_direct = take((size_t)S0 * In0);
+            crnn_conv3_seq_kernel<<<ew_grid(n * 5 * 12 * (hw.crnn_ch[2] / kOCT), sm_count), 256, 0, st>>>(
+                conv2_nhwc, hw.crnn_conv[2].w, hw.crnn_conv[2].b, seq_direct, n, hw.crnn_ch[1], hw.crnn_ch[2], 10, 24, act);
+            if ((rc = done())) return rc;
+            cin = hw.crnn_ch[2]; H = 5; W = 12;
+        }
+        for (int i = 0; i < hw.crnn_levels && conv2_nhwc == nullptr; ++i) {
             const int c = hw.crnn_ch[i];
             float* out = take((size_t)c * (H / 2) * (W / 2));
             conv3x3_kernel<true><<<ew_grid(n * (c / kOCT) * (H / 2) * (W / 2), sm_count), 256, 0, st>>>(
@@ -350,11 +364,13 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
             x = out; cin = c; H /= 2; W /= 2;
         }
         const int S = W, In = hw.gru_in, Hd = hw.gru_hidden, G3 = 3 * Hd;
-        float* seq = take((size_t)S * In);
+        float* seq = seq_direct ? seq_direct : take((size_t)S * In);
         float* gi_f = take((size_t)S * G3);
         float* gi_b = take((size_t)G3);
-        seq_pack_kernel<<<ew_grid(n * S * In, sm_count), 256, 0, st>>>(x, seq, n, cin, H, S);
-        if ((rc = done())) return rc;
+        if (!seq_direct) {
+            seq_pack_kernel<<<ew_grid(n * S * In, sm_count), 256, 0, st>>>(x, seq, n, cin, H, S);
+            if ((rc = done())) return rc;
+        }
         // input projections over rows (all S steps forward, the last step only backward), then the recurrence
         if (hw.gru_wih_f_kn && hw.gru_wih_b_kn) {
             const size_t rsm = rowgemm_smem_bytes(In);

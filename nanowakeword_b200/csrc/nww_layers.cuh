@@ -315,4 +315,70 @@ gru_kernel(const float* __restrict__ gi_f, const float* __restrict__ gi_b, const
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// CRNN third conv on the channel-last output of cnn2_stage_kernel: conv3x3(C -> Cout, pad 1) + folded BN + act +
+// MaxPool2d(2), written straight as the GRU input sequence (reference CRNNModel architectures.py:222-230, 272-276:
+// view (B, C*H, W) -> permute (B, W, C*H), i.e. feature index c * Ho + h at step w).
+// in [B][H*W][C]   w [C][9][Cout]   seq [B][Wo][Cout*Ho];  one thread = one pooled pixel x 8 output channels.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+crnn_conv3_seq_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                      float* __restrict__ seq, long long B, int C, int Cout, int H, int W, int act) {
+    const int Ho = H / 2, Wo = W / 2, groups = Cout / kOCT;
+    const long long total = B * Ho * Wo * groups;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(t % groups);
+        const long long pix = t / groups;
+        const int x = (int)(pix % Wo), y = (int)((pix / Wo) % Ho);
+        const long long b = pix / ((long long)Wo * Ho);
+        const float* src = in + b * (long long)H * W * C;
+        float acc[kOCT][4];
+#pragma unroll
+        for (int o = 0; o < kOCT; ++o) {
+            const float bv = __ldg(bias + g * kOCT + o);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[o][q] = bv;
+        }
+        for (int ic4 = 0; ic4 < C; ic4 += 4) {
+            float4 p[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int yy = 2 * y - 1 + r, xx = 2 * x - 1 + c;
+                    p[r][c] = (yy >= 0 && yy < H && xx >= 0 && xx < W)
+                                  ? __ldg(reinterpret_cast<const float4*>(src + ((long long)yy * W + xx) * C + ic4))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float* wk = w + ((long long)(ic4 + k) * 9) * Cout + g * kOCT;
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float4 wa = __ldg(reinterpret_cast<const float4*>(wk + (r * 3 + c) * Cout));
+                        const float4 wb = __ldg(reinterpret_cast<const float4*>(wk + (r * 3 + c) * Cout) + 1);
+                        const float wv[kOCT] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+                        auto comp = [&](const float4& v) { return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w; };
+                        const float i00 = comp(p[r][c]), i01 = comp(p[r][c + 1]), i10 = comp(p[r + 1][c]), i11 = comp(p[r + 1][c + 1]);
+#pragma unroll
+                        for (int o = 0; o < kOCT; ++o) {
+                            acc[o][0] = fmaf(i00, wv[o], acc[o][0]);
+                            acc[o][1] = fmaf(i01, wv[o], acc[o][1]);
+                            acc[o][2] = fmaf(i10, wv[o], acc[o][2]);
+                            acc[o][3] = fmaf(i11, wv[o], acc[o][3]);
+                        }
+                    }
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < kOCT; ++o) {
+            const float v = fmaxf(fmaxf(apply_act(acc[o][0], act), apply_act(acc[o][1], act)),
+                                  fmaxf(apply_act(acc[o][2], act), apply_act(acc[o][3], act)));
+            seq[(b * Wo + x) * (long long)(Cout * Ho) + (g * kOCT + o) * Ho + y] = v;
+        }
+    }
+}
+
 }  // namespace nww
