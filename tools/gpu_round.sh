@@ -9,6 +9,6 @@ done
 timeout 1200 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 timeout 600 python tools/quick_bench.py 4096 cnn,dnn > gpurun_out/quick_bench.log 2>&1
 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/bench.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-cnn2_stage} -s 4 -c 2 -f -o gpurun_out/prof python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-streams > gpurun_out/ncu_list.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-cnn2_stage} -s 4 -c 2 -f -o gpurun_out/prof python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-streams > gpurun_out/ncu_full.log 2>&1
 tail -4 gpurun_out/debug_cnn_v2.log; tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/quick_bench.log; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
