@@ -123,7 +123,7 @@ def run_reference_arm(args, rank, world):
         "note": "reference = pure-Python package on onnxruntime CPU (not installable offline); its per-window arithmetic "
                 "is timed through the oracle port on the host cores",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------- clocks
@@ -369,9 +369,28 @@ def run_gpu_arm(args, rank, world, local_rank):
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
         "streams": streams,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Keep stdout for the ONE JSON line: anything else that writes to fd 1 (NCCL's version banner, library
+    chatter) is sent to stderr for the duration of the run."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -387,6 +406,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
+        _quiet_stdout()
         run_reference_arm(args, rank, world)
         return
     if world != args.gpus and world == 1 and args.gpus > 1:
@@ -395,6 +415,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+    _quiet_stdout()
     run_gpu_arm(args, rank, world, local_rank)
 
 
