@@ -72,11 +72,7 @@ struct Cnn2Weights {
 
 // Stream mode: the log-mel of window w is read from the streams' mel ring (nww_stream_mel.cuh)
 // instead of being computed from PCM.  ring == nullptr selects the PCM path.
-struct Cnn2MelSource {
-    const float* ring;
-    const long long* count;     // per-stream sample counters (position of the window in the ring)
-    long long s0;               // stream index of window 0 of this launch
-};
+using Cnn2MelSource = MelRingRef;
 
 __device__ __forceinline__ uint32_t cnn2_pack_bf16(uint32_t lo16, uint32_t hi16) { return lo16 | (hi16 << 16); }
 

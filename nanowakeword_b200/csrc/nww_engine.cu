@@ -420,9 +420,12 @@ static int launch_stage_a(nww_engine* e, WindowSource pcm, int64_t n, float* mel
             }
             // fall through
         default:
+            if (from_ring && e->spec.arch == NWW_ARCH_TCN && e->heads.tcn_cone)     // the cone kernel reads the ring itself
+                return launch_head_stage_a(e->heads, e->tab64, e->spec.activation, e->sm_count, pcm, n, e->d_feat, e->d_scratch,
+                                           mel, st, &e->launches, &g_last_error, true, nullptr,
+                                           MelRingRef{e->d_mel_ring, e->streams.count, stream_s0});
             if (from_ring) {
-                const int tm = (e->spec.arch == NWW_ARCH_TCN && e->heads.tcn_cone) ? 1 : 0;   // the cone kernel reads (T, F) rows
-                stream_mel_gather_kernel<<<ew_grid(n * 3920, e->sm_count), 256, 0, st>>>(sub, ring0, e->d_scratch, tm);
+                stream_mel_gather_kernel<<<ew_grid(n * 3920, e->sm_count), 256, 0, st>>>(sub, ring0, e->d_scratch, 0);
                 e->launches++;
                 NWW_CUDA(cudaGetLastError());
             }

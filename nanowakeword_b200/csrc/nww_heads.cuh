@@ -223,7 +223,8 @@ inline int setup_head_weights(int arch, int geometry, const BlobLookup& get, con
 inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<double>& tab, int act, int sm_count,
                                WindowSource pcm, long long n, float* feat, float* scratch, float* mel_dump,
                                cudaStream_t st, int64_t* launches, std::string* err, bool mel_ready = false,
-                               const float* conv2_nhwc = nullptr /* CRNN: conv1 + conv2 output of cnn2_stage_kernel */) {
+                               const float* conv2_nhwc = nullptr /* CRNN: conv1 + conv2 output of cnn2_stage_kernel */,
+                               MelRingRef ring = MelRingRef{nullptr, nullptr, 0} /* TCN cone in stream mode */) {
     // mel_ready: the caller already placed the (n, F, T) log-mel at the start of `scratch` (stream mode)
     float* p = scratch;
     auto take = [&](size_t floats_per_window) {
@@ -267,7 +268,7 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
         const size_t smem = tcn_cone_smem_bytes(P);
         NWW_HCUDA(set_smem(tcn_cone_kernel, smem));
         const long long tiles = (n + P.wt - 1) / P.wt;
-        tcn_cone_kernel<<<(int)std::min<long long>(tiles, sm_count), kTcnNT, smem, st>>>(mel, (long long)F * T, n, P, feat);
+        tcn_cone_kernel<<<(int)std::min<long long>(tiles, sm_count), kTcnNT, smem, st>>>(mel, (long long)F * T, ring, n, P, feat);
         return done();
     }
     if (!mel_ready && !conv2_nhwc && (rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel, 0, st, launches, err))) return rc;

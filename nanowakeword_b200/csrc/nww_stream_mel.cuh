@@ -33,6 +33,14 @@ struct SMel {
     static constexpr size_t kTotal = kScratch + kTw + kPcm;
 };
 
+// Where a launch finds the log-mel of its windows in stream mode: window w of the launch is stream s0 + w.
+// ring == nullptr means "not in stream mode".
+struct MelRingRef {
+    const float* ring;
+    const long long* count;     // per-stream sample counters (position of the window in the ring)
+    long long s0;
+};
+
 __device__ __forceinline__ int smel_slot(long long a) {
     int r = (int)(a % SMel::T);
     return r < 0 ? r + SMel::T : r;

@@ -21,6 +21,7 @@
 #pragma once
 
 #include "nww_common.cuh"
+#include "nww_stream_mel.cuh"
 
 #ifndef NWW_CPUSIM
 #ifndef NWW_DYN_SMEM
@@ -233,8 +234,8 @@ inline size_t tcn_cone_smem_bytes(const TcnConeParams& P) {
 // mel_tm: time-major log-mel, window w at mel_tm + w * mel_win_stride, frame t at + t * c_in (only the last n_in
 // frames are read).  feat: [n][C_last].
 __global__ void __launch_bounds__(kTcnNT, 1)
-tcn_cone_kernel(const float* __restrict__ mel_tm, long long mel_win_stride, long long n_windows, TcnConeParams P,
-                float* __restrict__ feat) {
+tcn_cone_kernel(const float* __restrict__ mel_tm, long long mel_win_stride, MelRingRef ring, long long n_windows,
+                TcnConeParams P, float* __restrict__ feat) {
     NWW_DYN_SMEM(smem);
     float* wbuf = reinterpret_cast<float*>(smem);                       // [2][kTcnWBuf]
     float* act = wbuf + 2 * kTcnWBuf;
@@ -246,9 +247,21 @@ tcn_cone_kernel(const float* __restrict__ mel_tm, long long mel_win_stride, long
         __syncthreads();
         // the last n_in frames of each window, [pos][mel] rows
         const int n_in_f = P.n_in * P.c_in;
-        for (int i = tid; i < nw * n_in_f; i += kTcnNT) {
-            const int w = i / n_in_f, r = i - w * n_in_f;
-            act[(size_t)w * pw + P.off_in + r] = mel_tm[(w0 + w) * mel_win_stride + (size_t)(P.T - P.n_in) * P.c_in + r];
+        if (ring.ring != nullptr) {
+            // stream mode: straight out of the mirrored mel ring ([mel][2 T] rows, window = T slots from `head`)
+            for (int i = tid; i < nw * n_in_f; i += kTcnNT) {
+                const int w = i / n_in_f, r = i - w * n_in_f;
+                const int pos = r % P.n_in, m = r / P.n_in;            // consecutive threads walk the time axis
+                const long long s = ring.s0 + w0 + w;
+                const int head = smel_slot(ring.count[s] / SMel::HOP - 3 + 1);
+                act[(size_t)w * pw + P.off_in + pos * P.c_in + m] =
+                    ring.ring[s * SMel::STREAM_FLOATS + m * SMel::ROW + head + (P.T - P.n_in) + pos];
+            }
+        } else {
+            for (int i = tid; i < nw * n_in_f; i += kTcnNT) {
+                const int w = i / n_in_f, r = i - w * n_in_f;
+                act[(size_t)w * pw + P.off_in + r] = mel_tm[(w0 + w) * mel_win_stride + (size_t)(P.T - P.n_in) * P.c_in + r];
+            }
         }
         __syncthreads();
         const float* x = act + P.off_in;

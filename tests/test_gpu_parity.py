@@ -237,3 +237,25 @@ def test_cuda_core_variants_match_golden(torch_cuda, golden_frontend, mt, kw):
     g = load_golden_head(mt)
     scores = eng.score_device(torch_cuda.from_numpy(golden_frontend["pcm"]).cuda()).cpu().numpy()
     assert np.abs(scores - g["scores64"].ravel()).max() < SCORE_TOL
+
+
+def test_single_stream_with_chunks_longer_than_the_clip(torch_cuda, golden_frontend):
+    """One stream, chunks of 20000 samples (> clip_samples): only the last 16000 samples of a chunk
+    matter (nanointerpreter.py:751-756: the deque drops the rest), the counter passes clip_samples on the
+    first push, and the score is the batch score of that tail."""
+    from nanowakeword_b200 import StreamBank
+    from oracle.interp import OracleInterpreter
+    eng, sd, cfg = _engine("cnn")
+    g = golden_frontend["pcm"]
+    audio = np.concatenate([g[0], g[1], g[4], g[5], g[6]])[:80000]
+    bank = StreamBank(eng, 1)
+    oracle = OracleInterpreter(sd, cfg, name="m")
+    for s in range(4):
+        chunk = audio[s * 20000:(s + 1) * 20000]
+        got = bank.push(chunk[None, :])
+        want = oracle.predict(chunk)["m"]
+        assert abs(got[0] - want) < SCORE_TOL
+        assert abs(bank.raw_scores[0] - oracle.raw_scores["m"]) < SCORE_TOL
+        tail = eng.score_host(np.ascontiguousarray(chunk[-16000:][None, :]))
+        assert abs(bank.raw_scores[0] - tail[0]) < 1e-6
+    bank.close()
