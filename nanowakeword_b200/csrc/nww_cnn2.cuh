@@ -111,7 +111,7 @@ cnn2_stage_kernel(WindowSource src, Cnn2MelSource msrc, long long n_windows, Fro
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, D::TMEM_COLS);
-    fe2_build_twiddles(tw, tab.twiddle, tid, D::NT);
+    fe2_build_tables(tw, tab, tid, D::NT);
     fe3_build_window(win_s, tab.window, tid, D::NT);
     for (int i = tid; i < 16 * 9; i += D::NT) w1s[i] = wt.w1[i];
     for (int i = tid; i < 16; i += D::NT) b1s[i] = wt.b1[i];

@@ -149,6 +149,7 @@ static void fill_tables(nww_engine* e, const HostFrontendTables& h, FrontendTabl
     t.mel_w = reinterpret_cast<const float*>(e->arena.add(h.mel_w.data(), h.mel_w.size() * sizeof(float)));
     t.amin = 1e-10f;
     t.floor_db = -100.0f;            // 10*log10(1e-10)
+    t.mel_vec_ok = h.mel_vec_ok;
 }
 
 template <typename T> static void rebase_tables(FrontendTables<T>* t, unsigned char* base) {

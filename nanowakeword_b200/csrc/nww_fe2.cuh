@@ -38,7 +38,12 @@ struct Fe2 {
     static constexpr int N_FFT_TOTAL = 49, N_BATCH = 25;       // 98 frames = 49 packed FFTs = 24.5 batches of two
     static constexpr size_t kWorkBytes = (size_t)NGROUP * NFB * NPAD * sizeof(cplx<double>);   // 66560
     static constexpr size_t kPowBytes = (size_t)2 * NGROUP * NFB * 2 * PW_PITCH * sizeof(float);   // 33792 (double-buffered)
-    static constexpr size_t kTwBytes = (size_t)(7 * 64 + 7 * 8) * sizeof(cplx<double>);        // 8064
+    static constexpr int N_TW = 7 * 64 + 7 * 8;                // twiddle entries
+    static constexpr int MEL_ROW = 36;                         // padded filter row (32 weights + 4 to spread banks)
+    static constexpr int MEL_MAX = 40;
+    // "tables" block in shared memory: twiddles | padded mel weights [40][36] | per-filter (first bin, groups of 4)
+    static constexpr size_t kTwBytes = (size_t)N_TW * sizeof(cplx<double>) + (size_t)MEL_MAX * MEL_ROW * sizeof(float) +
+                                       (size_t)MEL_MAX * 2 * sizeof(int);                      // 14144
     static constexpr size_t kScratchBytes = kWorkBytes + kPowBytes;                            // reusable between windows
 };
 
@@ -54,13 +59,67 @@ __device__ __forceinline__ double fe2_i16_to_f64(int16_t v) {
 #endif
 }
 
-// Twiddle tables in shared memory, built once per CTA from the engine's exp(-2 pi i k / 512) table:
+// Tables in shared memory, built once per CTA.  Twiddles from the engine's exp(-2 pi i k / 512) table:
 //   tw1[(q-1) * 64 + j]  = W512^(j q)      (pass 1, j = 0..63)
 //   tw2[(q-1) * 8 + j2]  = W512^(8 j2 q)   (pass 2, j2 = 0..7)
-__device__ __forceinline__ void fe2_build_twiddles(cplx<double>* tw_smem, const cplx<double>* __restrict__ tw512, int tid,
-                                                   int nthreads) {
+// Mel filters for the vectorised dot product: filter m starts at bin ks and has cnt weights; its padded row holds
+// the weights of bins [ks & ~3, ...) in groups of four (zeros outside the filter), so power and weights are both
+// read as aligned 128-bit shared loads.
+__device__ __forceinline__ void fe2_build_tables(cplx<double>* tw_smem, const FrontendTables<double>& tab, int tid,
+                                                 int nthreads) {
+    const cplx<double>* __restrict__ tw512 = tab.twiddle;
     for (int i = tid; i < 7 * 64; i += nthreads) tw_smem[i] = tw512[((i & 63) * ((i >> 6) + 1)) & 511];
     for (int i = tid; i < 7 * 8; i += nthreads) tw_smem[7 * 64 + i] = tw512[(8 * (i & 7) * ((i >> 3) + 1)) & 511];
+    float* wpad = reinterpret_cast<float*>(tw_smem + Fe2::N_TW);
+    int* meta = reinterpret_cast<int*>(wpad + Fe2::MEL_MAX * Fe2::MEL_ROW);
+    if (tab.mel_vec_ok) {
+        for (int i = tid; i < GeoNS40x98::N_MELS * Fe2::MEL_ROW; i += nthreads) {
+            const int m = i / Fe2::MEL_ROW, j = i - m * Fe2::MEL_ROW;
+            const int ks = tab.mel_start[m], cnt = tab.mel_count[m];
+            const int bin = (ks & ~3) + j;
+            wpad[i] = (bin >= ks && bin < ks + cnt) ? tab.mel_w[tab.mel_woff[m] + bin - ks] : 0.0f;
+        }
+        for (int m = tid; m < GeoNS40x98::N_MELS; m += nthreads) {
+            const int ks = tab.mel_start[m], cnt = tab.mel_count[m];
+            meta[2 * m] = ks & ~3;
+            meta[2 * m + 1] = cnt ? ((ks & 3) + cnt + 3) >> 2 : 0;
+        }
+    }
+}
+
+// sum_k w_m[k] P[k] for filter m over one frame's power row (16-byte aligned, bins >= 257 must read as finite).
+// The summation order is part of the contract between the two front ends (fe2 / fe3): the stream mel ring must
+// be bit-identical to recomputing a window.
+__device__ __forceinline__ float fe2_mel_dot(const float* __restrict__ prow, int m, const cplx<double>* __restrict__ tw_smem,
+                                             const FrontendTables<double>& tab) {
+    if (tab.mel_vec_ok) {
+        const float* wpad = reinterpret_cast<const float*>(tw_smem + Fe2::N_TW);
+        const int* meta = reinterpret_cast<const int*>(wpad + Fe2::MEL_MAX * Fe2::MEL_ROW);
+        const int k0 = meta[2 * m], n4 = meta[2 * m + 1];
+        const float4* __restrict__ p4 = reinterpret_cast<const float4*>(prow + k0);
+        const float4* __restrict__ w4 = reinterpret_cast<const float4*>(wpad + m * Fe2::MEL_ROW);
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+        for (int g = 0; g < n4; ++g) {
+            const float4 p = p4[g], w = w4[g];
+            a0 = fmaf(w.x, p.x, a0);
+            a1 = fmaf(w.y, p.y, a1);
+            a2 = fmaf(w.z, p.z, a2);
+            a3 = fmaf(w.w, p.w, a3);
+        }
+        return (a0 + a1) + (a2 + a3);
+    }
+    const int ks = __ldg(tab.mel_start + m);
+    const int cnt = __ldg(tab.mel_count + m);
+    const float* __restrict__ w = tab.mel_w + __ldg(tab.mel_woff + m);
+    const float* __restrict__ p = prow + ks;
+    float acc0 = 0.0f, acc1 = 0.0f;
+    int i = 0;
+    for (; i + 1 < cnt; i += 2) {
+        acc0 = fmaf(__ldg(w + i), p[i], acc0);
+        acc1 = fmaf(__ldg(w + i + 1), p[i + 1], acc1);
+    }
+    if (i < cnt) acc0 = fmaf(__ldg(w + i), p[i], acc0);
+    return acc0 + acc1;
 }
 
 // A batch = up to four consecutive frames (hop 160) = two packed FFTs.  `x` points at sample 0 of the
@@ -111,18 +170,7 @@ __device__ __forceinline__ void fe2_run(int n_batches, BatchFn batch_of, StoreFn
             const int oct = slot >> 3;
             const int m = ((oct == 0) ? 32 : (oct == 1) ? 24 : (oct == 2) ? 0 : (oct == 3) ? 16 : 8) + (slot & 7);
             if (fr >= mb_frames) continue;
-            const int ks = __ldg(tab.mel_start + m);
-            const int cnt = __ldg(tab.mel_count + m);
-            const float* __restrict__ w = tab.mel_w + __ldg(tab.mel_woff + m);
-            const float* __restrict__ p = p0 + fr * Fe2::PW_PITCH + ks;
-            float acc0 = 0.0f, acc1 = 0.0f;
-            int i = 0;
-            for (; i + 1 < cnt; i += 2) {
-                acc0 = fmaf(__ldg(w + i), p[i], acc0);
-                acc1 = fmaf(__ldg(w + i + 1), p[i + 1], acc1);
-            }
-            if (i < cnt) acc0 = fmaf(__ldg(w + i), p[i], acc0);
-            const float pm = acc0 + acc1;
+            const float pm = fe2_mel_dot(p0 + fr * Fe2::PW_PITCH, m, tw_smem, tab);
             store(mb, fr, m, (pm <= tab.amin) ? tab.floor_db : 10.0f * log10f(pm));
         }
     };
@@ -206,6 +254,9 @@ __device__ __forceinline__ void fe2_run(int n_batches, BatchFn batch_of, StoreFn
                 const double ar = 2.0 * A[4].x, br = 2.0 * A[4].y;
                 pwa[256] = (float)(ar * ar);
                 pwb[256] = (float)(br * br);
+            } else if (c < 8) {                // the padded mel rows read a few bins past Nyquist: keep them finite
+                pwa[256 + c] = 0.0f;
+                pwb[256 + c] = 0.0f;
             }
           }
         } else if (b_prev >= 0) {
@@ -233,40 +284,6 @@ __device__ __forceinline__ void fe2_logmel_window(const int16_t* __restrict__ pc
             return Fe2Batch{pcm + 4 * b * GeoNS40x98::HOP, left < 4 ? left : 4};
         },
         [&](int b, int fr, int m, float db) { mel[m * stride_m + (4 * b + fr) * stride_t] = db; }, scratch, tw_smem, tab, tid);
-}
-
-// ----------------------------------------------------------------------------------------
-// Front end only (NS40x98): log-mel to global memory, (F, T) or (T, F) per window.
-// ----------------------------------------------------------------------------------------
-struct Fe2KernelSmem {
-    static constexpr size_t kScratch = (Fe2::kScratchBytes + 127) / 128 * 128;
-    static constexpr size_t kTw = (Fe2::kTwBytes + 127) / 128 * 128;
-    static constexpr size_t kTotal = kScratch + kTw + PcmStager<GeoNS40x98::CLIP>::kBytes;
-};
-
-__global__ void __launch_bounds__(Fe2::NT, 1)
-frontend2_kernel(WindowSource src, long long n_windows, FrontendTables<double> tab,
-                 float* __restrict__ mel_out, int time_major) {
-    using G = GeoNS40x98;
-    NWW_DYN_SMEM(smem);
-    const int tid = threadIdx.x;
-    cplx<double>* tw = reinterpret_cast<cplx<double>*>(smem + Fe2KernelSmem::kScratch);
-    PcmStager<G::CLIP> stager;
-    stager.carve(smem + Fe2KernelSmem::kScratch + Fe2KernelSmem::kTw);
-    stager.init(tid);
-    fe2_build_twiddles(tw, tab.twiddle, tid, Fe2::NT);
-    __syncthreads();
-
-    const int stride_m = time_major ? 1 : G::N_FRAMES;
-    const int stride_t = time_major ? G::N_MELS : 1;
-    long long w = blockIdx.x;
-    if (w < n_windows) stager.issue(0, src.at(w), tid);
-    for (int it = 0; w < n_windows; w += gridDim.x, ++it) {
-        const long long wn = w + gridDim.x;
-        if (wn < n_windows) stager.issue((it + 1) & 1, src.at(wn), tid);
-        const int16_t* x = stager.wait(it & 1, (it >> 1) & 1, src.at(w));
-        fe2_logmel_window(x, smem, tw, tab, mel_out + w * (long long)(G::N_MELS * G::N_FRAMES), stride_m, stride_t, tid);
-    }
 }
 
 }  // namespace nww

@@ -130,6 +130,9 @@ __device__ __forceinline__ void fe3_warp_fft(const int16_t* __restrict__ x, cplx
     if (lane == 0) {
         pwa[256] = pa_v[8];
         pwb[256] = pb_v[8];
+    } else if (lane < 8) {                                       // the padded mel rows read a few bins past Nyquist
+        pwa[256 + lane] = 0.0f;
+        pwb[256 + lane] = 0.0f;
     }
     __syncwarp();
     // ---- mel + dB: 40 filters x 2 frames over 32 lanes, widest filters first -------------------------------------
@@ -139,18 +142,7 @@ __device__ __forceinline__ void fe3_warp_fft(const int16_t* __restrict__ x, cplx
         if (slot >= GeoNS40x98::N_MELS) break;
         const int fr = lane & 1;
         const int m = GeoNS40x98::N_MELS - 1 - slot;
-        const int ks = __ldg(tab.mel_start + m);
-        const int cnt = __ldg(tab.mel_count + m);
-        const float* __restrict__ w = tab.mel_w + __ldg(tab.mel_woff + m);
-        const float* __restrict__ p = pwa + fr * Fe2::PW_PITCH + ks;
-        float acc0 = 0.0f, acc1 = 0.0f;
-        int i = 0;
-        for (; i + 1 < cnt; i += 2) {
-            acc0 = fmaf(__ldg(w + i), p[i], acc0);
-            acc1 = fmaf(__ldg(w + i + 1), p[i + 1], acc1);
-        }
-        if (i < cnt) acc0 = fmaf(__ldg(w + i), p[i], acc0);
-        const float pm = acc0 + acc1;
+        const float pm = fe2_mel_dot(pwa + fr * Fe2::PW_PITCH, m, tw_smem, tab);
         store(fr, m, (pm <= tab.amin) ? tab.floor_db : 10.0f * log10f(pm));
     }
     __syncwarp();                                                // the buffer is free for the warp's next FFT
@@ -196,7 +188,7 @@ frontend3_kernel(WindowSource src, long long n_windows, FrontendTables<double> t
     PcmStager<G::CLIP> stager;
     stager.carve(smem + Fe3::kWorkBytes + Fe3::kWinBytes + Fe3::kTwBytes);
     stager.init(tid);
-    fe2_build_twiddles(tw, tab.twiddle, tid, Fe3::NT);
+    fe2_build_tables(tw, tab, tid, Fe3::NT);
     fe3_build_window(win_s, tab.window, tid, Fe3::NT);
     __syncthreads();
 

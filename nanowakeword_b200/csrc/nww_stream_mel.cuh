@@ -53,7 +53,7 @@ stream_mel_update_kernel(StreamState st, float* __restrict__ mel_ring, FrontendT
     const int tid = threadIdx.x;
     cplx<double>* tw = reinterpret_cast<cplx<double>*>(smem + SMel::kScratch);
     int16_t* pcm_s = reinterpret_cast<int16_t*>(smem + SMel::kScratch + SMel::kTw);
-    fe2_build_twiddles(tw, tab.twiddle, tid, Fe2::NT);
+    fe2_build_tables(tw, tab, tid, Fe2::NT);
     const int nbps = (n_new + 3) >> 2;                              // batches per stream
     const int n_samp = SMel::HOP * (n_new - 1) + GeoNS40x98::WIN;   // samples the new frames span
     const int w_off = st.R - SMel::HOP * (n_new + 2);               // their offset inside the stream's current window

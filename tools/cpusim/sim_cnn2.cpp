@@ -37,7 +37,7 @@ int main(int argc, char** argv) {
     std::vector<double> ws(h.window_scaled.begin(), h.window_scaled.end()), wu(h.window_unscaled.begin(), h.window_unscaled.end());
     std::vector<cplx<double>> tw(512);
     for (int i = 0; i < 512; ++i) tw[i] = {h.tw_re[i], h.tw_im[i]};
-    FrontendTables<double> tab{ws.data(), wu.data(), tw.data(), h.binpos.data(), h.mel_start.data(), h.mel_count.data(), h.mel_woff.data(), h.mel_w.data(), 1e-10f, -100.0f};
+    FrontendTables<double> tab{ws.data(), wu.data(), tw.data(), h.binpos.data(), h.mel_start.data(), h.mel_count.data(), h.mel_woff.data(), h.mel_w.data(), 1e-10f, -100.0f, h.mel_vec_ok};
 
     // conv2 weights as UMMA operands (same code as nww_create)
     const float* w2 = b.f32("cnn.w2");

@@ -34,7 +34,7 @@ template <typename T, typename G, int NFB> void run(const std::string& dir) {
     std::vector<cplx<T>> tw(G::N_FFT);
     for (int i = 0; i < G::N_FFT; ++i) tw[i] = {(T)h.tw_re[i], (T)h.tw_im[i]};
     FrontendTables<T> tab{ws.data(), wu.data(), tw.data(), h.binpos.data(), h.mel_start.data(), h.mel_count.data(),
-                          h.mel_woff.data(), h.mel_w.data(), 1e-10f, -100.0f};
+                          h.mel_woff.data(), h.mel_w.data(), 1e-10f, -100.0f, h.mel_vec_ok};
     std::vector<float> mel((size_t)nw * G::N_MELS * G::N_FRAMES, -7777.f);
     constexpr int NT = 128;
     cudasim::launch(dim3(2), dim3(NT), FrontendSmem<T, G, NFB>::kTotal, [&] {

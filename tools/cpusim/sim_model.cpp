@@ -31,7 +31,7 @@ template <typename T, typename G> struct Tabs {
         if (!build_frontend_tables(G::N_FFT, G::WIN, G::N_MELS, rad, G::N_PASS, b.f32("frontend.window"), b.f32("frontend.fb"), &h, &err)) { fprintf(stderr, "%s\n", err.c_str()); exit(1); }
         ws.assign(h.window_scaled.begin(), h.window_scaled.end()); wu.assign(h.window_unscaled.begin(), h.window_unscaled.end());
         tw.resize(G::N_FFT); for (int i = 0; i < G::N_FFT; ++i) tw[i] = {(T)h.tw_re[i], (T)h.tw_im[i]};
-        dev = FrontendTables<T>{ws.data(), wu.data(), tw.data(), h.binpos.data(), h.mel_start.data(), h.mel_count.data(), h.mel_woff.data(), h.mel_w.data(), 1e-10f, -100.0f};
+        dev = FrontendTables<T>{ws.data(), wu.data(), tw.data(), h.binpos.data(), h.mel_start.data(), h.mel_count.data(), h.mel_woff.data(), h.mel_w.data(), 1e-10f, -100.0f, h.mel_vec_ok};
     }
 };
 
