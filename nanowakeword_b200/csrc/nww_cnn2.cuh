@@ -126,10 +126,15 @@ cnn2_stage_kernel(WindowSource src, Cnn2MelSource msrc, long long n_windows, Fro
     const uint32_t a1_addr = smem_u32(a1b), w2_addr = smem_u32(w2s);
     constexpr uint32_t kIdesc = umma_idesc_bf16(128, 32);
 
-    // One elected thread issues the 108 MMAs of M tile `tile` (4 quads x 9 taps x 3 split products).
+    // One elected thread issues the 108 MMAs of M tile `tile` (4 quads x 9 taps x 3 split products).  Every
+    // descriptor is a kernel-constant base plus a compile-time multiple of 16 bytes in the start-address field,
+    // so the issue loop is one 64-bit add per operand.
+    const uint64_t da_base = umma_desc_noswz(a1_addr, D::KG_BYTES, 128);
+    const uint64_t db_base = umma_desc_noswz(w2_addr, 512, 128);
     auto issue_tile = [&](int tile) {
         tc_fence_after();
-#pragma unroll 1
+        const uint64_t da_t = da_base + (uint64_t)(tile * 128);               // 128 positions x 16 B, in 16-byte units
+#pragma unroll
         for (int quad = 0; quad < 4; ++quad) {
             const int dy = quad >> 1, dx = quad & 1;
             const uint32_t d_tmem = tmem_base + (uint32_t)((tile * 4 + quad) * 32);
@@ -139,15 +144,11 @@ cnn2_stage_kernel(WindowSource src, Cnn2MelSource msrc, long long n_windows, Fro
                 for (int c = 0; c < 3; ++c) {
                     const int ry = dy + r - 1, cx = dx + c - 1;
                     const int plane = ((ry & 1) << 1) | (cx & 1);
-                    const int s0 = tile * 128 + 26 + 25 * (ry >> 1) + (cx >> 1);
-                    const uint32_t a_hi = a1_addr + (uint32_t)(plane * 2 * D::PLANE_BYTES + s0 * 16);
-                    const uint32_t a_lo = a_hi + D::PLANE_BYTES;
-                    const uint32_t b_hi = w2_addr + (uint32_t)((r * 3 + c) * 2 * D::W2_TAP_BYTES);
-                    const uint32_t b_lo = b_hi + D::W2_TAP_BYTES;
-                    const uint64_t da_hi = umma_desc_noswz(a_hi, D::KG_BYTES, 128);
-                    const uint64_t da_lo = umma_desc_noswz(a_lo, D::KG_BYTES, 128);
-                    const uint64_t db_hi = umma_desc_noswz(b_hi, 512, 128);
-                    const uint64_t db_lo = umma_desc_noswz(b_lo, 512, 128);
+                    const int s0 = 26 + 25 * (ry >> 1) + (cx >> 1);
+                    const uint64_t da_hi = da_t + (uint64_t)((plane * 2 * D::PLANE_BYTES) / 16 + s0);
+                    const uint64_t da_lo = da_hi + (uint64_t)(D::PLANE_BYTES / 16);
+                    const uint64_t db_hi = db_base + (uint64_t)(((r * 3 + c) * 2 * D::W2_TAP_BYTES) / 16);
+                    const uint64_t db_lo = db_hi + (uint64_t)(D::W2_TAP_BYTES / 16);
                     umma_bf16(d_tmem, da_hi, db_hi, kIdesc, (r | c) != 0);
                     umma_bf16(d_tmem, da_lo, db_hi, kIdesc, 1);
                     umma_bf16(d_tmem, da_hi, db_lo, kIdesc, 1);
