@@ -139,7 +139,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=open(self.path, "w"),
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=open(self.path, "w"),
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None

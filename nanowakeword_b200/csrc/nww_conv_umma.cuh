@@ -1,0 +1,261 @@
+// nww_conv_umma.cuh — 3x3 convolution (pad 1, stride 1) + bias + activation (+ 2x2 max pool) on channel-last
+// activations as a tcgen05 implicit GEMM with NO im2col, for small images that fit one CTA:
+//   E2E mel-CNN body: conv2 16 -> 32 on 32 x 50 (+pool), conv3 32 -> 64 on 16 x 25   (architectures.py:840-856)
+//   CRNN: conv3 32 -> 32 on 10 x 24 (+pool)                                               (architectures.py:222-230)
+// BatchNorm is folded into weights / bias by the packer.
+//
+// Same scheme as conv2 of nww_cnn2.cuh, generalised.  One window per CTA iteration:
+//   * the window's input [H][W][Cin] (FP32, global) is converted to bf16 hi / lo and stored as zero-bordered
+//     position lists, 16 bytes (8 channels) per position and K group:
+//       no pool: one plane,   s = (y + 1) * P + (x + 1),              P = W + 2,     GEMM row m = y * P + x
+//       pool:    four parity planes (y & 1, x & 1), s = ((y >> 1) + 1) * P + (x >> 1) + 1, P = W / 2 + 2,
+//                GEMM row m = ph * P + pw, one accumulator per pooling quad;
+//   * the A operand of a tap is that plane behind a descriptor whose start address is shifted by whole positions
+//     (K-major, un-swizzled: SBO = 128 B, LBO = plane K-group stride);
+//   * weights arrive pre-split from the engine: [tap][hi|lo][K group][Cout][8 ic] bf16;
+//   * per 128-row tile: (quads) x 9 taps x (Cin / 16) x 3 split products of tcgen05.mma 128 x Cout x 16, FP32
+//     accumulation in TMEM; epilogue = bias, activation, (max over the four quads), channel-last FP32 store.
+#pragma once
+
+#include <string.h>
+#include <vector>
+
+#include "nww_tc.cuh"
+
+#ifndef NWW_CPUSIM
+#ifndef NWW_DYN_SMEM
+#define NWW_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
+#endif
+#endif
+
+namespace nww {
+
+constexpr int kCuNT = 256;
+
+struct ConvUmmaPlan {
+    int H, W, Cin, Cout, pool;
+    int P;            // position pitch
+    int rows;         // GEMM rows that hold real outputs: (pool ? H/2 : H) * P
+    int tiles;        // 128-row tiles
+    int npos;         // positions allocated per plane and K group
+    int planes;       // 1 or 4
+    int kg;           // Cin / 8
+    int tmem_cols;    // power of two >= tiles * quads * Cout
+    size_t a_bytes, b_bytes, smem_bytes;
+};
+
+inline bool conv_umma_plan(int H, int W, int Cin, int Cout, int pool, ConvUmmaPlan* p) {
+    p->H = H; p->W = W; p->Cin = Cin; p->Cout = Cout; p->pool = pool;
+    if (Cin % 16 || Cout % 16 || Cout > 64 || (pool && ((H | W) & 1))) return false;
+    const int Ho = pool ? H / 2 : H;
+    p->P = (pool ? W / 2 : W) + 2;
+    p->rows = Ho * p->P;
+    p->tiles = (p->rows + 127) / 128;
+    p->planes = pool ? 4 : 1;
+    p->kg = Cin / 8;
+    p->npos = p->tiles * 128 + 2 * p->P + 8;
+    const int cols = p->tiles * (pool ? 4 : 1) * Cout;
+    if (cols > 512) return false;
+    p->tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+    p->a_bytes = (size_t)p->planes * 2 * p->kg * p->npos * 16;
+    p->b_bytes = (size_t)9 * 2 * p->kg * Cout * 16;
+    p->smem_bytes = p->a_bytes + p->b_bytes + Cout * sizeof(float) + 128;
+    return p->smem_bytes <= 220 * 1024;
+}
+
+// host: folded (Cin, 9, Cout) FP32 weights -> [tap][hi|lo][K group][Cout][8] bf16
+inline void conv_umma_pack_weights(const float* w, int Cin, int Cout, std::vector<uint16_t>* out) {
+    auto bf16_rn = [](float x) {
+        uint32_t u;
+        memcpy(&u, &x, 4);
+        u += 0x7FFFu + ((u >> 16) & 1u);
+        return (uint16_t)(u >> 16);
+    };
+    auto bf16_f = [](uint16_t b) {
+        uint32_t u = (uint32_t)b << 16;
+        float f;
+        memcpy(&f, &u, 4);
+        return f;
+    };
+    const size_t op = (size_t)(Cin / 8) * Cout * 8;              // elements per (tap, hi|lo) operand
+    out->assign((size_t)9 * 2 * op, 0);
+    for (int ic = 0; ic < Cin; ++ic)
+        for (int tap = 0; tap < 9; ++tap)
+            for (int oc = 0; oc < Cout; ++oc) {
+                const float v = w[((size_t)ic * 9 + tap) * Cout + oc];
+                const uint16_t hi = bf16_rn(v), lo = bf16_rn(v - bf16_f(hi));
+                const size_t base = (size_t)tap * 2 * op + (size_t)(ic >> 3) * Cout * 8 + (size_t)oc * 8 + (ic & 7);
+                (*out)[base] = hi;
+                (*out)[base + op] = lo;
+            }
+}
+
+// in [n][H*W][Cin] -> out [n][Ho*Wo][Cout]  (Ho, Wo = H/2, W/2 with pool)
+__global__ void __launch_bounds__(kCuNT, 1)
+conv3x3_umma_kernel(const float* __restrict__ in, const uint4* __restrict__ wq, const float* __restrict__ bias,
+                    float* __restrict__ out, long long n_windows, ConvUmmaPlan P, int act) {
+    NWW_DYN_SMEM(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned char* a_s = smem;
+    unsigned char* b_s = smem + P.a_bytes;
+    float* bias_s = reinterpret_cast<float*>(smem + P.a_bytes + P.b_bytes);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + P.a_bytes + P.b_bytes + P.Cout * sizeof(float));
+    bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bar) + 7) & ~(uintptr_t)7);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+    for (int i = tid; i < (int)(P.a_bytes / 16); i += kCuNT) reinterpret_cast<uint4*>(a_s)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < (int)(P.b_bytes / 16); i += kCuNT) reinterpret_cast<uint4*>(b_s)[i] = __ldg(wq + i);
+    for (int i = tid; i < P.Cout; i += kCuNT) bias_s[i] = bias[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t lbo_a = (uint32_t)P.npos * 16, lbo_b = (uint32_t)P.Cout * 16;
+    const uint32_t plane_bytes = (uint32_t)P.kg * lbo_a;            // one (plane, hi|lo)
+    const uint32_t bop_bytes = (uint32_t)P.kg * lbo_b;              // one (tap, hi|lo)
+    const uint64_t da_base = umma_desc_noswz(smem_u32(a_s), lbo_a, 128);
+    const uint64_t db_base = umma_desc_noswz(smem_u32(b_s), lbo_b, 128);
+    const uint32_t idesc = umma_idesc_bf16(128, P.Cout);
+    const int quads = P.pool ? 4 : 1;
+    const int Ho = P.pool ? P.H / 2 : P.H, Wo = P.pool ? P.W / 2 : P.W;
+    uint32_t phase = 0;
+
+    for (long long w = blockIdx.x; w < n_windows; w += gridDim.x) {
+        // ---- input window -> bf16 hi / lo position lists ------------------------------------------------------------
+        const float* src = in + w * (long long)P.H * P.W * P.Cin;
+        for (int i = tid; i < P.H * P.W * P.kg; i += kCuNT) {
+            const int g = i % P.kg, pix = i / P.kg;
+            const int y = pix / P.W, x = pix - y * P.W;
+            const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + (size_t)pix * P.Cin + 8 * g));
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + (size_t)pix * P.Cin + 8 * g) + 1);
+            const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            uint32_t h[8], l[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                h[k] = float_to_bf16_bits(v[k]);
+                l[k] = float_to_bf16_bits(v[k] - bf16_bits_to_float(h[k]));
+            }
+            int plane, s;
+            if (P.pool) {
+                plane = ((y & 1) << 1) | (x & 1);
+                s = ((y >> 1) + 1) * P.P + (x >> 1) + 1;
+            } else {
+                plane = 0;
+                s = (y + 1) * P.P + x + 1;
+            }
+            unsigned char* dst = a_s + (size_t)plane * 2 * plane_bytes + (size_t)g * lbo_a + (size_t)s * 16;
+            *reinterpret_cast<uint4*>(dst) = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+            *reinterpret_cast<uint4*>(dst + plane_bytes) =
+                make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        // ---- MMAs ----------------------------------------------------------------------------------------------------
+        if (tid == 0) {
+            tc_fence_after();
+            for (int t = 0; t < P.tiles; ++t)
+                for (int quad = 0; quad < quads; ++quad) {
+                    const int dy = quad >> 1, dx = quad & 1;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)((t * quads + quad) * P.Cout);
+                    bool first = true;
+                    for (int r = 0; r < 3; ++r)
+                        for (int c = 0; c < 3; ++c) {
+                            int plane, s0;
+                            if (P.pool) {
+                                const int ry = dy + r - 1, cx = dx + c - 1;
+                                plane = ((ry & 1) << 1) | (cx & 1);
+                                s0 = t * 128 + (1 + (ry >> 1)) * P.P + 1 + (cx >> 1);
+                            } else {
+                                plane = 0;
+                                s0 = t * 128 + r * P.P + c;
+                            }
+                            const uint64_t a_hi = da_base + (uint64_t)(((size_t)plane * 2 * plane_bytes) / 16 + s0);
+                            const uint64_t a_lo = a_hi + (uint64_t)(plane_bytes / 16);
+                            const uint64_t b_hi = db_base + (uint64_t)(((size_t)(r * 3 + c) * 2 * bop_bytes) / 16);
+                            const uint64_t b_lo = b_hi + (uint64_t)(bop_bytes / 16);
+                            for (int kh = 0; kh < P.Cin / 16; ++kh) {          // 16 channels = 2 K groups per MMA
+                                const uint64_t ao = (uint64_t)(2 * kh * lbo_a / 16), bo = (uint64_t)(2 * kh * lbo_b / 16);
+                                umma_bf16(d_tmem, a_hi + ao, b_hi + bo, idesc, first ? 0u : 1u);
+                                umma_bf16(d_tmem, a_lo + ao, b_hi + bo, idesc, 1);
+                                umma_bf16(d_tmem, a_hi + ao, b_lo + bo, idesc, 1);
+                                first = false;
+                            }
+                        }
+                }
+            umma_commit(bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        // ---- epilogue: warp -> TMEM lane quarter; tasks (tile, 16-column chunk) dealt to the two warps of a quarter ----
+        {
+            const int q = warp & 3, sub = warp >> 2;                 // 8 warps: two per quarter
+            const int chunks = P.Cout / 16;
+            float* dst_w = out + w * (long long)Ho * Wo * P.Cout;
+            for (int task = sub; task < P.tiles * chunks; task += 2) {
+                const int t = task / chunks, ch = task - t * chunks;
+                uint32_t r[4][16];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * quads * P.Cout + ch * 16);
+                tmem_ld_32x32b_x16_nowait(taddr, r[0]);
+                if (P.pool) {
+                    tmem_ld_32x32b_x16_nowait(taddr + P.Cout, r[1]);
+                    tmem_ld_32x32b_x16_nowait(taddr + 2 * P.Cout, r[2]);
+                    tmem_ld_32x32b_x16_nowait(taddr + 3 * P.Cout, r[3]);
+                }
+                tmem_ld_wait();
+                const int m = t * 128 + q * 32 + lane;
+                const int py = m / P.P, px = m - py * P.P;
+                if (py < Ho && px < Wo) {
+                    float v[16];
+#pragma unroll
+                    for (int o = 0; o < 16; ++o) {
+                        const float b = bias_s[ch * 16 + o];
+                        float x0 = apply_act(__uint_as_float(r[0][o]) + b, act);
+                        if (P.pool) {
+                            x0 = fmaxf(x0, apply_act(__uint_as_float(r[1][o]) + b, act));
+                            x0 = fmaxf(x0, apply_act(__uint_as_float(r[2][o]) + b, act));
+                            x0 = fmaxf(x0, apply_act(__uint_as_float(r[3][o]) + b, act));
+                        }
+                        v[o] = x0;
+                    }
+                    float4* d4 = reinterpret_cast<float4*>(dst_w + ((size_t)py * Wo + px) * P.Cout + ch * 16);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+            }
+            tc_fence_before();
+        }
+        __syncthreads();          // TMEM and the position lists are free again
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+    }
+}
+
+// AdaptiveAvgPool2d((1, OW)) in its deployed AvgPool2d form (_export/onnx.py:139-147) on channel-last input:
+// in [B][H*W][C] -> out [B][C*OW]  (feature index c * OW + j, the reference's flatten of (C, 1, OW))
+__global__ void __launch_bounds__(256)
+avgpool_row_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, long long B, int C, int H, int W, int OW) {
+    const int sw = W / OW, kw = W - (OW - 1) * sw;
+    const long long total = B * C * OW;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(t % C);
+        const int j = (int)((t / C) % OW);
+        const long long b = t / ((long long)C * OW);
+        const float* src = in + b * (long long)H * W * C + c;
+        float s = 0.0f;
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < kw; ++x) s += __ldg(src + ((long long)y * W + j * sw + x) * C);
+        out[b * (long long)C * OW + c * OW + j] = s / (float)(H * kw);
+    }
+}
+
+}  // namespace nww

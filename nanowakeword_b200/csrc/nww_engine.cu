@@ -86,6 +86,7 @@ struct nww_engine {
     float* d_nhwc = nullptr;                          // [chunk][7680] channel-last conv2 output for that path
     uint4* d_w2_umma = nullptr;
     void* d_bc_wq[3] = {nullptr, nullptr, nullptr};   // BcResNet 1x1 weights as bf16 UMMA operands
+    void* d_conv_wq[3] = {nullptr, nullptr, nullptr}; // 3x3 conv weights as bf16 UMMA operands (E2E mel-CNN, CRNN conv3)
     Cnn2Weights cnn2{};
     CUtensorMap tm_xhi{}, tm_xlo{}, tm_whi{}, tm_wlo{};
     TailParams tail_rest{};                           // layers 1.. (after the tensor-core layer)
@@ -550,6 +551,19 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
                 if (rc) return rc;
                 e->crnn_cnn2 = true;
             }
+            if (spec->arch == NWW_ARCH_E2E_MELCNN && !(spec->reserved[0] & 1)) {
+                // conv2 (16 -> 32 on 32 x 50, pool) and conv3 (32 -> 64 on 16 x 25) as tcgen05 implicit GEMMs
+                const int cin[3] = {1, 16, 32}, cout[3] = {16, 32, 64}, hh[3] = {64, 32, 16}, ww[3] = {101, 50, 25}, pool[3] = {1, 1, 0};
+                bool ok = true;
+                for (int j = 1; j <= 2; ++j) ok = ok && conv_umma_plan(hh[j], ww[j], cin[j], cout[j], pool[j], &e->heads.e2e_plan[j]);
+                for (int j = 1; j <= 2 && ok; ++j) {
+                    std::vector<uint16_t> wq;
+                    conv_umma_pack_weights(e->blob.f32("e2e.conv" + std::to_string(j) + ".w"), cin[j], cout[j], &wq);
+                    NWW_CUDA(cudaMalloc(&e->d_conv_wq[j], wq.size() * sizeof(uint16_t)));
+                    NWW_CUDA(cudaMemcpy(e->d_conv_wq[j], wq.data(), wq.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+                    e->heads.e2e_wq[j] = reinterpret_cast<const uint4*>(e->d_conv_wq[j]);
+                }
+            }
             if (spec->arch == NWW_ARCH_BCRESNET && !(spec->reserved[0] & 1)) {
                 // pointwise + shortcut weights as pre-split bf16 UMMA operands (reserved[0] bit 0 keeps the FP32 row GEMM)
                 const int ch[4] = {32, 64, 128, 256};
@@ -675,6 +689,7 @@ void nww_destroy(nww_engine* e) {
     cudaFree(e->d_w2_umma);
     cudaFree(e->d_nhwc);
     for (int j = 0; j < 3; ++j) cudaFree(e->d_bc_wq[j]);
+    for (int j = 0; j < 3; ++j) cudaFree(e->d_conv_wq[j]);
     cudaFree(e->d_pcm[0]);
     cudaFree(e->d_pcm[1]);
     cudaFree(e->d_scores);

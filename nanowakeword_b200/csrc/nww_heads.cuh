@@ -16,6 +16,7 @@
 #include "nww_tcn.cuh"
 #include "nww_bc.cuh"
 #include "nww_rowgemm.cuh"
+#include "nww_conv_umma.cuh"
 
 namespace nww {
 
@@ -47,6 +48,11 @@ struct HeadWeights {
     const float *gru_wih_f_kn = nullptr, *gru_wih_b_kn = nullptr;    // [In][3H] copies for the row GEMM (preferred)
     // E2E mel-CNN
     ConvW e2e_conv[3];
+    const uint4* e2e_wq[3] = {nullptr, nullptr, nullptr};    // conv2 / conv3 weights as bf16 UMMA operands (index 1, 2)
+    ConvUmmaPlan e2e_plan[3];
+    // CRNN conv3 on the same kernel
+    const uint4* crnn_wq3 = nullptr;
+    ConvUmmaPlan crnn_plan3;
     // scratch layout (floats per window)
     size_t scratch_floats = 0;
 };
@@ -245,6 +251,22 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
         float* a2 = take(32 * 16 * 25);
         float* a3 = take(64 * 16 * 25);
         if ((rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel, 0, st, launches, err))) return rc;
+        if (hw.e2e_wq[1] && hw.e2e_wq[2]) {
+            // channel-last pipeline: conv1 (FP32, pool) -> conv2 (tcgen05, pool) -> conv3 (tcgen05) -> avg pool
+            bc_init_conv_kernel<<<ew_grid(n * 2 * 32 * 50, sm_count), 256, 0, st>>>(mel, hw.e2e_conv[0].w, hw.e2e_conv[0].b, a1, n, 64, 101, 16, act);
+            if ((rc = done())) return rc;
+            for (int j = 1; j <= 2; ++j) {
+                const ConvUmmaPlan& P = hw.e2e_plan[j];
+                NWW_HCUDA(set_smem(conv3x3_umma_kernel, P.smem_bytes));
+                conv3x3_umma_kernel<<<(int)std::min<long long>(n, sm_count), kCuNT, P.smem_bytes, st>>>(
+                    j == 1 ? a1 : a2, hw.e2e_wq[j], hw.e2e_conv[j].b, j == 1 ? a2 : a3, n, P, act);
+                if ((rc = done())) return rc;
+            }
+            avgpool_row_nhwc_kernel<<<ew_grid(n * 256, sm_count), 256, 0, st>>>(a3, feat, n, 64, 16, 25, 4);
+            if ((rc = done())) return rc;
+            if (mel_dump) NWW_HCUDA(cudaMemcpyAsync(mel_dump, mel, (size_t)n * 64 * 101 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            return NWW_OK;
+        }
         conv3x3_kernel<true><<<ew_grid(n * 2 * 32 * 50, sm_count), 256, 0, st>>>(mel, hw.e2e_conv[0].w, hw.e2e_conv[0].b, a1, n, 1, 16, 64, 101, act);
         if ((rc = done())) return rc;
         conv3x3_kernel<true><<<ew_grid(n * 4 * 16 * 25, sm_count), 256, 0, st>>>(a1, hw.e2e_conv[1].w, hw.e2e_conv[1].b, a2, n, 16, 32, 32, 50, act);

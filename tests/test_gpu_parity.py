@@ -259,3 +259,19 @@ def test_single_stream_with_chunks_longer_than_the_clip(torch_cuda, golden_front
         tail = eng.score_host(np.ascontiguousarray(chunk[-16000:][None, :]))
         assert abs(bank.raw_scores[0] - tail[0]) < 1e-6
     bank.close()
+
+
+@pytest.mark.parametrize("act", ["gelu", "silu"])
+@pytest.mark.parametrize("mt", ["cnn", "dnn", "bcresnet", "crnn", "e2e_dnn"])
+def test_other_activations_match_oracle(torch_cuda, mt, act):
+    """model.py:81-87 lets a model use GELU (exact erf) or SiLU instead of ReLU; the fused kernels carry the
+    activation as a template / runtime code, so every variant is held to the oracle."""
+    from nanowakeword_b200 import Engine
+    from oracle.heads import forward_scores
+    cfg = default_config(mt, activation_function=act)
+    sd = make_state_dict(cfg, seed=1)
+    eng = Engine(sd, cfg, device=0)
+    pcm = np.concatenate([synth_pcm(24, seed=31, kind="gauss"), synth_pcm(8, seed=32, kind="uniform")])
+    ref = forward_scores(pcm, sd, cfg).ravel()
+    got = eng.score_device(torch_cuda.from_numpy(pcm).cuda()).cpu().numpy()
+    assert np.abs(got - ref).max() < SCORE_TOL, (mt, act, np.abs(got - ref).max())
