@@ -102,8 +102,10 @@ conv3x3_umma_kernel(const float* __restrict__ in, const uint4* __restrict__ wq, 
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + P.a_bytes + P.b_bytes + P.Cout * sizeof(float));
     bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bar) + 7) & ~(uintptr_t)7);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    const int n_acc = P.tiles * (P.pool ? 4 : 1);                  // accumulators = (tile, quad) pairs
+    const int n_issuers = n_acc < 4 ? n_acc : 4;                   // lane 0 of warps 0..3 each issue the MMAs of their accumulators
     if (tid == 0) {
-        mbar_init(bar, 1);
+        mbar_init(bar, (uint32_t)n_issuers);
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
@@ -156,10 +158,11 @@ conv3x3_umma_kernel(const float* __restrict__ in, const uint4* __restrict__ wq, 
         tc_fence_before();
         __syncthreads();
         // ---- MMAs ----------------------------------------------------------------------------------------------------
-        if (tid == 0) {
+        if (lane == 0 && warp < n_issuers) {
             tc_fence_after();
-            for (int t = 0; t < P.tiles; ++t)
-                for (int quad = 0; quad < quads; ++quad) {
+            for (int acc = warp; acc < n_acc; acc += n_issuers) {
+                const int t = acc / quads, quad = acc - t * quads;
+                {
                     const int dy = quad >> 1, dx = quad & 1;
                     const uint32_t d_tmem = tmem_base + (uint32_t)((t * quads + quad) * P.Cout);
                     bool first = true;
@@ -187,6 +190,7 @@ conv3x3_umma_kernel(const float* __restrict__ in, const uint4* __restrict__ wq, 
                             }
                         }
                 }
+            }
             umma_commit(bar);
         }
         mbar_wait(bar, phase);

@@ -550,6 +550,13 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
                                         e->heads.crnn_conv[0].b, e->heads.crnn_conv[1].b);
                 if (rc) return rc;
                 e->crnn_cnn2 = true;
+                if (conv_umma_plan(10, 24, e->heads.crnn_ch[1], e->heads.crnn_ch[2], 1, &e->heads.crnn_plan3)) {
+                    std::vector<uint16_t> wq;
+                    conv_umma_pack_weights(e->blob.f32("crnn.conv2.w"), e->heads.crnn_ch[1], e->heads.crnn_ch[2], &wq);
+                    NWW_CUDA(cudaMalloc(&e->d_conv_wq[0], wq.size() * sizeof(uint16_t)));
+                    NWW_CUDA(cudaMemcpy(e->d_conv_wq[0], wq.data(), wq.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+                    e->heads.crnn_wq3 = reinterpret_cast<const uint4*>(e->d_conv_wq[0]);
+                }
             }
             if (spec->arch == NWW_ARCH_E2E_MELCNN && !(spec->reserved[0] & 1)) {
                 // conv2 (16 -> 32 on 32 x 50, pool) and conv3 (32 -> 64 on 16 x 25) as tcgen05 implicit GEMMs

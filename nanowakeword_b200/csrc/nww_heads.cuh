@@ -207,7 +207,7 @@ inline int setup_head_weights(int arch, int geometry, const BlobLookup& get, con
         *feat_dim = 2 * H;
         // mel + conv activations + seq [w][gru_in] + gi_f [w][3H] + gi_b [3H]
         hw->scratch_floats = 3920 + act_floats + (size_t)w * hw->gru_in + (size_t)w * 3 * H + 3 * H;
-        if (hw->crnn_cnn2) hw->scratch_floats = 3920 + 7680 + (size_t)w * hw->gru_in + (size_t)w * 3 * H + 3 * H;
+        if (hw->crnn_cnn2) hw->scratch_floats = 3920 + 7680 + 2 * (size_t)w * hw->gru_in + (size_t)w * 3 * H + 3 * H;
         if (gru_smem_bytes(H) > 200 * 1024) { *err = "GRU hidden size too large for shared memory"; return NWW_EUNSUPPORTED; }
     } else if (arch == NWW_ARCH_E2E_MELCNN) {
         if (geometry != NWW_GEOM_REF64X101) { *err = "e2e mel-CNN is built for the REF64x101 geometry"; return NWW_EUNSUPPORTED; }
@@ -373,9 +373,21 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
         if (conv2_nhwc != nullptr) {
             // conv1 + conv2 already done by cnn2_stage_kernel (channel-last, 10 x 24 x 32): third conv -> sequence
             seq_direct = take((size_t)S0 * In0);
-            crnn_conv3_seq_kernel<<<ew_grid(n * 5 * 12 * (hw.crnn_ch[2] / kOCT), sm_count), 256, 0, st>>>(
-                conv2_nhwc, hw.crnn_conv[2].w, hw.crnn_conv[2].b, seq_direct, n, hw.crnn_ch[1], hw.crnn_ch[2], 10, 24, act);
-            if ((rc = done())) return rc;
+            if (hw.crnn_wq3 != nullptr) {
+                // third conv on tcgen05 (nww_conv_umma.cuh), then the (c, h) -> feature repack
+                float* a3 = take((size_t)S0 * In0);
+                const ConvUmmaPlan& P = hw.crnn_plan3;
+                NWW_HCUDA(set_smem(conv3x3_umma_kernel, P.smem_bytes));
+                conv3x3_umma_kernel<<<(int)std::min<long long>(n, sm_count), kCuNT, P.smem_bytes, st>>>(
+                    conv2_nhwc, hw.crnn_wq3, hw.crnn_conv[2].b, a3, n, P, act);
+                if ((rc = done())) return rc;
+                seq_pack_nhwc_kernel<<<ew_grid(n * S0 * In0, sm_count), 256, 0, st>>>(a3, seq_direct, n, hw.crnn_ch[2], 5, 12);
+                if ((rc = done())) return rc;
+            } else {
+                crnn_conv3_seq_kernel<<<ew_grid(n * 5 * 12 * (hw.crnn_ch[2] / kOCT), sm_count), 256, 0, st>>>(
+                    conv2_nhwc, hw.crnn_conv[2].w, hw.crnn_conv[2].b, seq_direct, n, hw.crnn_ch[1], hw.crnn_ch[2], 10, 24, act);
+                if ((rc = done())) return rc;
+            }
             cin = hw.crnn_ch[2]; H = 5; W = 12;
         }
         for (int i = 0; i < hw.crnn_levels && conv2_nhwc == nullptr; ++i) {

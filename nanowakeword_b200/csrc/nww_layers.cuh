@@ -381,4 +381,17 @@ crnn_conv3_seq_kernel(const float* __restrict__ in, const float* __restrict__ w,
     }
 }
 
+// channel-last pooled conv output [B][Ho*Wo][C] -> GRU sequence [B][Wo][C*Ho] (feature index c * Ho + h at step w)
+__global__ void __launch_bounds__(256)
+seq_pack_nhwc_kernel(const float* __restrict__ a, float* __restrict__ seq, long long B, int C, int Ho, int Wo) {
+    const long long total = B * C * Ho * Wo;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int x = (int)((i / C) % Wo);
+        const int y = (int)((i / ((long long)C * Wo)) % Ho);
+        const long long b = i / ((long long)C * Wo * Ho);
+        seq[(b * Wo + x) * (long long)(C * Ho) + c * Ho + y] = a[i];
+    }
+}
+
 }  // namespace nww
