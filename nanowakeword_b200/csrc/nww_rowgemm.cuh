@@ -45,7 +45,7 @@ rowgemm_kernel(const float* __restrict__ A, long long a_row_mul, long long a_row
 // feat [B][2H] = [h_fwd(S-1) | h_bwd(first step)].  gh = h W_hh^T + b_hh is the row GEMM above per step.
 // ---------------------------------------------------------------------------------------
 constexpr int kGru2TM = 32;
-inline size_t gru2_smem_bytes(int Hd) { return sizeof(float) * ((size_t)2 * kTcnWBuf + (size_t)kGru2TM * Hd * 4); }
+inline size_t gru2_smem_bytes(int Hd) { return sizeof(float) * ((size_t)2 * kTcnWBuf + (size_t)kGru2TM * Hd * 7); }
 
 __global__ void __launch_bounds__(kTcnNT, 1)
 gru2_kernel(const float* __restrict__ gi_f, const float* __restrict__ gi_b, const float* __restrict__ whh,
@@ -54,6 +54,7 @@ gru2_kernel(const float* __restrict__ gi_f, const float* __restrict__ gi_b, cons
     float* wbuf = reinterpret_cast<float*>(smem);
     float* h = wbuf + 2 * kTcnWBuf;                       // [TM][Hd]
     float* gh = h + (size_t)kGru2TM * Hd;                 // [TM][3Hd]
+    float* gis = gh + (size_t)kGru2TM * 3 * Hd;           // [TM][3Hd] this step's input projections, fetched behind the GEMM
     const int tid = threadIdx.x;
     const int G = 3 * Hd;
     for (long long w0 = (long long)blockIdx.x * kGru2TM; w0 < B; w0 += (long long)gridDim.x * kGru2TM) {
@@ -62,6 +63,12 @@ gru2_kernel(const float* __restrict__ gi_f, const float* __restrict__ gi_b, cons
         for (int i = tid; i < kGru2TM * Hd; i += kTcnNT) h[i] = 0.0f;
         __syncthreads();
         for (int s = 0; s < S; ++s) {
+            // gi of this step -> shared memory (cp.async; the row GEMM's own wait_group calls drain it)
+            for (int i = tid; i < mt * (G / 4); i += kTcnNT) {
+                const int m = i / (G / 4), c4 = i - m * (G / 4);
+                tcn_cp_async16(gis + (size_t)m * G + 4 * c4, gi_f + ((w0 + m) * S + s) * (long long)G + 4 * c4);
+            }
+            tcn_cp_commit();
             for (int n0 = 0; n0 < G; n0 += 128) {
                 const int nc = (G - n0 < 128) ? (G - n0) : 128;
                 tcn_layer_any(TcnLayerArgs{h, 0, 1, 0, Hd, Hd, whh + n0, bhh + n0, gh + n0, 0, nc, mt, 1, 0, nullptr, 0, 0, 0, G, G, 0, 0},
@@ -70,7 +77,7 @@ gru2_kernel(const float* __restrict__ gi_f, const float* __restrict__ gi_b, cons
             __syncthreads();
             for (int i = tid; i < mt * Hd; i += kTcnNT) {
                 const int m = i / Hd, j = i - m * Hd;
-                const float* gi = gi_f + ((w0 + m) * S + s) * (long long)G;
+                const float* gi = gis + (size_t)m * G;
                 const float* g = gh + m * G;
                 const float r = sigmoidf_acc(gi[j] + g[j]);
                 const float z = sigmoidf_acc(gi[Hd + j] + g[Hd + j]);

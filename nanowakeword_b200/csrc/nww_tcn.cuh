@@ -126,7 +126,9 @@ struct TcnLayerArgs {
 template <int RN, int ROWS>
 __device__ __forceinline__ void tcn_layer(const TcnLayerArgs& L, float* __restrict__ wbuf /* [2][kTcnWBuf] shared */, int tid) {
     const int tn = tid & 15, tm = tid >> 4;
-    const int oc0 = tn * RN;
+    // a thread's columns: group c4 (of 4 columns) starts at c4 * 64 + tn * 4 — the 16 lanes of a half-warp read 256
+    // contiguous bytes of a weight row per group, so the 128-bit shared loads are conflict-free for 64 and 128 columns
+    const int oc0 = tn * 4;
     const bool col_ok = oc0 < L.Cout;
     const int rows = L.n_win * L.n_pos;
     const int n_chunks = (L.K + kTcnKC - 1) / kTcnKC;
@@ -151,7 +153,10 @@ __device__ __forceinline__ void tcn_layer(const TcnLayerArgs& L, float* __restri
             const int w = r / L.n_pos, p = r - w * L.n_pos;
             aoff[i] = w * L.in_pitch + (L.in_mul * p + L.in_off) * L.Cin;
 #pragma unroll
-            for (int c = 0; c < RN; ++c) acc[i][c] = col_ok ? __ldg(L.bias + oc0 + c) : 0.0f;
+            for (int c = 0; c < RN; ++c) {
+                const int col = (c >> 2) * 64 + oc0 + (c & 3);
+                acc[i][c] = col < L.Cout ? __ldg(L.bias + col) : 0.0f;
+            }
         }
         // rows this warp really has (its two tm values differ by one row at most): the FMA blocks of the
         // other register rows are skipped, which is most of them in the small late layers
@@ -177,7 +182,7 @@ __device__ __forceinline__ void tcn_layer(const TcnLayerArgs& L, float* __restri
                     for (int q = 0; q < 4; ++q)
 #pragma unroll
                         for (int c4 = 0; c4 < RN / 4; ++c4) {
-                            const float4 t = *reinterpret_cast<const float4*>(wb + (kk + q) * L.Cout + 4 * c4);
+                            const float4 t = *reinterpret_cast<const float4*>(wb + (kk + q) * L.Cout + 64 * c4);
                             wv[q][4 * c4] = t.x; wv[q][4 * c4 + 1] = t.y; wv[q][4 * c4 + 2] = t.z; wv[q][4 * c4 + 3] = t.w;
                         }
 #pragma unroll
@@ -208,15 +213,20 @@ __device__ __forceinline__ void tcn_layer(const TcnLayerArgs& L, float* __restri
 #pragma unroll
                 for (int c = 0; c < RN; ++c)
                     v[c] = L.relu == 0 ? acc[i][c] : L.relu == 1 ? fmaxf(acc[i][c], 0.0f) : apply_act(acc[i][c], L.relu - 2);
-                if (L.res != nullptr) {
-                    const float* rr = L.res + (size_t)w * L.res_pitch + (size_t)(L.res_mul * p + L.res_off) * ldr + oc0;
-#pragma unroll
-                    for (int c = 0; c < RN; ++c) v[c] = L.res_relu ? fmaxf(v[c] + rr[c], 0.0f) : v[c] + rr[c];
-                }
+                const float* rr = L.res ? L.res + (size_t)w * L.res_pitch + (size_t)(L.res_mul * p + L.res_off) * ldr + oc0 : nullptr;
                 float* o = L.out + (size_t)w * L.out_pitch + (size_t)p * ldo + oc0;
 #pragma unroll
-                for (int c4 = 0; c4 < RN / 4; ++c4)
-                    reinterpret_cast<float4*>(o)[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+                for (int c4 = 0; c4 < RN / 4; ++c4) {
+                    if (64 * c4 + oc0 >= L.Cout) continue;
+                    if (rr != nullptr) {
+                        const float4 rv = *reinterpret_cast<const float4*>(rr + 64 * c4);
+                        const float r4[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            v[4 * c4 + c] = L.res_relu ? fmaxf(v[4 * c4 + c] + r4[c], 0.0f) : v[4 * c4 + c] + r4[c];
+                    }
+                    *reinterpret_cast<float4*>(o + 64 * c4) = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+                }
             }
         }
     }
