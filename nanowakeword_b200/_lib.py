@@ -75,6 +75,16 @@ def load_library(path: str | None = None) -> C.CDLL:
     if _lib is not None and path is None:
         return _lib
     p = path or LIB_PATH
+    if path is None and not os.path.exists(p):
+        # a fresh checkout: the library is a build product (git-ignored).  Build it if a compiler is here;
+        # there is still no fallback — without nvcc this raises.
+        try:
+            from .build import build
+            build(force=True, verbose=False)
+        except Exception as ex:
+            raise RuntimeError(
+                f"CUDA engine library not found at {p} and building it failed ({ex}). "
+                "nanowakeword_b200 has no CPU fallback.") from ex
     if not os.path.exists(p):
         raise RuntimeError(
             f"CUDA engine library not found at {p}. Build it with `python -m nanowakeword_b200.build` "

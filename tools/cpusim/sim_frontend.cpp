@@ -38,7 +38,7 @@ template <typename T, typename G, int NFB> void run(const std::string& dir) {
     std::vector<float> mel((size_t)nw * G::N_MELS * G::N_FRAMES, -7777.f);
     constexpr int NT = 128;
     cudasim::launch(dim3(2), dim3(NT), FrontendSmem<T, G, NFB>::kTotal, [&] {
-        frontend_kernel<T, G, NFB, NT>(pcm.data(), nw, tab, mel.data(), 0);
+        frontend_kernel<T, G, NFB, NT>(WindowSource{pcm.data(), nullptr, G::CLIP}, nw, tab, mel.data(), 0);
     });
     FILE* f = fopen((dir + "/mel.f32").c_str(), "wb");
     fwrite(mel.data(), sizeof(float), mel.size(), f);

@@ -66,7 +66,7 @@ int main(int argc, char** argv) {
         CnnWeights wt{b.f32("cnn.w1"), b.f32("cnn.b1"), b.f32("cnn.w2"), b.f32("cnn.b2")};
         feat.assign(nw * CnnDims<G>::FEAT, -7777.f); mel.assign(nw * 40 * 98, -7777.f);
         cudasim::launch(dim3(3), dim3(NT), CnnSmem<T, G, NFB>::kTotal, [&] {
-            cnn_stage_kernel<T, G, NFB, NT>(pcm.data(), nw, tabs.dev, wt, 0, feat.data(), mel.data());
+            cnn_stage_kernel<T, G, NFB, NT>(WindowSource{pcm.data(), nullptr, 16000}, nw, tabs.dev, wt, 0, feat.data(), mel.data());
         });
     } else { fprintf(stderr, "arch?\n"); return 1; }
     TailParams P = make_tail(b);
