@@ -31,6 +31,7 @@
 
 namespace nww {
 
+constexpr int kTcnKC = 32;            // weight rows per staged chunk of the row GEMM
 constexpr int kTcnMaxLevels = 4;
 constexpr int kTcnWTMax = 8;         // windows per CTA tile (upper bound; the plan picks what fits in shared memory)
 constexpr int kTcnNT = 256;
@@ -81,7 +82,7 @@ inline bool tcn_plan(TcnConeParams* P) {
     P->per_window = (off + 3) & ~3;
     P->wt = 0;
     for (int wt = kTcnWTMax; wt >= 1; --wt)
-        if (sizeof(float) * ((size_t)2 * 16 * 128 + (size_t)P->per_window * wt) <= (size_t)220 * 1024) {
+        if (sizeof(float) * ((size_t)2 * kTcnKC * 128 + (size_t)P->per_window * wt) <= (size_t)220 * 1024) {
             P->wt = wt;
             break;
         }
@@ -96,7 +97,6 @@ inline bool tcn_plan(TcnConeParams* P) {
 // registers across the whole K loop.
 //   post: relu ? max(., 0) : identity;  then, with res != nullptr,  max(. + res[w][p][oc], 0)
 //   (res rows have pitch res_pitch per window and Cout per position, positions res_mul * p + res_off).
-constexpr int kTcnKC = 16;            // weight rows per staged chunk
 constexpr int kTcnRows = 14;          // rows per thread at 4 columns (16 x 14 = 224 rows per pass); half of that at 8 columns
 constexpr int kTcnWBuf = kTcnKC * 128;   // floats per weight buffer (Cout <= 128)
 
