@@ -558,6 +558,14 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
                     e->heads.crnn_wq3 = reinterpret_cast<const uint4*>(e->d_conv_wq[0]);
                 }
             }
+            if (spec->arch == NWW_ARCH_CRNN_GRU && e->heads.gru_hidden == kGruTcH && e->heads.gru_wih_f_kn &&
+                !(spec->reserved[0] & 1)) {
+                std::vector<uint16_t> wq;                         // blob w_hh is (H, 3H) = [k][n]
+                gru_tc_pack_whh(e->blob.f32("crnn.gru.fwd.w_hh"), &wq);
+                NWW_CUDA(cudaMalloc(&e->d_conv_wq[1], wq.size() * sizeof(uint16_t)));
+                NWW_CUDA(cudaMemcpy(e->d_conv_wq[1], wq.data(), wq.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+                e->heads.gru_whh_q = reinterpret_cast<const uint4*>(e->d_conv_wq[1]);
+            }
             if (spec->arch == NWW_ARCH_E2E_MELCNN && !(spec->reserved[0] & 1)) {
                 // conv2 (16 -> 32 on 32 x 50, pool) and conv3 (32 -> 64 on 16 x 25) as tcgen05 implicit GEMMs
                 const int cin[3] = {1, 16, 32}, cout[3] = {16, 32, 64}, hh[3] = {64, 32, 16}, ww[3] = {101, 50, 25}, pool[3] = {1, 1, 0};

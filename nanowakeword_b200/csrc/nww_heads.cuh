@@ -46,6 +46,7 @@ struct HeadWeights {
     const float *gru_wih_b = nullptr, *gru_bih_b = nullptr, *gru_bhh_b = nullptr;
     const float *gru_wih_f_nk = nullptr, *gru_wih_b_nk = nullptr;    // [3H][In] copies for the dense kernel
     const float *gru_wih_f_kn = nullptr, *gru_wih_b_kn = nullptr;    // [In][3H] copies for the row GEMM (preferred)
+    const uint4* gru_whh_q = nullptr;                                // W_hh^T pre-split for gru_tc_kernel (H = 128)
     // E2E mel-CNN
     ConvW e2e_conv[3];
     const uint4* e2e_wq[3] = {nullptr, nullptr, nullptr};    // conv2 / conv3 weights as bf16 UMMA operands (index 1, 2)
@@ -417,6 +418,13 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
             rowgemm_kernel<<<(int)std::min<long long>((n + kRgRows - 1) / kRgRows, sm_count), kTcnNT, rsm, st>>>(
                 seq, S, S - 1, hw.gru_wih_b_kn, hw.gru_bih_b, gi_b, n, In, G3);
             if ((rc = done())) return rc;
+            if (hw.gru_whh_q != nullptr && Hd == kGruTcH) {
+                const size_t gsm = gru_tc_smem_bytes();
+                NWW_HCUDA(set_smem(gru_tc_kernel, gsm));
+                gru_tc_kernel<<<(int)std::min<long long>((n + kGruTcTM - 1) / kGruTcTM, (long long)sm_count), kGruTcNT, gsm, st>>>(
+                    gi_f, gi_b, hw.gru_whh_q, hw.gru_bhh_f, hw.gru_bhh_b, feat, n, S);
+                return done();
+            }
             const size_t gsm = gru2_smem_bytes(Hd);
             NWW_HCUDA(set_smem(gru2_kernel, gsm));
             gru2_kernel<<<(int)std::min<long long>((n + kGru2TM - 1) / kGru2TM, (long long)sm_count), kTcnNT, gsm, st>>>(

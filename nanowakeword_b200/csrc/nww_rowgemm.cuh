@@ -5,6 +5,10 @@
 // product h W_hh^T of every step.
 #pragma once
 
+#include <string.h>
+#include <vector>
+
+#include "nww_tc.cuh"
 #include "nww_tcn.cuh"
 
 namespace nww {
@@ -95,6 +99,177 @@ gru2_kernel(const float* __restrict__ gi_f, const float* __restrict__ gi_b, cons
             const float nn = tanhf(gi[2 * Hd + j] + r * __ldg(bhh_b + 2 * Hd + j));
             feat[(w0 + m) * (long long)(2 * Hd) + Hd + j] = (1.0f - z) * nn;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// GRU recurrence with the recurrent product on tcgen05 (default for H = 128).
+// Same contract as gru2_kernel.  One CTA = 32 windows = rows 0..31 of a 128-row MMA tile (rows 32..127 of the A
+// descriptor fall on whatever shared memory follows and produce accumulator rows nobody reads).  Per step:
+//   h (FP32, shared) -> bf16 hi / lo un-swizzled K-major operand [K group 16][32 rows][8]   (LBO 512 B, SBO 128 B)
+//   for each block of 128 gate columns: pre-split W_hh^T block (engine: [block][hi|lo][K group][128][8] bf16, 64 KB)
+//     -> shared; 8 K steps x 3 split products of tcgen05.mma 128 x 128 x 16 -> TMEM columns [128 nb, +128)
+//   TMEM lanes 0..31 -> gh in shared memory (warps 0 and 4), then the gate update by all 256 threads with this
+//   step's input projections (prefetched by cp.async while the MMAs ran).
+// ---------------------------------------------------------------------------------------
+constexpr int kGruTcH = 128, kGruTcTM = 32, kGruTcNT = 256;
+constexpr int kGruTcGhPitch = 3 * kGruTcH + 4;           // floats; +4 spreads the 32 row starts over the banks
+constexpr size_t kGruTcABytes = (size_t)2 * 16 * 512;    // hi, lo x 16 K groups x (32 rows x 16 B)
+constexpr size_t kGruTcBBytes = (size_t)2 * 16 * 128 * 16;   // hi, lo x 16 K groups x 128 columns x 16 B = 64 KB
+inline size_t gru_tc_smem_bytes() {
+    return kGruTcABytes + 4096 /* rows 32..127 of the last K group read past the operand */ + kGruTcBBytes +
+           sizeof(float) * ((size_t)kGruTcTM * kGruTcH + (size_t)kGruTcTM * kGruTcGhPitch + (size_t)kGruTcTM * 3 * kGruTcH) + 128;
+}
+
+// host: w_hh (H, 3H) = [k][n] FP32 -> [block 3][hi|lo][K group 16][n 128][8 k] bf16
+inline void gru_tc_pack_whh(const float* whh, std::vector<uint16_t>* out) {
+    auto bf16_rn = [](float x) {
+        uint32_t u;
+        memcpy(&u, &x, 4);
+        u += 0x7FFFu + ((u >> 16) & 1u);
+        return (uint16_t)(u >> 16);
+    };
+    auto bf16_f = [](uint16_t b) {
+        uint32_t u = (uint32_t)b << 16;
+        float f;
+        memcpy(&f, &u, 4);
+        return f;
+    };
+    const int H = kGruTcH, G = 3 * H;
+    const size_t op = (size_t)16 * 128 * 8;                 // elements per (block, hi|lo)
+    out->assign((size_t)3 * 2 * op, 0);
+    for (int k = 0; k < H; ++k)
+        for (int n = 0; n < G; ++n) {
+            const float v = whh[(size_t)k * G + n];
+            const uint16_t hi = bf16_rn(v), lo = bf16_rn(v - bf16_f(hi));
+            const int nb = n / 128, nn = n % 128;
+            const size_t base = (size_t)nb * 2 * op + (size_t)(k >> 3) * 128 * 8 + (size_t)nn * 8 + (k & 7);
+            (*out)[base] = hi;
+            (*out)[base + op] = lo;
+        }
+}
+
+__global__ void __launch_bounds__(kGruTcNT, 1)
+gru_tc_kernel(const float* __restrict__ gi_f, const float* __restrict__ gi_b, const uint4* __restrict__ whh_q,
+              const float* __restrict__ bhh, const float* __restrict__ bhh_b, float* __restrict__ feat, long long B, int S) {
+    constexpr int H = kGruTcH, G = 3 * H, TM = kGruTcTM;
+    NWW_DYN_SMEM(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned char* a_s = smem;                                            // [hi|lo][kg 16][32 rows][16 B]
+    unsigned char* b_s = smem + kGruTcABytes + 4096;
+    float* h = reinterpret_cast<float*>(b_s + kGruTcBBytes);              // [TM][H]
+    float* gh = h + TM * H;                                               // [TM][kGruTcGhPitch]
+    float* gis = gh + TM * kGruTcGhPitch;                                 // [TM][3H]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(gis + TM * G);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint64_t da_hi = umma_desc_noswz(smem_u32(a_s), 512, 128);
+    const uint64_t da_lo = da_hi + (uint64_t)((16 * 512) / 16);
+    const uint64_t db_hi = umma_desc_noswz(smem_u32(b_s), 128 * 16, 128);
+    const uint64_t db_lo = db_hi + (uint64_t)((16 * 128 * 16) / 16);
+    const uint32_t idesc = umma_idesc_bf16(128, 128);
+    uint32_t phase = 0;
+
+    for (long long w0 = (long long)blockIdx.x * TM; w0 < B; w0 += (long long)gridDim.x * TM) {
+        const int mt = (B - w0 < TM) ? (int)(B - w0) : TM;
+        __syncthreads();
+        for (int i = tid; i < TM * H; i += kGruTcNT) h[i] = 0.0f;
+        __syncthreads();
+        for (int s = 0; s < S; ++s) {
+            // this step's input projections -> shared memory, in flight during the MMAs
+            for (int i = tid; i < mt * (G / 4); i += kGruTcNT) {
+                const int m = i / (G / 4), c4 = i - m * (G / 4);
+                tcn_cp_async16(gis + (size_t)m * G + 4 * c4, gi_f + ((w0 + m) * S + s) * (long long)G + 4 * c4);
+            }
+            tcn_cp_commit();
+            // h -> bf16 hi / lo operand: thread = (row m, K group g)
+            for (int i = tid; i < TM * 16; i += kGruTcNT) {
+                const int g = i / TM, m = i - g * TM;
+                const float4 v0 = *reinterpret_cast<const float4*>(h + m * H + 8 * g);
+                const float4 v1 = *reinterpret_cast<const float4*>(h + m * H + 8 * g + 4);
+                const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                uint32_t hb[8], lb[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    hb[k] = float_to_bf16_bits(v[k]);
+                    lb[k] = float_to_bf16_bits(v[k] - bf16_bits_to_float(hb[k]));
+                }
+                unsigned char* dst = a_s + (size_t)g * 512 + (size_t)m * 16;
+                *reinterpret_cast<uint4*>(dst) = make_uint4(hb[0] | (hb[1] << 16), hb[2] | (hb[3] << 16), hb[4] | (hb[5] << 16), hb[6] | (hb[7] << 16));
+                *reinterpret_cast<uint4*>(dst + 16 * 512) =
+                    make_uint4(lb[0] | (lb[1] << 16), lb[2] | (lb[3] << 16), lb[4] | (lb[5] << 16), lb[6] | (lb[7] << 16));
+            }
+            for (int nb = 0; nb < 3; ++nb) {
+                // W_hh^T block nb (64 KB, L2-resident) -> shared
+                const uint4* src = whh_q + (size_t)nb * (kGruTcBBytes / 16);
+                for (int i = tid; i < (int)(kGruTcBBytes / 16); i += kGruTcNT) reinterpret_cast<uint4*>(b_s)[i] = __ldg(src + i);
+                fence_proxy_async();
+                tc_fence_before();
+                __syncthreads();
+                if (tid == 0) {
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(nb * 128);
+#pragma unroll
+                    for (int ks = 0; ks < H / 16; ++ks) {                 // 16 K = 2 K groups per MMA
+                        const uint64_t ao = (uint64_t)((2 * ks * 512) / 16), bo = (uint64_t)((2 * ks * 128 * 16) / 16);
+                        umma_bf16(d_tmem, da_hi + ao, db_hi + bo, idesc, ks != 0);
+                        umma_bf16(d_tmem, da_lo + ao, db_hi + bo, idesc, 1);
+                        umma_bf16(d_tmem, da_hi + ao, db_lo + bo, idesc, 1);
+                    }
+                    umma_commit(bar);
+                }
+                mbar_wait(bar, phase);                                    // the block's MMAs are done: b_s can be refilled
+                phase ^= 1;
+                tc_fence_after();
+            }
+            // TMEM lanes 0..31 (the 32 windows) -> gh; warps 0 and 4 own lane quarter 0, six 32-column loads each
+            if ((warp & 3) == 0) {
+                const int half = warp >> 2;
+                for (int c = half * 6; c < half * 6 + 6; ++c) {
+                    float v[32];
+                    tmem_ld_32x32b_x32(tmem_base + (uint32_t)(c * 32), v);
+                    float4* dst = reinterpret_cast<float4*>(gh + (size_t)lane * kGruTcGhPitch + c * 32);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+            }
+            tcn_cp_wait<0>();
+            tc_fence_before();
+            __syncthreads();
+            for (int i = tid; i < mt * H; i += kGruTcNT) {
+                const int m = i / H, j = i - m * H;
+                const float* gi = gis + (size_t)m * G;
+                const float* g = gh + (size_t)m * kGruTcGhPitch;
+                const float r = sigmoidf_acc(gi[j] + g[j] + __ldg(bhh + j));
+                const float z = sigmoidf_acc(gi[H + j] + g[H + j] + __ldg(bhh + H + j));
+                const float nn = tanhf(gi[2 * H + j] + r * (g[2 * H + j] + __ldg(bhh + 2 * H + j)));
+                h[m * H + j] = (1.0f - z) * nn + z * h[m * H + j];
+            }
+            __syncthreads();
+        }
+        for (int i = tid; i < mt * H; i += kGruTcNT) {
+            const int m = i / H, j = i - m * H;
+            feat[(w0 + m) * (long long)(2 * H) + j] = h[m * H + j];
+            const float* gi = gi_b + (w0 + m) * (long long)G;
+            const float r = sigmoidf_acc(gi[j] + __ldg(bhh_b + j));
+            const float z = sigmoidf_acc(gi[H + j] + __ldg(bhh_b + H + j));
+            const float nn = tanhf(gi[2 * H + j] + r * __ldg(bhh_b + 2 * H + j));
+            feat[(w0 + m) * (long long)(2 * H) + H + j] = (1.0f - z) * nn;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
     }
 }
 
