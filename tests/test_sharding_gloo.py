@@ -42,11 +42,12 @@ def _worker(rank, world, port, n_total, q):
         got = scorer.score_from_root(full if rank == 0 else None, n_total)
         start, count = partition(n_total, world, rank)
         got2 = scorer.score_resident(full[start:start + count], n_total)
+        got3 = scorer.score_from_root_pipelined(full if rank == 0 else None, n_total, n_chunks=4)
         if rank == 0:
             ref = _fake_score(full)
-            q.put((torch.equal(got, ref), torch.equal(got2, ref)))
+            q.put((torch.equal(got, ref), torch.equal(got2, ref) and torch.equal(got3, ref)))
         else:
-            assert got is None and got2 is None
+            assert got is None and got2 is None and got3 is None
     finally:
         dist.destroy_process_group()
 

@@ -25,6 +25,18 @@ for _ in range(5):
     out = sc.score_from_root(root, n)
 b.record(); torch.cuda.synchronize()
 ms = a.elapsed_time(b) / 5
+for _ in range(2):
+    out_p = sc.score_from_root_pipelined(root, n, n_chunks=8)
+torch.cuda.synchronize(); dist.barrier()
+a.record()
+for _ in range(5):
+    out_p = sc.score_from_root_pipelined(root, n, n_chunks=8)
+b.record(); torch.cuda.synchronize()
+ms_p = a.elapsed_time(b) / 5
+if rank == 0:
+    print(f"world {world}: pipelined (8 pieces, transfers on a side stream) {ms_p:.3f} ms = {n / ms_p * 1e3 / 1e6:.3f} M windows/s; "
+          f"identical: {bool(torch.equal(out_p, out))}")
+    assert torch.equal(out_p, out)
 if rank == 0:
     ref = eng.score_device(root)
     torch.cuda.synchronize()
