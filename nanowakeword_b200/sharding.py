@@ -84,7 +84,7 @@ class ShardedScorer:
         scores = self.score_local(local)
         return gather_scores(scores, n_total, self.rank, self.world)
 
-    def score_from_root_pipelined(self, pcm_root, n_total: int, n_chunks: int = 8):
+    def score_from_root_pipelined(self, pcm_root, n_total: int, n_chunks: int = 2):
         """Same result as :meth:`score_from_root`, with the ingest overlapped with compute: every rank's block is
         cut into ``n_chunks`` pieces; all transfers are queued on a side CUDA stream (rank ``0`` sends piece k of
         every block as one grouped NCCL call) and the engine scores piece k as soon as its event fires, while

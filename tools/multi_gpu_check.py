@@ -25,18 +25,19 @@ for _ in range(5):
     out = sc.score_from_root(root, n)
 b.record(); torch.cuda.synchronize()
 ms = a.elapsed_time(b) / 5
-for _ in range(2):
-    out_p = sc.score_from_root_pipelined(root, n, n_chunks=8)
-torch.cuda.synchronize(); dist.barrier()
-a.record()
-for _ in range(5):
-    out_p = sc.score_from_root_pipelined(root, n, n_chunks=8)
-b.record(); torch.cuda.synchronize()
-ms_p = a.elapsed_time(b) / 5
-if rank == 0:
-    print(f"world {world}: pipelined (8 pieces, transfers on a side stream) {ms_p:.3f} ms = {n / ms_p * 1e3 / 1e6:.3f} M windows/s; "
-          f"identical: {bool(torch.equal(out_p, out))}")
-    assert torch.equal(out_p, out)
+for pieces in (2, 4, 8):
+    for _ in range(2):
+        out_p = sc.score_from_root_pipelined(root, n, n_chunks=pieces)
+    torch.cuda.synchronize(); dist.barrier()
+    a.record()
+    for _ in range(5):
+        out_p = sc.score_from_root_pipelined(root, n, n_chunks=pieces)
+    b.record(); torch.cuda.synchronize()
+    ms_p = a.elapsed_time(b) / 5
+    if rank == 0:
+        print(f"world {world}: pipelined ({pieces} pieces, transfers on a side stream) {ms_p:.3f} ms = {n / ms_p * 1e3 / 1e6:.3f} M windows/s; "
+              f"identical: {bool(torch.equal(out_p, out))}")
+        assert torch.equal(out_p, out)
 if rank == 0:
     ref = eng.score_device(root)
     torch.cuda.synchronize()
