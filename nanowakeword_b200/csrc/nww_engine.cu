@@ -558,6 +558,26 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
                     e->heads.crnn_wq3 = reinterpret_cast<const uint4*>(e->d_conv_wq[0]);
                 }
             }
+            if (spec->arch == NWW_ARCH_TCN && e->heads.tcn_cone && !(spec->reserved[0] & 1)) {
+                // every layer of the cone on tcgen05: layer program + weights pre-split into the chunks the kernel eats
+                std::vector<TuHostLayer> hl;
+                int cin = e->heads.tcn_in;
+                for (int l = 0; l < e->heads.tcn_levels; ++l) {
+                    const std::string p = "tcn." + std::to_string(l);
+                    const int c = e->heads.tcn_ch[l];
+                    hl.push_back(TuHostLayer{e->blob.f32(p + ".conv1.w"), e->heads.tcn_c1[l].b, cin, 3, c});
+                    if (cin != c) hl.push_back(TuHostLayer{e->blob.f32(p + ".down.w"), e->heads.tcn_down[l].b, cin, 1, c});
+                    hl.push_back(TuHostLayer{e->blob.f32(p + ".conv2.w"), e->heads.tcn_c2[l].b, c, 3, c});
+                    cin = c;
+                }
+                std::vector<uint16_t> wq;
+                if (tcn_umma_build(e->heads.tcn_plan, hl, &e->heads.tcn_uplan, &wq)) {
+                    NWW_CUDA(cudaMalloc(&e->d_conv_wq[2], wq.size() * sizeof(uint16_t)));
+                    NWW_CUDA(cudaMemcpy(e->d_conv_wq[2], wq.data(), wq.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+                    e->heads.tcn_wq = reinterpret_cast<const uint4*>(e->d_conv_wq[2]);
+                    e->heads.tcn_umma = true;
+                }
+            }
             if (spec->arch == NWW_ARCH_CRNN_GRU && e->heads.gru_hidden == kGruTcH && e->heads.gru_wih_f_kn &&
                 !(spec->reserved[0] & 1)) {
                 std::vector<uint16_t> wq;                         // blob w_hh is (H, 3H) = [k][n]

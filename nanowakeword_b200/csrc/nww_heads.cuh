@@ -14,6 +14,7 @@
 #include "nww_stage.cuh"
 #include "nww_tail.cuh"
 #include "nww_tcn.cuh"
+#include "nww_tcn_umma.cuh"
 #include "nww_bc.cuh"
 #include "nww_rowgemm.cuh"
 #include "nww_conv_umma.cuh"
@@ -35,6 +36,9 @@ struct HeadWeights {
     bool crnn_cnn2 = false;           // conv1 + conv2 through cnn2_stage_kernel (default channel counts 16, 32, 32)
     bool tcn_cone = false;            // fused dependency-cone kernel (nww_tcn.cuh) instead of the layer kernels
     TcnConeParams tcn_plan{};
+    bool tcn_umma = false;            // ... with the layer GEMMs on tcgen05 (nww_tcn_umma.cuh)
+    TcnUmmaParams tcn_uplan{};
+    const uint4* tcn_wq = nullptr;
     // BcResNet
     ConvW bc_init, bc_pw[3], bc_sc[3];
     const float* bc_dw[3] = {nullptr, nullptr, nullptr};
@@ -288,6 +292,14 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
         const int frame_lo = (T - P.n_in) & ~1;
         if (!mel_ready && (rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel, 1, st, launches, err, frame_lo))) return rc;
         if (mel_dump && (rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel_dump, 0, st, launches, err))) return rc;
+        if (hw.tcn_umma) {
+            const size_t usm = tcn_umma_smem_bytes(hw.tcn_uplan);
+            NWW_HCUDA(set_smem(tcn_cone_umma_kernel, usm));
+            const long long utiles = (n + kTuWT - 1) / kTuWT;
+            tcn_cone_umma_kernel<<<(int)std::min<long long>(utiles, sm_count), kTuNT, usm, st>>>(mel, (long long)F * T, ring, n,
+                                                                                              hw.tcn_uplan, hw.tcn_wq, feat);
+            return done();
+        }
         const size_t smem = tcn_cone_smem_bytes(P);
         NWW_HCUDA(set_smem(tcn_cone_kernel, smem));
         const long long tiles = (n + P.wt - 1) / P.wt;

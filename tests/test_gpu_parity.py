@@ -230,7 +230,8 @@ def test_incremental_stream_mel_is_bit_identical_to_full_recompute(torch_cuda, m
 
 @pytest.mark.parametrize("mt,kw", [("cnn", dict(tensor_cores=False)), ("cnn", dict(cnn_stage="v1")),
                                    ("dnn", dict(tensor_cores=False)), ("bcresnet", dict(tensor_cores=False)),
-                                   ("crnn", dict(tensor_cores=False)), ("e2e_dnn", dict(tensor_cores=False))])
+                                   ("crnn", dict(tensor_cores=False)), ("e2e_dnn", dict(tensor_cores=False)),
+                                   ("tcn", dict(tensor_cores=False))])
 def test_cuda_core_variants_match_golden(torch_cuda, golden_frontend, mt, kw):
     """The FP32 CUDA-core variants kept for A/B measurements (no tcgen05 dense layer / conv2 / 1x1 GEMMs)
     must meet the same tolerances as the default tensor-core paths."""
