@@ -210,13 +210,15 @@ tcn_cone_umma_kernel(const float* __restrict__ mel_tm, long long mel_win_stride,
                     const uint32_t lbo_b = (uint32_t)Ck.ncols * 16, hl_b = (uint32_t)Ck.kgs * lbo_b;
                     const uint32_t idesc = umma_idesc_bf16(128, Ck.ncols);
                     const uint32_t d_tmem = tmem_base + (uint32_t)Ck.n0;
-                    for (int ks = 0; ks < Ck.kgs / 2; ++ks) {
-                        const uint32_t ao = a_addr + (uint32_t)(Ck.kg0 + 2 * ks) * lbo_a, bo = b_addr + (uint32_t)(2 * ks) * lbo_b;
-                        const uint64_t da_h = umma_desc_noswz(ao, lbo_a, 128), da_l = umma_desc_noswz(ao + hl_a, lbo_a, 128);
-                        const uint64_t db_h = umma_desc_noswz(bo, lbo_b, 128), db_l = umma_desc_noswz(bo + hl_b, lbo_b, 128);
+                    // descriptors = one base per operand + a multiple of 16 bytes in the start-address field
+                    uint64_t da_h = umma_desc_noswz(a_addr + (uint32_t)Ck.kg0 * lbo_a, lbo_a, 128);
+                    uint64_t db_h = umma_desc_noswz(b_addr, lbo_b, 128);
+                    const uint64_t a_lo = (uint64_t)(hl_a >> 4), b_lo = (uint64_t)(hl_b >> 4);
+                    const uint64_t a_step = (uint64_t)((2 * lbo_a) >> 4), b_step = (uint64_t)((2 * lbo_b) >> 4);
+                    for (int ks = 0; ks < Ck.kgs / 2; ++ks, da_h += a_step, db_h += b_step) {
                         umma_bf16(d_tmem, da_h, db_h, idesc, (Ck.kg0 | ks) != 0);
-                        umma_bf16(d_tmem, da_l, db_h, idesc, 1);
-                        umma_bf16(d_tmem, da_h, db_l, idesc, 1);
+                        umma_bf16(d_tmem, da_h + a_lo, db_h, idesc, 1);
+                        umma_bf16(d_tmem, da_h, db_h + b_lo, idesc, 1);
                     }
                     umma_commit(bar);
                 }
