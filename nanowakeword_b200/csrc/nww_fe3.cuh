@@ -43,8 +43,8 @@ __device__ __forceinline__ void fe3_warp_fft(const int16_t* __restrict__ x, cplx
                                              const FrontendTables<double>& tab, StoreFn store, int lane) {
     const cplx<double>* tw1 = tw_smem;
     const cplx<double>* tw2 = tw_smem + 7 * 64;
-    // ---- pass 1: butterflies j = lane, lane + 32 ------------------------------------------------------------
-#pragma unroll 1
+    // ---- pass 1: butterflies j = lane, lane + 32 (unrolled: the two independent butterflies interleave) -------
+#pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int jj = lane + 32 * h;
         const int16_t* xa = x + jj;
@@ -65,7 +65,7 @@ __device__ __forceinline__ void fe3_warp_fft(const int16_t* __restrict__ x, cplx
     }
     __syncwarp();
     // ---- pass 2 ----------------------------------------------------------------------------------------------
-#pragma unroll 1
+#pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int jj = lane + 32 * h;
         const int b2 = jj >> 3, j2 = jj & 7;
