@@ -296,9 +296,9 @@ def run_gpu_arm(args, rank, world, local_rank):
         "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
         "peak_source": peak_src,
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel per launch, from the committed ncu --set full capture
-        # (profiles/r01_v4_ncu_full.txt: 131.2 MB read = the PCM, 197.6 MB written = the TF32 hi/lo feature rows that
+        # (profiles/r01_v8_ncu_full.txt: 131.3 MB read = the PCM, 196.0 MB written = the TF32 hi/lo feature rows that
         # do not fit L2 at 4096 windows per launch and are re-read by the fc1 GEMM), scaled to this launch size
-        "traffic": (131.2384e6 + 197.5839e6) / 4096.0 * a_win,
+        "traffic": (131.339e6 + 195.956e6) / 4096.0 * a_win,
         "avg_launch_ms": a_ms, "windows_per_launch": a_win, "share_of_step": share,
         "algorithmic_bytes_per_window": alg_bytes,
         "intermediate_bytes_per_window": 2 * 4 * 7680,                   # TF32 hi/lo feature row handed to the fc1 GEMM (L2-resident)

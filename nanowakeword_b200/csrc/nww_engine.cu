@@ -585,6 +585,19 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
                 NWW_CUDA(cudaMalloc(&e->d_conv_wq[1], wq.size() * sizeof(uint16_t)));
                 NWW_CUDA(cudaMemcpy(e->d_conv_wq[1], wq.data(), wq.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
                 e->heads.gru_whh_q = reinterpret_cast<const uint4*>(e->d_conv_wq[1]);
+                // input projections on tcgen05 too: W_ih^T (In, 3H) in 64-column chunks, both directions in one buffer
+                const int In = e->heads.gru_in, G3 = 3 * kGruTcH;
+                if (In % 16 == 0 && rowgemm_umma_smem_bytes(In) <= 220 * 1024) {
+                    std::vector<uint16_t> qf, qb;
+                    rowgemm_umma_pack(e->blob.f32("crnn.gru.fwd.w_ih_kn"), In, G3, &qf);
+                    rowgemm_umma_pack(e->blob.f32("crnn.gru.bwd.w_ih_kn"), In, G3, &qb);
+                    NWW_CUDA(cudaMalloc(&e->d_conv_wq[2], (qf.size() + qb.size()) * sizeof(uint16_t)));
+                    NWW_CUDA(cudaMemcpy(e->d_conv_wq[2], qf.data(), qf.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+                    NWW_CUDA(cudaMemcpy(static_cast<uint16_t*>(e->d_conv_wq[2]) + qf.size(), qb.data(), qb.size() * sizeof(uint16_t),
+                                        cudaMemcpyHostToDevice));
+                    e->heads.gru_wih_f_q = reinterpret_cast<const uint4*>(e->d_conv_wq[2]);
+                    e->heads.gru_wih_b_q = reinterpret_cast<const uint4*>(static_cast<uint16_t*>(e->d_conv_wq[2]) + qf.size());
+                }
             }
             if (spec->arch == NWW_ARCH_E2E_MELCNN && !(spec->reserved[0] & 1)) {
                 // conv2 (16 -> 32 on 32 x 50, pool) and conv3 (32 -> 64 on 16 x 25) as tcgen05 implicit GEMMs

@@ -51,6 +51,7 @@ struct HeadWeights {
     const float *gru_wih_f_nk = nullptr, *gru_wih_b_nk = nullptr;    // [3H][In] copies for the dense kernel
     const float *gru_wih_f_kn = nullptr, *gru_wih_b_kn = nullptr;    // [In][3H] copies for the row GEMM (preferred)
     const uint4* gru_whh_q = nullptr;                                // W_hh^T pre-split for gru_tc_kernel (H = 128)
+    const uint4 *gru_wih_f_q = nullptr, *gru_wih_b_q = nullptr;      // W_ih^T pre-split for rowgemm_umma_kernel
     // E2E mel-CNN
     ConvW e2e_conv[3];
     const uint4* e2e_wq[3] = {nullptr, nullptr, nullptr};    // conv2 / conv3 weights as bf16 UMMA operands (index 1, 2)
@@ -421,15 +422,26 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
         }
         // input projections over rows (all S steps forward, the last step only backward), then the recurrence
         if (hw.gru_wih_f_kn && hw.gru_wih_b_kn) {
-            const size_t rsm = rowgemm_smem_bytes(In);
-            NWW_HCUDA(set_smem(rowgemm_kernel, rsm));
             const long long rows = n * S;
-            rowgemm_kernel<<<(int)std::min<long long>((rows + kRgRows - 1) / kRgRows, sm_count), kTcnNT, rsm, st>>>(
-                seq, 1, 0, hw.gru_wih_f_kn, hw.gru_bih_f, gi_f, rows, In, G3);
-            if ((rc = done())) return rc;
-            rowgemm_kernel<<<(int)std::min<long long>((n + kRgRows - 1) / kRgRows, sm_count), kTcnNT, rsm, st>>>(
-                seq, S, S - 1, hw.gru_wih_b_kn, hw.gru_bih_b, gi_b, n, In, G3);
-            if ((rc = done())) return rc;
+            if (hw.gru_wih_f_q && hw.gru_wih_b_q) {
+                const size_t usm = rowgemm_umma_smem_bytes(In);
+                NWW_HCUDA(set_smem(rowgemm_umma_kernel, usm));
+                rowgemm_umma_kernel<<<(int)std::min<long long>((rows + kRuRows - 1) / kRuRows, sm_count), kRuNT, usm, st>>>(
+                    seq, 1, 0, hw.gru_wih_f_q, hw.gru_bih_f, gi_f, rows, In, G3);
+                if ((rc = done())) return rc;
+                rowgemm_umma_kernel<<<(int)std::min<long long>((n + kRuRows - 1) / kRuRows, sm_count), kRuNT, usm, st>>>(
+                    seq, S, S - 1, hw.gru_wih_b_q, hw.gru_bih_b, gi_b, n, In, G3);
+                if ((rc = done())) return rc;
+            } else {
+                const size_t rsm = rowgemm_smem_bytes(In);
+                NWW_HCUDA(set_smem(rowgemm_kernel, rsm));
+                rowgemm_kernel<<<(int)std::min<long long>((rows + kRgRows - 1) / kRgRows, sm_count), kTcnNT, rsm, st>>>(
+                    seq, 1, 0, hw.gru_wih_f_kn, hw.gru_bih_f, gi_f, rows, In, G3);
+                if ((rc = done())) return rc;
+                rowgemm_kernel<<<(int)std::min<long long>((n + kRgRows - 1) / kRgRows, sm_count), kTcnNT, rsm, st>>>(
+                    seq, S, S - 1, hw.gru_wih_b_kn, hw.gru_bih_b, gi_b, n, In, G3);
+                if ((rc = done())) return rc;
+            }
             if (hw.gru_whh_q != nullptr && Hd == kGruTcH) {
                 const size_t gsm = gru_tc_smem_bytes();
                 NWW_HCUDA(set_smem(gru_tc_kernel, gsm));

@@ -273,4 +273,128 @@ gru_tc_kernel(const float* __restrict__ gi_f, const float* __restrict__ gi_b, co
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Row GEMM on tcgen05: out[r][n] = bias[n] + sum_k A[r * a_row_mul + a_row_off][k] W[k][n]   (K % 16 == 0, N % 64 == 0)
+// Tiles of 128 rows: FP32 rows -> bf16 hi / lo un-swizzled K-major operand; weights pre-split by the engine in
+// 64-column chunks ([chunk][hi|lo][K group][64][8] bf16); (K / 16) x 3 tcgen05.mma 128 x 64 x 16 per chunk.
+// Used for the GRU input projections (K = 160, N = 384).
+// ---------------------------------------------------------------------------------------
+constexpr int kRuRows = 128, kRuNC = 64, kRuNT = 256;
+inline size_t rowgemm_umma_smem_bytes(int K) { return (size_t)2 * kRuRows * K * 2 + (size_t)2 * kRuNC * K * 2 + 128; }
+
+inline void rowgemm_umma_pack(const float* w /* [K][N] */, int K, int N, std::vector<uint16_t>* out) {
+    auto bf16_rn = [](float x) {
+        uint32_t u;
+        memcpy(&u, &x, 4);
+        u += 0x7FFFu + ((u >> 16) & 1u);
+        return (uint16_t)(u >> 16);
+    };
+    auto bf16_f = [](uint16_t b) {
+        uint32_t u = (uint32_t)b << 16;
+        float f;
+        memcpy(&f, &u, 4);
+        return f;
+    };
+    const size_t op = (size_t)(K / 8) * kRuNC * 8;
+    out->assign((size_t)(N / kRuNC) * 2 * op, 0);
+    for (int k = 0; k < K; ++k)
+        for (int n = 0; n < N; ++n) {
+            const float v = w[(size_t)k * N + n];
+            const uint16_t hi = bf16_rn(v), lo = bf16_rn(v - bf16_f(hi));
+            const size_t base = (size_t)(n / kRuNC) * 2 * op + (size_t)(k >> 3) * kRuNC * 8 + (size_t)(n % kRuNC) * 8 + (k & 7);
+            (*out)[base] = hi;
+            (*out)[base + op] = lo;
+        }
+}
+
+__global__ void __launch_bounds__(kRuNT, 1)
+rowgemm_umma_kernel(const float* __restrict__ A, long long a_row_mul, long long a_row_off, const uint4* __restrict__ wq,
+                    const float* __restrict__ bias, float* __restrict__ out, long long rows, int K, int N) {
+    NWW_DYN_SMEM(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int kg_n = K / 8;
+    const int a_op = kRuRows * K * 2, b_op = kRuNC * K * 2;          // bytes of one (hi | lo) operand
+    unsigned char* a_s = smem;
+    unsigned char* b_s = smem + 2 * a_op;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * a_op + 2 * b_op);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 64);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t idesc = umma_idesc_bf16(128, kRuNC);
+    const uint64_t da_h0 = umma_desc_noswz(smem_u32(a_s), kRuRows * 16, 128), da_l0 = da_h0 + (uint64_t)(a_op >> 4);
+    const uint64_t db_h0 = umma_desc_noswz(smem_u32(b_s), kRuNC * 16, 128), db_l0 = db_h0 + (uint64_t)(b_op >> 4);
+    uint32_t phase = 0;
+    for (long long r0 = (long long)blockIdx.x * kRuRows; r0 < rows; r0 += (long long)gridDim.x * kRuRows) {
+        for (int i = tid; i < kRuRows * kg_n; i += kRuNT) {
+            const int g = i / kRuRows, r = i - g * kRuRows;
+            uint4 hv = make_uint4(0, 0, 0, 0), lv = hv;
+            if (r0 + r < rows) {
+                const float4* p = reinterpret_cast<const float4*>(A + ((r0 + r) * a_row_mul + a_row_off) * K + 8 * g);
+                const float4 v0 = __ldg(p), v1 = __ldg(p + 1);
+                const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                uint32_t h[8], l[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    h[e] = float_to_bf16_bits(v[e]);
+                    l[e] = float_to_bf16_bits(v[e] - bf16_bits_to_float(h[e]));
+                }
+                hv = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+                lv = make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
+            }
+            const int off = (g * kRuRows + r) * 16;
+            *reinterpret_cast<uint4*>(a_s + off) = hv;
+            *reinterpret_cast<uint4*>(a_s + a_op + off) = lv;
+        }
+        for (int nc = 0; nc < N / kRuNC; ++nc) {
+            const uint4* src = wq + (size_t)nc * (2 * b_op / 16);
+            for (int i = tid; i < 2 * b_op / 16; i += kRuNT) reinterpret_cast<uint4*>(b_s)[i] = __ldg(src + i);
+            fence_proxy_async();
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                for (int ks = 0; ks < K / 16; ++ks) {
+                    const uint64_t ao = (uint64_t)((2 * ks * kRuRows * 16) >> 4), bo = (uint64_t)((2 * ks * kRuNC * 16) >> 4);
+                    umma_bf16(tmem_base, da_h0 + ao, db_h0 + bo, idesc, ks != 0);
+                    umma_bf16(tmem_base, da_l0 + ao, db_h0 + bo, idesc, 1);
+                    umma_bf16(tmem_base, da_h0 + ao, db_l0 + bo, idesc, 1);
+                }
+                umma_commit(bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            tc_fence_after();
+            {
+                const int q = warp & 3, hcol = warp >> 2;
+                float v[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hcol * 32), v);
+                tc_fence_before();
+                const long long r = r0 + q * 32 + lane;
+                if (r < rows) {
+                    const int n0 = nc * kRuNC + hcol * 32;
+                    float4* dst = reinterpret_cast<float4*>(out + r * N + n0);
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4)
+                        dst[j4] = make_float4(v[4 * j4] + __ldg(bias + n0 + 4 * j4), v[4 * j4 + 1] + __ldg(bias + n0 + 4 * j4 + 1),
+                                              v[4 * j4 + 2] + __ldg(bias + n0 + 4 * j4 + 2), v[4 * j4 + 3] + __ldg(bias + n0 + 4 * j4 + 3));
+                }
+            }
+            __syncthreads();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 64);
+    }
+}
+
 }  // namespace nww
