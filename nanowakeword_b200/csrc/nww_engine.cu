@@ -427,7 +427,8 @@ static int launch_stage_a(nww_engine* e, WindowSource pcm, int64_t n, float* mel
                                            mel, st, &e->launches, &g_last_error, true, nullptr,
                                            MelRingRef{e->d_mel_ring, e->streams.count, stream_s0});
             if (from_ring) {
-                stream_mel_gather_kernel<<<ew_grid(n * 3920, e->sm_count), 256, 0, st>>>(sub, ring0, e->d_scratch, 0);
+                const int tm = e->spec.arch == NWW_ARCH_GRU || e->spec.arch == NWW_ARCH_LSTM;     // sequence heads read (T, F)
+                stream_mel_gather_kernel<<<ew_grid(n * 3920, e->sm_count), 256, 0, st>>>(sub, ring0, e->d_scratch, tm);
                 e->launches++;
                 NWW_CUDA(cudaGetLastError());
             }
@@ -599,6 +600,19 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
                     e->heads.gru_wih_b_q = reinterpret_cast<const uint4*>(static_cast<uint16_t*>(e->d_conv_wq[2]) + qf.size());
                 }
             }
+            if (spec->arch == NWW_ARCH_GRU || spec->arch == NWW_ARCH_LSTM) {
+                // gate matrices as two-term half UMMA operands (nww_rnn.cuh); this head has no CUDA-core variant
+                const int H = e->heads.rnn_hidden, KX = RnnDims<128, GeoNS40x98::N_MELS>::KX;
+                std::vector<uint16_t> qf, qb;
+                rnn_pack_weights(e->blob.f32("rnn.fwd.w"), KX + H, 4 * H, &qf);
+                rnn_pack_weights(e->blob.f32("rnn.bwd.w"), KX, 4 * H, &qb);
+                NWW_CUDA(cudaMalloc(&e->d_conv_wq[1], qf.size() * sizeof(uint16_t)));
+                NWW_CUDA(cudaMemcpy(e->d_conv_wq[1], qf.data(), qf.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+                NWW_CUDA(cudaMalloc(&e->d_conv_wq[2], qb.size() * sizeof(uint16_t)));
+                NWW_CUDA(cudaMemcpy(e->d_conv_wq[2], qb.data(), qb.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+                e->heads.rnn_wq_f = reinterpret_cast<const uint4*>(e->d_conv_wq[1]);
+                e->heads.rnn_wq_b = reinterpret_cast<const uint4*>(e->d_conv_wq[2]);
+            }
             if (spec->arch == NWW_ARCH_E2E_MELCNN && !(spec->reserved[0] & 1)) {
                 // conv2 (16 -> 32 on 32 x 50, pool) and conv3 (32 -> 64 on 16 x 25) as tcgen05 implicit GEMMs
                 const int cin[3] = {1, 16, 32}, cout[3] = {16, 32, 64}, hh[3] = {64, 32, 16}, ww[3] = {101, 50, 25}, pool[3] = {1, 1, 0};
@@ -635,7 +649,9 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
     // intermediates need not stay L2-resident), so take up to 28 windows per SM within a 2 GB budget.
     {
         const size_t per_window = (size_t)e->feat_dim * sizeof(float) * 3 + e->scratch_per_window;
-        int mult = (int)std::max<size_t>(1, std::min<size_t>(28, ((size_t)2 << 30) / (per_window * e->sm_count)));
+        // the recurrent heads work on 128-window tiles, one per SM: two waves of those per chunk
+        const bool rnn = spec->arch == NWW_ARCH_GRU || spec->arch == NWW_ARCH_LSTM;
+        int mult = (int)std::max<size_t>(1, std::min<size_t>(rnn ? 2 * kRnnTM : 28, ((size_t)2 << 30) / (per_window * e->sm_count)));
         e->chunk = spec->chunk_windows > 0 ? spec->chunk_windows : e->sm_count * mult;
     }
     NWW_CUDA(cudaMalloc(&e->d_feat, (size_t)e->chunk * e->feat_dim * sizeof(float)));
@@ -804,7 +820,7 @@ int nww_run_windows_f32(nww_engine* e, const float* pcm_dev, int64_t n, float* s
     NWW_CUDA(cudaSetDevice(e->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);   // NULL = the legacy default stream, as in CUDA
     if (!e->d_pcm[0]) {
-        e->host_chunk = std::min<int64_t>(e->chunk, (int64_t)e->sm_count * 8);
+        e->host_chunk = std::min<int64_t>(e->chunk, (int64_t)e->sm_count * (e->heads.rnn_hidden ? 32 : 8));
         for (int i = 0; i < 2; ++i) NWW_CUDA(cudaMalloc(&e->d_pcm[i], (size_t)e->host_chunk * e->clip * sizeof(int16_t)));
     }
     const int64_t mel_stride = (int64_t)e->n_mels * e->n_frames;
@@ -829,7 +845,7 @@ int nww_run_windows_host(nww_engine* e, const int16_t* pcm_host, int64_t n, floa
     NWW_CUDA(cudaSetDevice(e->device));
     if (!e->d_pcm[0]) {
         // copy / compute overlap wants several chunks per call: 8 windows per SM (38 MB) per copy
-        e->host_chunk = std::min<int64_t>(e->chunk, (int64_t)e->sm_count * 8);
+        e->host_chunk = std::min<int64_t>(e->chunk, (int64_t)e->sm_count * (e->heads.rnn_hidden ? 32 : 8));
         for (int i = 0; i < 2; ++i) NWW_CUDA(cudaMalloc(&e->d_pcm[i], (size_t)e->host_chunk * e->clip * sizeof(int16_t)));
     }
     if (e->scores_cap < n) {

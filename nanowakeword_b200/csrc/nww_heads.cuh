@@ -18,6 +18,7 @@
 #include "nww_bc.cuh"
 #include "nww_rowgemm.cuh"
 #include "nww_conv_umma.cuh"
+#include "nww_rnn.cuh"
 
 namespace nww {
 
@@ -59,6 +60,9 @@ struct HeadWeights {
     // CRNN conv3 on the same kernel
     const uint4* crnn_wq3 = nullptr;
     ConvUmmaPlan crnn_plan3;
+    // GRU / LSTM / RNN heads (nww_rnn.cuh)
+    int rnn_cell = 0, rnn_hidden = 0;
+    const uint4 *rnn_wq_f = nullptr, *rnn_wq_b = nullptr;
     // scratch layout (floats per window)
     size_t scratch_floats = 0;
 };
@@ -215,6 +219,21 @@ inline int setup_head_weights(int arch, int geometry, const BlobLookup& get, con
         hw->scratch_floats = 3920 + act_floats + (size_t)w * hw->gru_in + (size_t)w * 3 * H + 3 * H;
         if (hw->crnn_cnn2) hw->scratch_floats = 3920 + 7680 + 2 * (size_t)w * hw->gru_in + (size_t)w * 3 * H + 3 * H;
         if (gru_smem_bytes(H) > 200 * 1024) { *err = "GRU hidden size too large for shared memory"; return NWW_EUNSUPPORTED; }
+    } else if (arch == NWW_ARCH_GRU || arch == NWW_ARCH_LSTM) {
+        if (geometry != NWW_GEOM_NS40X98) { *err = "recurrent heads are built for the NS40x98 geometry"; return NWW_EUNSUPPORTED; }
+        auto df = dims("rnn.fwd.w"), db = dims("rnn.bwd.w");
+        if (df.size() != 2 || db.size() != 2) { *err = "weight blob: rnn.fwd.w / rnn.bwd.w missing"; return NWW_EINVAL; }
+        const int H = (int)df[1] / 4;
+        constexpr int KX = RnnDims<128, GeoNS40x98::N_MELS>::KX;
+        if ((H != 64 && H != 128) || (int)df[0] != KX + H || (int)db[0] != KX || db[1] != df[1]) {
+            *err = "recurrent heads are built for 64 or 128 hidden units on 40 mel bands";
+            return NWW_EUNSUPPORTED;
+        }
+        if (!need("rnn.fwd.w", (size_t)(KX + H) * 4 * H) || !need("rnn.bwd.w", (size_t)KX * 4 * H)) return NWW_EINVAL;
+        hw->rnn_cell = arch == NWW_ARCH_GRU ? RNN_GRU : RNN_LSTM;
+        hw->rnn_hidden = H;
+        *feat_dim = 2 * H;
+        hw->scratch_floats = (size_t)GeoNS40x98::N_FRAMES * GeoNS40x98::N_MELS;      // the (T, F) log-mel
     } else if (arch == NWW_ARCH_E2E_MELCNN) {
         if (geometry != NWW_GEOM_REF64X101) { *err = "e2e mel-CNN is built for the REF64x101 geometry"; return NWW_EUNSUPPORTED; }
         const int ch[4] = {1, 16, 32, 64};
@@ -306,6 +325,24 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
         const long long tiles = (n + P.wt - 1) / P.wt;
         tcn_cone_kernel<<<(int)std::min<long long>(tiles, sm_count), kTcnNT, smem, st>>>(mel, (long long)F * T, ring, n, P, feat);
         return done();
+    }
+    if (hw.arch == NWW_ARCH_GRU || hw.arch == NWW_ARCH_LSTM) {
+        // time-major log-mel (or, in stream mode, gathered that way by the caller), then the whole sequence in one kernel
+        if (!mel_ready && (rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel, 1, st, launches, err))) return rc;
+        if (mel_dump && (rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel_dump, 0, st, launches, err))) return rc;
+        // rows per CTA: a full 128-row tile when there is a wave of them, fewer when the batch is small
+        const int tm = (int)std::min<long long>(kRnnTM, std::max<long long>(32, ((n + sm_count - 1) / sm_count + 31) / 32 * 32));
+        const int grid = (int)std::min<long long>((n + tm - 1) / tm, sm_count);
+        auto go = [&](auto kernel, size_t smem) -> int {
+            NWW_HCUDA(set_smem(kernel, smem));
+            kernel<<<grid, kRnnNT, smem, st>>>(mel, (long long)F * T, T, n, tm, hw.rnn_wq_f, hw.rnn_wq_b, feat);
+            return done();
+        };
+        if (hw.rnn_cell == RNN_GRU)
+            return hw.rnn_hidden == 128 ? go(rnn_seq_kernel<RNN_GRU, 128, F>, RnnDims<128, F>::SMEM)
+                                        : go(rnn_seq_kernel<RNN_GRU, 64, F>, RnnDims<64, F>::SMEM);
+        return hw.rnn_hidden == 128 ? go(rnn_seq_kernel<RNN_LSTM, 128, F>, RnnDims<128, F>::SMEM)
+                                    : go(rnn_seq_kernel<RNN_LSTM, 64, F>, RnnDims<64, F>::SMEM);
     }
     if (!mel_ready && !conv2_nhwc && (rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel, 0, st, launches, err))) return rc;
     if (mel_dump && !conv2_nhwc) NWW_HCUDA(cudaMemcpyAsync(mel_dump, mel, (size_t)n * F * T * sizeof(float), cudaMemcpyDeviceToDevice, st));

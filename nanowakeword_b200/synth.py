@@ -25,10 +25,14 @@ _LOGIT_CAL = {
     "bcresnet": (58.1, -7.41),
     "crnn": (292.7, 32.75),
     "e2e_dnn": (132.1, 14.09),
+    "gru": (94.2, -12.01),
+    "lstm": (56.6, 9.78),
+    "rnn": (97.1, -18.93),
 }
 
 DEFAULT_INPUT_SHAPE = {
     "dnn": (98, 40), "tcn": (98, 40),                     # (T, F)
+    "gru": (98, 40), "lstm": (98, 40), "rnn": (98, 40),
     "cnn": (40, 98), "bcresnet": (40, 98), "crnn": (40, 98),   # (F, T)
     "e2e_dnn": (16000,),
 }
@@ -153,6 +157,15 @@ def make_state_dict(cfg: dict, seed: int = 0) -> dict[str, np.ndarray]:
                            ("bias_ih_l0", (3 * hid,)), ("bias_hh_l0", (3 * hid,))):
                 g.uniform(f"model.rnn.{nm}{sfx}", sh, hid)
         g.linear("model.fc", emb, 2 * hid)
+    elif mt in ("gru", "lstm", "rnn"):                # architectures.py:129-146, 83-99, 149-161
+        name, gates, hid = {"gru": ("gru", 3, ld), "lstm": ("lstm", 4, ld), "rnn": ("layer1", 4, 64)}[mt]
+        for layer in range(nb):
+            rnn_in = shape[1] if layer == 0 else 2 * hid
+            for sfx in ("", "_reverse"):
+                for nm, sh in ((f"weight_ih_l{layer}", (gates * hid, rnn_in)), (f"weight_hh_l{layer}", (gates * hid, hid)),
+                               (f"bias_ih_l{layer}", (gates * hid,)), (f"bias_hh_l{layer}", (gates * hid,))):
+                    g.uniform(f"model.{name}.{nm}{sfx}", sh, hid)
+        g.linear("model.layer2" if mt == "rnn" else "model.fc", emb, 2 * hid)
     elif mt == "e2e_dnn":                             # architectures.py:820-888
         for i, (cin, cout) in zip((0, 4, 8), ((1, 16), (16, 32), (32, 64))):
             g.conv(f"model.conv_block.{i}", cout, cin, 3, 3)

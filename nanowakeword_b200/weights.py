@@ -23,7 +23,7 @@ import numpy as np
 
 BN_EPS = 1e-5
 
-ARCH_IDS = {"dnn": 0, "cnn": 1, "tcn": 2, "bcresnet": 3, "crnn": 4, "e2e_dnn": 5}
+ARCH_IDS = {"dnn": 0, "cnn": 1, "tcn": 2, "bcresnet": 3, "crnn": 4, "e2e_dnn": 5, "gru": 6, "lstm": 7, "rnn": 7}
 ACT_IDS = {"relu": 0, "gelu": 1, "silu": 2}
 POST_NONE, POST_ACT, POST_LN_ACT = 0, 1, 2
 
@@ -152,6 +152,35 @@ def pack_tensors(sd: dict, cfg: dict) -> dict[str, np.ndarray]:
             out[f"crnn.gru.{tag}.b_ih"] = _f64(sd, "model.rnn.bias_ih_l0" + sfx).astype(np.float32)
             out[f"crnn.gru.{tag}.b_hh"] = _f64(sd, "model.rnn.bias_hh_l0" + sfx).astype(np.float32)
         layers.append((_f64(sd, "model.fc.weight"), _f64(sd, "model.fc.bias"), POST_NONE, None))
+    elif mt in ("gru", "lstm", "rnn"):
+        # GRUModel / LSTMModel / RNNModel (architectures.py:129-146, 83-99, 149-161): one bidirectional layer,
+        # out[:, -1, :].  Packed for csrc/nww_rnn.cuh: per direction ONE matrix whose rows are
+        # [x (In) | constant 1 -> bias | zero padding to a multiple of 16 | h (H)] and whose 4H columns are all gates.
+        name = {"gru": "model.gru", "lstm": "model.lstm", "rnn": "model.layer1"}[mt]
+        if f"{name}.weight_ih_l1" in sd:
+            raise ValueError(f"{mt}: only single-layer recurrent heads (n_blocks = 1) are built into the B200 engine")
+        for sfx, tag in (("", "fwd"), ("_reverse", "bwd")):
+            w_ih, w_hh = _f64(sd, f"{name}.weight_ih_l0{sfx}"), _f64(sd, f"{name}.weight_hh_l0{sfx}")
+            b_ih, b_hh = _f64(sd, f"{name}.bias_ih_l0{sfx}"), _f64(sd, f"{name}.bias_hh_l0{sfx}")
+            hid, n_in = w_hh.shape[1], w_ih.shape[1]
+            kx = (n_in + 1 + 15) // 16 * 16
+            w = np.zeros((kx + hid, 4 * hid))
+            if mt == "gru":                                    # torch gate order r, z, n -> columns [r | z | n_x | n_h]
+                w[:n_in, :3 * hid] = w_ih.T
+                w[n_in, :2 * hid] = b_ih[:2 * hid] + b_hh[:2 * hid]
+                w[n_in, 2 * hid:3 * hid] = b_ih[2 * hid:]
+                w[n_in, 3 * hid:] = b_hh[2 * hid:]
+                w[kx:, :2 * hid] = w_hh.T[:, :2 * hid]
+                w[kx:, 3 * hid:] = w_hh.T[:, 2 * hid:]
+            else:                                              # torch gate order i, f, g, o
+                w[:n_in] = w_ih.T
+                w[n_in] = b_ih + b_hh
+                w[kx:] = w_hh.T
+            # the reverse direction contributes its first step only (zero state): x rows suffice
+            out[f"rnn.{tag}.w"] = np.ascontiguousarray(w if tag == "fwd" else w[:kx]).astype(np.float32)
+        out["rnn.cell"] = np.array([0 if mt == "gru" else 1], dtype=np.int32)
+        fc = "model.layer2" if mt == "rnn" else "model.fc"
+        layers.append((_f64(sd, fc + ".weight"), _f64(sd, fc + ".bias"), POST_NONE, None))
     elif mt == "e2e_dnn":
         for j, i in enumerate((0, 4, 8)):
             w, b = fold_bn(_f64(sd, f"model.conv_block.{i}.weight"), _f64(sd, f"model.conv_block.{i}.bias"),

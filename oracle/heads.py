@@ -11,6 +11,9 @@ Reference anchors (all under /root/reference/nanowakeword/):
   TCNModel/TemporalBlock    modules/architectures.py:290-362
   BcResNetModel/Block       modules/architectures.py:620-687
   CRNNModel (GRU)           modules/architectures.py:209-287
+  LSTMModel                 modules/architectures.py:83-99
+  GRUModel                  modules/architectures.py:129-146
+  RNNModel (bi-LSTM, H=64)  modules/architectures.py:149-161
   E2E_MelSpectrogram_CNN    modules/architectures.py:820-888
   Model.classifier/forward  modules/model.py:291-296, 562-571
   sigmoid + view(-1,1,1)    _export/onnx.py:164-172
@@ -30,7 +33,7 @@ LN_EPS = 1e-5
 
 # Heads whose input is (T, F) rather than (F, T)  (model.py:128-236 passes input_shape[1]
 # as the feature dim for dnn/tcn; cnn/bcresnet/crnn treat input_shape as (freq, time)).
-TIME_MAJOR_HEADS = ("dnn", "tcn")
+TIME_MAJOR_HEADS = ("dnn", "tcn", "gru", "lstm", "rnn")
 
 
 # ----------------------------------------------------------------------------- primitives
@@ -154,6 +157,64 @@ def gru_last_output_bidir(x, sd, prefix):
     return np.concatenate([h, hb], axis=1)
 
 
+def _rnn_cell(kind, sd, prefix, layer, sfx):
+    """One direction of one layer of torch.nn.GRU / torch.nn.LSTM as a step function
+    ``(x_t, state) -> state`` with ``state = (h,)`` or ``(h, c)``.
+    GRU gate order r, z, n;  LSTM gate order i, f, g, o  (torch docs; both zero initial state)."""
+    w_ih, w_hh = sd[f"{prefix}.weight_ih_l{layer}{sfx}"], sd[f"{prefix}.weight_hh_l{layer}{sfx}"]
+    b_ih, b_hh = sd[f"{prefix}.bias_ih_l{layer}{sfx}"], sd[f"{prefix}.bias_hh_l{layer}{sfx}"]
+    hsz = w_hh.shape[1]
+
+    def gru(xt, st):
+        (h,) = st
+        gi = xt @ w_ih.T + b_ih
+        gh = h @ w_hh.T + b_hh
+        r = sigmoid(gi[:, :hsz] + gh[:, :hsz])
+        z = sigmoid(gi[:, hsz:2 * hsz] + gh[:, hsz:2 * hsz])
+        n = np.tanh(gi[:, 2 * hsz:] + r * gh[:, 2 * hsz:])
+        return ((1.0 - z) * n + z * h,)
+
+    def lstm(xt, st):
+        h, c = st
+        g = xt @ w_ih.T + b_ih + h @ w_hh.T + b_hh
+        i, f = sigmoid(g[:, :hsz]), sigmoid(g[:, hsz:2 * hsz])
+        gg, o = np.tanh(g[:, 2 * hsz:3 * hsz]), sigmoid(g[:, 3 * hsz:])
+        c = f * c + i * gg
+        return (o * np.tanh(c), c)
+
+    return (gru if kind == "gru" else lstm), hsz, (1 if kind == "gru" else 2)
+
+
+def rnn_last_output_bidir(x, sd, prefix, kind):
+    """Bidirectional, batch_first, n_layers >= 1 GRU / LSTM; returns ``out[:, -1, :]`` (B, 2H) of the
+    top layer (architectures.py:95-96, 141-142, 157-158).  Layers below the top run both directions
+    over the whole sequence (their concatenated outputs feed the next layer); at the top the reverse
+    direction only needs its first step, the one that consumes x[:, -1]."""
+    n_layers = 0
+    while f"{prefix}.weight_ih_l{n_layers}" in sd:
+        n_layers += 1
+    bsz, steps, _ = x.shape
+    seq = x
+    for layer in range(n_layers):
+        top = layer == n_layers - 1
+        outs = []
+        for sfx in ("", "_reverse"):
+            step, hsz, n_state = _rnn_cell(kind, sd, prefix, layer, sfx)
+            st = tuple(np.zeros((bsz, hsz), dtype=x.dtype) for _ in range(n_state))
+            order = range(steps) if sfx == "" else range(steps - 1, -1, -1)
+            if top and sfx:
+                order = [steps - 1]
+            hs = {}
+            for t in order:
+                st = step(seq[:, t], st)
+                hs[t] = st[0]
+            outs.append(hs)
+        if top:
+            return np.concatenate([outs[0][steps - 1], outs[1][steps - 1]], axis=1)
+        seq = np.stack([np.concatenate([outs[0][t], outs[1][t]], axis=1) for t in range(steps)], axis=1)
+    raise ValueError("no recurrent layers found under " + prefix)
+
+
 # ----------------------------------------------------------------------------- backbones
 def _dnn(x, sd, cfg):
     act = cfg.get("activation_function", "relu")
@@ -230,6 +291,21 @@ def _crnn(x, sd, cfg):
     return linear(last, sd["model.fc.weight"], sd["model.fc.bias"])
 
 
+def _gru(x, sd, cfg):
+    """GRUModel on a (T, F) sequence (architectures.py:129-146)."""
+    return linear(rnn_last_output_bidir(x, sd, "model.gru", "gru"), sd["model.fc.weight"], sd["model.fc.bias"])
+
+
+def _lstm(x, sd, cfg):
+    """LSTMModel (architectures.py:83-99)."""
+    return linear(rnn_last_output_bidir(x, sd, "model.lstm", "lstm"), sd["model.fc.weight"], sd["model.fc.bias"])
+
+
+def _rnn(x, sd, cfg):
+    """RNNModel: bidirectional LSTM with 64 hidden units and n_blocks layers (architectures.py:149-161)."""
+    return linear(rnn_last_output_bidir(x, sd, "model.layer1", "lstm"), sd["model.layer2.weight"], sd["model.layer2.bias"])
+
+
 def _e2e_melcnn_body(mel, sd, cfg):
     act = cfg.get("activation_function", "relu")
     h = mel[:, None]
@@ -245,7 +321,7 @@ def _e2e_melcnn_body(mel, sd, cfg):
 
 
 _BACKBONES = {"dnn": _dnn, "cnn": _cnn, "tcn": _tcn, "bcresnet": _bcresnet, "crnn": _crnn,
-              "e2e_dnn": _e2e_melcnn_body}
+              "e2e_dnn": _e2e_melcnn_body, "gru": _gru, "lstm": _lstm, "rnn": _rnn}
 
 
 def classifier(emb, sd, cfg):

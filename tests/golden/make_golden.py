@@ -1,7 +1,8 @@
 """Generate golden vectors by running the REFERENCE's own modules (build container only).
 
 Usage (from the repo root, in the container that has /root/reference):
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py                 # everything
+    python tests/golden/make_golden.py gru lstm rnn    # only the named heads (front-end file untouched)
 
 Imports ``nanowakeword.modules.model.Model`` and ``nanowakeword._export.onnx`` from
 /root/reference (read-only; ``torchinfo``/``matplotlib`` are stubbed because they are
@@ -100,11 +101,15 @@ def main():
         out[f"{gname}.fb"] = m32.mel_scale.fb.numpy()
         out[f"{gname}.window"] = m32.spectrogram.window.numpy()
         mels[gname] = mel64
-    np.savez_compressed(os.path.join(HERE, "frontend.npz"), **out)
-    print("frontend.npz written")
+    only = sys.argv[1:]
+    if not only:
+        np.savez_compressed(os.path.join(HERE, "frontend.npz"), **out)
+        print("frontend.npz written")
 
     # ---- heads (fed the float64 torchaudio mel so head errors are isolated) -----------
-    for mt in ("dnn", "cnn", "tcn", "bcresnet", "crnn", "e2e_dnn"):
+    for mt in ("dnn", "cnn", "tcn", "bcresnet", "crnn", "e2e_dnn", "gru", "lstm", "rnn"):
+        if only and mt not in only:
+            continue
         cfg = default_config(mt)
         sd_np = make_state_dict(cfg, seed=0)
         model = Model(cfg, "golden", input_shape=tuple(cfg["input_shape"]), model_type=mt,
@@ -138,7 +143,7 @@ def main():
             else:
                 geom = "NS40x98"
                 mel = mels[geom]
-                feat = mel.transpose(1, 2).contiguous() if mt in ("dnn", "tcn") else mel
+                feat = mel.transpose(1, 2).contiguous() if mt in ("dnn", "tcn", "gru", "lstm", "rnn") else mel
                 logits64 = model.double()(feat)
                 res["logits64"] = logits64.numpy()
                 res["logits32"] = model.float()(feat.float()).numpy()
