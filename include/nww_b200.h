@@ -39,6 +39,7 @@ extern "C" {
 #define NWW_ARCH_E2E_MELCNN 5 /* E2E_MelSpectrogram_CNN   :820-888 */
 #define NWW_ARCH_GRU 6       /* GRUModel (bidirectional)  :129-146 */
 #define NWW_ARCH_LSTM 7      /* LSTMModel :83-99, and RNNModel :149-161 (a bidirectional LSTM, 64 hidden units) */
+#define NWW_ARCH_QUARTZNET 8 /* QuartzNetModel / QuartzNetBlock :366-437 */
 
 #define NWW_ACT_RELU 0       /* reference nanowakeword/modules/model.py:81-87 */
 #define NWW_ACT_GELU 1

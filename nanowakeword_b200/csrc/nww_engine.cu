@@ -86,6 +86,7 @@ struct nww_engine {
     float* d_nhwc = nullptr;                          // [chunk][7680] channel-last conv2 output for that path
     uint4* d_w2_umma = nullptr;
     void* d_bc_wq[3] = {nullptr, nullptr, nullptr};   // BcResNet 1x1 weights as bf16 UMMA operands
+    std::vector<void*> d_extra;                       // further pre-split weight buffers (QuartzNet blocks)
     void* d_conv_wq[3] = {nullptr, nullptr, nullptr}; // 3x3 conv weights as bf16 UMMA operands (E2E mel-CNN, CRNN conv3)
     Cnn2Weights cnn2{};
     CUtensorMap tm_xhi{}, tm_xlo{}, tm_whi{}, tm_wlo{};
@@ -427,7 +428,8 @@ static int launch_stage_a(nww_engine* e, WindowSource pcm, int64_t n, float* mel
                                            mel, st, &e->launches, &g_last_error, true, nullptr,
                                            MelRingRef{e->d_mel_ring, e->streams.count, stream_s0});
             if (from_ring) {
-                const int tm = e->spec.arch == NWW_ARCH_GRU || e->spec.arch == NWW_ARCH_LSTM;     // sequence heads read (T, F)
+                const int tm = e->spec.arch == NWW_ARCH_GRU || e->spec.arch == NWW_ARCH_LSTM ||
+                               e->spec.arch == NWW_ARCH_QUARTZNET;                               // sequence heads read (T, F)
                 stream_mel_gather_kernel<<<ew_grid(n * 3920, e->sm_count), 256, 0, st>>>(sub, ring0, e->d_scratch, tm);
                 e->launches++;
                 NWW_CUDA(cudaGetLastError());
@@ -613,6 +615,19 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
                 e->heads.rnn_wq_f = reinterpret_cast<const uint4*>(e->d_conv_wq[1]);
                 e->heads.rnn_wq_b = reinterpret_cast<const uint4*>(e->d_conv_wq[2]);
             }
+            if (spec->arch == NWW_ARCH_QUARTZNET) {
+                // folded pointwise (+ residual) weights of every block as bf16 UMMA operand streams (nww_rowgemm.cuh)
+                for (int i = 0; i < e->heads.qn_blocks; ++i) {
+                    auto& B = e->heads.qn[i];
+                    std::vector<uint16_t> wq;
+                    rowgemm_kc_pack(e->blob.f32("qn." + std::to_string(i) + ".w"), B.K, B.N, &wq);
+                    void* d = nullptr;
+                    NWW_CUDA(cudaMalloc(&d, wq.size() * sizeof(uint16_t)));
+                    e->d_extra.push_back(d);
+                    NWW_CUDA(cudaMemcpy(d, wq.data(), wq.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+                    B.wq = reinterpret_cast<const uint4*>(d);
+                }
+            }
             if (spec->arch == NWW_ARCH_E2E_MELCNN && !(spec->reserved[0] & 1)) {
                 // conv2 (16 -> 32 on 32 x 50, pool) and conv3 (32 -> 64 on 16 x 25) as tcgen05 implicit GEMMs
                 const int cin[3] = {1, 16, 32}, cout[3] = {16, 32, 64}, hh[3] = {64, 32, 16}, ww[3] = {101, 50, 25}, pool[3] = {1, 1, 0};
@@ -754,6 +769,7 @@ void nww_destroy(nww_engine* e) {
     cudaFree(e->d_nhwc);
     for (int j = 0; j < 3; ++j) cudaFree(e->d_bc_wq[j]);
     for (int j = 0; j < 3; ++j) cudaFree(e->d_conv_wq[j]);
+    for (void* p : e->d_extra) cudaFree(p);
     cudaFree(e->d_pcm[0]);
     cudaFree(e->d_pcm[1]);
     cudaFree(e->d_scores);

@@ -63,6 +63,10 @@ struct HeadWeights {
     // GRU / LSTM / RNN heads (nww_rnn.cuh)
     int rnn_cell = 0, rnn_hidden = 0;
     const uint4 *rnn_wq_f = nullptr, *rnn_wq_b = nullptr;
+    // QuartzNet (qn_dw_kernel + rowgemm_kc_umma_kernel)
+    struct QnBlock { int C = 0, Cp = 0, N = 0, k = 0, K = 0, has_res = 0; const float *dw = nullptr, *b = nullptr; const uint4* wq = nullptr; };
+    int qn_blocks = 0, qn_max_k = 0, qn_max_n = 0;
+    QnBlock qn[16];
     // scratch layout (floats per window)
     size_t scratch_floats = 0;
 };
@@ -234,6 +238,34 @@ inline int setup_head_weights(int arch, int geometry, const BlobLookup& get, con
         hw->rnn_hidden = H;
         *feat_dim = 2 * H;
         hw->scratch_floats = (size_t)GeoNS40x98::N_FRAMES * GeoNS40x98::N_MELS;      // the (T, F) log-mel
+    } else if (arch == NWW_ARCH_QUARTZNET) {
+        if (geometry != NWW_GEOM_NS40X98) { *err = "quartznet head is built for the NS40x98 geometry"; return NWW_EUNSUPPORTED; }
+        int cin = GeoNS40x98::N_MELS, nb = 0;
+        for (; nb < 16; ++nb) {
+            const std::string p = "qn." + std::to_string(nb);
+            auto dw = dims((p + ".w").c_str()), dd = dims((p + ".dw").c_str());
+            if (dw.size() != 2 || dd.size() != 2) break;
+            HeadWeights::QnBlock& B = hw->qn[nb];
+            B.K = (int)dw[0]; B.N = (int)dw[1]; B.k = (int)dd[0]; B.Cp = (int)dd[1];
+            B.C = cin;
+            B.has_res = B.K == 2 * B.Cp;
+            if ((B.K != B.Cp && !B.has_res) || B.K % kKcKC || B.N % kKcNC || B.N > 512 || B.C % 4 || B.C > B.Cp ||
+                (!B.has_res && B.C != B.N)) {
+                *err = p + ": unsupported QuartzNet block shape (channels must be multiples of 4, outputs multiples of 64 up to 512)";
+                return NWW_EUNSUPPORTED;
+            }
+            B.dw = need(p + ".dw", (size_t)B.k * B.Cp);
+            B.b = need(p + ".b", (size_t)B.N);
+            if (!need(p + ".w", (size_t)B.K * B.N)) return NWW_EINVAL;
+            hw->qn_max_k = std::max(hw->qn_max_k, B.K);
+            hw->qn_max_n = std::max(hw->qn_max_n, B.N);
+            cin = B.N;
+        }
+        if (nb == 0) { *err = "weight blob: qn.* missing"; return NWW_EINVAL; }
+        hw->qn_blocks = nb;
+        *feat_dim = cin;
+        // (T, F) log-mel + the GEMM operand rows + two activation planes
+        hw->scratch_floats = (size_t)GeoNS40x98::N_FRAMES * (GeoNS40x98::N_MELS + hw->qn_max_k + 2 * (size_t)hw->qn_max_n);
     } else if (arch == NWW_ARCH_E2E_MELCNN) {
         if (geometry != NWW_GEOM_REF64X101) { *err = "e2e mel-CNN is built for the REF64x101 geometry"; return NWW_EUNSUPPORTED; }
         const int ch[4] = {1, 16, 32, 64};
@@ -343,6 +375,29 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
                                         : go(rnn_seq_kernel<RNN_GRU, 64, F>, RnnDims<64, F>::SMEM);
         return hw.rnn_hidden == 128 ? go(rnn_seq_kernel<RNN_LSTM, 128, F>, RnnDims<128, F>::SMEM)
                                     : go(rnn_seq_kernel<RNN_LSTM, 64, F>, RnnDims<64, F>::SMEM);
+    }
+    if (hw.arch == NWW_ARCH_QUARTZNET) {
+        if (!mel_ready && (rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel, 1, st, launches, err))) return rc;
+        if (mel_dump && (rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel_dump, 0, st, launches, err))) return rc;
+        float* a = take((size_t)T * hw.qn_max_k);
+        float* plane[2] = {take((size_t)T * hw.qn_max_n), take((size_t)T * hw.qn_max_n)};
+        const float* x = mel;
+        int pitch = F;
+        const long long rows = n * T;
+        NWW_HCUDA(set_smem(rowgemm_kc_umma_kernel, rowgemm_kc_smem_bytes()));
+        for (int i = 0; i < hw.qn_blocks; ++i) {
+            const HeadWeights::QnBlock& B = hw.qn[i];
+            qn_dw_kernel<<<ew_grid(rows * (B.Cp / 4), sm_count), 256, 0, st>>>(x, pitch, B.dw, a, n, T, B.C, B.Cp, B.k, B.K);
+            if ((rc = done())) return rc;
+            float* y = plane[i & 1];
+            rowgemm_kc_umma_kernel<<<(int)std::min<long long>((rows + kKcRows - 1) / kKcRows, sm_count), kKcNT, rowgemm_kc_smem_bytes(), st>>>(
+                a, B.K, B.wq, B.b, B.has_res ? nullptr : x, y, rows, B.N, 1);
+            if ((rc = done())) return rc;
+            x = y;
+            pitch = B.N;
+        }
+        bc_gap_kernel<<<ew_grid(n * pitch, sm_count), 256, 0, st>>>(x, feat, n, T, pitch);
+        return done();
     }
     if (!mel_ready && !conv2_nhwc && (rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel, 0, st, launches, err))) return rc;
     if (mel_dump && !conv2_nhwc) NWW_HCUDA(cudaMemcpyAsync(mel_dump, mel, (size_t)n * F * T * sizeof(float), cudaMemcpyDeviceToDevice, st));

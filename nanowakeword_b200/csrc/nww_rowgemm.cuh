@@ -397,4 +397,211 @@ rowgemm_umma_kernel(const float* __restrict__ A, long long a_row_mul, long long 
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Row GEMM on tcgen05 for long K and wide N (QuartzNet's pointwise + residual 1x1 convolutions, K up to 512,
+// N up to 512):  out[r][n] = act(bias[n] + sum_k A[r][k] W[k][n] + res[r][n])   (K % 64 == 0, N % 64 == 0, N <= 512)
+// Tiles of 128 rows; K is walked in chunks of 64: the FP32 rows of a chunk become bf16 hi / lo un-swizzled K-major
+// operands in one of two shared-memory buffers (the conversion of chunk c + 1 overlaps the MMAs of chunk c), the
+// weights stream from L2 in 16 KB sub-blocks (chunk, 64 columns, hi | lo) through a ring of four slots filled by
+// cp.async.bulk, 4 K steps x 3 products of tcgen05.mma 128 x 64 x 16 per sub-block accumulate into TMEM columns
+// [64 nc, +64) across all chunks; one epilogue per tile.
+// ---------------------------------------------------------------------------------------
+constexpr int kKcRows = 128, kKcNT = 256, kKcKC = 64, kKcNC = 64, kKcRing = 4;
+constexpr int kKcABuf = 2 * (kKcKC / 8) * kKcRows * 16;           // hi | lo of one chunk: 32 KB
+constexpr int kKcSub = 2 * (kKcKC / 8) * kKcNC * 16;              // one weight sub-block: 16 KB
+inline size_t rowgemm_kc_smem_bytes() { return (size_t)2 * kKcABuf + (size_t)kKcRing * kKcSub + 256; }
+
+// host: w [K][N] FP32 -> the stream the kernel consumes: for every K chunk, for every 64-column group:
+// [hi | lo][K group 8][64 columns][8 k] bf16
+inline void rowgemm_kc_pack(const float* w, int K, int N, std::vector<uint16_t>* out) {
+    auto bf16_rn = [](float x) {
+        uint32_t u;
+        memcpy(&u, &x, 4);
+        u += 0x7FFFu + ((u >> 16) & 1u);
+        return (uint16_t)(u >> 16);
+    };
+    auto bf16_f = [](uint16_t b) {
+        uint32_t u = (uint32_t)b << 16;
+        float f;
+        memcpy(&f, &u, 4);
+        return f;
+    };
+    const size_t plane = (size_t)(kKcKC / 8) * kKcNC * 8, sub = 2 * plane;
+    const int n_nc = N / kKcNC;
+    out->assign((size_t)(K / kKcKC) * n_nc * sub, 0);
+    for (int k = 0; k < K; ++k)
+        for (int n = 0; n < N; ++n) {
+            const float v = w[(size_t)k * N + n];
+            const uint16_t hi = bf16_rn(v), lo = bf16_rn(v - bf16_f(hi));
+            const int kk = k % kKcKC;
+            const size_t base = ((size_t)(k / kKcKC) * n_nc + (size_t)(n / kKcNC)) * sub + (size_t)(kk >> 3) * kKcNC * 8 +
+                                (size_t)(n % kKcNC) * 8 + (kk & 7);
+            (*out)[base] = hi;
+            (*out)[base + plane] = lo;
+        }
+}
+
+__global__ void __launch_bounds__(kKcNT, 1)
+rowgemm_kc_umma_kernel(const float* __restrict__ A, int K, const uint4* __restrict__ wq, const float* __restrict__ bias,
+                       const float* __restrict__ res, float* __restrict__ out, long long rows, int N, int relu) {
+    NWW_DYN_SMEM(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned char* a_s = smem;                                         // two chunk buffers
+    unsigned char* b_s = smem + 2 * kKcABuf;                           // weight ring
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(b_s + kKcRing * kKcSub);
+    uint64_t* bar_empty = bar_full + kKcRing;
+    uint64_t* bar_afree = bar_full + 2 * kKcRing;                      // [2]: the MMAs that read chunk buffer b are done
+    uint64_t* bar_done = bar_full + 2 * kKcRing + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + 2 * kKcRing + 3);
+    const uint32_t tmem_cols = N <= 64 ? 64u : N <= 128 ? 128u : N <= 256 ? 256u : 512u;
+    if (tid == 0) {
+        for (int i = 0; i < 2 * kKcRing + 3; ++i) mbar_init(bar_full + i, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t idesc = umma_idesc_bf16(128, kKcNC);
+    const uint64_t da_buf0 = umma_desc_noswz(smem_u32(a_s), kKcRows * 16, 128);
+    const uint64_t db_ring = umma_desc_noswz(smem_u32(b_s), kKcNC * 16, 128);
+    const int n_kc = K / kKcKC, n_nc = N / kKcNC, total = n_kc * n_nc;
+    uint32_t c_slot = 0, c_par = 0, p_slot = 0, done_phase = 0;
+    uint32_t g = 0;                                                    // chunks converted so far: buffer g & 1
+    for (long long r0 = (long long)blockIdx.x * kKcRows; r0 < rows; r0 += (long long)gridDim.x * kKcRows) {
+        int p_pos = 0, prev_slot = -1;
+        uint32_t prev_par = 0;
+        auto produce = [&]() {                                         // thread 0: next sub-block of the tile's stream
+            mbar_expect_tx(bar_full + p_slot, kKcSub);
+            bulk_g2s(b_s + (size_t)p_slot * kKcSub, reinterpret_cast<const unsigned char*>(wq) + (size_t)p_pos * kKcSub, kKcSub,
+                     bar_full + p_slot);
+            p_slot = p_slot + 1 == kKcRing ? 0 : p_slot + 1;
+            ++p_pos;
+        };
+        if (tid == 0)
+            for (int i = 0; i < kKcRing && p_pos < total; ++i) produce();
+        for (int kc = 0; kc < n_kc; ++kc, ++g) {
+            const uint32_t buf = g & 1u;
+            if (g >= 2) mbar_wait(bar_afree + buf, ((g >> 1) - 1u) & 1u);   // chunk g - 2's MMAs have read this buffer
+            unsigned char* ab = a_s + (size_t)buf * kKcABuf;
+            for (int i = tid; i < kKcRows * (kKcKC / 8); i += kKcNT) {
+                const int gq = i / kKcRows, r = i - gq * kKcRows;
+                uint4 hv = make_uint4(0, 0, 0, 0), lv = hv;
+                if (r0 + r < rows) {
+                    const float4* p = reinterpret_cast<const float4*>(A + (r0 + r) * (long long)K + kc * kKcKC + 8 * gq);
+                    const float4 v0 = __ldg(p), v1 = __ldg(p + 1);
+                    const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                    uint32_t h[8], l[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        h[e] = float_to_bf16_bits(v[e]);
+                        l[e] = float_to_bf16_bits(v[e] - bf16_bits_to_float(h[e]));
+                    }
+                    hv = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+                    lv = make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
+                }
+                *reinterpret_cast<uint4*>(ab + i * 16) = hv;
+                *reinterpret_cast<uint4*>(ab + kKcABuf / 2 + i * 16) = lv;
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                const uint64_t da_h = da_buf0 + (uint64_t)((buf * (uint32_t)kKcABuf) >> 4), da_l = da_h + (uint64_t)((kKcABuf / 2) >> 4);
+                for (int nc = 0; nc < n_nc; ++nc) {
+                    mbar_wait(bar_full + c_slot, c_par);
+                    tc_fence_after();
+                    const uint64_t db_h = db_ring + (uint64_t)((c_slot * (uint32_t)kKcSub) >> 4), db_l = db_h + (uint64_t)((kKcSub / 2) >> 4);
+                    const uint32_t d = tmem_base + (uint32_t)(nc * kKcNC);
+#pragma unroll
+                    for (int ks = 0; ks < kKcKC / 16; ++ks) {
+                        const uint64_t ao = (uint64_t)((2 * ks * kKcRows * 16) >> 4), bo = (uint64_t)((2 * ks * kKcNC * 16) >> 4);
+                        umma_bf16(d, da_h + ao, db_h + bo, idesc, (kc | ks) != 0);
+                        umma_bf16(d, da_l + ao, db_h + bo, idesc, 1);
+                        umma_bf16(d, da_h + ao, db_l + bo, idesc, 1);
+                    }
+                    umma_commit(bar_empty + c_slot);
+                    if (prev_slot >= 0) {                              // refill the previous sub-block's slot
+                        mbar_wait(bar_empty + prev_slot, prev_par);
+                        if (p_pos < total) produce();
+                    }
+                    prev_slot = (int)c_slot;
+                    prev_par = c_par;
+                    if (++c_slot == kKcRing) { c_slot = 0; c_par ^= 1u; }
+                }
+                umma_commit(bar_afree + buf);
+            }
+        }
+        if (tid == 0) {
+            umma_commit(bar_done);
+            mbar_wait(bar_empty + prev_slot, prev_par);
+        }
+        mbar_wait(bar_done, done_phase);
+        done_phase ^= 1u;
+        tc_fence_after();
+        {
+            const int q = warp & 3, hcol = warp >> 2;
+            const long long r = r0 + q * 32 + lane;
+            for (int c0 = hcol * (N / 2); c0 < (hcol + 1) * (N / 2); c0 += 32) {
+                float v[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                if (r < rows) {
+                    float4* dst = reinterpret_cast<float4*>(out + r * N + c0);
+                    const float4* rs = res ? reinterpret_cast<const float4*>(res + r * N + c0) : nullptr;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        float4 o = make_float4(v[4 * j4] + __ldg(bias + c0 + 4 * j4), v[4 * j4 + 1] + __ldg(bias + c0 + 4 * j4 + 1),
+                                               v[4 * j4 + 2] + __ldg(bias + c0 + 4 * j4 + 2), v[4 * j4 + 3] + __ldg(bias + c0 + 4 * j4 + 3));
+                        if (rs) {
+                            const float4 t = __ldg(rs + j4);
+                            o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+                        }
+                        if (relu) { o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f); }
+                        dst[j4] = o;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// QuartzNet depthwise Conv1d (padding 'same', no bias: it is folded into the pointwise bias) on channel-last rows.
+// x [n][T][in_pitch] (first C channels used), dw [k][Cp];  a [n * T][K]: columns [0, Cp) = depthwise output
+// (zero beyond C), and, when K == 2 Cp, columns [Cp, 2 Cp) = x itself (the residual 1x1 convolution's input).
+__global__ void __launch_bounds__(256)
+qn_dw_kernel(const float* __restrict__ x, int in_pitch, const float* __restrict__ dw, float* __restrict__ a, long long n, int T,
+             int C, int Cp, int k, int K) {
+    const int left = (k - 1) / 2, q4 = Cp / 4;
+    const long long total = n * T * q4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % q4) * 4;
+        const long long row = i / q4;
+        const int t = (int)(row % T);
+        const float* xw = x + (row - t) * in_pitch;                    // the window's first row
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), ctr = acc;
+        if (c < C) {                                                   // C % 4 == 0
+            const int j_lo = left - t > 0 ? left - t : 0, j_hi = (T - 1 - t + left < k - 1) ? T - 1 - t + left : k - 1;
+            for (int j = j_lo; j <= j_hi; ++j) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(xw + (long long)(t + j - left) * in_pitch + c));
+                const float4 w = __ldg(reinterpret_cast<const float4*>(dw + (long long)j * Cp + c));
+                acc.x = fmaf(v.x, w.x, acc.x); acc.y = fmaf(v.y, w.y, acc.y);
+                acc.z = fmaf(v.z, w.z, acc.z); acc.w = fmaf(v.w, w.w, acc.w);
+            }
+            ctr = __ldg(reinterpret_cast<const float4*>(xw + (long long)t * in_pitch + c));
+        }
+        *reinterpret_cast<float4*>(a + row * K + c) = acc;
+        if (K == 2 * Cp) *reinterpret_cast<float4*>(a + row * K + Cp + c) = ctr;
+    }
+}
+
 }  // namespace nww

@@ -115,6 +115,10 @@ tail_kernel_t(const float* __restrict__ feat, long long n_windows, TailParams P,
                 tail_layernorm_act(cur, P.max_width, TM, P.pre_N, P.pre_g, P.pre_beta, P.act, tid, kTailNT);
                 __syncthreads();
             }
+            if (emb_dump != nullptr && P.n_layers == 2) {           // the pre-stage layer is the backbone's last layer
+                for (int i = tid; i < mt * P.pre_N; i += kTailNT)
+                    emb_dump[(w0 + i / P.pre_N) * (long long)P.pre_N + i % P.pre_N] = cur[(size_t)(i / P.pre_N) * P.max_width + i % P.pre_N];
+            }
         }
         for (int li = 0; li < P.n_layers; ++li) {
             const TailLayer L = P.layers[li];

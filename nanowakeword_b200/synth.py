@@ -28,11 +28,12 @@ _LOGIT_CAL = {
     "gru": (94.2, -12.01),
     "lstm": (56.6, 9.78),
     "rnn": (97.1, -18.93),
+    "quartznet": (40.3, -6.82),
 }
 
 DEFAULT_INPUT_SHAPE = {
     "dnn": (98, 40), "tcn": (98, 40),                     # (T, F)
-    "gru": (98, 40), "lstm": (98, 40), "rnn": (98, 40),
+    "gru": (98, 40), "lstm": (98, 40), "rnn": (98, 40), "quartznet": (98, 40),
     "cnn": (40, 98), "bcresnet": (40, 98), "crnn": (40, 98),   # (F, T)
     "e2e_dnn": (16000,),
 }
@@ -52,6 +53,8 @@ def default_config(model_type: str, **overrides) -> dict:
         cfg.update(tcn_channels=[64, 64, 128], tcn_kernel_size=3)
     if model_type == "crnn":
         cfg.update(crnn_cnn_channels=[16, 32, 32], crnn_rnn_type="gru")
+    if model_type == "quartznet":
+        cfg.update(quartznet_config=[[256, 33, 1], [256, 33, 1], [512, 39, 1]])      # model.py:240
     cfg.update(overrides)
     return cfg
 
@@ -166,6 +169,20 @@ def make_state_dict(cfg: dict, seed: int = 0) -> dict[str, np.ndarray]:
                                (f"bias_ih_l{layer}", (gates * hid,)), (f"bias_hh_l{layer}", (gates * hid,))):
                     g.uniform(f"model.{name}.{nm}{sfx}", sh, hid)
         g.linear("model.layer2" if mt == "rnn" else "model.fc", emb, 2 * hid)
+    elif mt == "quartznet":                           # architectures.py:366-437
+        cin, i = shape[1], 0
+        for channels, k, reps in cfg.get("quartznet_config", [[256, 33, 1], [256, 33, 1], [512, 39, 1]]):
+            for _ in range(reps):
+                p = f"model.quartznet_blocks.{i}"
+                g.conv1d(p + ".depthwise_conv", cin, 1, k)
+                g.conv1d(p + ".pointwise_conv", channels, cin, 1)
+                g.batchnorm(p + ".batch_norm", channels)
+                if cin != channels:
+                    g.conv1d(p + ".residual_connector.0", channels, cin, 1)
+                    g.batchnorm(p + ".residual_connector.1", channels)
+                cin = channels
+                i += 1
+        g.linear("model.fc", emb, cin)
     elif mt == "e2e_dnn":                             # architectures.py:820-888
         for i, (cin, cout) in zip((0, 4, 8), ((1, 16), (16, 32), (32, 64))):
             g.conv(f"model.conv_block.{i}", cout, cin, 3, 3)

@@ -23,7 +23,7 @@ import numpy as np
 
 BN_EPS = 1e-5
 
-ARCH_IDS = {"dnn": 0, "cnn": 1, "tcn": 2, "bcresnet": 3, "crnn": 4, "e2e_dnn": 5, "gru": 6, "lstm": 7, "rnn": 7}
+ARCH_IDS = {"dnn": 0, "cnn": 1, "tcn": 2, "bcresnet": 3, "crnn": 4, "e2e_dnn": 5, "gru": 6, "lstm": 7, "rnn": 7, "quartznet": 8}
 ACT_IDS = {"relu": 0, "gelu": 1, "silu": 2}
 POST_NONE, POST_ACT, POST_LN_ACT = 0, 1, 2
 
@@ -181,6 +181,35 @@ def pack_tensors(sd: dict, cfg: dict) -> dict[str, np.ndarray]:
         out["rnn.cell"] = np.array([0 if mt == "gru" else 1], dtype=np.int32)
         fc = "model.layer2" if mt == "rnn" else "model.fc"
         layers.append((_f64(sd, fc + ".weight"), _f64(sd, fc + ".bias"), POST_NONE, None))
+    elif mt == "quartznet":
+        # QuartzNetModel (architectures.py:366-437).  Per block the engine runs a depthwise FIR (no bias) and ONE row
+        # GEMM [dw(x) | x] @ W + b: BatchNorm folded into the pointwise / residual 1x1 weights, the depthwise bias
+        # pushed through the pointwise weights into b.  Channel counts are padded so that K is a multiple of 64.
+        i = 0
+        while f"model.quartznet_blocks.{i}.depthwise_conv.weight" in sd:
+            p = f"model.quartznet_blocks.{i}"
+            wd, bd = _f64(sd, p + ".depthwise_conv.weight")[:, 0, :], _f64(sd, p + ".depthwise_conv.bias")    # (C, k)
+            wp, bp = _f64(sd, p + ".pointwise_conv.weight")[:, :, 0], _f64(sd, p + ".pointwise_conv.bias")    # (N, C)
+            c, k = wd.shape
+            n_out = wp.shape[0]
+            wp_f, b = fold_bn(wp, bp + wp @ bd, sd, p + ".batch_norm")
+            has_res = p + ".residual_connector.0.weight" in sd
+            cp = -(-c // 32) * 32 if has_res else -(-c // 64) * 64
+            w = np.zeros((cp * (2 if has_res else 1), n_out))
+            w[:c] = wp_f.T
+            if has_res:
+                wr_f, br = fold_bn(_f64(sd, p + ".residual_connector.0.weight")[:, :, 0],
+                                   _f64(sd, p + ".residual_connector.0.bias"), sd, p + ".residual_connector.1")
+                w[cp:cp + c] = wr_f.T
+                b = b + br
+            dw = np.zeros((k, cp))
+            dw[:, :c] = wd.T
+            out[f"qn.{i}.dw"] = dw.astype(np.float32)
+            out[f"qn.{i}.w"] = w.astype(np.float32)
+            out[f"qn.{i}.b"] = b.astype(np.float32)
+            out[f"qn.{i}.meta"] = np.array([c, n_out, k, int(has_res)], dtype=np.int32)
+            i += 1
+        layers.append((_f64(sd, "model.fc.weight"), _f64(sd, "model.fc.bias"), POST_NONE, None))
     elif mt == "e2e_dnn":
         for j, i in enumerate((0, 4, 8)):
             w, b = fold_bn(_f64(sd, f"model.conv_block.{i}.weight"), _f64(sd, f"model.conv_block.{i}.bias"),

@@ -14,6 +14,7 @@ Reference anchors (all under /root/reference/nanowakeword/):
   LSTMModel                 modules/architectures.py:83-99
   GRUModel                  modules/architectures.py:129-146
   RNNModel (bi-LSTM, H=64)  modules/architectures.py:149-161
+  QuartzNetModel/Block      modules/architectures.py:366-437
   E2E_MelSpectrogram_CNN    modules/architectures.py:820-888
   Model.classifier/forward  modules/model.py:291-296, 562-571
   sigmoid + view(-1,1,1)    _export/onnx.py:164-172
@@ -33,7 +34,7 @@ LN_EPS = 1e-5
 
 # Heads whose input is (T, F) rather than (F, T)  (model.py:128-236 passes input_shape[1]
 # as the feature dim for dnn/tcn; cnn/bcresnet/crnn treat input_shape as (freq, time)).
-TIME_MAJOR_HEADS = ("dnn", "tcn", "gru", "lstm", "rnn")
+TIME_MAJOR_HEADS = ("dnn", "tcn", "gru", "lstm", "rnn", "quartznet")
 
 
 # ----------------------------------------------------------------------------- primitives
@@ -306,6 +307,33 @@ def _rnn(x, sd, cfg):
     return linear(rnn_last_output_bidir(x, sd, "model.layer1", "lstm"), sd["model.layer2.weight"], sd["model.layer2.bias"])
 
 
+def _quartznet(x, sd, cfg):
+    """QuartzNetModel on a (T, F) sequence (architectures.py:366-437): per block a depthwise Conv1d
+    (padding='same': for a kernel k torch pads (k-1)//2 on the left and the rest on the right), a 1x1 Conv1d,
+    BatchNorm1d, plus the residual (1x1 Conv1d + BatchNorm1d when the channel count changes, else the
+    identity), ReLU; then the mean over time and a Linear."""
+    h = np.swapaxes(x, 1, 2)                                        # (B, C, T)
+    i = 0
+    while f"model.quartznet_blocks.{i}.depthwise_conv.weight" in sd:
+        p = f"model.quartznet_blocks.{i}"
+        wd = sd[p + ".depthwise_conv.weight"]                       # (C, 1, k)
+        k = wd.shape[2]
+        left = (k - 1) // 2
+        xp = np.pad(h, ((0, 0), (0, 0), (left, k - 1 - left)))
+        y = np.einsum("bctk,ck->bct", sliding_window_view(xp, k, axis=2), wd[:, 0], optimize=True)
+        y = y + sd[p + ".depthwise_conv.bias"].reshape(1, -1, 1)
+        y = np.einsum("oc,bct->bot", sd[p + ".pointwise_conv.weight"][:, :, 0], y, optimize=True)
+        y = batchnorm(y + sd[p + ".pointwise_conv.bias"].reshape(1, -1, 1), sd, p + ".batch_norm")
+        if p + ".residual_connector.0.weight" in sd:
+            r = np.einsum("oc,bct->bot", sd[p + ".residual_connector.0.weight"][:, :, 0], h, optimize=True)
+            r = batchnorm(r + sd[p + ".residual_connector.0.bias"].reshape(1, -1, 1), sd, p + ".residual_connector.1")
+        else:
+            r = h
+        h = np.maximum(y + r, 0)
+        i += 1
+    return linear(h.mean(axis=2), sd["model.fc.weight"], sd["model.fc.bias"])
+
+
 def _e2e_melcnn_body(mel, sd, cfg):
     act = cfg.get("activation_function", "relu")
     h = mel[:, None]
@@ -321,7 +349,7 @@ def _e2e_melcnn_body(mel, sd, cfg):
 
 
 _BACKBONES = {"dnn": _dnn, "cnn": _cnn, "tcn": _tcn, "bcresnet": _bcresnet, "crnn": _crnn,
-              "e2e_dnn": _e2e_melcnn_body, "gru": _gru, "lstm": _lstm, "rnn": _rnn}
+              "e2e_dnn": _e2e_melcnn_body, "gru": _gru, "lstm": _lstm, "rnn": _rnn, "quartznet": _quartznet}
 
 
 def classifier(emb, sd, cfg):

@@ -107,7 +107,7 @@ def main():
         print("frontend.npz written")
 
     # ---- heads (fed the float64 torchaudio mel so head errors are isolated) -----------
-    for mt in ("dnn", "cnn", "tcn", "bcresnet", "crnn", "e2e_dnn", "gru", "lstm", "rnn"):
+    for mt in ("dnn", "cnn", "tcn", "bcresnet", "crnn", "e2e_dnn", "gru", "lstm", "rnn", "quartznet"):
         if only and mt not in only:
             continue
         cfg = default_config(mt)
@@ -143,7 +143,7 @@ def main():
             else:
                 geom = "NS40x98"
                 mel = mels[geom]
-                feat = mel.transpose(1, 2).contiguous() if mt in ("dnn", "tcn", "gru", "lstm", "rnn") else mel
+                feat = mel.transpose(1, 2).contiguous() if mt in ("dnn", "tcn", "gru", "lstm", "rnn", "quartznet") else mel
                 logits64 = model.double()(feat)
                 res["logits64"] = logits64.numpy()
                 res["logits32"] = model.float()(feat.float()).numpy()

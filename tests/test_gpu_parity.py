@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 SCORE_TOL = 1e-3
 MEL_TOL = 1e-4
 
-HEADS = ["dnn", "cnn", "tcn", "bcresnet", "crnn", "e2e_dnn", "gru", "lstm", "rnn"]
+HEADS = ["dnn", "cnn", "tcn", "bcresnet", "crnn", "e2e_dnn", "gru", "lstm", "rnn", "quartznet"]
 
 
 @pytest.fixture(scope="module")
@@ -194,7 +194,7 @@ def test_stream_push_device_equals_batch_scoring(torch_cuda):
         eng.stream_push_host(np.zeros((n, 100), np.int16))      # closed: no streams are open
 
 
-@pytest.mark.parametrize("mt", ["cnn", "dnn", "tcn", "bcresnet", "crnn", "gru", "lstm", "rnn"])
+@pytest.mark.parametrize("mt", ["cnn", "dnn", "tcn", "bcresnet", "crnn", "gru", "lstm", "rnn", "quartznet"])
 def test_incremental_stream_mel_is_bit_identical_to_full_recompute(torch_cuda, mt):
     """The mel ring (nww_stream_mel.cuh) only computes the frames a chunk completes; because the
     NS40x98 front end is not centred those are the same arithmetic on the same samples as in a
