@@ -387,7 +387,16 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
         NWW_HCUDA(set_smem(rowgemm_kc_umma_kernel, rowgemm_kc_smem_bytes()));
         for (int i = 0; i < hw.qn_blocks; ++i) {
             const HeadWeights::QnBlock& B = hw.qn[i];
-            qn_dw_kernel<<<ew_grid(rows * (B.Cp / 4), sm_count), 256, 0, st>>>(x, pitch, B.dw, a, n, T, B.C, B.Cp, B.k, B.K);
+            const int tgrid = (int)std::min<long long>(n * (B.Cp / 32), (long long)sm_count * 8);
+            if (B.Cp % 32 == 0 && T <= kQnSeg * kQnSegs && (B.k == 33 || B.k == 39 || B.k == 11 || B.k == 13 || B.k == 17)) {
+                if (B.k == 33) qn_dw_tile_kernel<33><<<tgrid, 256, 0, st>>>(x, pitch, B.dw, a, n, T, B.C, B.Cp, B.K);
+                else if (B.k == 39) qn_dw_tile_kernel<39><<<tgrid, 256, 0, st>>>(x, pitch, B.dw, a, n, T, B.C, B.Cp, B.K);
+                else if (B.k == 11) qn_dw_tile_kernel<11><<<tgrid, 256, 0, st>>>(x, pitch, B.dw, a, n, T, B.C, B.Cp, B.K);
+                else if (B.k == 13) qn_dw_tile_kernel<13><<<tgrid, 256, 0, st>>>(x, pitch, B.dw, a, n, T, B.C, B.Cp, B.K);
+                else qn_dw_tile_kernel<17><<<tgrid, 256, 0, st>>>(x, pitch, B.dw, a, n, T, B.C, B.Cp, B.K);
+            } else {
+                qn_dw_kernel<<<ew_grid(rows * (B.Cp / 4), sm_count), 256, 0, st>>>(x, pitch, B.dw, a, n, T, B.C, B.Cp, B.k, B.K);
+            }
             if ((rc = done())) return rc;
             float* y = plane[i & 1];
             rowgemm_kc_umma_kernel<<<(int)std::min<long long>((rows + kKcRows - 1) / kKcRows, sm_count), kKcNT, rowgemm_kc_smem_bytes(), st>>>(

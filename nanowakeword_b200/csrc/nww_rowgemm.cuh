@@ -604,4 +604,52 @@ qn_dw_kernel(const float* __restrict__ x, int in_pitch, const float* __restrict_
     }
 }
 
+// The same depthwise FIR with the window's rows staged in shared memory and the taps in registers: one CTA iteration =
+// (window, 32-channel slab); thread = (channel, segment of 13 output steps), a sliding window of inputs feeds the 13
+// accumulators (KW + 12 shared-memory loads for 13 KW FMAs).  T = 98 (NS40x98).
+constexpr int kQnSeg = 13, kQnSegs = 8;
+template <int KW>
+__global__ void __launch_bounds__(256)
+qn_dw_tile_kernel(const float* __restrict__ x, int in_pitch, const float* __restrict__ dw, float* __restrict__ a, long long n, int T,
+                  int C, int Cp, int K) {
+    constexpr int LEFT = (KW - 1) / 2, ROWS = kQnSeg * kQnSegs + KW - 1;
+    __shared__ float xs[ROWS * 32];
+    const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
+    const int slabs = Cp / 32;
+    for (long long it = blockIdx.x; it < n * slabs; it += gridDim.x) {
+        const long long w = it / slabs;
+        const int c = (int)(it - w * slabs) * 32 + lane;
+        const float* xw = x + w * T * in_pitch;
+        __syncthreads();
+        for (int i = threadIdx.x; i < ROWS * 32; i += 256) {
+            const int t = (i >> 5) - LEFT;                             // source step of shared row i / 32
+            xs[i] = (t >= 0 && t < T && c < C) ? __ldg(xw + (long long)t * in_pitch + c) : 0.0f;
+        }
+        float wt[KW];
+#pragma unroll
+        for (int j = 0; j < KW; ++j) wt[j] = c < C ? __ldg(dw + (long long)j * Cp + c) : 0.0f;
+        __syncthreads();
+        float acc[kQnSeg];
+#pragma unroll
+        for (int r = 0; r < kQnSeg; ++r) acc[r] = 0.0f;
+        const int t0 = seg * kQnSeg;
+#pragma unroll
+        for (int j = 0; j < kQnSeg + KW - 1; ++j) {
+            const float v = xs[(t0 + j) * 32 + lane];
+#pragma unroll
+            for (int r = 0; r < kQnSeg; ++r)
+                if (j - r >= 0 && j - r < KW) acc[r] = fmaf(wt[j - r], v, acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < kQnSeg; ++r) {
+            const int t = t0 + r;
+            if (t < T) {
+                float* row = a + (w * T + t) * (long long)K;
+                row[c] = acc[r];
+                if (K == 2 * Cp) row[Cp + c] = xs[(t + LEFT) * 32 + lane];
+            }
+        }
+    }
+}
+
 }  // namespace nww
