@@ -277,3 +277,32 @@ def test_other_activations_match_oracle(torch_cuda, mt, act):
     ref = forward_scores(pcm, sd, cfg).ravel()
     got = eng.score_device(torch_cuda.from_numpy(pcm).cuda()).cpu().numpy()
     assert np.abs(got - ref).max() < SCORE_TOL, (mt, act, np.abs(got - ref).max())
+
+
+@pytest.mark.parametrize("mt,kw", [("gru", dict(layer_dim=64)), ("lstm", dict(layer_dim=64)), ("gru", dict(activation_function="gelu")),
+                                   ("quartznet", dict(quartznet_config=[[64, 11, 1], [64, 13, 2], [128, 17, 1], [128, 5, 1]]))])
+def test_sequence_head_variants_match_oracle(torch_cuda, mt, kw):
+    """Other shapes of the §8(f) sequence heads: 64 hidden units (the second template instantiation of
+    rnn_seq_kernel), a non-ReLU classifier, and a QuartzNet config with repeated blocks (identity residual), the
+    e2e-style kernel sizes 11 / 13 / 17 and one size (5) that takes the generic depthwise kernel."""
+    from nanowakeword_b200 import Engine
+    from oracle.heads import forward_scores
+    cfg = default_config(mt, **kw)
+    sd = make_state_dict(cfg, seed=2)
+    eng = Engine(sd, cfg, device=0)
+    pcm = np.concatenate([synth_pcm(45, seed=41, kind="gauss"), synth_pcm(25, seed=42, kind="uniform")])
+    ref = forward_scores(pcm, sd, cfg).ravel()
+    got = eng.score_device(torch_cuda.from_numpy(pcm).cuda()).cpu().numpy()
+    assert np.abs(got - ref).max() < SCORE_TOL, (mt, kw, np.abs(got - ref).max())
+
+
+@pytest.mark.parametrize("mt", ["gru", "lstm", "quartznet"])
+def test_sequence_heads_do_not_depend_on_batch_composition(torch_cuda, mt):
+    """A window's score must not depend on which tile / CTA / chunk it lands in: the recurrent kernel uses 32-row tiles
+    for small batches and 128-row tiles for large ones, the row GEMM walks K in a fixed order."""
+    eng, sd, cfg = _engine(mt)
+    base = np.concatenate([synth_pcm(50, seed=51, kind="gauss"), synth_pcm(20, seed=52, kind="uniform")])
+    small = eng.score_device(torch_cuda.from_numpy(base).cuda()).cpu().numpy()
+    reps = 203 if mt != "quartznet" else 60                     # 14 210 windows: 128-row tiles, ragged last tile
+    big = eng.score_device(torch_cuda.from_numpy(np.tile(base, (reps, 1))).cuda()).cpu().numpy()
+    assert np.array_equal(big.reshape(reps, -1), np.tile(small, (reps, 1)))

@@ -246,3 +246,48 @@ def test_stream_bank_matches_per_stream_oracle_interpreters(mode):
         bank.push(chunks, patience=2)                       # threshold missing
     with pytest.raises(ValueError):
         bank.push(chunks, patience=2, debounce_time=0.5, threshold=0.5)
+
+
+def test_multi_layer_recurrent_heads_are_refused():
+    """The engine builds single-layer GRU / LSTM / RNN heads (the reference default, n_blocks = 1); deeper stacks must
+    fail loudly at pack time instead of being scored wrongly."""
+    for mt in ("gru", "lstm", "rnn"):
+        cfg = default_config(mt, n_blocks=2)
+        sd = make_state_dict(cfg, 0)
+        with pytest.raises(ValueError, match="single-layer"):
+            pack_tensors(sd, cfg)
+
+
+def test_recurrent_gate_matrix_layout():
+    """weights.py packs each direction as one [x | 1 | pad | h] x [4H gate columns] matrix (csrc/nww_rnn.cuh): evaluate
+    that matrix in numpy and compare with the oracle's GRU / LSTM."""
+    from oracle.heads import _cast_sd, rnn_last_output_bidir
+    sig = lambda v: 1.0 / (1.0 + np.exp(-v))
+    x = np.random.default_rng(3).normal(-20, 30, (4, 98, 40))
+    for mt, prefix, kind in (("gru", "model.gru", "gru"), ("lstm", "model.lstm", "lstm"), ("rnn", "model.layer1", "lstm")):
+        cfg = default_config(mt)
+        sd = make_state_dict(cfg, 0)
+        t = pack_tensors(sd, cfg)
+        wf, wb = t["rnn.fwd.w"].astype(np.float64), t["rnn.bwd.w"].astype(np.float64)
+        hid, kx = wf.shape[1] // 4, wb.shape[0]
+        assert wf.shape[0] == kx + hid and kx % 16 == 0 and kx > 40
+
+        def step(xt, h, c, w):
+            a = np.zeros((xt.shape[0], w.shape[0]))
+            a[:, :40], a[:, 40] = xt, 1.0
+            if w.shape[0] > kx:
+                a[:, kx:] = h
+            g = a @ w
+            g0, g1, g2, g3 = g[:, :hid], g[:, hid:2 * hid], g[:, 2 * hid:3 * hid], g[:, 3 * hid:]
+            if kind == "lstm":
+                c = sig(g1) * c + sig(g0) * np.tanh(g2)
+                return sig(g3) * np.tanh(c), c
+            r, z = sig(g0), sig(g1)
+            hn = (1 - z) * np.tanh(g2 + r * g3) + z * h
+            return hn, hn
+        h = c = np.zeros((4, hid))
+        for s in range(98):
+            h, c = step(x[:, s], h, c, wf)
+        hb, _ = step(x[:, 97], np.zeros((4, hid)), np.zeros((4, hid)), wb)
+        ref = rnn_last_output_bidir(x, _cast_sd(sd, np.float64), prefix, kind)
+        assert np.abs(np.concatenate([h, hb], 1) - ref).max() < 1e-6
