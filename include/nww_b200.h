@@ -40,6 +40,8 @@ extern "C" {
 #define NWW_ARCH_GRU 6       /* GRUModel (bidirectional)  :129-146 */
 #define NWW_ARCH_LSTM 7      /* LSTMModel :83-99, and RNNModel :149-161 (a bidirectional LSTM, 64 hidden units) */
 #define NWW_ARCH_QUARTZNET 8 /* QuartzNetModel / QuartzNetBlock :366-437 */
+#define NWW_ARCH_E2E_QUARTZNET 9 /* E2ERawQuartzNet :796-817 = RawAudioFrontend :695-714 on the audio itself + QuartzNetModel;
+                                    no log-mel: the spec's geometry is ignored and mel dumps are refused */
 
 #define NWW_ACT_RELU 0       /* reference nanowakeword/modules/model.py:81-87 */
 #define NWW_ACT_GELU 1

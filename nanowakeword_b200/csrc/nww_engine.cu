@@ -615,7 +615,19 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
                 e->heads.rnn_wq_f = reinterpret_cast<const uint4*>(e->d_conv_wq[1]);
                 e->heads.rnn_wq_b = reinterpret_cast<const uint4*>(e->d_conv_wq[2]);
             }
-            if (spec->arch == NWW_ARCH_QUARTZNET) {
+            if (spec->arch == NWW_ARCH_E2E_QUARTZNET) {
+                for (int i = 0; i < e->heads.raw_layers; ++i) {        // strided Conv1d layers as row-GEMM weight streams
+                    auto& L = e->heads.raw[i];
+                    std::vector<uint16_t> wq;
+                    rowgemm_kc_pack(e->blob.f32("raw." + std::to_string(i) + ".w"), L.K, L.Npad, &wq);
+                    void* d = nullptr;
+                    NWW_CUDA(cudaMalloc(&d, wq.size() * sizeof(uint16_t)));
+                    e->d_extra.push_back(d);
+                    NWW_CUDA(cudaMemcpy(d, wq.data(), wq.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+                    L.wq = reinterpret_cast<const uint4*>(d);
+                }
+            }
+            if (spec->arch == NWW_ARCH_QUARTZNET || spec->arch == NWW_ARCH_E2E_QUARTZNET) {
                 // folded pointwise (+ residual) weights of every block as bf16 UMMA operand streams (nww_rowgemm.cuh)
                 for (int i = 0; i < e->heads.qn_blocks; ++i) {
                     auto& B = e->heads.qn[i];
@@ -910,7 +922,7 @@ int nww_stream_open(nww_engine* e, int64_t n_streams) {
     // incremental log-mel (nww_stream_mel.cuh): un-centred geometry, and a stage A that can start from mel
     const bool v1_cnn = e->spec.arch == NWW_ARCH_CNN && !e->cnn2_enabled;
     if (e->spec.geometry == NWW_GEOM_NS40X98 && e->spec.frontend_precision == NWW_FRONTEND_FP64 && !v1_cnn &&
-        !(e->spec.reserved[0] & 4)) {
+        e->spec.arch != NWW_ARCH_E2E_QUARTZNET /* no log-mel in a raw-audio model */ && !(e->spec.reserved[0] & 4)) {
         NWW_CUDA(cudaMalloc(&e->d_mel_ring, (size_t)n_streams * SMel::STREAM_FLOATS * sizeof(float)));
         NWW_CUDA(cudaMemsetAsync(e->d_mel_ring, 0, (size_t)n_streams * SMel::STREAM_FLOATS * sizeof(float), e->stream));
         e->mel_inc = true;

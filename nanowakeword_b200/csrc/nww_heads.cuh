@@ -65,8 +65,17 @@ struct HeadWeights {
     const uint4 *rnn_wq_f = nullptr, *rnn_wq_b = nullptr;
     // QuartzNet (qn_dw_kernel + rowgemm_kc_umma_kernel)
     struct QnBlock { int C = 0, Cp = 0, N = 0, k = 0, K = 0, has_res = 0; const float *dw = nullptr, *b = nullptr; const uint4* wq = nullptr; };
-    int qn_blocks = 0, qn_max_k = 0, qn_max_n = 0;
+    int qn_blocks = 0, qn_max_k = 0, qn_max_n = 0, qn_t = 0, qn_cin = 0;    // sequence length / channels the blocks see
     QnBlock qn[16];
+    // raw-audio front end (E2ERawQuartzNet): strided Conv1d layers as row GEMMs over channel-last buffers
+    struct RawLayer {
+        int cin = 0, cout = 0, k = 0, stride = 0, pad = 0, K = 0, Npad = 0, t_in = 0, t_out = 0;
+        long long in_len = 0;          // floats per window of the layer's (zero-padded) input buffer
+        const float* b = nullptr;
+        const uint4* wq = nullptr;
+    };
+    int raw_layers = 0;
+    RawLayer raw[4];
     // scratch layout (floats per window)
     size_t scratch_floats = 0;
 };
@@ -238,9 +247,46 @@ inline int setup_head_weights(int arch, int geometry, const BlobLookup& get, con
         hw->rnn_hidden = H;
         *feat_dim = 2 * H;
         hw->scratch_floats = (size_t)GeoNS40x98::N_FRAMES * GeoNS40x98::N_MELS;      // the (T, F) log-mel
-    } else if (arch == NWW_ARCH_QUARTZNET) {
-        if (geometry != NWW_GEOM_NS40X98) { *err = "quartznet head is built for the NS40x98 geometry"; return NWW_EUNSUPPORTED; }
-        int cin = GeoNS40x98::N_MELS, nb = 0;
+    } else if (arch == NWW_ARCH_QUARTZNET || arch == NWW_ARCH_E2E_QUARTZNET) {
+        int cin = GeoNS40x98::N_MELS, tq = GeoNS40x98::N_FRAMES;
+        size_t raw_floats = 0;
+        if (arch == NWW_ARCH_QUARTZNET) {
+            if (geometry != NWW_GEOM_NS40X98) { *err = "quartznet head is built for the NS40x98 geometry"; return NWW_EUNSUPPORTED; }
+        } else {
+            // RawAudioFrontend (architectures.py:695-714): k = 41 / stride 16 first, then k = 13 / stride 4, padding k / 2
+            cin = 1;
+            tq = 16000;
+            int nl = 0;
+            for (; nl < 4; ++nl) {
+                const std::string p = "raw." + std::to_string(nl);
+                auto dw = dims((p + ".w").c_str()), db = dims((p + ".b").c_str());
+                if (dw.size() != 2 || db.size() != 1) break;
+                HeadWeights::RawLayer& L = hw->raw[nl];
+                L.cin = cin; L.cout = (int)db[0]; L.k = nl == 0 ? 41 : 13; L.stride = nl == 0 ? 16 : 4; L.pad = L.k / 2;
+                L.K = (int)dw[0]; L.Npad = (int)dw[1];
+                L.t_in = tq; L.t_out = (tq + 2 * L.pad - L.k) / L.stride + 1;
+                if (L.K != (L.k * cin + 63) / 64 * 64 || L.Npad != (L.cout + 63) / 64 * 64 || L.cout % 32 || L.Npad > 512 ||
+                    (cin != 1 && cin % 4) || L.t_out < 1) {
+                    *err = p + ": unsupported raw-audio front-end layer shape";
+                    return NWW_EUNSUPPORTED;
+                }
+                // input buffer: pad rows, the data, and whatever the last GEMM row reads past it (zeros)
+                const long long need_rows = (long long)L.stride * (L.t_out - 1) * cin + L.K;
+                L.in_len = (std::max<long long>((long long)(L.pad + L.t_in + L.pad) * cin, need_rows) + 3) / 4 * 4;
+                L.b = need(p + ".b", (size_t)L.cout);
+                if (!need(p + ".w", (size_t)L.K * L.Npad)) return NWW_EINVAL;
+                raw_floats += (size_t)L.in_len;
+                cin = L.cout;
+                tq = L.t_out;
+            }
+            if (nl == 0) { *err = "weight blob: raw.* missing"; return NWW_EINVAL; }
+            if (tq > kQnSeg * kQnSegs && false) { *err = "raw-audio front end leaves too long a sequence"; return NWW_EUNSUPPORTED; }
+            hw->raw_layers = nl;
+            raw_floats += (size_t)tq * cin;                                        // the last layer's plain output
+        }
+        hw->qn_t = tq;
+        hw->qn_cin = cin;
+        int nb = 0;
         for (; nb < 16; ++nb) {
             const std::string p = "qn." + std::to_string(nb);
             auto dw = dims((p + ".w").c_str()), dd = dims((p + ".dw").c_str());
@@ -264,8 +310,9 @@ inline int setup_head_weights(int arch, int geometry, const BlobLookup& get, con
         if (nb == 0) { *err = "weight blob: qn.* missing"; return NWW_EINVAL; }
         hw->qn_blocks = nb;
         *feat_dim = cin;
-        // (T, F) log-mel + the GEMM operand rows + two activation planes
-        hw->scratch_floats = (size_t)GeoNS40x98::N_FRAMES * (GeoNS40x98::N_MELS + hw->qn_max_k + 2 * (size_t)hw->qn_max_n);
+        // input (log-mel, or the raw front end's buffers) + the GEMM operand rows + two activation planes
+        hw->scratch_floats = (arch == NWW_ARCH_QUARTZNET ? (size_t)tq * GeoNS40x98::N_MELS : raw_floats) +
+                             (size_t)tq * (hw->qn_max_k + 2 * (size_t)hw->qn_max_n);
     } else if (arch == NWW_ARCH_E2E_MELCNN) {
         if (geometry != NWW_GEOM_REF64X101) { *err = "e2e mel-CNN is built for the REF64x101 geometry"; return NWW_EUNSUPPORTED; }
         const int ch[4] = {1, 16, 32, 64};
@@ -280,6 +327,85 @@ inline int setup_head_weights(int arch, int geometry, const BlobLookup& get, con
         return NWW_EUNSUPPORTED;
     }
     return err->empty() ? NWW_OK : NWW_EINVAL;
+}
+
+// QuartzNet blocks + mean over time on channel-last rows x [n][hw.qn_t][pitch]; `arena` provides the GEMM operand rows
+// and two activation planes (n windows each)
+inline int launch_quartznet_blocks(const HeadWeights& hw, const float* x, int pitch, long long n, float* arena, float* feat,
+                                   int sm_count, cudaStream_t st, int64_t* launches, std::string* err) {
+    auto done = [&]() -> int {
+        (*launches)++;
+        NWW_HCUDA(cudaGetLastError());
+        return NWW_OK;
+    };
+    int rc;
+    const int T = hw.qn_t;
+    float* a = arena;
+    float* plane[2] = {a + (size_t)n * T * hw.qn_max_k, a + (size_t)n * T * hw.qn_max_k + (size_t)n * T * hw.qn_max_n};
+    const long long rows = n * T;
+    NWW_HCUDA(set_smem(rowgemm_kc_umma_kernel, rowgemm_kc_smem_bytes()));
+    for (int i = 0; i < hw.qn_blocks; ++i) {
+        const HeadWeights::QnBlock& B = hw.qn[i];
+        const int tgrid = (int)std::min<long long>(n * (B.Cp / 32), (long long)sm_count * 8);
+        if (B.Cp % 32 == 0 && T <= kQnSeg * kQnSegs && (B.k == 33 || B.k == 39 || B.k == 11 || B.k == 13 || B.k == 17)) {
+            if (B.k == 33) qn_dw_tile_kernel<33><<<tgrid, 256, 0, st>>>(x, pitch, B.dw, a, n, T, B.C, B.Cp, B.K);
+            else if (B.k == 39) qn_dw_tile_kernel<39><<<tgrid, 256, 0, st>>>(x, pitch, B.dw, a, n, T, B.C, B.Cp, B.K);
+            else if (B.k == 11) qn_dw_tile_kernel<11><<<tgrid, 256, 0, st>>>(x, pitch, B.dw, a, n, T, B.C, B.Cp, B.K);
+            else if (B.k == 13) qn_dw_tile_kernel<13><<<tgrid, 256, 0, st>>>(x, pitch, B.dw, a, n, T, B.C, B.Cp, B.K);
+            else qn_dw_tile_kernel<17><<<tgrid, 256, 0, st>>>(x, pitch, B.dw, a, n, T, B.C, B.Cp, B.K);
+        } else {
+            qn_dw_kernel<<<ew_grid(rows * (B.Cp / 4), sm_count), 256, 0, st>>>(x, pitch, B.dw, a, n, T, B.C, B.Cp, B.k, B.K);
+        }
+        if ((rc = done())) return rc;
+        float* y = plane[i & 1];
+        rowgemm_kc_umma_kernel<<<(int)std::min<long long>((rows + kKcRows - 1) / kKcRows, sm_count), kKcNT, rowgemm_kc_smem_bytes(), st>>>(
+            a, KcView{rows, 0, B.K, 0}, B.K, B.wq, B.b, B.has_res ? nullptr : x, y, KcView{rows, 0, B.N, 0}, rows, B.N, B.N, 1);
+        if ((rc = done())) return rc;
+        x = y;
+        pitch = B.N;
+    }
+    bc_gap_kernel<<<ew_grid(n * pitch, sm_count), 256, 0, st>>>(x, feat, n, T, pitch);
+    return done();
+}
+
+// E2ERawQuartzNet: audio -> float -> strided Conv1d layers (row GEMMs over overlapping rows) -> QuartzNet blocks
+inline int launch_raw_quartznet(const HeadWeights& hw, int sm_count, WindowSource pcm, long long n, float* feat, float* scratch,
+                                cudaStream_t st, int64_t* launches, std::string* err) {
+    auto done = [&]() -> int {
+        (*launches)++;
+        NWW_HCUDA(cudaGetLastError());
+        return NWW_OK;
+    };
+    int rc;
+    float* p = scratch;
+    const HeadWeights::RawLayer& L0 = hw.raw[0];
+    float* in = p;
+    p += (size_t)n * L0.in_len;
+    raw_pcm_kernel<<<ew_grid(n * (L0.in_len / 4), sm_count), 256, 0, st>>>(pcm, n, in, (int)L0.in_len, L0.pad);
+    if ((rc = done())) return rc;
+    NWW_HCUDA(set_smem(rowgemm_kc_umma_kernel, rowgemm_kc_smem_bytes()));
+    for (int i = 0; i < hw.raw_layers; ++i) {
+        const HeadWeights::RawLayer& L = hw.raw[i];
+        const bool last = i + 1 == hw.raw_layers;
+        // output: the next layer's padded input buffer (data rows start after its pad rows), or a plain matrix
+        const long long out_len = last ? (long long)L.t_out * L.cout : hw.raw[i + 1].in_len;
+        const int out_pad = last ? 0 : hw.raw[i + 1].pad;
+        float* out = p;
+        p += (size_t)n * out_len;
+        if (!last) {
+            const int head = out_pad * L.cout, tail_off = (out_pad + L.t_out) * L.cout;
+            zero_pads_kernel<<<ew_grid(n * (head + (out_len - tail_off)), sm_count), 256, 0, st>>>(out, n, out_len, head, tail_off,
+                                                                                               (int)(out_len - tail_off));
+            if ((rc = done())) return rc;
+        }
+        const long long rows = n * L.t_out;
+        rowgemm_kc_umma_kernel<<<(int)std::min<long long>((rows + kKcRows - 1) / kKcRows, sm_count), kKcNT, rowgemm_kc_smem_bytes(), st>>>(
+            in, KcView{L.t_out, L.in_len, (long long)L.stride * L.cin, 0}, L.K, L.wq, L.b, nullptr, out,
+            KcView{L.t_out, out_len, L.cout, out_pad}, rows, L.Npad, L.cout, 1);
+        if ((rc = done())) return rc;
+        in = out;
+    }
+    return launch_quartznet_blocks(hw, in, hw.qn_cin, n, p, feat, sm_count, st, launches, err);
 }
 
 // ------------------------------------------------------------------------------ launches
@@ -301,6 +427,10 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
         return NWW_OK;
     };
     int rc;
+    if (hw.arch == NWW_ARCH_E2E_QUARTZNET) {
+        if (mel_dump != nullptr) { *err = "a raw-audio model has no log-mel to return"; return NWW_EINVAL; }
+        return launch_raw_quartznet(hw, sm_count, pcm, n, feat, scratch, st, launches, err);
+    }
     if (hw.arch == NWW_ARCH_E2E_MELCNN) {
         using G = GeoREF64x101;
         float* mel = take(64 * 101);
@@ -379,36 +509,10 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
     if (hw.arch == NWW_ARCH_QUARTZNET) {
         if (!mel_ready && (rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel, 1, st, launches, err))) return rc;
         if (mel_dump && (rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel_dump, 0, st, launches, err))) return rc;
-        float* a = take((size_t)T * hw.qn_max_k);
-        float* plane[2] = {take((size_t)T * hw.qn_max_n), take((size_t)T * hw.qn_max_n)};
-        const float* x = mel;
-        int pitch = F;
-        const long long rows = n * T;
-        NWW_HCUDA(set_smem(rowgemm_kc_umma_kernel, rowgemm_kc_smem_bytes()));
-        for (int i = 0; i < hw.qn_blocks; ++i) {
-            const HeadWeights::QnBlock& B = hw.qn[i];
-            const int tgrid = (int)std::min<long long>(n * (B.Cp / 32), (long long)sm_count * 8);
-            if (B.Cp % 32 == 0 && T <= kQnSeg * kQnSegs && (B.k == 33 || B.k == 39 || B.k == 11 || B.k == 13 || B.k == 17)) {
-                if (B.k == 33) qn_dw_tile_kernel<33><<<tgrid, 256, 0, st>>>(x, pitch, B.dw, a, n, T, B.C, B.Cp, B.K);
-                else if (B.k == 39) qn_dw_tile_kernel<39><<<tgrid, 256, 0, st>>>(x, pitch, B.dw, a, n, T, B.C, B.Cp, B.K);
-                else if (B.k == 11) qn_dw_tile_kernel<11><<<tgrid, 256, 0, st>>>(x, pitch, B.dw, a, n, T, B.C, B.Cp, B.K);
-                else if (B.k == 13) qn_dw_tile_kernel<13><<<tgrid, 256, 0, st>>>(x, pitch, B.dw, a, n, T, B.C, B.Cp, B.K);
-                else qn_dw_tile_kernel<17><<<tgrid, 256, 0, st>>>(x, pitch, B.dw, a, n, T, B.C, B.Cp, B.K);
-            } else {
-                qn_dw_kernel<<<ew_grid(rows * (B.Cp / 4), sm_count), 256, 0, st>>>(x, pitch, B.dw, a, n, T, B.C, B.Cp, B.k, B.K);
-            }
-            if ((rc = done())) return rc;
-            float* y = plane[i & 1];
-            rowgemm_kc_umma_kernel<<<(int)std::min<long long>((rows + kKcRows - 1) / kKcRows, sm_count), kKcNT, rowgemm_kc_smem_bytes(), st>>>(
-                a, B.K, B.wq, B.b, B.has_res ? nullptr : x, y, rows, B.N, 1);
-            if ((rc = done())) return rc;
-            x = y;
-            pitch = B.N;
-        }
-        bc_gap_kernel<<<ew_grid(n * pitch, sm_count), 256, 0, st>>>(x, feat, n, T, pitch);
-        return done();
+        return launch_quartznet_blocks(hw, mel, F, n, p, feat, sm_count, st, launches, err);
     }
     if (!mel_ready && !conv2_nhwc && (rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel, 0, st, launches, err))) return rc;
+    if (mel_dump && !conv2_nhwc)    if (!mel_ready && !conv2_nhwc && (rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel, 0, st, launches, err))) return rc;
     if (mel_dump && !conv2_nhwc) NWW_HCUDA(cudaMemcpyAsync(mel_dump, mel, (size_t)n * F * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
 
     if (hw.arch == NWW_ARCH_TCN) {

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "nww_tc.cuh"
+#include "nww_stage.cuh"
 #include "nww_tcn.cuh"
 
 namespace nww {
@@ -441,9 +442,22 @@ inline void rowgemm_kc_pack(const float* w, int K, int N, std::vector<uint16_t>*
         }
 }
 
+// Where GEMM row r lives: rows are grouped per window (rpw rows each); row r of the GEMM is
+//   base + (r / rpw) * win_stride + (r % rpw + row_off) * row_stride            (all in floats)
+// A plain [rows][pitch] matrix is {rows, 0, pitch, 0}.  For the strided Conv1d layers of the raw-audio front end the A
+// rows OVERLAP (row_stride = conv stride * C_in < K = k * C_in) and the output skips the next layer's zero padding rows.
+struct KcView {
+    long long rpw, win_stride, row_stride, row_off;
+    __device__ __forceinline__ long long at(long long r) const {
+        const long long w = r / rpw;
+        return w * win_stride + (r - w * rpw + row_off) * row_stride;
+    }
+};
+
+// n_valid (a multiple of 32, <= N): columns actually stored (the weight matrix is padded to 64 columns)
 __global__ void __launch_bounds__(kKcNT, 1)
-rowgemm_kc_umma_kernel(const float* __restrict__ A, int K, const uint4* __restrict__ wq, const float* __restrict__ bias,
-                       const float* __restrict__ res, float* __restrict__ out, long long rows, int N, int relu) {
+rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, int K, const uint4* __restrict__ wq, const float* __restrict__ bias,
+                       const float* __restrict__ res, float* __restrict__ out, KcView ov, long long rows, int N, int n_valid, int relu) {
     NWW_DYN_SMEM(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned char* a_s = smem;                                         // two chunk buffers
@@ -489,7 +503,7 @@ rowgemm_kc_umma_kernel(const float* __restrict__ A, int K, const uint4* __restri
                 const int gq = i / kKcRows, r = i - gq * kKcRows;
                 uint4 hv = make_uint4(0, 0, 0, 0), lv = hv;
                 if (r0 + r < rows) {
-                    const float4* p = reinterpret_cast<const float4*>(A + (r0 + r) * (long long)K + kc * kKcKC + 8 * gq);
+                    const float4* p = reinterpret_cast<const float4*>(A + av.at(r0 + r) + kc * kKcKC + 8 * gq);
                     const float4 v0 = __ldg(p), v1 = __ldg(p + 1);
                     const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
                     uint32_t h[8], l[8];
@@ -544,11 +558,12 @@ rowgemm_kc_umma_kernel(const float* __restrict__ A, int K, const uint4* __restri
         {
             const int q = warp & 3, hcol = warp >> 2;
             const long long r = r0 + q * 32 + lane;
-            for (int c0 = hcol * (N / 2); c0 < (hcol + 1) * (N / 2); c0 += 32) {
+            const long long o_at = r < rows ? ov.at(r) : 0;
+            for (int c0 = hcol * (N / 2); c0 < (hcol + 1) * (N / 2) && c0 < n_valid; c0 += 32) {
                 float v[32];
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
                 if (r < rows) {
-                    float4* dst = reinterpret_cast<float4*>(out + r * N + c0);
+                    float4* dst = reinterpret_cast<float4*>(out + o_at + c0);
                     const float4* rs = res ? reinterpret_cast<const float4*>(res + r * N + c0) : nullptr;
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
@@ -601,6 +616,36 @@ qn_dw_kernel(const float* __restrict__ x, int in_pitch, const float* __restrict_
         }
         *reinterpret_cast<float4*>(a + row * K + c) = acc;
         if (K == 2 * Cp) *reinterpret_cast<float4*>(a + row * K + Cp + c) = ctr;
+    }
+}
+
+// Raw-audio front end, step 0: int16 window -> float samples / 32768 (nanointerpreter.py:750) in a zero-padded row
+// p [n][len]: p[w][i] = pcm[w][i - pad] for pad <= i < pad + clip, else 0
+__global__ void __launch_bounds__(256)
+raw_pcm_kernel(WindowSource src, long long n, float* __restrict__ p, int len, int pad) {
+    const int q4 = len / 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n * q4; i += (long long)gridDim.x * blockDim.x) {
+        const long long w = i / q4;
+        const int i0 = (int)(i - w * q4) * 4;
+        const int16_t* x = src.at(w);
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j = i0 + e - pad;
+            v[e] = (j >= 0 && j < src.clip) ? (float)x[j] * (1.0f / 32768.0f) : 0.0f;
+        }
+        *reinterpret_cast<float4*>(p + w * len + i0) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+// zero the padding rows of a per-window buffer: floats [0, head) and [tail_off, tail_off + tail_len) of every window
+__global__ void __launch_bounds__(256)
+zero_pads_kernel(float* __restrict__ buf, long long n, long long win_stride, int head, int tail_off, int tail_len) {
+    const int per = head + tail_len;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n * per; i += (long long)gridDim.x * blockDim.x) {
+        const long long w = i / per;
+        const int j = (int)(i - w * per);
+        buf[w * win_stride + (j < head ? j : tail_off + j - head)] = 0.0f;
     }
 }
 

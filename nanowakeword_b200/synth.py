@@ -29,13 +29,14 @@ _LOGIT_CAL = {
     "lstm": (56.6, 9.78),
     "rnn": (97.1, -18.93),
     "quartznet": (40.3, -6.82),
+    "e2e_quartznet": (36.2, 2.44),
 }
 
 DEFAULT_INPUT_SHAPE = {
     "dnn": (98, 40), "tcn": (98, 40),                     # (T, F)
     "gru": (98, 40), "lstm": (98, 40), "rnn": (98, 40), "quartznet": (98, 40),
     "cnn": (40, 98), "bcresnet": (40, 98), "crnn": (40, 98),   # (F, T)
-    "e2e_dnn": (16000,),
+    "e2e_dnn": (16000,), "e2e_quartznet": (16000,),
 }
 
 
@@ -53,6 +54,8 @@ def default_config(model_type: str, **overrides) -> dict:
         cfg.update(tcn_channels=[64, 64, 128], tcn_kernel_size=3)
     if model_type == "crnn":
         cfg.update(crnn_cnn_channels=[16, 32, 32], crnn_rnn_type="gru")
+    if model_type == "e2e_quartznet":                                              # model.py:99-131
+        cfg.update(e2e_frontend_channels=32, e2e_frontend_depth=3, e2e_quartznet_config=[[64, 11, 1], [64, 13, 1], [64, 17, 1]])
     if model_type == "quartznet":
         cfg.update(quartznet_config=[[256, 33, 1], [256, 33, 1], [512, 39, 1]])      # model.py:240
     cfg.update(overrides)
@@ -169,11 +172,24 @@ def make_state_dict(cfg: dict, seed: int = 0) -> dict[str, np.ndarray]:
                                (f"bias_ih_l{layer}", (gates * hid,)), (f"bias_hh_l{layer}", (gates * hid,))):
                     g.uniform(f"model.{name}.{nm}{sfx}", sh, hid)
         g.linear("model.layer2" if mt == "rnn" else "model.fc", emb, 2 * hid)
-    elif mt == "quartznet":                           # architectures.py:366-437
-        cin, i = shape[1], 0
-        for channels, k, reps in cfg.get("quartznet_config", [[256, 33, 1], [256, 33, 1], [512, 39, 1]]):
+    elif mt in ("quartznet", "e2e_quartznet"):        # architectures.py:366-437, 695-714, 796-817
+        pre = "model"
+        if mt == "e2e_quartznet":
+            pre, cin = "model.backbone", 1
+            for layer in range(cfg.get("e2e_frontend_depth", 3)):
+                cout, k = cfg.get("e2e_frontend_channels", 32) * 2 ** layer, 41 if layer == 0 else 13
+                g.uniform(f"model.frontend.conv_blocks.{3 * layer}.weight", (cout, cin, k), cin * k)
+                if layer == 0:     # audio is in [-1, 1): a x100 first layer lets it move the BatchNorm-ed ReLUs, as a trained one does
+                    g.sd["model.frontend.conv_blocks.0.weight"] = (g.sd["model.frontend.conv_blocks.0.weight"] * 100.0).astype(np.float32)
+                g.batchnorm(f"model.frontend.conv_blocks.{3 * layer + 1}", cout)
+                cin = cout
+            qcfg = cfg.get("e2e_quartznet_config", [[64, 11, 1], [64, 13, 1], [64, 17, 1]])
+        else:
+            cin, qcfg = shape[1], cfg.get("quartznet_config", [[256, 33, 1], [256, 33, 1], [512, 39, 1]])
+        i = 0
+        for channels, k, reps in qcfg:
             for _ in range(reps):
-                p = f"model.quartznet_blocks.{i}"
+                p = f"{pre}.quartznet_blocks.{i}"
                 g.conv1d(p + ".depthwise_conv", cin, 1, k)
                 g.conv1d(p + ".pointwise_conv", channels, cin, 1)
                 g.batchnorm(p + ".batch_norm", channels)
@@ -182,7 +198,7 @@ def make_state_dict(cfg: dict, seed: int = 0) -> dict[str, np.ndarray]:
                     g.batchnorm(p + ".residual_connector.1", channels)
                 cin = channels
                 i += 1
-        g.linear("model.fc", emb, cin)
+        g.linear(pre + ".fc", emb, cin)
     elif mt == "e2e_dnn":                             # architectures.py:820-888
         for i, (cin, cout) in zip((0, 4, 8), ((1, 16), (16, 32), (32, 64))):
             g.conv(f"model.conv_block.{i}", cout, cin, 3, 3)

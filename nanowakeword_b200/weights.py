@@ -23,7 +23,7 @@ import numpy as np
 
 BN_EPS = 1e-5
 
-ARCH_IDS = {"dnn": 0, "cnn": 1, "tcn": 2, "bcresnet": 3, "crnn": 4, "e2e_dnn": 5, "gru": 6, "lstm": 7, "rnn": 7, "quartznet": 8}
+ARCH_IDS = {"dnn": 0, "cnn": 1, "tcn": 2, "bcresnet": 3, "crnn": 4, "e2e_dnn": 5, "gru": 6, "lstm": 7, "rnn": 7, "quartznet": 8, "e2e_quartznet": 9}
 ACT_IDS = {"relu": 0, "gelu": 1, "silu": 2}
 POST_NONE, POST_ACT, POST_LN_ACT = 0, 1, 2
 
@@ -181,13 +181,31 @@ def pack_tensors(sd: dict, cfg: dict) -> dict[str, np.ndarray]:
         out["rnn.cell"] = np.array([0 if mt == "gru" else 1], dtype=np.int32)
         fc = "model.layer2" if mt == "rnn" else "model.fc"
         layers.append((_f64(sd, fc + ".weight"), _f64(sd, fc + ".bias"), POST_NONE, None))
-    elif mt == "quartznet":
+    elif mt in ("quartznet", "e2e_quartznet"):
+        pre = "model"
+        if mt == "e2e_quartznet":
+            # E2ERawQuartzNet (architectures.py:796-817): RawAudioFrontend (:695-714) = strided Conv1d (no bias) +
+            # BatchNorm + ReLU layers straight on the audio.  On channel-last buffers a strided Conv1d is a row GEMM
+            # whose row t is the CONTIGUOUS slice of k * C_in floats starting at input step stride * t - pad, so each
+            # layer is packed as one [k * C_in (padded to 64)][C_out (padded to 64)] matrix with BatchNorm folded in.
+            pre = "model.backbone"
+            i = 0
+            while f"model.frontend.conv_blocks.{3 * i}.weight" in sd:
+                w, b = fold_bn(_f64(sd, f"model.frontend.conv_blocks.{3 * i}.weight"), None, sd,
+                               f"model.frontend.conv_blocks.{3 * i + 1}")
+                cout, cin, k = w.shape
+                kk = -(-(k * cin) // 64) * 64
+                g = np.zeros((kk, -(-cout // 64) * 64))
+                g[:k * cin, :cout] = w.transpose(2, 1, 0).reshape(k * cin, cout)        # row = tap * C_in + channel
+                out[f"raw.{i}.w"] = g.astype(np.float32)
+                out[f"raw.{i}.b"] = b.astype(np.float32)
+                i += 1
         # QuartzNetModel (architectures.py:366-437).  Per block the engine runs a depthwise FIR (no bias) and ONE row
         # GEMM [dw(x) | x] @ W + b: BatchNorm folded into the pointwise / residual 1x1 weights, the depthwise bias
         # pushed through the pointwise weights into b.  Channel counts are padded so that K is a multiple of 64.
         i = 0
-        while f"model.quartznet_blocks.{i}.depthwise_conv.weight" in sd:
-            p = f"model.quartznet_blocks.{i}"
+        while f"{pre}.quartznet_blocks.{i}.depthwise_conv.weight" in sd:
+            p = f"{pre}.quartznet_blocks.{i}"
             wd, bd = _f64(sd, p + ".depthwise_conv.weight")[:, 0, :], _f64(sd, p + ".depthwise_conv.bias")    # (C, k)
             wp, bp = _f64(sd, p + ".pointwise_conv.weight")[:, :, 0], _f64(sd, p + ".pointwise_conv.bias")    # (N, C)
             c, k = wd.shape
@@ -209,7 +227,7 @@ def pack_tensors(sd: dict, cfg: dict) -> dict[str, np.ndarray]:
             out[f"qn.{i}.b"] = b.astype(np.float32)
             out[f"qn.{i}.meta"] = np.array([c, n_out, k, int(has_res)], dtype=np.int32)
             i += 1
-        layers.append((_f64(sd, "model.fc.weight"), _f64(sd, "model.fc.bias"), POST_NONE, None))
+        layers.append((_f64(sd, pre + ".fc.weight"), _f64(sd, pre + ".fc.bias"), POST_NONE, None))
     elif mt == "e2e_dnn":
         for j, i in enumerate((0, 4, 8)):
             w, b = fold_bn(_f64(sd, f"model.conv_block.{i}.weight"), _f64(sd, f"model.conv_block.{i}.bias"),

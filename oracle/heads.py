@@ -15,6 +15,8 @@ Reference anchors (all under /root/reference/nanowakeword/):
   GRUModel                  modules/architectures.py:129-146
   RNNModel (bi-LSTM, H=64)  modules/architectures.py:149-161
   QuartzNetModel/Block      modules/architectures.py:366-437
+  RawAudioFrontend          modules/architectures.py:695-714
+  E2ERawQuartzNet           modules/architectures.py:796-817
   E2E_MelSpectrogram_CNN    modules/architectures.py:820-888
   Model.classifier/forward  modules/model.py:291-296, 562-571
   sigmoid + view(-1,1,1)    _export/onnx.py:164-172
@@ -307,15 +309,15 @@ def _rnn(x, sd, cfg):
     return linear(rnn_last_output_bidir(x, sd, "model.layer1", "lstm"), sd["model.layer2.weight"], sd["model.layer2.bias"])
 
 
-def _quartznet(x, sd, cfg):
+def _quartznet(x, sd, cfg, prefix="model"):
     """QuartzNetModel on a (T, F) sequence (architectures.py:366-437): per block a depthwise Conv1d
     (padding='same': for a kernel k torch pads (k-1)//2 on the left and the rest on the right), a 1x1 Conv1d,
     BatchNorm1d, plus the residual (1x1 Conv1d + BatchNorm1d when the channel count changes, else the
     identity), ReLU; then the mean over time and a Linear."""
     h = np.swapaxes(x, 1, 2)                                        # (B, C, T)
     i = 0
-    while f"model.quartznet_blocks.{i}.depthwise_conv.weight" in sd:
-        p = f"model.quartznet_blocks.{i}"
+    while f"{prefix}.quartznet_blocks.{i}.depthwise_conv.weight" in sd:
+        p = f"{prefix}.quartznet_blocks.{i}"
         wd = sd[p + ".depthwise_conv.weight"]                       # (C, 1, k)
         k = wd.shape[2]
         left = (k - 1) // 2
@@ -331,7 +333,32 @@ def _quartznet(x, sd, cfg):
             r = h
         h = np.maximum(y + r, 0)
         i += 1
-    return linear(h.mean(axis=2), sd["model.fc.weight"], sd["model.fc.bias"])
+    return linear(h.mean(axis=2), sd[prefix + ".fc.weight"], sd[prefix + ".fc.bias"])
+
+
+def raw_audio_frontend(x, sd, prefix="model.frontend"):
+    """RawAudioFrontend (architectures.py:695-714): depth x [Conv1d(k = 41 / 13, stride 16 / 4, padding k // 2,
+    no bias) -> BatchNorm1d -> ReLU] on (B, 1, N) float audio; returns (B, C, T)."""
+    h = x[:, None, :]
+    i = 0
+    while f"{prefix}.conv_blocks.{3 * i}.weight" in sd:
+        w = sd[f"{prefix}.conv_blocks.{3 * i}.weight"]             # (Cout, Cin, k)
+        cout, cin, k = w.shape
+        stride, pad = (16, 20) if i == 0 else (4, 6)
+        assert k == (41 if i == 0 else 13)
+        xp = np.pad(h, ((0, 0), (0, 0), (pad, pad)))
+        win = sliding_window_view(xp, k, axis=2)[:, :, ::stride]   # (B, Cin, T_out, k)
+        y = np.einsum("bctk,ock->bot", win, w, optimize=True)
+        h = np.maximum(batchnorm(y, sd, f"{prefix}.conv_blocks.{3 * i + 1}"), 0)
+        i += 1
+    return h
+
+
+def _e2e_quartznet(x, sd, cfg):
+    """E2ERawQuartzNet (architectures.py:796-817) on float audio (B, N) already scaled by 1 / 32768
+    (nanointerpreter.py:750)."""
+    h = raw_audio_frontend(x, sd)                                   # (B, C, T)
+    return _quartznet(np.swapaxes(h, 1, 2), sd, cfg, prefix="model.backbone")
 
 
 def _e2e_melcnn_body(mel, sd, cfg):
@@ -349,7 +376,11 @@ def _e2e_melcnn_body(mel, sd, cfg):
 
 
 _BACKBONES = {"dnn": _dnn, "cnn": _cnn, "tcn": _tcn, "bcresnet": _bcresnet, "crnn": _crnn,
-              "e2e_dnn": _e2e_melcnn_body, "gru": _gru, "lstm": _lstm, "rnn": _rnn, "quartznet": _quartznet}
+              "e2e_dnn": _e2e_melcnn_body, "gru": _gru, "lstm": _lstm, "rnn": _rnn, "quartznet": _quartznet,
+              "e2e_quartznet": _e2e_quartznet}
+
+# Heads that consume the audio itself (no log-mel front end): float samples = int16 / 32768 (nanointerpreter.py:750)
+RAW_AUDIO_HEADS = ("e2e_quartznet",)
 
 
 def classifier(emb, sd, cfg):
@@ -379,6 +410,11 @@ def embedding_from_features(x, sd, cfg, dtype=np.float64):
 def forward_logits(pcm, sd, cfg, frontend: FrontendSpec | str | None = None, dtype=np.float64,
                    return_mel=False):
     """int16 PCM (B, N) -> logits (B, 1): front end + backbone + classifier."""
+    if cfg["model_type"] in RAW_AUDIO_HEADS:
+        sd = _cast_sd(sd, dtype)
+        x = np.asarray(pcm).astype(dtype) / dtype(32768.0)
+        logits = classifier(_BACKBONES[cfg["model_type"]](x, sd, cfg), sd, cfg)
+        return (logits, None) if return_mel else logits
     if frontend is None:
         frontend = "REF64x101" if cfg["model_type"] == "e2e_dnn" else "NS40x98"
     if isinstance(frontend, str):
