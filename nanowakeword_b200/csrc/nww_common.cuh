@@ -77,6 +77,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// a wait executed by ONE thread of the CTA (the MMA / copy issuer): the same instruction on the device; in the host
+// model MMAs and bulk copies are synchronous, so it is a no-op there (mbar_wait itself models a CTA-wide barrier)
+__device__ __forceinline__ void mbar_wait_one(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 #else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)((const unsigned char*)p - cudasim::g_dyn_smem); }
 __device__ __forceinline__ void mbar_init(uint64_t*, uint32_t) {}
@@ -86,6 +89,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t*, uint32_t) {}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t*) { memcpy(dst, src, bytes); }
 // every thread of the block calls wait(), so a block barrier orders the (synchronous) copy
 __device__ __forceinline__ void mbar_wait(uint64_t*, uint32_t) { __syncthreads(); }
+__device__ __forceinline__ void mbar_wait_one(uint64_t*, uint32_t) {}
 #endif
 
 }  // namespace nww

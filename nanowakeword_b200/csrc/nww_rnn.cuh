@@ -234,7 +234,7 @@ rnn_seq_kernel(const float* __restrict__ x_tm, long long win_stride, int S, long
                 for (int ks = 0; ks < nks; ++ks) {
                     const uint64_t ao = (uint64_t)((ks * 2 * TM * 16) >> 4);
                     for (int t = 0; t < 2; ++t) {
-                        mbar_wait(bar_full + c_slot, c_par);
+                        mbar_wait_one(bar_full + c_slot, c_par);
                         tc_fence_after();
                         const uint64_t db = db_ring + (uint64_t)((c_slot * (uint32_t)D::SUB) >> 4);
 #pragma unroll
@@ -248,7 +248,7 @@ rnn_seq_kernel(const float* __restrict__ x_tm, long long win_stride, int S, long
                         umma_commit(bar_empty + c_slot);
                         // refill the slot of the PREVIOUS sub-slice (its MMAs finish while this one's run)
                         if (prev_slot >= 0) {
-                            mbar_wait(bar_empty + prev_slot, prev_par);
+                            mbar_wait_one(bar_empty + prev_slot, prev_par);
                             if (p_pos < tile_subs) produce();
                         }
                         prev_slot = (int)c_slot;
@@ -257,7 +257,7 @@ rnn_seq_kernel(const float* __restrict__ x_tm, long long win_stride, int S, long
                     }
                 }
                 umma_commit(bar_done);
-                mbar_wait(bar_empty + prev_slot, prev_par);           // == all of this step's MMAs are complete
+                mbar_wait_one(bar_empty + prev_slot, prev_par);           // == all of this step's MMAs are complete
                 if (p_pos < tile_subs) produce();
             }
             mbar_wait(bar_done, done_phase);

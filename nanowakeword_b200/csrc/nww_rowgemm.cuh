@@ -525,7 +525,7 @@ rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, int K, const uint
                 tc_fence_after();
                 const uint64_t da_h = da_buf0 + (uint64_t)((buf * (uint32_t)kKcABuf) >> 4), da_l = da_h + (uint64_t)((kKcABuf / 2) >> 4);
                 for (int nc = 0; nc < n_nc; ++nc) {
-                    mbar_wait(bar_full + c_slot, c_par);
+                    mbar_wait_one(bar_full + c_slot, c_par);
                     tc_fence_after();
                     const uint64_t db_h = db_ring + (uint64_t)((c_slot * (uint32_t)kKcSub) >> 4), db_l = db_h + (uint64_t)((kKcSub / 2) >> 4);
                     const uint32_t d = tmem_base + (uint32_t)(nc * kKcNC);
@@ -538,7 +538,7 @@ rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, int K, const uint
                     }
                     umma_commit(bar_empty + c_slot);
                     if (prev_slot >= 0) {                              // refill the previous sub-block's slot
-                        mbar_wait(bar_empty + prev_slot, prev_par);
+                        mbar_wait_one(bar_empty + prev_slot, prev_par);
                         if (p_pos < total) produce();
                     }
                     prev_slot = (int)c_slot;
@@ -550,7 +550,7 @@ rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, int K, const uint
         }
         if (tid == 0) {
             umma_commit(bar_done);
-            mbar_wait(bar_empty + prev_slot, prev_par);
+            mbar_wait_one(bar_empty + prev_slot, prev_par);
         }
         mbar_wait(bar_done, done_phase);
         done_phase ^= 1u;

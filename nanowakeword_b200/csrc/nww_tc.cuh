@@ -151,6 +151,10 @@ inline void tmem_ld_32x32b_x16_nowait(uint32_t taddr, uint32_t* r) {
     const int lane = (int)(taddr >> 16) + (cudasim::linear_tid() & 31), col = (int)(taddr & 0xFFFF);
     for (int i = 0; i < 16; ++i) memcpy(&r[i], &sim::g_tmem[lane][col + i], 4);
 }
+inline void tmem_ld_32x32b_x32(uint32_t taddr, float* v) {
+    const int lane = (int)(taddr >> 16) + (cudasim::linear_tid() & 31), col = (int)(taddr & 0xFFFF);
+    for (int i = 0; i < 32; ++i) v[i] = sim::g_tmem[lane][col + i];
+}
 inline void named_bar_sync(int id, int count) { cudasim::named_barrier(id, count); }
 inline float bf16_bits_to_float(uint32_t b) { return sim::bf16f((uint16_t)b); }
 inline uint32_t float_to_bf16_bits(float x) {
