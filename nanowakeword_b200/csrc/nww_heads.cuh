@@ -359,7 +359,7 @@ inline int launch_quartznet_blocks(const HeadWeights& hw, const float* x, int pi
         if ((rc = done())) return rc;
         float* y = plane[i & 1];
         rowgemm_kc_umma_kernel<<<(int)std::min<long long>((rows + kKcRows - 1) / kKcRows, sm_count), kKcNT, rowgemm_kc_smem_bytes(), st>>>(
-            a, KcView{rows, 0, B.K, 0}, B.K, B.wq, B.b, B.has_res ? nullptr : x, y, KcView{rows, 0, B.N, 0}, rows, B.N, B.N, 1);
+            a, kc_plain(rows, B.K), kc_one_seg(B.K), B.K, B.wq, B.b, B.has_res ? nullptr : x, y, kc_plain(rows, B.N), rows, B.N, B.N, 1);
         if ((rc = done())) return rc;
         x = y;
         pitch = B.N;
@@ -400,8 +400,8 @@ inline int launch_raw_quartznet(const HeadWeights& hw, int sm_count, WindowSourc
         }
         const long long rows = n * L.t_out;
         rowgemm_kc_umma_kernel<<<(int)std::min<long long>((rows + kKcRows - 1) / kKcRows, sm_count), kKcNT, rowgemm_kc_smem_bytes(), st>>>(
-            in, KcView{L.t_out, L.in_len, (long long)L.stride * L.cin, 0}, L.K, L.wq, L.b, nullptr, out,
-            KcView{L.t_out, out_len, L.cout, out_pad}, rows, L.Npad, L.cout, 1);
+            in, kc_seq(L.t_out, L.in_len, (long long)L.stride * L.cin, 0), kc_one_seg(L.k * L.cin), L.K, L.wq, L.b, nullptr, out,
+            kc_seq(L.t_out, out_len, L.cout, out_pad), rows, L.Npad, L.cout, 1);
         if ((rc = done())) return rc;
         in = out;
     }

@@ -442,22 +442,34 @@ inline void rowgemm_kc_pack(const float* w, int K, int N, std::vector<uint16_t>*
         }
 }
 
-// Where GEMM row r lives: rows are grouped per window (rpw rows each); row r of the GEMM is
-//   base + (r / rpw) * win_stride + (r % rpw + row_off) * row_stride            (all in floats)
-// A plain [rows][pitch] matrix is {rows, 0, pitch, 0}.  For the strided Conv1d layers of the raw-audio front end the A
-// rows OVERLAP (row_stride = conv stride * C_in < K = k * C_in) and the output skips the next layer's zero padding rows.
+// Where GEMM row r lives: rows are grouped per window (rpw rows each) and, inside a window, in lines of `inner` rows
+// (an image row of a strided Conv2d; inner = rpw for sequences).  Row r is at
+//   base + (r / rpw) * win_stride + (t / inner) * outer_stride + (t % inner + row_off) * row_stride,  t = r % rpw   (floats)
+// A plain [rows][pitch] matrix is kc_plain(rows, pitch).  For strided convolutions on channel-last buffers the A rows
+// OVERLAP (row_stride = conv stride * C_in < K) and the output view skips the next layer's zero padding.
 struct KcView {
-    long long rpw, win_stride, row_stride, row_off;
+    long long rpw, win_stride, row_stride, row_off, inner, outer_stride;
     __device__ __forceinline__ long long at(long long r) const {
-        const long long w = r / rpw;
-        return w * win_stride + (r - w * rpw + row_off) * row_stride;
+        const long long w = r / rpw, t = r - w * rpw, o = t / inner;
+        return w * win_stride + o * outer_stride + (t - o * inner + row_off) * row_stride;
     }
 };
+inline KcView kc_plain(long long rows, long long pitch) { return KcView{rows, 0, pitch, 0, rows, 0}; }
+inline KcView kc_seq(long long rpw, long long win_stride, long long row_stride, long long row_off) {
+    return KcView{rpw, win_stride, row_stride, row_off, rpw, 0};
+}
+// The K axis of an A row may be cut into segments of seg_len floats (a multiple of 8) that lie seg_stride apart: the three
+// kernel rows of a 3x3 convolution on an NHWC image (seg_len = 3 C_in, seg_stride = one padded image row).  Columns
+// k >= k_valid (the padding of K to a multiple of 64) read as zero.
+struct KcSegs { int seg_len; long long seg_stride; int k_valid; };
+inline KcSegs kc_one_seg(int k_valid) { return KcSegs{1 << 30, 0, k_valid}; }
 
-// n_valid (a multiple of 32, <= N): columns actually stored (the weight matrix is padded to 64 columns)
+// n_valid (a multiple of 4, <= N): columns actually stored (the weight matrix is padded to 64 columns)
+// act: 0 none, 1 ReLU, 2 GELU, 3 SiLU (apply_act codes + 1)
 __global__ void __launch_bounds__(kKcNT, 1)
-rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, int K, const uint4* __restrict__ wq, const float* __restrict__ bias,
-                       const float* __restrict__ res, float* __restrict__ out, KcView ov, long long rows, int N, int n_valid, int relu) {
+rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, KcSegs sg, int K, const uint4* __restrict__ wq,
+                       const float* __restrict__ bias, const float* __restrict__ res, float* __restrict__ out, KcView ov, long long rows,
+                       int N, int n_valid, int act) {
     NWW_DYN_SMEM(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned char* a_s = smem;                                         // two chunk buffers
@@ -502,10 +514,17 @@ rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, int K, const uint
             for (int i = tid; i < kKcRows * (kKcKC / 8); i += kKcNT) {
                 const int gq = i / kKcRows, r = i - gq * kKcRows;
                 uint4 hv = make_uint4(0, 0, 0, 0), lv = hv;
-                if (r0 + r < rows) {
-                    const float4* p = reinterpret_cast<const float4*>(A + av.at(r0 + r) + kc * kKcKC + 8 * gq);
+                const int k8 = kc * kKcKC + 8 * gq;
+                if (r0 + r < rows && k8 < sg.k_valid) {
+                    const int seg = k8 / sg.seg_len;
+                    const float4* p = reinterpret_cast<const float4*>(A + av.at(r0 + r) + seg * sg.seg_stride + (k8 - seg * sg.seg_len));
                     const float4 v0 = __ldg(p), v1 = __ldg(p + 1);
-                    const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                    float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                    if (k8 + 8 > sg.k_valid) {                         // the group straddles the end of the valid columns
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            if (k8 + e >= sg.k_valid) v[e] = 0.0f;
+                    }
                     uint32_t h[8], l[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
@@ -567,13 +586,14 @@ rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, int K, const uint
                     const float4* rs = res ? reinterpret_cast<const float4*>(res + r * N + c0) : nullptr;
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
+                        if (c0 + 4 * j4 >= n_valid) break;
                         float4 o = make_float4(v[4 * j4] + __ldg(bias + c0 + 4 * j4), v[4 * j4 + 1] + __ldg(bias + c0 + 4 * j4 + 1),
                                                v[4 * j4 + 2] + __ldg(bias + c0 + 4 * j4 + 2), v[4 * j4 + 3] + __ldg(bias + c0 + 4 * j4 + 3));
                         if (rs) {
                             const float4 t = __ldg(rs + j4);
                             o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
                         }
-                        if (relu) { o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f); }
+                        if (act) { o.x = apply_act(o.x, act - 1); o.y = apply_act(o.y, act - 1); o.z = apply_act(o.z, act - 1); o.w = apply_act(o.w, act - 1); }
                         dst[j4] = o;
                     }
                 }

@@ -30,13 +30,14 @@ _LOGIT_CAL = {
     "rnn": (97.1, -18.93),
     "quartznet": (40.3, -6.82),
     "e2e_quartznet": (36.2, 2.44),
+    "e2e_cnn": (100.0, 3.64),        # global average pooling flattens a random-init model: gain capped, logits spread ~ +-0.3
 }
 
 DEFAULT_INPUT_SHAPE = {
     "dnn": (98, 40), "tcn": (98, 40),                     # (T, F)
     "gru": (98, 40), "lstm": (98, 40), "rnn": (98, 40), "quartznet": (98, 40),
     "cnn": (40, 98), "bcresnet": (40, 98), "crnn": (40, 98),   # (F, T)
-    "e2e_dnn": (16000,), "e2e_quartznet": (16000,),
+    "e2e_dnn": (16000,), "e2e_quartznet": (16000,), "e2e_cnn": (16000,),
 }
 
 
@@ -56,6 +57,8 @@ def default_config(model_type: str, **overrides) -> dict:
         cfg.update(crnn_cnn_channels=[16, 32, 32], crnn_rnn_type="gru")
     if model_type == "e2e_quartznet":                                              # model.py:99-131
         cfg.update(e2e_frontend_channels=32, e2e_frontend_depth=3, e2e_quartznet_config=[[64, 11, 1], [64, 13, 1], [64, 17, 1]])
+    if model_type == "e2e_cnn":                                                    # model.py:109-117
+        cfg.update(e2e_frontend_channels=32, e2e_frontend_depth=2)
     if model_type == "quartznet":
         cfg.update(quartznet_config=[[256, 33, 1], [256, 33, 1], [512, 39, 1]])      # model.py:240
     cfg.update(overrides)
@@ -199,6 +202,19 @@ def make_state_dict(cfg: dict, seed: int = 0) -> dict[str, np.ndarray]:
                 cin = channels
                 i += 1
         g.linear(pre + ".fc", emb, cin)
+    elif mt == "e2e_cnn":                             # architectures.py:738-793
+        cin = 1
+        for layer in range(cfg.get("e2e_frontend_depth", 2)):
+            cout, k = cfg.get("e2e_frontend_channels", 32) * 2 ** layer, 41 if layer == 0 else 13
+            g.uniform(f"model.frontend.conv_blocks.{3 * layer}.weight", (cout, cin, k), cin * k)
+            g.batchnorm(f"model.frontend.conv_blocks.{3 * layer + 1}", cout)
+            if layer == 0:     # as for e2e_quartznet: lets [-1, 1) audio move the BatchNorm-ed ReLUs
+                g.sd["model.frontend.conv_blocks.0.weight"] = (g.sd["model.frontend.conv_blocks.0.weight"] * 100.0).astype(np.float32)
+            cin = cout
+        for name, ci, co in (("conv1", 1, 24), ("conv2", 24, 48), ("conv3", 48, 64), ("conv4", 64, 96)):
+            g.conv(f"model.backbone.{name}.0", co, ci, 3, 3, bias=False)
+            g.batchnorm(f"model.backbone.{name}.1", co)
+        g.linear("model.backbone.fc", emb, 96)
     elif mt == "e2e_dnn":                             # architectures.py:820-888
         for i, (cin, cout) in zip((0, 4, 8), ((1, 16), (16, 32), (32, 64))):
             g.conv(f"model.conv_block.{i}", cout, cin, 3, 3)

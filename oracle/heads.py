@@ -17,6 +17,7 @@ Reference anchors (all under /root/reference/nanowakeword/):
   QuartzNetModel/Block      modules/architectures.py:366-437
   RawAudioFrontend          modules/architectures.py:695-714
   E2ERawQuartzNet           modules/architectures.py:796-817
+  E2ERawCNN / RawAudioBackbone  modules/architectures.py:738-793
   E2E_MelSpectrogram_CNN    modules/architectures.py:820-888
   Model.classifier/forward  modules/model.py:291-296, 562-571
   sigmoid + view(-1,1,1)    _export/onnx.py:164-172
@@ -379,8 +380,22 @@ _BACKBONES = {"dnn": _dnn, "cnn": _cnn, "tcn": _tcn, "bcresnet": _bcresnet, "crn
               "e2e_dnn": _e2e_melcnn_body, "gru": _gru, "lstm": _lstm, "rnn": _rnn, "quartznet": _quartznet,
               "e2e_quartznet": _e2e_quartznet}
 
+def _e2e_cnn(x, sd, cfg):
+    """E2ERawCNN (architectures.py:777-793): RawAudioFrontend (depth 2) -> (B, 1, C, T) image -> RawAudioBackbone
+    (:738-774): four Conv2d 3x3 (no bias; strides (1,2), (2,2), (2,2), 1) + BatchNorm + activation, global average
+    pool, Linear."""
+    act = cfg.get("activation_function", "relu")
+    h = raw_audio_frontend(x, sd)[:, None]                          # (B, 1, C, T)
+    for name, stride in (("conv1", (1, 2)), ("conv2", (2, 2)), ("conv3", (2, 2)), ("conv4", (1, 1))):
+        p = f"model.backbone.{name}"
+        h = activation(batchnorm(conv2d(h, sd[p + ".0.weight"], None, stride=stride), sd, p + ".1"), act)
+    return linear(h.mean(axis=(2, 3)), sd["model.backbone.fc.weight"], sd["model.backbone.fc.bias"])
+
+
+_BACKBONES["e2e_cnn"] = _e2e_cnn
+
 # Heads that consume the audio itself (no log-mel front end): float samples = int16 / 32768 (nanointerpreter.py:750)
-RAW_AUDIO_HEADS = ("e2e_quartznet",)
+RAW_AUDIO_HEADS = ("e2e_quartznet", "e2e_cnn")
 
 
 def classifier(emb, sd, cfg):

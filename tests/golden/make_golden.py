@@ -107,7 +107,7 @@ def main():
         print("frontend.npz written")
 
     # ---- heads (fed the float64 torchaudio mel so head errors are isolated) -----------
-    for mt in ("dnn", "cnn", "tcn", "bcresnet", "crnn", "e2e_dnn", "gru", "lstm", "rnn", "quartznet", "e2e_quartznet"):
+    for mt in ("dnn", "cnn", "tcn", "bcresnet", "crnn", "e2e_dnn", "gru", "lstm", "rnn", "quartznet", "e2e_quartznet", "e2e_cnn"):
         if only and mt not in only:
             continue
         cfg = default_config(mt)
@@ -140,7 +140,7 @@ def main():
                 safe_pool(wrapped, x32[:1].unsqueeze(1))
                 res["scores32_deployed"] = wrapped(x32.unsqueeze(1)).numpy()
                 res["logits32"] = logits32.numpy()
-            elif mt == "e2e_quartznet":   # raw audio in, no mel: the reference module is the whole graph
+            elif mt in ("e2e_quartznet", "e2e_cnn"):   # raw audio in, no mel: the reference module is the whole graph
                 res["logits64"] = model.double()(x64).numpy()
                 res["emb64"] = model.double().model(x64).numpy()
                 res["logits32"] = model.float()(x32).numpy()
