@@ -42,6 +42,7 @@ extern "C" {
 #define NWW_ARCH_QUARTZNET 8 /* QuartzNetModel / QuartzNetBlock :366-437 */
 #define NWW_ARCH_E2E_QUARTZNET 9 /* E2ERawQuartzNet :796-817 = RawAudioFrontend :695-714 on the audio itself + QuartzNetModel;
                                     no log-mel: the spec's geometry is ignored and mel dumps are refused */
+#define NWW_ARCH_E2E_CNN 10  /* E2ERawCNN :777-793 = RawAudioFrontend + RawAudioBackbone :738-774 (raw audio, no log-mel) */
 
 #define NWW_ACT_RELU 0       /* reference nanowakeword/modules/model.py:81-87 */
 #define NWW_ACT_GELU 1

@@ -615,7 +615,19 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
                 e->heads.rnn_wq_f = reinterpret_cast<const uint4*>(e->d_conv_wq[1]);
                 e->heads.rnn_wq_b = reinterpret_cast<const uint4*>(e->d_conv_wq[2]);
             }
-            if (spec->arch == NWW_ARCH_E2E_QUARTZNET) {
+            if (spec->arch == NWW_ARCH_E2E_CNN) {
+                for (int j = 0; j < 3; ++j) {                          // conv2..4 of RawAudioBackbone as row-GEMM weight streams
+                    auto& L = e->heads.rc[j];
+                    std::vector<uint16_t> wq;
+                    rowgemm_kc_pack(e->blob.f32("rawcnn.conv" + std::to_string(j + 2) + ".w"), L.K, L.Npad, &wq);
+                    void* d = nullptr;
+                    NWW_CUDA(cudaMalloc(&d, wq.size() * sizeof(uint16_t)));
+                    e->d_extra.push_back(d);
+                    NWW_CUDA(cudaMemcpy(d, wq.data(), wq.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+                    L.wq = reinterpret_cast<const uint4*>(d);
+                }
+            }
+            if (spec->arch == NWW_ARCH_E2E_QUARTZNET || spec->arch == NWW_ARCH_E2E_CNN) {
                 for (int i = 0; i < e->heads.raw_layers; ++i) {        // strided Conv1d layers as row-GEMM weight streams
                     auto& L = e->heads.raw[i];
                     std::vector<uint16_t> wq;
@@ -922,7 +934,8 @@ int nww_stream_open(nww_engine* e, int64_t n_streams) {
     // incremental log-mel (nww_stream_mel.cuh): un-centred geometry, and a stage A that can start from mel
     const bool v1_cnn = e->spec.arch == NWW_ARCH_CNN && !e->cnn2_enabled;
     if (e->spec.geometry == NWW_GEOM_NS40X98 && e->spec.frontend_precision == NWW_FRONTEND_FP64 && !v1_cnn &&
-        e->spec.arch != NWW_ARCH_E2E_QUARTZNET /* no log-mel in a raw-audio model */ && !(e->spec.reserved[0] & 4)) {
+        e->spec.arch != NWW_ARCH_E2E_QUARTZNET && e->spec.arch != NWW_ARCH_E2E_CNN /* raw-audio models: no log-mel */ &&
+        !(e->spec.reserved[0] & 4)) {
         NWW_CUDA(cudaMalloc(&e->d_mel_ring, (size_t)n_streams * SMel::STREAM_FLOATS * sizeof(float)));
         NWW_CUDA(cudaMemsetAsync(e->d_mel_ring, 0, (size_t)n_streams * SMel::STREAM_FLOATS * sizeof(float), e->stream));
         e->mel_inc = true;

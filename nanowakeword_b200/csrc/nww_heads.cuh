@@ -76,6 +76,11 @@ struct HeadWeights {
     };
     int raw_layers = 0;
     RawLayer raw[4];
+    // E2ERawCNN backbone: conv1 direct, conv2..4 as row GEMMs on zero-padded NHWC images
+    struct RcLayer { int cin = 0, cout = 0, K = 0, Npad = 0, s = 0, Hin = 0, Win = 0, Hout = 0, Wout = 0; const float* b = nullptr; const uint4* wq = nullptr; };
+    const float *rc_w1 = nullptr, *rc_b1 = nullptr;
+    int rc_c1 = 0, rc_h1 = 0, rc_w1o = 0;       // conv1 output: channels, height (= front-end channels), width
+    RcLayer rc[3];
     // scratch layout (floats per window)
     size_t scratch_floats = 0;
 };
@@ -247,7 +252,7 @@ inline int setup_head_weights(int arch, int geometry, const BlobLookup& get, con
         hw->rnn_hidden = H;
         *feat_dim = 2 * H;
         hw->scratch_floats = (size_t)GeoNS40x98::N_FRAMES * GeoNS40x98::N_MELS;      // the (T, F) log-mel
-    } else if (arch == NWW_ARCH_QUARTZNET || arch == NWW_ARCH_E2E_QUARTZNET) {
+    } else if (arch == NWW_ARCH_QUARTZNET || arch == NWW_ARCH_E2E_QUARTZNET || arch == NWW_ARCH_E2E_CNN) {
         int cin = GeoNS40x98::N_MELS, tq = GeoNS40x98::N_FRAMES;
         size_t raw_floats = 0;
         if (arch == NWW_ARCH_QUARTZNET) {
@@ -286,6 +291,38 @@ inline int setup_head_weights(int arch, int geometry, const BlobLookup& get, con
         }
         hw->qn_t = tq;
         hw->qn_cin = cin;
+        if (arch == NWW_ARCH_E2E_CNN) {
+            // RawAudioBackbone (architectures.py:738-774) on the (H = cin, W = tq) one-channel image
+            auto d1 = dims("rawcnn.conv1.w");
+            if (d1.size() != 2 || d1[0] != 9 || d1[1] % 4) { *err = "weight blob: rawcnn.conv1.w missing or malformed"; return NWW_EINVAL; }
+            hw->rc_c1 = (int)d1[1];
+            hw->rc_w1 = need("rawcnn.conv1.w", (size_t)9 * hw->rc_c1);
+            hw->rc_b1 = need("rawcnn.conv1.b", (size_t)hw->rc_c1);
+            hw->rc_h1 = cin;
+            hw->rc_w1o = (tq + 2 - 3) / 2 + 1;
+            int c = hw->rc_c1, H = hw->rc_h1, W = hw->rc_w1o;
+            size_t img_floats = (size_t)(H + 2) * (W + 2) * c;
+            const int strides[3] = {2, 2, 1};
+            for (int j = 0; j < 3; ++j) {
+                const std::string p = "rawcnn.conv" + std::to_string(j + 2);
+                auto dw = dims((p + ".w").c_str()), db = dims((p + ".b").c_str());
+                if (dw.size() != 2 || db.size() != 1) { *err = "weight blob: " + p + " missing"; return NWW_EINVAL; }
+                HeadWeights::RcLayer& L = hw->rc[j];
+                L.cin = c; L.cout = (int)db[0]; L.K = (int)dw[0]; L.Npad = (int)dw[1]; L.s = strides[j];
+                L.Hin = H; L.Win = W; L.Hout = (H + 2 - 3) / L.s + 1; L.Wout = (W + 2 - 3) / L.s + 1;
+                if (L.K != (9 * c + 63) / 64 * 64 || L.Npad != (L.cout + 63) / 64 * 64 || L.cout % 4 || (3 * c) % 8 || L.Npad > 512) {
+                    *err = p + ": unsupported RawAudioBackbone layer shape";
+                    return NWW_EUNSUPPORTED;
+                }
+                L.b = need(p + ".b", (size_t)L.cout);
+                if (!need(p + ".w", (size_t)L.K * L.Npad)) return NWW_EINVAL;
+                c = L.cout; H = L.Hout; W = L.Wout;
+                img_floats += j < 2 ? (size_t)(H + 2) * (W + 2) * c : (size_t)H * W * c;
+            }
+            *feat_dim = c;
+            hw->scratch_floats = raw_floats + img_floats;
+            return err->empty() ? NWW_OK : NWW_EINVAL;
+        }
         int nb = 0;
         for (; nb < 16; ++nb) {
             const std::string p = "qn." + std::to_string(nb);
@@ -368,9 +405,10 @@ inline int launch_quartznet_blocks(const HeadWeights& hw, const float* x, int pi
     return done();
 }
 
-// E2ERawQuartzNet: audio -> float -> strided Conv1d layers (row GEMMs over overlapping rows) -> QuartzNet blocks
-inline int launch_raw_quartznet(const HeadWeights& hw, int sm_count, WindowSource pcm, long long n, float* feat, float* scratch,
-                                cudaStream_t st, int64_t* launches, std::string* err) {
+// RawAudioFrontend: audio -> float -> strided Conv1d layers (row GEMMs over overlapping rows).  *last_out = the last
+// layer's plain [n][t_out][c_out] output, *next_free = the scratch after it.
+inline int launch_raw_frontend(const HeadWeights& hw, int sm_count, WindowSource pcm, long long n, float* scratch, const float** last_out,
+                               float** next_free, cudaStream_t st, int64_t* launches, std::string* err) {
     auto done = [&]() -> int {
         (*launches)++;
         NWW_HCUDA(cudaGetLastError());
@@ -405,7 +443,63 @@ inline int launch_raw_quartznet(const HeadWeights& hw, int sm_count, WindowSourc
         if ((rc = done())) return rc;
         in = out;
     }
-    return launch_quartznet_blocks(hw, in, hw.qn_cin, n, p, feat, sm_count, st, launches, err);
+    *last_out = in;
+    *next_free = p;
+    return NWW_OK;
+}
+
+// E2ERawQuartzNet: raw front end -> QuartzNet blocks
+inline int launch_raw_quartznet(const HeadWeights& hw, int sm_count, WindowSource pcm, long long n, float* feat, float* scratch,
+                                cudaStream_t st, int64_t* launches, std::string* err) {
+    const float* x = nullptr;
+    float* p = nullptr;
+    int rc = launch_raw_frontend(hw, sm_count, pcm, n, scratch, &x, &p, st, launches, err);
+    if (rc) return rc;
+    return launch_quartznet_blocks(hw, x, hw.qn_cin, n, p, feat, sm_count, st, launches, err);
+}
+
+// E2ERawCNN: raw front end -> conv1 (direct) -> conv2..4 (row GEMMs on padded NHWC images) -> global average pool
+inline int launch_raw_cnn(const HeadWeights& hw, int act, int sm_count, WindowSource pcm, long long n, float* feat, float* scratch,
+                          cudaStream_t st, int64_t* launches, std::string* err) {
+    auto done = [&]() -> int {
+        (*launches)++;
+        NWW_HCUDA(cudaGetLastError());
+        return NWW_OK;
+    };
+    const float* bf = nullptr;
+    float* p = nullptr;
+    int rc = launch_raw_frontend(hw, sm_count, pcm, n, scratch, &bf, &p, st, launches, err);
+    if (rc) return rc;
+    int C = hw.rc_c1, H = hw.rc_h1, W = hw.rc_w1o;
+    float* img = p;
+    p += (size_t)n * (H + 2) * (W + 2) * C;
+    zero_border_kernel<<<ew_grid(n * (H + 2) * (W + 2) * (C / 4), sm_count), 256, 0, st>>>(img, n, H + 2, W + 2, C, H, W);
+    if ((rc = done())) return rc;
+    rawcnn_conv1_kernel<<<ew_grid(n * H * W * (C / 4), sm_count), 256, 0, st>>>(bf, hw.rc_w1, hw.rc_b1, img, n, hw.qn_cin, hw.qn_t, W, C, act);
+    if ((rc = done())) return rc;
+    for (int j = 0; j < 3; ++j) {
+        const HeadWeights::RcLayer& L = hw.rc[j];
+        const bool last = j == 2;
+        const int Hp = L.Hin + 2, Wp = L.Win + 2;
+        const int Hp2 = last ? L.Hout : L.Hout + 2, Wp2 = last ? L.Wout : L.Wout + 2;
+        float* out = p;
+        p += (size_t)n * Hp2 * Wp2 * L.cout;
+        if (!last) {
+            zero_border_kernel<<<ew_grid(n * Hp2 * Wp2 * (L.cout / 4), sm_count), 256, 0, st>>>(out, n, Hp2, Wp2, L.cout, L.Hout, L.Wout);
+            if ((rc = done())) return rc;
+        }
+        const long long rpw = (long long)L.Hout * L.Wout, rows = n * rpw;
+        const KcView av{rpw, (long long)Hp * Wp * L.cin, (long long)L.s * L.cin, 0, L.Wout, (long long)L.s * Wp * L.cin};
+        const KcView ov{rpw, (long long)Hp2 * Wp2 * L.cout, L.cout, 0, L.Wout, (long long)Wp2 * L.cout};
+        rowgemm_kc_umma_kernel<<<(int)std::min<long long>((rows + kKcRows - 1) / kKcRows, sm_count), kKcNT, rowgemm_kc_smem_bytes(), st>>>(
+            img, av, KcSegs{3 * L.cin, (long long)Wp * L.cin, 9 * L.cin}, L.K, L.wq, L.b, nullptr,
+            out + (last ? 0 : (size_t)(Wp2 + 1) * L.cout), ov, rows, L.Npad, L.cout, act + 1);
+        if ((rc = done())) return rc;
+        img = out;
+        C = L.cout; H = L.Hout; W = L.Wout;
+    }
+    bc_gap_kernel<<<ew_grid(n * C, sm_count), 256, 0, st>>>(img, feat, n, H * W, C);
+    return done();
 }
 
 // ------------------------------------------------------------------------------ launches
@@ -427,9 +521,10 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
         return NWW_OK;
     };
     int rc;
-    if (hw.arch == NWW_ARCH_E2E_QUARTZNET) {
+    if (hw.arch == NWW_ARCH_E2E_QUARTZNET || hw.arch == NWW_ARCH_E2E_CNN) {
         if (mel_dump != nullptr) { *err = "a raw-audio model has no log-mel to return"; return NWW_EINVAL; }
-        return launch_raw_quartznet(hw, sm_count, pcm, n, feat, scratch, st, launches, err);
+        return hw.arch == NWW_ARCH_E2E_CNN ? launch_raw_cnn(hw, act, sm_count, pcm, n, feat, scratch, st, launches, err)
+                                           : launch_raw_quartznet(hw, sm_count, pcm, n, feat, scratch, st, launches, err);
     }
     if (hw.arch == NWW_ARCH_E2E_MELCNN) {
         using G = GeoREF64x101;

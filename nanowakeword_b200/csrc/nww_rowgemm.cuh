@@ -669,6 +669,49 @@ zero_pads_kernel(float* __restrict__ buf, long long n, long long win_stride, int
     }
 }
 
+// RawAudioBackbone conv1 (architectures.py:741-745): 3x3, 1 -> CO channels, stride (1, 2), padding 1, BatchNorm folded,
+// on the raw front end's output read as a one-channel image img[h][w] = bf[w][h] (h = front-end channel, w = time step).
+// Writes the zero-padded NHWC image o1[(oh + 1)][(ow + 1)][co] the next layer's GEMM view reads.
+__global__ void __launch_bounds__(256)
+rawcnn_conv1_kernel(const float* __restrict__ bf, const float* __restrict__ w1 /* [9][CO] */, const float* __restrict__ b1,
+                    float* __restrict__ o1, long long n, int H, int W, int Wo, int CO, int act) {
+    const int q4 = CO / 4;
+    const long long per = (long long)H * Wo * q4, total = n * per;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long w = i / per;
+        int r = (int)(i - w * per);
+        const int c = (r % q4) * 4;
+        r /= q4;
+        const int ow = r % Wo, oh = r / Wo;
+        const float* img = bf + w * (long long)W * H;
+        float4 acc = __ldg(reinterpret_cast<const float4*>(b1 + c));
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int ih = oh + kh - 1, iw = 2 * ow + kw - 1;
+                if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
+                const float v = __ldg(img + (long long)iw * H + ih);
+                const float4 k4 = __ldg(reinterpret_cast<const float4*>(w1 + (kh * 3 + kw) * CO + c));
+                acc.x = fmaf(v, k4.x, acc.x); acc.y = fmaf(v, k4.y, acc.y); acc.z = fmaf(v, k4.z, acc.z); acc.w = fmaf(v, k4.w, acc.w);
+            }
+        acc.x = apply_act(acc.x, act); acc.y = apply_act(acc.y, act); acc.z = apply_act(acc.z, act); acc.w = apply_act(acc.w, act);
+        *reinterpret_cast<float4*>(o1 + ((w * (H + 2) + oh + 1) * (long long)(Wo + 2) + ow + 1) * CO + c) = acc;
+    }
+}
+
+// zero the one-pixel border (and any spare rows / columns) of padded NHWC images buf[n][Hp][Wp][C]; interior = H x W at (1, 1)
+__global__ void __launch_bounds__(256)
+zero_border_kernel(float* __restrict__ buf, long long n, int Hp, int Wp, int C, int H, int W) {
+    const int q4 = C / 4;
+    const long long per = (long long)Hp * Wp * q4, total = n * per;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)((i % per) / q4);
+        const int y = r / Wp, x = r - y * Wp;
+        if (y == 0 || y > H || x == 0 || x > W) reinterpret_cast<float4*>(buf)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
 // The same depthwise FIR with the window's rows staged in shared memory and the taps in registers: one CTA iteration =
 // (window, 32-channel slab); thread = (channel, segment of 13 output steps), a sliding window of inputs feeds the 13
 // accumulators (KW + 12 shared-memory loads for 13 KW FMAs).  T = 98 (NS40x98).

@@ -23,7 +23,7 @@ import numpy as np
 
 BN_EPS = 1e-5
 
-ARCH_IDS = {"dnn": 0, "cnn": 1, "tcn": 2, "bcresnet": 3, "crnn": 4, "e2e_dnn": 5, "gru": 6, "lstm": 7, "rnn": 7, "quartznet": 8, "e2e_quartznet": 9}
+ARCH_IDS = {"dnn": 0, "cnn": 1, "tcn": 2, "bcresnet": 3, "crnn": 4, "e2e_dnn": 5, "gru": 6, "lstm": 7, "rnn": 7, "quartznet": 8, "e2e_quartznet": 9, "e2e_cnn": 10}
 ACT_IDS = {"relu": 0, "gelu": 1, "silu": 2}
 POST_NONE, POST_ACT, POST_LN_ACT = 0, 1, 2
 
@@ -181,9 +181,9 @@ def pack_tensors(sd: dict, cfg: dict) -> dict[str, np.ndarray]:
         out["rnn.cell"] = np.array([0 if mt == "gru" else 1], dtype=np.int32)
         fc = "model.layer2" if mt == "rnn" else "model.fc"
         layers.append((_f64(sd, fc + ".weight"), _f64(sd, fc + ".bias"), POST_NONE, None))
-    elif mt in ("quartznet", "e2e_quartznet"):
+    elif mt in ("quartznet", "e2e_quartznet", "e2e_cnn"):
         pre = "model"
-        if mt == "e2e_quartznet":
+        if mt in ("e2e_quartznet", "e2e_cnn"):
             # E2ERawQuartzNet (architectures.py:796-817): RawAudioFrontend (:695-714) = strided Conv1d (no bias) +
             # BatchNorm + ReLU layers straight on the audio.  On channel-last buffers a strided Conv1d is a row GEMM
             # whose row t is the CONTIGUOUS slice of k * C_in floats starting at input step stride * t - pad, so each
@@ -200,6 +200,23 @@ def pack_tensors(sd: dict, cfg: dict) -> dict[str, np.ndarray]:
                 out[f"raw.{i}.w"] = g.astype(np.float32)
                 out[f"raw.{i}.b"] = b.astype(np.float32)
                 i += 1
+        if mt == "e2e_cnn":
+            # RawAudioBackbone (architectures.py:738-774): the front end's (C, T) output is a one-channel image; four 3x3
+            # Conv2d (no bias) + BatchNorm + activation.  conv1 (1 -> 24) is a direct kernel; conv2..4 are row GEMMs on
+            # zero-padded NHWC images whose K axis is three segments (kernel rows) of 3 * C_in contiguous floats:
+            # weight row = (kh * 3 + kw) * C_in + ci.
+            w, b = fold_bn(_f64(sd, "model.backbone.conv1.0.weight"), None, sd, "model.backbone.conv1.1")
+            out["rawcnn.conv1.w"] = np.ascontiguousarray(w.reshape(w.shape[0], 9).T).astype(np.float32)        # (9, 24)
+            out["rawcnn.conv1.b"] = b.astype(np.float32)
+            for j in (2, 3, 4):
+                w, b = fold_bn(_f64(sd, f"model.backbone.conv{j}.0.weight"), None, sd, f"model.backbone.conv{j}.1")
+                cout, cin = w.shape[:2]
+                kk = -(-(9 * cin) // 64) * 64
+                g = np.zeros((kk, -(-cout // 64) * 64))
+                g[:9 * cin, :cout] = w.transpose(2, 3, 1, 0).reshape(9 * cin, cout)
+                out[f"rawcnn.conv{j}.w"] = g.astype(np.float32)
+                out[f"rawcnn.conv{j}.b"] = b.astype(np.float32)
+            layers.append((_f64(sd, "model.backbone.fc.weight"), _f64(sd, "model.backbone.fc.bias"), POST_NONE, None))
         # QuartzNetModel (architectures.py:366-437).  Per block the engine runs a depthwise FIR (no bias) and ONE row
         # GEMM [dw(x) | x] @ W + b: BatchNorm folded into the pointwise / residual 1x1 weights, the depthwise bias
         # pushed through the pointwise weights into b.  Channel counts are padded so that K is a multiple of 64.
@@ -227,7 +244,8 @@ def pack_tensors(sd: dict, cfg: dict) -> dict[str, np.ndarray]:
             out[f"qn.{i}.b"] = b.astype(np.float32)
             out[f"qn.{i}.meta"] = np.array([c, n_out, k, int(has_res)], dtype=np.int32)
             i += 1
-        layers.append((_f64(sd, pre + ".fc.weight"), _f64(sd, pre + ".fc.bias"), POST_NONE, None))
+        if mt != "e2e_cnn":
+            layers.append((_f64(sd, pre + ".fc.weight"), _f64(sd, pre + ".fc.bias"), POST_NONE, None))
     elif mt == "e2e_dnn":
         for j, i in enumerate((0, 4, 8)):
             w, b = fold_bn(_f64(sd, f"model.conv_block.{i}.weight"), _f64(sd, f"model.conv_block.{i}.bias"),

@@ -14,8 +14,8 @@ pytestmark = pytest.mark.gpu
 SCORE_TOL = 1e-3
 MEL_TOL = 1e-4
 
-HEADS = ["dnn", "cnn", "tcn", "bcresnet", "crnn", "e2e_dnn", "gru", "lstm", "rnn", "quartznet", "e2e_quartznet"]
-RAW_HEADS = ("e2e_quartznet",)          # audio in, no log-mel to compare
+HEADS = ["dnn", "cnn", "tcn", "bcresnet", "crnn", "e2e_dnn", "gru", "lstm", "rnn", "quartznet", "e2e_quartznet", "e2e_cnn"]
+RAW_HEADS = ("e2e_quartznet", "e2e_cnn")          # audio in, no log-mel to compare
 
 
 @pytest.fixture(scope="module")
@@ -286,7 +286,8 @@ def test_other_activations_match_oracle(torch_cuda, mt, act):
 
 
 @pytest.mark.parametrize("mt,kw", [("gru", dict(layer_dim=64)), ("lstm", dict(layer_dim=64)), ("gru", dict(activation_function="gelu")),
-                                   ("quartznet", dict(quartznet_config=[[64, 11, 1], [64, 13, 2], [128, 17, 1], [128, 5, 1]]))])
+                                   ("quartznet", dict(quartznet_config=[[64, 11, 1], [64, 13, 2], [128, 17, 1], [128, 5, 1]])),
+                                   ("e2e_cnn", dict(activation_function="silu")), ("e2e_cnn", dict(activation_function="gelu"))])
 def test_sequence_head_variants_match_oracle(torch_cuda, mt, kw):
     """Other shapes of the §8(f) sequence heads: 64 hidden units (the second template instantiation of
     rnn_seq_kernel), a non-ReLU classifier, and a QuartzNet config with repeated blocks (identity residual), the
@@ -302,13 +303,13 @@ def test_sequence_head_variants_match_oracle(torch_cuda, mt, kw):
     assert np.abs(got - ref).max() < SCORE_TOL, (mt, kw, np.abs(got - ref).max())
 
 
-@pytest.mark.parametrize("mt", ["gru", "lstm", "quartznet", "e2e_quartznet"])
+@pytest.mark.parametrize("mt", ["gru", "lstm", "quartznet", "e2e_quartznet", "e2e_cnn"])
 def test_sequence_heads_do_not_depend_on_batch_composition(torch_cuda, mt):
     """A window's score must not depend on which tile / CTA / chunk it lands in: the recurrent kernel uses 32-row tiles
     for small batches and 128-row tiles for large ones, the row GEMM walks K in a fixed order."""
     eng, sd, cfg = _engine(mt)
     base = np.concatenate([synth_pcm(50, seed=51, kind="gauss"), synth_pcm(20, seed=52, kind="uniform")])
     small = eng.score_device(torch_cuda.from_numpy(base).cuda()).cpu().numpy()
-    reps = 203 if "quartznet" not in mt else 60                     # 14 210 windows: 128-row tiles, ragged last tile
+    reps = 203 if mt in ("gru", "lstm") else 60                     # 14 210 windows: 128-row tiles, ragged last tile
     big = eng.score_device(torch_cuda.from_numpy(np.tile(base, (reps, 1))).cuda()).cpu().numpy()
     assert np.array_equal(big.reshape(reps, -1), np.tile(small, (reps, 1)))

@@ -42,7 +42,7 @@ def test_create_fails_loudly_without_gpu_or_with_bad_blob():
         assert "no CUDA device" in msg and "no CPU fallback" in msg
 
 
-@pytest.mark.parametrize("mt", ["dnn", "cnn", "tcn", "bcresnet", "crnn", "e2e_dnn", "gru", "lstm", "rnn", "quartznet", "e2e_quartznet"])
+@pytest.mark.parametrize("mt", ["dnn", "cnn", "tcn", "bcresnet", "crnn", "e2e_dnn", "gru", "lstm", "rnn", "quartznet", "e2e_quartznet", "e2e_cnn"])
 def test_pack_tensors_layouts(mt):
     cfg = default_config(mt)
     sd = make_state_dict(cfg, 0)
