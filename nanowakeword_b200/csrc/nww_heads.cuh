@@ -380,7 +380,7 @@ inline int launch_quartznet_blocks(const HeadWeights& hw, const float* x, int pi
     float* a = arena;
     float* plane[2] = {a + (size_t)n * T * hw.qn_max_k, a + (size_t)n * T * hw.qn_max_k + (size_t)n * T * hw.qn_max_n};
     const long long rows = n * T;
-    NWW_HCUDA(set_smem(rowgemm_kc_umma_kernel, rowgemm_kc_smem_bytes()));
+    NWW_HCUDA(set_smem(rowgemm_kc_umma_kernel<false>, rowgemm_kc_smem_bytes()));
     for (int i = 0; i < hw.qn_blocks; ++i) {
         const HeadWeights::QnBlock& B = hw.qn[i];
         const int tgrid = (int)std::min<long long>(n * (B.Cp / 32), (long long)sm_count * 8);
@@ -395,7 +395,7 @@ inline int launch_quartznet_blocks(const HeadWeights& hw, const float* x, int pi
         }
         if ((rc = done())) return rc;
         float* y = plane[i & 1];
-        rowgemm_kc_umma_kernel<<<(int)std::min<long long>((rows + kKcRows - 1) / kKcRows, sm_count), kKcNT, rowgemm_kc_smem_bytes(), st>>>(
+        rowgemm_kc_umma_kernel<false><<<(int)std::min<long long>((rows + kKcRows - 1) / kKcRows, sm_count), kKcNT, rowgemm_kc_smem_bytes(), st>>>(
             a, kc_plain(rows, B.K), kc_one_seg(B.K), B.K, B.wq, B.b, B.has_res ? nullptr : x, y, kc_plain(rows, B.N), rows, B.N, B.N, 1);
         if ((rc = done())) return rc;
         x = y;
@@ -421,7 +421,7 @@ inline int launch_raw_frontend(const HeadWeights& hw, int sm_count, WindowSource
     p += (size_t)n * L0.in_len;
     raw_pcm_kernel<<<ew_grid(n * (L0.in_len / 4), sm_count), 256, 0, st>>>(pcm, n, in, (int)L0.in_len, L0.pad);
     if ((rc = done())) return rc;
-    NWW_HCUDA(set_smem(rowgemm_kc_umma_kernel, rowgemm_kc_smem_bytes()));
+    NWW_HCUDA(set_smem(rowgemm_kc_umma_kernel<true>, rowgemm_kc_smem_bytes()));
     for (int i = 0; i < hw.raw_layers; ++i) {
         const HeadWeights::RawLayer& L = hw.raw[i];
         const bool last = i + 1 == hw.raw_layers;
@@ -437,7 +437,7 @@ inline int launch_raw_frontend(const HeadWeights& hw, int sm_count, WindowSource
             if ((rc = done())) return rc;
         }
         const long long rows = n * L.t_out;
-        rowgemm_kc_umma_kernel<<<(int)std::min<long long>((rows + kKcRows - 1) / kKcRows, sm_count), kKcNT, rowgemm_kc_smem_bytes(), st>>>(
+        rowgemm_kc_umma_kernel<true><<<(int)std::min<long long>((rows + kKcRows - 1) / kKcRows, sm_count), kKcNT, rowgemm_kc_smem_bytes(), st>>>(
             in, kc_seq(L.t_out, L.in_len, (long long)L.stride * L.cin, 0), kc_one_seg(L.k * L.cin), L.K, L.wq, L.b, nullptr, out,
             kc_seq(L.t_out, out_len, L.cout, out_pad), rows, L.Npad, L.cout, 1);
         if ((rc = done())) return rc;
@@ -491,7 +491,7 @@ inline int launch_raw_cnn(const HeadWeights& hw, int act, int sm_count, WindowSo
         const long long rpw = (long long)L.Hout * L.Wout, rows = n * rpw;
         const KcView av{rpw, (long long)Hp * Wp * L.cin, (long long)L.s * L.cin, 0, L.Wout, (long long)L.s * Wp * L.cin};
         const KcView ov{rpw, (long long)Hp2 * Wp2 * L.cout, L.cout, 0, L.Wout, (long long)Wp2 * L.cout};
-        rowgemm_kc_umma_kernel<<<(int)std::min<long long>((rows + kKcRows - 1) / kKcRows, sm_count), kKcNT, rowgemm_kc_smem_bytes(), st>>>(
+        rowgemm_kc_umma_kernel<true><<<(int)std::min<long long>((rows + kKcRows - 1) / kKcRows, sm_count), kKcNT, rowgemm_kc_smem_bytes(), st>>>(
             img, av, KcSegs{3 * L.cin, (long long)Wp * L.cin, 9 * L.cin}, L.K, L.wq, L.b, nullptr,
             out + (last ? 0 : (size_t)(Wp2 + 1) * L.cout), ov, rows, L.Npad, L.cout, act + 1);
         if ((rc = done())) return rc;

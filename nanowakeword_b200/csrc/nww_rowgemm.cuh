@@ -410,7 +410,7 @@ rowgemm_umma_kernel(const float* __restrict__ A, long long a_row_mul, long long 
 constexpr int kKcRows = 128, kKcNT = 256, kKcKC = 64, kKcNC = 64, kKcRing = 4;
 constexpr int kKcABuf = 2 * (kKcKC / 8) * kKcRows * 16;           // hi | lo of one chunk: 32 KB
 constexpr int kKcSub = 2 * (kKcKC / 8) * kKcNC * 16;              // one weight sub-block: 16 KB
-inline size_t rowgemm_kc_smem_bytes() { return (size_t)2 * kKcABuf + (size_t)kKcRing * kKcSub + 256; }
+inline size_t rowgemm_kc_smem_bytes() { return (size_t)2 * kKcABuf + (size_t)kKcRing * kKcSub + 256 + kKcRows * sizeof(long long); }
 
 // host: w [K][N] FP32 -> the stream the kernel consumes: for every K chunk, for every 64-column group:
 // [hi | lo][K group 8][64 columns][8 k] bf16
@@ -466,6 +466,9 @@ inline KcSegs kc_one_seg(int k_valid) { return KcSegs{1 << 30, 0, k_valid}; }
 
 // n_valid (a multiple of 4, <= N): columns actually stored (the weight matrix is padded to 64 columns)
 // act: 0 none, 1 ReLU, 2 GELU, 3 SiLU (apply_act codes + 1)
+// VIEWS = false is the fast path for plain matrices (A = [rows][K], out = [rows][N], all columns stored, act 0 / 1):
+// no per-row address table, no segment arithmetic, no column masks.
+template <bool VIEWS>
 __global__ void __launch_bounds__(kKcNT, 1)
 rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, KcSegs sg, int K, const uint4* __restrict__ wq,
                        const float* __restrict__ bias, const float* __restrict__ res, float* __restrict__ out, KcView ov, long long rows,
@@ -479,6 +482,7 @@ rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, KcSegs sg, int K,
     uint64_t* bar_afree = bar_full + 2 * kKcRing;                      // [2]: the MMAs that read chunk buffer b are done
     uint64_t* bar_done = bar_full + 2 * kKcRing + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + 2 * kKcRing + 3);
+    long long* row_at = reinterpret_cast<long long*>(b_s + kKcRing * kKcSub + 256);   // A offsets of the tile's rows
     const uint32_t tmem_cols = N <= 64 ? 64u : N <= 128 ? 128u : N <= 256 ? 256u : 512u;
     if (tid == 0) {
         for (int i = 0; i < 2 * kKcRing + 3; ++i) mbar_init(bar_full + i, 1);
@@ -507,6 +511,11 @@ rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, KcSegs sg, int K,
         };
         if (tid == 0)
             for (int i = 0; i < kKcRing && p_pos < total; ++i) produce();
+        if (VIEWS) {
+            __syncthreads();                                           // the previous tile's last conversion has read row_at
+            if (tid < kKcRows) row_at[tid] = r0 + tid < rows ? av.at(r0 + tid) : -1;
+            __syncthreads();
+        }
         for (int kc = 0; kc < n_kc; ++kc, ++g) {
             const uint32_t buf = g & 1u;
             if (g >= 2) mbar_wait(bar_afree + buf, ((g >> 1) - 1u) & 1u);   // chunk g - 2's MMAs have read this buffer
@@ -515,12 +524,13 @@ rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, KcSegs sg, int K,
                 const int gq = i / kKcRows, r = i - gq * kKcRows;
                 uint4 hv = make_uint4(0, 0, 0, 0), lv = hv;
                 const int k8 = kc * kKcKC + 8 * gq;
-                if (r0 + r < rows && k8 < sg.k_valid) {
-                    const int seg = k8 / sg.seg_len;
-                    const float4* p = reinterpret_cast<const float4*>(A + av.at(r0 + r) + seg * sg.seg_stride + (k8 - seg * sg.seg_len));
+                const long long ra = VIEWS ? row_at[r] : (r0 + r < rows ? (r0 + r) * (long long)K : -1);
+                if (ra >= 0 && (!VIEWS || k8 < sg.k_valid)) {
+                    const int seg = VIEWS ? k8 / sg.seg_len : 0;
+                    const float4* p = reinterpret_cast<const float4*>(A + ra + (VIEWS ? seg * sg.seg_stride + (k8 - seg * sg.seg_len) : k8));
                     const float4 v0 = __ldg(p), v1 = __ldg(p + 1);
                     float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-                    if (k8 + 8 > sg.k_valid) {                         // the group straddles the end of the valid columns
+                    if (VIEWS && k8 + 8 > sg.k_valid) {                // the group straddles the end of the valid columns
 #pragma unroll
                         for (int e = 0; e < 8; ++e)
                             if (k8 + e >= sg.k_valid) v[e] = 0.0f;
@@ -577,7 +587,7 @@ rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, KcSegs sg, int K,
         {
             const int q = warp & 3, hcol = warp >> 2;
             const long long r = r0 + q * 32 + lane;
-            const long long o_at = r < rows ? ov.at(r) : 0;
+            const long long o_at = r < rows ? (VIEWS ? ov.at(r) : r * (long long)N) : 0;
             for (int c0 = hcol * (N / 2); c0 < (hcol + 1) * (N / 2) && c0 < n_valid; c0 += 32) {
                 float v[32];
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
@@ -586,14 +596,18 @@ rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, KcSegs sg, int K,
                     const float4* rs = res ? reinterpret_cast<const float4*>(res + r * N + c0) : nullptr;
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
-                        if (c0 + 4 * j4 >= n_valid) break;
+                        if (VIEWS && c0 + 4 * j4 >= n_valid) break;
                         float4 o = make_float4(v[4 * j4] + __ldg(bias + c0 + 4 * j4), v[4 * j4 + 1] + __ldg(bias + c0 + 4 * j4 + 1),
                                                v[4 * j4 + 2] + __ldg(bias + c0 + 4 * j4 + 2), v[4 * j4 + 3] + __ldg(bias + c0 + 4 * j4 + 3));
                         if (rs) {
                             const float4 t = __ldg(rs + j4);
                             o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
                         }
-                        if (act) { o.x = apply_act(o.x, act - 1); o.y = apply_act(o.y, act - 1); o.z = apply_act(o.z, act - 1); o.w = apply_act(o.w, act - 1); }
+                        if (!VIEWS) {
+                            if (act) { o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f); }
+                        } else if (act) {
+                            o.x = apply_act(o.x, act - 1); o.y = apply_act(o.y, act - 1); o.z = apply_act(o.z, act - 1); o.w = apply_act(o.w, act - 1);
+                        }
                         dst[j4] = o;
                     }
                 }

@@ -27,7 +27,7 @@ static double run_case(const char* name, long long n_win, KcView av, KcSegs sg, 
     std::vector<uint16_t> wq;
     rowgemm_kc_pack(W.data(), K, N, &wq);
     cudasim::launch(dim3(grid), dim3(kKcNT), rowgemm_kc_smem_bytes(), [&] {
-        rowgemm_kc_umma_kernel(A.data(), av, sg, K, reinterpret_cast<const uint4*>(wq.data()), bias.data(), with_res ? res.data() : nullptr,
+        rowgemm_kc_umma_kernel<true>(A.data(), av, sg, K, reinterpret_cast<const uint4*>(wq.data()), bias.data(), with_res ? res.data() : nullptr,
                                out.data(), ov, rows, N, n_valid, act);
     });
     double worst = 0;
@@ -67,6 +67,32 @@ int main() {
         KcView av{Ho * Wo, (long long)Hp * Wp * C, 2 * C, 0, Wo, 2LL * Wp * C};
         KcView ov{Ho * Wo, (long long)Hp2 * Wp2 * Co, Co, 0, Wo, (long long)Wp2 * Co};
         bad += run_case("conv2d 3x3 s2 c24 -> 48, SiLU", 3, av, KcSegs{3 * C, (long long)Wp * C, 9 * C}, 256, 64, Co, ov, false, 3, 2);
+    }
+    {   // the plain fast path (no views) against the same reference
+        const long long rows = 300;
+        const int K = 192, N = 256;
+        std::mt19937 rng(9);
+        std::normal_distribution<float> nd(0.f, 1.f);
+        std::vector<float> A(rows * K), W((size_t)K * N), bias(N), res(rows * N), out(rows * N, -7777.f);
+        for (auto& v : A) v = 3.f * nd(rng);
+        for (auto& v : W) v = 0.1f * nd(rng);
+        for (auto& v : bias) v = nd(rng);
+        for (auto& v : res) v = nd(rng);
+        std::vector<uint16_t> wq;
+        rowgemm_kc_pack(W.data(), K, N, &wq);
+        cudasim::launch(dim3(2), dim3(kKcNT), rowgemm_kc_smem_bytes(), [&] {
+            rowgemm_kc_umma_kernel<false>(A.data(), kc_plain(rows, K), kc_one_seg(K), K, reinterpret_cast<const uint4*>(wq.data()), bias.data(),
+                                          res.data(), out.data(), kc_plain(rows, N), rows, N, N, 1);
+        });
+        double worst = 0;
+        for (long long r = 0; r < rows; ++r)
+            for (int c = 0; c < N; ++c) {
+                double s = bias[c] + res[r * N + c];
+                for (int k = 0; k < K; ++k) s += (double)A[r * K + k] * W[(size_t)k * N + c];
+                worst = std::max(worst, fabs((double)out[r * N + c] - (s > 0 ? s : 0)));
+            }
+        printf("%-34s rows %6lld K %4d N %3d               max |err| %.3e\n", "plain fast path", rows, K, N, worst);
+        bad += worst;
     }
     return bad < 5e-3 ? 0 : 1;
 }
