@@ -381,6 +381,7 @@ inline int launch_quartznet_blocks(const HeadWeights& hw, const float* x, int pi
     float* plane[2] = {a + (size_t)n * T * hw.qn_max_k, a + (size_t)n * T * hw.qn_max_k + (size_t)n * T * hw.qn_max_n};
     const long long rows = n * T;
     NWW_HCUDA(set_smem(rowgemm_kc_umma_kernel<false>, rowgemm_kc_smem_bytes()));
+    NWW_HCUDA(cudaFuncSetAttribute(rowgemm_kc_umma_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     for (int i = 0; i < hw.qn_blocks; ++i) {
         const HeadWeights::QnBlock& B = hw.qn[i];
         const int tgrid = (int)std::min<long long>(n * (B.Cp / 32), (long long)sm_count * 8);
@@ -395,8 +396,9 @@ inline int launch_quartznet_blocks(const HeadWeights& hw, const float* x, int pi
         }
         if ((rc = done())) return rc;
         float* y = plane[i & 1];
-        rowgemm_kc_umma_kernel<false><<<(int)std::min<long long>((rows + kKcRows - 1) / kKcRows, sm_count), kKcNT, rowgemm_kc_smem_bytes(), st>>>(
-            a, kc_plain(rows, B.K), kc_one_seg(B.K), B.K, B.wq, B.b, B.has_res ? nullptr : x, y, kc_plain(rows, B.N), rows, B.N, B.N, 1);
+        const KcLaunch kl = rowgemm_kc_launch(rows, B.N, sm_count);
+        rowgemm_kc_umma_kernel<false><<<kl.grid, kKcNT, kl.smem, st>>>(
+            a, kc_plain(rows, B.K), kc_one_seg(B.K), B.K, B.wq, B.b, B.has_res ? nullptr : x, y, kc_plain(rows, B.N), rows, B.N, B.N, 1, kl.ring);
         if ((rc = done())) return rc;
         x = y;
         pitch = B.N;
@@ -422,6 +424,7 @@ inline int launch_raw_frontend(const HeadWeights& hw, int sm_count, WindowSource
     raw_pcm_kernel<<<ew_grid(n * (L0.in_len / 4), sm_count), 256, 0, st>>>(pcm, n, in, (int)L0.in_len, L0.pad);
     if ((rc = done())) return rc;
     NWW_HCUDA(set_smem(rowgemm_kc_umma_kernel<true>, rowgemm_kc_smem_bytes()));
+    NWW_HCUDA(cudaFuncSetAttribute(rowgemm_kc_umma_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     for (int i = 0; i < hw.raw_layers; ++i) {
         const HeadWeights::RawLayer& L = hw.raw[i];
         const bool last = i + 1 == hw.raw_layers;
@@ -437,9 +440,10 @@ inline int launch_raw_frontend(const HeadWeights& hw, int sm_count, WindowSource
             if ((rc = done())) return rc;
         }
         const long long rows = n * L.t_out;
-        rowgemm_kc_umma_kernel<true><<<(int)std::min<long long>((rows + kKcRows - 1) / kKcRows, sm_count), kKcNT, rowgemm_kc_smem_bytes(), st>>>(
+        const KcLaunch kl = rowgemm_kc_launch(rows, L.Npad, sm_count);
+        rowgemm_kc_umma_kernel<true><<<kl.grid, kKcNT, kl.smem, st>>>(
             in, kc_seq(L.t_out, L.in_len, (long long)L.stride * L.cin, 0), kc_one_seg(L.k * L.cin), L.K, L.wq, L.b, nullptr, out,
-            kc_seq(L.t_out, out_len, L.cout, out_pad), rows, L.Npad, L.cout, 1);
+            kc_seq(L.t_out, out_len, L.cout, out_pad), rows, L.Npad, L.cout, 1, kl.ring);
         if ((rc = done())) return rc;
         in = out;
     }
@@ -473,9 +477,12 @@ inline int launch_raw_cnn(const HeadWeights& hw, int act, int sm_count, WindowSo
     int C = hw.rc_c1, H = hw.rc_h1, W = hw.rc_w1o;
     float* img = p;
     p += (size_t)n * (H + 2) * (W + 2) * C;
-    zero_border_kernel<<<ew_grid(n * (H + 2) * (W + 2) * (C / 4), sm_count), 256, 0, st>>>(img, n, H + 2, W + 2, C, H, W);
+    zero_border_kernel<<<ew_grid(n * 2 * (H + W + 2) * (C / 4), sm_count), 256, 0, st>>>(img, n, H + 2, W + 2, C, H, W);
     if ((rc = done())) return rc;
-    rawcnn_conv1_kernel<<<ew_grid(n * H * W * (C / 4), sm_count), 256, 0, st>>>(bf, hw.rc_w1, hw.rc_b1, img, n, hw.qn_cin, hw.qn_t, W, C, act);
+    if (C == 24)
+        rawcnn_conv1_px_kernel<6><<<ew_grid(n * H * W, sm_count), 256, 0, st>>>(bf, hw.rc_w1, hw.rc_b1, img, n, hw.qn_cin, hw.qn_t, W, act);
+    else
+        rawcnn_conv1_kernel<<<ew_grid(n * H * W * (C / 4), sm_count), 256, 0, st>>>(bf, hw.rc_w1, hw.rc_b1, img, n, hw.qn_cin, hw.qn_t, W, C, act);
     if ((rc = done())) return rc;
     for (int j = 0; j < 3; ++j) {
         const HeadWeights::RcLayer& L = hw.rc[j];
@@ -485,15 +492,16 @@ inline int launch_raw_cnn(const HeadWeights& hw, int act, int sm_count, WindowSo
         float* out = p;
         p += (size_t)n * Hp2 * Wp2 * L.cout;
         if (!last) {
-            zero_border_kernel<<<ew_grid(n * Hp2 * Wp2 * (L.cout / 4), sm_count), 256, 0, st>>>(out, n, Hp2, Wp2, L.cout, L.Hout, L.Wout);
+            zero_border_kernel<<<ew_grid(n * 2 * (Hp2 + Wp2) * (L.cout / 4), sm_count), 256, 0, st>>>(out, n, Hp2, Wp2, L.cout, L.Hout, L.Wout);
             if ((rc = done())) return rc;
         }
         const long long rpw = (long long)L.Hout * L.Wout, rows = n * rpw;
         const KcView av{rpw, (long long)Hp * Wp * L.cin, (long long)L.s * L.cin, 0, L.Wout, (long long)L.s * Wp * L.cin};
         const KcView ov{rpw, (long long)Hp2 * Wp2 * L.cout, L.cout, 0, L.Wout, (long long)Wp2 * L.cout};
-        rowgemm_kc_umma_kernel<true><<<(int)std::min<long long>((rows + kKcRows - 1) / kKcRows, sm_count), kKcNT, rowgemm_kc_smem_bytes(), st>>>(
+        const KcLaunch kl = rowgemm_kc_launch(rows, L.Npad, sm_count);
+        rowgemm_kc_umma_kernel<true><<<kl.grid, kKcNT, kl.smem, st>>>(
             img, av, KcSegs{3 * L.cin, (long long)Wp * L.cin, 9 * L.cin}, L.K, L.wq, L.b, nullptr,
-            out + (last ? 0 : (size_t)(Wp2 + 1) * L.cout), ov, rows, L.Npad, L.cout, act + 1);
+            out + (last ? 0 : (size_t)(Wp2 + 1) * L.cout), ov, rows, L.Npad, L.cout, act + 1, kl.ring);
         if ((rc = done())) return rc;
         img = out;
         C = L.cout; H = L.Hout; W = L.Wout;

@@ -410,7 +410,16 @@ rowgemm_umma_kernel(const float* __restrict__ A, long long a_row_mul, long long 
 constexpr int kKcRows = 128, kKcNT = 256, kKcKC = 64, kKcNC = 64, kKcRing = 4;
 constexpr int kKcABuf = 2 * (kKcKC / 8) * kKcRows * 16;           // hi | lo of one chunk: 32 KB
 constexpr int kKcSub = 2 * (kKcKC / 8) * kKcNC * 16;              // one weight sub-block: 16 KB
-inline size_t rowgemm_kc_smem_bytes() { return (size_t)2 * kKcABuf + (size_t)kKcRing * kKcSub + 256 + kKcRows * sizeof(long long); }
+inline size_t rowgemm_kc_smem_bytes(int ring = kKcRing) { return (size_t)2 * kKcABuf + (size_t)ring * kKcSub + 256 + kKcRows * sizeof(long long); }
+// Narrow outputs (N <= 128) leave a tile little MMA work between its operand conversion and its epilogue: a two-slot
+// weight ring makes the CTA small enough (97 KB, <= 128 TMEM columns) for two CTAs per SM to overlap those phases.
+struct KcLaunch { int ring, grid; size_t smem; };
+inline KcLaunch rowgemm_kc_launch(long long rows, int N, int sm_count) {
+    const int ring = N <= 128 ? 2 : kKcRing;
+    const long long tiles = (rows + kKcRows - 1) / kKcRows;
+    const long long cap = (long long)sm_count * (N <= 128 ? 2 : 1);
+    return KcLaunch{ring, (int)(tiles < cap ? tiles : cap), rowgemm_kc_smem_bytes(ring)};
+}
 
 // host: w [K][N] FP32 -> the stream the kernel consumes: for every K chunk, for every 64-column group:
 // [hi | lo][K group 8][64 columns][8 k] bf16
@@ -469,20 +478,20 @@ inline KcSegs kc_one_seg(int k_valid) { return KcSegs{1 << 30, 0, k_valid}; }
 // VIEWS = false is the fast path for plain matrices (A = [rows][K], out = [rows][N], all columns stored, act 0 / 1):
 // no per-row address table, no segment arithmetic, no column masks.
 template <bool VIEWS>
-__global__ void __launch_bounds__(kKcNT, 1)
+__global__ void __launch_bounds__(kKcNT, VIEWS ? 2 : 1)
 rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, KcSegs sg, int K, const uint4* __restrict__ wq,
                        const float* __restrict__ bias, const float* __restrict__ res, float* __restrict__ out, KcView ov, long long rows,
-                       int N, int n_valid, int act) {
+                       int N, int n_valid, int act, int ring) {
     NWW_DYN_SMEM(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned char* a_s = smem;                                         // two chunk buffers
     unsigned char* b_s = smem + 2 * kKcABuf;                           // weight ring
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(b_s + kKcRing * kKcSub);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(b_s + ring * kKcSub);
     uint64_t* bar_empty = bar_full + kKcRing;
     uint64_t* bar_afree = bar_full + 2 * kKcRing;                      // [2]: the MMAs that read chunk buffer b are done
     uint64_t* bar_done = bar_full + 2 * kKcRing + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + 2 * kKcRing + 3);
-    long long* row_at = reinterpret_cast<long long*>(b_s + kKcRing * kKcSub + 256);   // A offsets of the tile's rows
+    long long* row_at = reinterpret_cast<long long*>(b_s + ring * kKcSub + 256);   // A offsets of the tile's rows
     const uint32_t tmem_cols = N <= 64 ? 64u : N <= 128 ? 128u : N <= 256 ? 256u : 512u;
     if (tid == 0) {
         for (int i = 0; i < 2 * kKcRing + 3; ++i) mbar_init(bar_full + i, 1);
@@ -506,11 +515,11 @@ rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, KcSegs sg, int K,
             mbar_expect_tx(bar_full + p_slot, kKcSub);
             bulk_g2s(b_s + (size_t)p_slot * kKcSub, reinterpret_cast<const unsigned char*>(wq) + (size_t)p_pos * kKcSub, kKcSub,
                      bar_full + p_slot);
-            p_slot = p_slot + 1 == kKcRing ? 0 : p_slot + 1;
+            p_slot = (int)p_slot + 1 == ring ? 0 : p_slot + 1;
             ++p_pos;
         };
         if (tid == 0)
-            for (int i = 0; i < kKcRing && p_pos < total; ++i) produce();
+            for (int i = 0; i < ring && p_pos < total; ++i) produce();
         if (VIEWS) {
             __syncthreads();                                           // the previous tile's last conversion has read row_at
             if (tid < kKcRows) row_at[tid] = r0 + tid < rows ? av.at(r0 + tid) : -1;
@@ -572,7 +581,7 @@ rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, KcSegs sg, int K,
                     }
                     prev_slot = (int)c_slot;
                     prev_par = c_par;
-                    if (++c_slot == kKcRing) { c_slot = 0; c_par ^= 1u; }
+                    if ((int)++c_slot == ring) { c_slot = 0; c_par ^= 1u; }
                 }
                 umma_commit(bar_afree + buf);
             }
@@ -714,15 +723,64 @@ rawcnn_conv1_kernel(const float* __restrict__ bf, const float* __restrict__ w1 /
     }
 }
 
-// zero the one-pixel border (and any spare rows / columns) of padded NHWC images buf[n][Hp][Wp][C]; interior = H x W at (1, 1)
+// the same with one thread per output pixel and all CO = 4 Q4 channels in registers (9 input loads per pixel instead of 9 per
+// channel quad; the default CO = 24 takes this one)
+template <int Q4>
+__global__ void __launch_bounds__(256)
+rawcnn_conv1_px_kernel(const float* __restrict__ bf, const float* __restrict__ w1 /* [9][4 Q4] */, const float* __restrict__ b1,
+                       float* __restrict__ o1, long long n, int H, int W, int Wo, int act) {
+    constexpr int CO = 4 * Q4;
+    const long long per = (long long)H * Wo, total = n * per;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long w = i / per;
+        const int r = (int)(i - w * per);
+        const int oh = r % H, ow = r / H;           // consecutive threads walk h: img[h][w] = bf[w][h] is contiguous in h
+        const float* img = bf + w * (long long)W * H;
+        float4 acc[Q4];
+#pragma unroll
+        for (int q = 0; q < Q4; ++q) acc[q] = __ldg(reinterpret_cast<const float4*>(b1) + q);
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int ih = oh + kh - 1, iw = 2 * ow + kw - 1;
+                const float v = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(img + (long long)iw * H + ih) : 0.0f;
+#pragma unroll
+                for (int q = 0; q < Q4; ++q) {
+                    const float4 k4 = __ldg(reinterpret_cast<const float4*>(w1 + (kh * 3 + kw) * CO) + q);
+                    acc[q].x = fmaf(v, k4.x, acc[q].x); acc[q].y = fmaf(v, k4.y, acc[q].y);
+                    acc[q].z = fmaf(v, k4.z, acc[q].z); acc[q].w = fmaf(v, k4.w, acc[q].w);
+                }
+            }
+        float4* dst = reinterpret_cast<float4*>(o1 + ((w * (H + 2) + oh + 1) * (long long)(Wo + 2) + ow + 1) * CO);
+#pragma unroll
+        for (int q = 0; q < Q4; ++q)
+            dst[q] = make_float4(apply_act(acc[q].x, act), apply_act(acc[q].y, act), apply_act(acc[q].z, act), apply_act(acc[q].w, act));
+    }
+}
+
+// zero the one-pixel border (and any spare rows / columns) of padded NHWC images buf[n][Hp][Wp][C]; interior = H x W at (1, 1).
+// Only border cells are visited: the full rows 0 and H + 1 .. Hp - 1, then columns 0 and W + 1 .. Wp - 1 of rows 1 .. H.
 __global__ void __launch_bounds__(256)
 zero_border_kernel(float* __restrict__ buf, long long n, int Hp, int Wp, int C, int H, int W) {
-    const int q4 = C / 4;
-    const long long per = (long long)Hp * Wp * q4, total = n * per;
+    const int q4 = C / 4, row_cells = Wp * (Hp - H), side = Wp - W, cells = row_cells + H * side;
+    const long long total = n * cells * q4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int r = (int)((i % per) / q4);
-        const int y = r / Wp, x = r - y * Wp;
-        if (y == 0 || y > H || x == 0 || x > W) reinterpret_cast<float4*>(buf)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int c4 = (int)(i % q4);
+        const long long t = i / q4;
+        const long long w = t / cells;
+        const int c = (int)(t - w * cells);
+        int y, x;
+        if (c < row_cells) {
+            const int j = c / Wp;
+            y = j == 0 ? 0 : H + j;
+            x = c - j * Wp;
+        } else {
+            const int cc = c - row_cells, j = cc / side, xx = cc - j * side;
+            y = 1 + j;
+            x = xx == 0 ? 0 : W + xx;
+        }
+        reinterpret_cast<float4*>(buf)[((w * Hp + y) * Wp + x) * q4 + c4] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 

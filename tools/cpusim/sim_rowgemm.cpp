@@ -28,7 +28,7 @@ static double run_case(const char* name, long long n_win, KcView av, KcSegs sg, 
     rowgemm_kc_pack(W.data(), K, N, &wq);
     cudasim::launch(dim3(grid), dim3(kKcNT), rowgemm_kc_smem_bytes(), [&] {
         rowgemm_kc_umma_kernel<true>(A.data(), av, sg, K, reinterpret_cast<const uint4*>(wq.data()), bias.data(), with_res ? res.data() : nullptr,
-                               out.data(), ov, rows, N, n_valid, act);
+                               out.data(), ov, rows, N, n_valid, act, N <= 128 ? 2 : kKcRing);
     });
     double worst = 0;
     std::vector<char> written(out.size(), 0);
@@ -82,7 +82,7 @@ int main() {
         rowgemm_kc_pack(W.data(), K, N, &wq);
         cudasim::launch(dim3(2), dim3(kKcNT), rowgemm_kc_smem_bytes(), [&] {
             rowgemm_kc_umma_kernel<false>(A.data(), kc_plain(rows, K), kc_one_seg(K), K, reinterpret_cast<const uint4*>(wq.data()), bias.data(),
-                                          res.data(), out.data(), kc_plain(rows, N), rows, N, N, 1);
+                                          res.data(), out.data(), kc_plain(rows, N), rows, N, N, 1, kKcRing);
         });
         double worst = 0;
         for (long long r = 0; r < rows; ++r)
