@@ -8,4 +8,4 @@ __version__ = "0.1.0"
 
 from .interpreter import DetectionResult, NanoInterpreter  # noqa: F401
 from .session import B200Session, Engine, load_artifacts, save_model  # noqa: F401
-from .streams import StreamBank  # noqa: F401
+from .streams import CascadeBank, StreamBank  # noqa: F401

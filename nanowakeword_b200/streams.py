@@ -96,3 +96,56 @@ class StreamBank:
         self.post_processed_scores[sel] = 0.0
         self._hist[sel] = 0.0
         self._hist_len[sel] = 0
+
+
+class CascadeBank:
+    """Two-stage cascade (gate -> verifier) for many streams: the reference's ``load_model(cascade=True)``
+    (nanointerpreter.py:476-496) evaluated per stream as ``_predict_e2e`` does (:758-769).  Both models keep their own
+    ring, counters and history for every stream and both receive every chunk; a stream's verifier result is
+    reported (and remembered) as 0.0 — raw score included — whenever its gate score of the same call, after the
+    gate's own warm-up zeroing, is below ``gate_threshold``.  ``push`` returns the verifier's post-processed scores,
+    like ``DetectionResult.score``; ``gate_scores`` holds the gate's (``DetectionResult.gate_score``).
+
+    The verifier engine still scores every stream (the rings must advance anyway); skipping the gated-off ones
+    inside the engine is a throughput optimisation this class leaves open.
+    """
+
+    def __init__(self, gate_engine, verifier_engine, n_streams: int, gate_threshold: float = 0.3):
+        self.gate = StreamBank(gate_engine, n_streams)
+        self.verifier = StreamBank(verifier_engine, n_streams)
+        self.n = int(n_streams)
+        self.gate_threshold = float(gate_threshold)
+        self.gate_scores = np.zeros(self.n, np.float32)
+
+    def close(self):
+        self.gate.close()
+        self.verifier.close()
+
+    def push(self, chunks: np.ndarray, patience: int = 0, threshold: float = 0.0, debounce_time: float = 0.0) -> np.ndarray:
+        if not isinstance(chunks, np.ndarray):
+            raise ValueError("Input audio `chunks` must be a Numpy array.")
+        if chunks.dtype != np.int16:
+            chunks = chunks.astype(np.int16)
+        g = self.gate
+        graw = g.engine.stream_push_host(chunks)
+        gcur = graw.astype(np.float32, copy=True)
+        gcur[g._hist_len < WARMUP] = 0.0                      # what `current[gate]` holds when the verifier is reached
+        self.gate_scores = g._finish(graw, chunks.shape[1], 0, 0.0, 0.0)   # filters are keyed by the verifier's name
+        vraw = self.verifier.engine.stream_push_host(chunks).astype(np.float32, copy=True)
+        vraw[gcur < self.gate_threshold] = 0.0                # skipped: score and raw score are 0.0 (:760-766)
+        return self.verifier._finish(vraw, chunks.shape[1], patience, threshold, debounce_time)
+
+    @property
+    def raw_scores(self):
+        return self.verifier.raw_scores
+
+    def detected(self, threshold: float) -> np.ndarray:
+        return self.verifier.detected(threshold)
+
+    def reset(self, ids: Optional[np.ndarray] = None):
+        self.gate.reset(ids)
+        self.verifier.reset(ids)
+        if ids is None:
+            self.gate_scores[:] = 0.0
+        else:
+            self.gate_scores[np.asarray(ids, dtype=np.int64)] = 0.0

@@ -291,3 +291,43 @@ def test_recurrent_gate_matrix_layout():
         hb, _ = step(x[:, 97], np.zeros((4, hid)), np.zeros((4, hid)), wb)
         ref = rnn_last_output_bidir(x, _cast_sd(sd, np.float64), prefix, kind)
         assert np.abs(np.concatenate([h, hb], 1) - ref).max() < 1e-6
+
+
+def test_cascade_bank_matches_cascade_interpreters():
+    """CascadeBank (many streams, gate -> verifier) against one cascade NanoInterpreter per stream: the verifier's
+    score, raw score and history must follow nanointerpreter.py:758-769 — skipped (0.0) whenever the gate's
+    warm-up-zeroed score of the same call is below the gate threshold."""
+    from nanowakeword_b200.streams import CascadeBank
+
+    class Gate(_FakeSession):
+        @staticmethod
+        def fn(pcm16):
+            v = np.abs(pcm16.astype(np.float64)).mean(axis=-1) / 2500.0
+            return (1.0 / (1.0 + np.exp(-(v - 1.2) * 3))).astype(np.float32)
+
+    n, L, thr = 4, 4000, 0.45
+    gate_eng = _FakeStreamEngine(16000, lambda w: float(Gate.fn(w[None, :])[0]))
+    ver_eng = _FakeStreamEngine(16000, lambda w: float(_FakeSession.fn(w[None, :])[0]))
+    bank = CascadeBank(gate_eng, ver_eng, n, gate_threshold=thr)
+    interps = []
+    for _ in range(n):
+        it = NanoInterpreter(["/x/wake_lite.pt", "/x/wake.pt"], sessions={"wake_lite": Gate(), "wake": _FakeSession()})
+        it.cascade_config = {"gate": "wake_lite", "verifier": "wake", "gate_threshold": thr}
+        interps.append(it)
+    rng = np.random.default_rng(5)
+    skipped = passed = 0
+    for step in range(30):
+        amp = rng.uniform(1000, 6000, size=(n, 1))
+        chunks = np.clip(rng.normal(0, 1, (n, L)) * amp, -32768, 32767).astype(np.int16)
+        if step == 14:
+            bank.reset([2])
+            interps[2].reset()
+        got = bank.push(chunks, patience=2, threshold=0.3)
+        for i, it in enumerate(interps):
+            r = it.predict(chunks[i], patience={"wake": 2}, threshold={"wake": 0.3})
+            assert abs(got[i] - r.score) < 1e-6, (step, i, got[i], r.score)
+            assert abs(bank.gate_scores[i] - r.gate_score) < 1e-6
+            assert abs(bank.raw_scores[i] - it.raw_scores["wake"]) < 1e-6
+            skipped += r.gate_score < thr
+            passed += r.gate_score >= thr
+    assert skipped > 10 and passed > 10          # both branches exercised
