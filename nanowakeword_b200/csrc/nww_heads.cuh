@@ -285,7 +285,6 @@ inline int setup_head_weights(int arch, int geometry, const BlobLookup& get, con
                 tq = L.t_out;
             }
             if (nl == 0) { *err = "weight blob: raw.* missing"; return NWW_EINVAL; }
-            if (tq > kQnSeg * kQnSegs && false) { *err = "raw-audio front end leaves too long a sequence"; return NWW_EUNSUPPORTED; }
             hw->raw_layers = nl;
             raw_floats += (size_t)tq * cin;                                        // the last layer's plain output
         }
