@@ -346,6 +346,32 @@ def run_gpu_arm(args, rank, world, local_rank):
         except Exception as ex:                                  # never let the secondary block break the contract line
             streams = {"error": repr(ex)}
 
+    # ---- secondary: the other model types the engine builds, same 4096-window batch resident in HBM -----------------
+    other = None
+    if world == 1 and not args.no_streams:
+        other = {}
+        from nanowakeword_b200 import Engine
+        for mt in ("dnn", "tcn", "bcresnet", "crnn", "e2e_dnn", "gru", "lstm", "rnn", "quartznet", "e2e_quartznet", "e2e_cnn"):
+            try:
+                cfg_o = default_config(mt)
+                eng_o = Engine(make_state_dict(cfg_o, 0), cfg_o, device=local_rank)
+                out_o = torch.empty(WINDOWS_PER_GPU, dtype=torch.float32, device=dev)
+                for _ in range(2):
+                    eng_o.score_device(dev_batches[0], out=out_o)
+                torch.cuda.synchronize()
+                o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                o0.record()
+                for i in range(5):
+                    eng_o.score_device(dev_batches[i % N_ROTATE], out=out_o)
+                o1.record()
+                torch.cuda.synchronize()
+                other[mt] = round(WINDOWS_PER_GPU * 5 / (o0.elapsed_time(o1) * 1e-3), 1)
+                eng_o.close()
+            except Exception as ex:                              # never let the secondary block break the contract line
+                other[mt] = repr(ex)
+        other = {"workload": f"batch={WINDOWS_PER_GPU} windows resident in HBM, full path per model type (reference model_type names)",
+                 "unit": UNIT, "values": other}
+
     cores = os.cpu_count() or 1
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -369,7 +395,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_total * CLIP * 2, "d2h_bytes_per_step": n_total * 4,
                 "api": "B200Session.run(None, {'input': int16 (4096,16000) pinned host array}) per rank"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
-        "streams": streams,
+        "streams": streams, "other_models": other,
     }
     emit(line)
     if world > 1:
