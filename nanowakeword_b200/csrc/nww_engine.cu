@@ -606,8 +606,8 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
                 // gate matrices as two-term half UMMA operands (nww_rnn.cuh); this head has no CUDA-core variant
                 const int H = e->heads.rnn_hidden, KX = RnnDims<128, GeoNS40x98::N_MELS>::KX;
                 std::vector<uint16_t> qf, qb;
-                rnn_pack_weights(e->blob.f32("rnn.fwd.w"), KX + H, 4 * H, &qf);
-                rnn_pack_weights(e->blob.f32("rnn.bwd.w"), KX, 4 * H, &qb);
+                rnn_pack_weights(e->blob.f32("rnn.fwd.w"), KX + H, H, &qf);
+                rnn_pack_weights(e->blob.f32("rnn.bwd.w"), KX, H, &qb);
                 NWW_CUDA(cudaMalloc(&e->d_conv_wq[1], qf.size() * sizeof(uint16_t)));
                 NWW_CUDA(cudaMemcpy(e->d_conv_wq[1], qf.data(), qf.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
                 NWW_CUDA(cudaMalloc(&e->d_conv_wq[2], qb.size() * sizeof(uint16_t)));
