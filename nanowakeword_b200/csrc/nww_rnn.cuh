@@ -121,7 +121,13 @@ inline void rnn_pack_weights(const float* w, int K, int H, std::vector<uint16_t>
 __device__ __forceinline__ float rnn_e1(float x) { return __expf(-fminf(fmaxf(x, -28.0f), 28.0f)); }
 __device__ __forceinline__ float rnn_e2(float x) { return __expf(-2.0f * fminf(fmaxf(x, -14.0f), 14.0f)); }
 
-__device__ __forceinline__ uint32_t rnn_half_bits(float x) { return (uint32_t)__half_as_ushort(__float2half_rn(x)); }
+// IEEE half bits of x, round to nearest even: the packed conversion runs on the ALU pipe (F2FP), the scalar one on the XU pipe
+// that the gate math already saturates
+__device__ __forceinline__ uint32_t rnn_half_bits(float x) {
+    uint32_t d;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(0.0f), "f"(x));
+    return d & 0xFFFFu;
+}
 __device__ __forceinline__ float rnn_half_value(uint32_t b) { return __half2float(__ushort_as_half((unsigned short)b)); }
 __device__ __forceinline__ uint4 rnn_pack8(const uint32_t* b) {
     return make_uint4(b[0] | (b[1] << 16), b[2] | (b[3] << 16), b[4] | (b[5] << 16), b[6] | (b[7] << 16));

@@ -105,10 +105,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 __device__ __forceinline__ float bf16_bits_to_float(uint32_t b) { return __uint_as_float(b << 16); }
-__device__ __forceinline__ uint32_t float_to_bf16_bits(float x) {          // round to nearest even
-    uint32_t u = __float_as_uint(x);
-    u += 0x7FFFu + ((u >> 16) & 1u);
-    return u >> 16;
+// round to nearest even.  The packed form compiles to F2FP.BF16.F32.PACK_AB on the ALU pipe; the scalar cvt.rn.bf16.f32
+// becomes F2F on the quarter-rate XU pipe, and the integer emulation used before cost three ALU operations.
+__device__ __forceinline__ uint32_t float_to_bf16_bits(float x) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(0.0f), "f"(x));
+    return d & 0xFFFFu;
 }
 __device__ __forceinline__ float round_tf32(float x) {
     uint32_t t;
