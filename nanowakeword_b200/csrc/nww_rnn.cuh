@@ -27,7 +27,9 @@
 // saves), so it is compiled out.
 #pragma once
 
+#ifndef NWW_CPUSIM
 #include <cuda_fp16.h>
+#endif
 
 #include <cstring>
 #include <vector>
@@ -121,6 +123,7 @@ inline void rnn_pack_weights(const float* w, int K, int H, std::vector<uint16_t>
 __device__ __forceinline__ float rnn_e1(float x) { return __expf(-fminf(fmaxf(x, -28.0f), 28.0f)); }
 __device__ __forceinline__ float rnn_e2(float x) { return __expf(-2.0f * fminf(fmaxf(x, -14.0f), 14.0f)); }
 
+#ifndef NWW_CPUSIM
 // IEEE half bits of x, round to nearest even: the packed conversion runs on the ALU pipe (F2FP), the scalar one on the XU pipe
 // that the gate math already saturates
 __device__ __forceinline__ uint32_t rnn_half_bits(float x) {
@@ -129,6 +132,10 @@ __device__ __forceinline__ uint32_t rnn_half_bits(float x) {
     return d & 0xFFFFu;
 }
 __device__ __forceinline__ float rnn_half_value(uint32_t b) { return __half2float(__ushort_as_half((unsigned short)b)); }
+#else
+inline uint32_t rnn_half_bits(float x) { return rnn_f2h(x); }
+inline float rnn_half_value(uint32_t b) { return rnn_h2f((uint16_t)b); }
+#endif
 __device__ __forceinline__ uint4 rnn_pack8(const uint32_t* b) {
     return make_uint4(b[0] | (b[1] << 16), b[2] | (b[3] << 16), b[4] | (b[5] << 16), b[6] | (b[7] << 16));
 }

@@ -122,6 +122,17 @@ __device__ __forceinline__ float round_tf32(float x) {
 namespace sim {
 inline float g_tmem[128][512];
 inline float bf16f(uint16_t b) { uint32_t u = (uint32_t)b << 16; float f; memcpy(&f, &u, 4); return f; }
+inline float halff(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16, e = (h >> 10) & 0x1Fu, m = h & 0x3FFu;
+    float f;
+    if (e == 0) {
+        f = (float)m * (1.0f / 16777216.0f);
+        return sign ? -f : f;
+    }
+    const uint32_t u = sign | ((e + 112u) << 23) | (m << 13);
+    memcpy(&f, &u, 4);
+    return f;
+}
 }
 __device__ __forceinline__ void tc_fence_before() {}
 __device__ __forceinline__ void tc_fence_after() {}
@@ -134,6 +145,7 @@ inline void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
     const uint32_t a0 = field(da, 0), alb = field(da, 16), asb = field(da, 32);
     const uint32_t b0 = field(db, 0), blb = field(db, 16), bsb = field(db, 32);
     const int col0 = (int)(tmem_d & 0xFFFF), lane0 = (int)(tmem_d >> 16);
+    const bool half_fmt = ((idesc >> 7) & 7u) == 0u;
     for (int m = 0; m < M; ++m)
         for (int n = 0; n < N; ++n) {
             float s = 0.f;
@@ -141,7 +153,7 @@ inline void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
                 uint16_t av, bv;
                 memcpy(&av, base + a0 + (m / 8) * asb + (m % 8) * 16 + (k / 8) * alb + (k % 8) * 2, 2);
                 memcpy(&bv, base + b0 + (n / 8) * bsb + (n % 8) * 16 + (k / 8) * blb + (k % 8) * 2, 2);
-                s += sim::bf16f(av) * sim::bf16f(bv);
+                s += half_fmt ? sim::halff(av) * sim::halff(bv) : sim::bf16f(av) * sim::bf16f(bv);
             }
             float& d = sim::g_tmem[lane0 + m][col0 + n];
             d = accumulate ? d + s : s;
