@@ -12,11 +12,11 @@
 // Operands are two-term IEEE-half splits of the FP32 values (hi = half(v), lo = half(v - hi): 22 significant bits,
 // which the 100 dB range of the log-mel inputs needs; bf16 pairs carry 16) with three products per K step
 // (hi hi + lo hi + hi lo) and FP32 accumulation in TMEM, un-swizzled K-major core matrices as everywhere in
-// this engine.  The weights (L2-resident, ~400 KB per step for H = 128) stream
-// through a ring of shared-memory slots by cp.async.bulk in sub-slices of (16 K rows) x (all 4H columns) x (one
-// half term): each sub-slice feeds one or two MMAs of N = 256 per column half, so the A operand is fetched once
-// per 256 columns (with N = 64 blocks the MMAs were shared-memory bound at 54 cycles each, measured) and several
-// copies are in flight while earlier ones are consumed.  The gate math reads the accumulators straight out of
+// this engine.  The weights (L2-resident, ~350 KB per step for H = 128) stream through a ring of six 16 KB
+// shared-memory slots by cp.async.bulk in sub-slices of (16 K rows) x (256 columns) x (both half terms): each
+// sub-slice feeds the three split products as MMAs of N = 256, so the A operand is fetched once per 256 columns
+// (with N = 64 blocks the MMAs were shared-memory bound at 54 cycles each, measured) and several copies are in
+// flight while earlier ones are consumed.  The gate math reads the accumulators straight out of
 // TMEM (thread = one window x H/2 hidden units, its c / h state lives in registers), with the sigmoid / tanh
 // quotients of a gate update merged so that it costs 7 (LSTM) or 5 (GRU) MUFU operations instead of 10 / 6, and
 // writes the new h back into the A operand as half terms.  With H = 128 the gate columns are grouped by hidden-unit
