@@ -12,8 +12,11 @@
  * message retrievable with nww_last_error() (thread-local).  Pointers named *_dev are CUDA
  * device pointers on the engine's device, *_host are host pointers (pinned memory makes the
  * copies asynchronous).  The engine owns weights, tables and workspaces; the caller owns all
- * I/O buffers.  Calls on one engine are serialised by an internal mutex.  There is no CPU
- * fallback: without a CUDA device nww_create fails.
+ * I/O buffers.  Calls on one engine are serialised by an internal mutex AND ordered on the
+ * device: the engine's workspaces and stream rings are shared between calls, so every entry
+ * point makes its CUDA stream wait for the work the previous call enqueued (an event chain),
+ * whichever stream that was — calls on different streams behave like calls on one stream.
+ * There is no CPU fallback: without a CUDA device nww_create fails.
  */
 #ifndef NWW_B200_H
 #define NWW_B200_H
@@ -96,7 +99,10 @@ int nww_run_windows(nww_engine* e, const int16_t* pcm_dev, int64_t n_windows, fl
                     float* logits_dev, float* emb_dev, void* stream);
 
 /* Same computation from float32 PCM already scaled by 1/32768 — the tensor the reference
- * feeds its session (nanointerpreter.py:750, 771-775). */
+ * feeds its session (nanointerpreter.py:750, 771-775).  The samples are used AS THEY ARE (no
+ * rounding to the int16 grid, no clipping at +-1): FP64 front end on the float samples (or the
+ * raw-audio layers for the E2ERaw* models), then the same head kernels.  For audio that is on
+ * the int16 grid the int16 entry points compute the same thing from half the bytes. */
 int nww_run_windows_f32(nww_engine* e, const float* pcm_dev, int64_t n_windows, float* scores_dev, float* mel_dev,
                         float* logits_dev, float* emb_dev, void* stream);
 

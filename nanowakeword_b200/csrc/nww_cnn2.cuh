@@ -218,12 +218,15 @@ cnn2_stage_kernel(WindowSource src, Cnn2MelSource msrc, long long n_windows, Fro
     for (int it = 0; w < n_windows; w += gridDim.x, ++it) {
         if (from_mel) {
             // ---- stream mode: the window's 98 frames are contiguous per mel row in the mirrored ring ---------
+            // (count == nullptr: a plain (n, F, T) log-mel buffer — float feeds, nww_run_windows_f32)
             const long long s = msrc.s0 + w;
-            const int head = smel_slot(msrc.count[s] / SMel::HOP - 3 + 1);
-            const float* ring = msrc.ring + s * SMel::STREAM_FLOATS + head;
+            const bool plain = msrc.count == nullptr;
+            const int row = plain ? D::TT : SMel::ROW;
+            const float* ring = plain ? msrc.ring + s * (long long)(D::F * D::TT)
+                                      : msrc.ring + s * SMel::STREAM_FLOATS + smel_slot(msrc.count[s] / SMel::HOP - 3 + 1);
             for (int i = tid; i < D::F * D::TT; i += D::NT) {
                 const int m = i / D::TT, t = i - m * D::TT;
-                melp[(m + 1) * D::MEL_P + t + 1] = ring[m * SMel::ROW + t];
+                melp[(m + 1) * D::MEL_P + t + 1] = ring[m * row + t];
             }
             __syncthreads();
         } else {

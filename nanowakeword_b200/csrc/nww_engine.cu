@@ -105,6 +105,14 @@ struct nww_engine {
 
     int64_t launches = 0, windows = 0;
 
+    // Cross-stream ordering of the shared workspaces (d_feat, d_scratch, d_part, d_pcm, the stream rings): every
+    // enqueueing entry point makes its stream wait for the previous call's last event and records a new one, so calls
+    // on different CUDA streams are ordered like calls on one stream (the mutex only serialises the enqueueing).
+    cudaEvent_t ev_last = nullptr;
+    bool last_valid = false;
+    cudaStream_t last_stream = nullptr;
+    float* d_melf = nullptr;             // [chunk][F][T] log-mel of float feeds for the stage kernels that start from mel
+
     // multi-stream mode (nww_stream_*): mirrored int16 rings in HBM
     StreamState streams{};
     float* d_mel_ring = nullptr;         // [n_streams][40][2 x 98] incremental log-mel (NS40x98 only)
@@ -130,7 +138,23 @@ struct nww_engine {
         const BlobTensor* t = blob.find(name);
         return t ? reinterpret_cast<const float*>(d_blob + t->offset) : nullptr;
     }
+    ~nww_engine();                       // frees every device buffer: a failing nww_create leaks nothing
 };
+
+// Order this call after whatever the previous call enqueued (possibly on another stream).
+static cudaError_t order_enter(nww_engine* e, cudaStream_t st) {
+    if (e->last_valid && e->last_stream != st) return cudaStreamWaitEvent(st, e->ev_last, 0);
+    return cudaSuccess;
+}
+static cudaError_t order_leave(nww_engine* e, cudaStream_t st) {
+    if (!e->ev_last) {
+        cudaError_t ce = cudaEventCreateWithFlags(&e->ev_last, cudaEventDisableTiming);
+        if (ce != cudaSuccess) return ce;
+    }
+    e->last_valid = true;
+    e->last_stream = st;
+    return cudaEventRecord(e->ev_last, st);
+}
 
 // ------------------------------------------------------------------------------ helpers
 template <typename T>
@@ -284,6 +308,8 @@ static int grid_for(const nww_engine* e, int64_t n, int per_sm = 1) {
 
 template <typename G>
 static int launch_frontend(nww_engine* e, WindowSource pcm, int64_t n, float* mel, int time_major, cudaStream_t st) {
+    if (pcm.fbase != nullptr)            // float feed: the generic FP64 front end on float samples
+        return launch_frontend_f64<G>(e->tab64, e->sm_count, pcm, n, mel, time_major, st, &e->launches, &g_last_error);
     if (e->spec.frontend_precision == NWW_FRONTEND_FP32) {
         auto k = frontend_kernel<float, G, kNfb32, kStageNT>;
         NWW_CUDA(set_smem(k, FrontendSmem<float, G, kNfb32>::kTotal));
@@ -373,6 +399,17 @@ static int launch_stage_a(nww_engine* e, WindowSource pcm, int64_t n, float* mel
         sub.n_streams = n;
     }
     const float* ring0 = from_ring ? e->d_mel_ring + stream_s0 * (int64_t)SMel::STREAM_FLOATS : nullptr;
+    // Float feed into a stage kernel that stages int16 PCM itself (cnn2_stage_kernel): log-mel by the float front end
+    // into d_melf first, then the kernel starts from that plain (n, F, T) buffer (count == nullptr marks the layout).
+    Cnn2MelSource cnn2_src{from_ring ? e->d_mel_ring : nullptr, e->streams.count, from_ring ? stream_s0 : 0};
+    if (pcm.fbase != nullptr && (e->cnn2_enabled || e->crnn_cnn2)) {
+        if (!e->d_melf) NWW_CUDA(cudaMalloc(&e->d_melf, (size_t)e->chunk * e->n_mels * e->n_frames * sizeof(float)));
+        int rc = launch_frontend<GeoNS40x98>(e, pcm, n, e->d_melf, 0, st);
+        if (rc) return rc;
+        if (mel) NWW_CUDA(cudaMemcpyAsync(mel, e->d_melf, (size_t)n * e->n_mels * e->n_frames * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        mel = nullptr;
+        cnn2_src = Cnn2MelSource{e->d_melf, nullptr, 0};
+    }
     switch (e->spec.arch) {
         case NWW_ARCH_DNN: {
             if (from_ring) {
@@ -394,12 +431,12 @@ static int launch_stage_a(nww_engine* e, WindowSource pcm, int64_t n, float* mel
                          : e->spec.activation == NWW_ACT_GELU ? cnn2_stage_kernel<ACT_GELU>
                                                               : cnn2_stage_kernel<ACT_SILU>;
                 NWW_CUDA(set_smem(k, Cnn2::kTotal));
-                const Cnn2MelSource ms{from_ring ? e->d_mel_ring : nullptr, e->streams.count, from_ring ? stream_s0 : 0};
-                k<<<grid_for(e, n), Cnn2::NT, Cnn2::kTotal, st>>>(pcm, ms, n, e->tab64, e->cnn2, e->d_feat_hi, e->d_feat_lo, mel);
+                k<<<grid_for(e, n), Cnn2::NT, Cnn2::kTotal, st>>>(pcm, cnn2_src, n, e->tab64, e->cnn2, e->d_feat_hi, e->d_feat_lo, mel);
                 e->launches++;
                 NWW_CUDA(cudaGetLastError());
                 return NWW_OK;
             }
+            if (pcm.fbase != nullptr) return fail(NWW_EUNSUPPORTED, "float feeds need the default (v2) CNN stage");
             auto k = cnn_stage_kernel<double, G, kNfb64, kStageNT>;
             const size_t smem = CnnSmem<double, G, kNfb64>::kTotal;
             NWW_CUDA(set_smem(k, smem));
@@ -414,8 +451,7 @@ static int launch_stage_a(nww_engine* e, WindowSource pcm, int64_t n, float* mel
                          : e->spec.activation == NWW_ACT_GELU ? cnn2_stage_kernel<ACT_GELU>
                                                               : cnn2_stage_kernel<ACT_SILU>;
                 NWW_CUDA(set_smem(k, Cnn2::kTotal));
-                const Cnn2MelSource ms{from_ring ? e->d_mel_ring : nullptr, e->streams.count, from_ring ? stream_s0 : 0};
-                k<<<grid_for(e, n), Cnn2::NT, Cnn2::kTotal, st>>>(pcm, ms, n, e->tab64, e->cnn2, e->d_nhwc, nullptr, mel);
+                k<<<grid_for(e, n), Cnn2::NT, Cnn2::kTotal, st>>>(pcm, cnn2_src, n, e->tab64, e->cnn2, e->d_nhwc, nullptr, mel);
                 e->launches++;
                 NWW_CUDA(cudaGetLastError());
                 return launch_head_stage_a(e->heads, e->tab64, e->spec.activation, e->sm_count, pcm, n, e->d_feat, e->d_scratch,
@@ -440,7 +476,8 @@ static int launch_stage_a(nww_engine* e, WindowSource pcm, int64_t n, float* mel
 }
 
 static int run_device(nww_engine* e, const int16_t* pcm, int64_t n, float* scores, float* mel, float* logits, float* emb,
-                      cudaStream_t st, const long long* win_off = nullptr, bool from_mel_ring = false) {
+                      cudaStream_t st, const long long* win_off = nullptr, bool from_mel_ring = false,
+                      const float* pcm_f32 = nullptr) {
     const int64_t mel_stride = (int64_t)e->n_mels * e->n_frames;
     for (int64_t w0 = 0; w0 < n; w0 += e->chunk) {
         const int64_t m = std::min<int64_t>(e->chunk, n - w0);
@@ -449,8 +486,9 @@ static int run_device(nww_engine* e, const int16_t* pcm, int64_t n, float* score
             ea = e->get_event(); eb = e->get_event(); ec = e->get_event();
             cudaEventRecord(ea, st);
         }
-        const WindowSource src = win_off ? WindowSource{pcm, win_off + w0, e->clip}
-                                         : WindowSource{pcm + w0 * e->clip, nullptr, e->clip};
+        const WindowSource src = pcm_f32  ? WindowSource{nullptr, nullptr, e->clip, pcm_f32 + w0 * e->clip}
+                                 : win_off ? WindowSource{pcm, win_off + w0, e->clip}
+                                           : WindowSource{pcm + w0 * e->clip, nullptr, e->clip};
         int rc = launch_stage_a(e, src, m, mel ? mel + w0 * mel_stride : nullptr, st, from_mel_ring ? w0 : -1);
         if (rc) return rc;
         if (e->profiling) cudaEventRecord(eb, st);
@@ -780,6 +818,15 @@ void nww_destroy(nww_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
+    delete e;
+}
+
+}  // extern "C"
+
+nww_engine::~nww_engine() {
+    nww_engine* e = this;
+    cudaFree(e->d_melf);
+    if (e->ev_last) cudaEventDestroy(e->ev_last);
     cudaFree(e->d_blob);
     cudaFree(e->arena.dev);
     cudaFree(e->d_feat);
@@ -808,8 +855,9 @@ void nww_destroy(nww_engine* e) {
     }
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
-    delete e;
 }
+
+extern "C" {
 
 int nww_get_info(nww_engine* e, nww_info_t* info) {
     if (!e || !info) return fail(NWW_EINVAL, "nww_get_info: null argument");
@@ -835,7 +883,10 @@ int nww_run_windows(nww_engine* e, const int16_t* pcm_dev, int64_t n, float* sco
     std::lock_guard<std::mutex> lock(e->mu);
     NWW_CUDA(cudaSetDevice(e->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);   // NULL = the legacy default stream, as in CUDA
-    return run_device(e, pcm_dev, n, scores_dev, mel_dev, logits_dev, emb_dev, st);
+    NWW_CUDA(order_enter(e, st));
+    int rc = run_device(e, pcm_dev, n, scores_dev, mel_dev, logits_dev, emb_dev, st);
+    NWW_CUDA(order_leave(e, st));
+    return rc;
 }
 
 int nww_logmel(nww_engine* e, const int16_t* pcm_dev, int64_t n, float* mel_dev, int time_major, void* stream) {
@@ -846,36 +897,29 @@ int nww_logmel(nww_engine* e, const int16_t* pcm_dev, int64_t n, float* mel_dev,
     NWW_CUDA(cudaSetDevice(e->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);   // NULL = the legacy default stream, as in CUDA
     const WindowSource src{pcm_dev, nullptr, e->clip};
-    return e->spec.geometry == NWW_GEOM_NS40X98 ? launch_frontend<GeoNS40x98>(e, src, n, mel_dev, time_major, st)
-                                                : launch_frontend<GeoREF64x101>(e, src, n, mel_dev, time_major, st);
+    NWW_CUDA(order_enter(e, st));
+    int rc = e->spec.geometry == NWW_GEOM_NS40X98 ? launch_frontend<GeoNS40x98>(e, src, n, mel_dev, time_major, st)
+                                                  : launch_frontend<GeoREF64x101>(e, src, n, mel_dev, time_major, st);
+    NWW_CUDA(order_leave(e, st));
+    return rc;
 }
 
 int nww_run_windows_f32(nww_engine* e, const float* pcm_dev, int64_t n, float* scores_dev, float* mel_dev, float* logits_dev,
                         float* emb_dev, void* stream) {
-    // Float PCM is quantised back to the int16 grid it came from (x * 32768 is exact for the
-    // reference's x = int16 / 32768, nanointerpreter.py:750) and takes the int16 path, chunk by chunk.
+    // Float PCM as the reference feeds its session (x = int16 / 32768, nanointerpreter.py:750, 771-775) — but ANY float32
+    // audio is taken as it is: the samples go through the FP64 front end (or the raw-audio layers) unquantised.  For
+    // samples on the int16 grid the result is bit-identical to the generic int16 front end (x * Hann in FP64 is exact
+    // either way); host callers that know their feed is on the grid should prefer the int16 entry points (half the bytes).
     if (!e || (n > 0 && (!pcm_dev || !scores_dev))) return fail(NWW_EINVAL, "nww_run_windows_f32: null argument");
     if (n <= 0) return n == 0 ? NWW_OK : fail(NWW_EINVAL, "nww_run_windows_f32: negative window count");
+    if (reinterpret_cast<uintptr_t>(pcm_dev) & 15) return fail(NWW_EINVAL, "nww_run_windows_f32: pcm_dev must be 16-byte aligned");
     std::lock_guard<std::mutex> lock(e->mu);
     NWW_CUDA(cudaSetDevice(e->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);   // NULL = the legacy default stream, as in CUDA
-    if (!e->d_pcm[0]) {
-        e->host_chunk = std::min<int64_t>(e->chunk, (int64_t)e->sm_count * (e->heads.rnn_hidden ? 32 : 8));
-        for (int i = 0; i < 2; ++i) NWW_CUDA(cudaMalloc(&e->d_pcm[i], (size_t)e->host_chunk * e->clip * sizeof(int16_t)));
-    }
-    const int64_t mel_stride = (int64_t)e->n_mels * e->n_frames;
-    for (int64_t w0 = 0; w0 < n; w0 += e->host_chunk) {
-        const int64_t m = std::min<int64_t>(e->host_chunk, n - w0);
-        const int64_t total = m * e->clip;
-        f32_to_i16_kernel<<<(int)std::min<int64_t>((total + 255) / 256, (int64_t)e->sm_count * 16), 256, 0, st>>>(
-            pcm_dev + w0 * e->clip, e->d_pcm[0], total);
-        e->launches++;
-        NWW_CUDA(cudaGetLastError());
-        int rc = run_device(e, e->d_pcm[0], m, scores_dev + w0, mel_dev ? mel_dev + w0 * mel_stride : nullptr,
-                            logits_dev ? logits_dev + w0 : nullptr, emb_dev ? emb_dev + w0 * e->emb_dim : nullptr, st);
-        if (rc) return rc;
-    }
-    return NWW_OK;
+    NWW_CUDA(order_enter(e, st));
+    int rc = run_device(e, nullptr, n, scores_dev, mel_dev, logits_dev, emb_dev, st, nullptr, false, pcm_dev);
+    NWW_CUDA(order_leave(e, st));
+    return rc;
 }
 
 int nww_run_windows_host(nww_engine* e, const int16_t* pcm_host, int64_t n, float* scores_host) {
@@ -896,6 +940,7 @@ int nww_run_windows_host(nww_engine* e, const int16_t* pcm_host, int64_t n, floa
     }
     // copy(c) on copy_stream -> ev_copy[slot]; compute(c) on stream waits for it and records
     // ev_done[slot], which copy(c + 2) waits for before overwriting the slot.
+    NWW_CUDA(order_enter(e, e->stream));
     int64_t c = 0;
     for (int64_t w0 = 0; w0 < n; w0 += e->host_chunk, ++c) {
         const int slot = (int)(c & 1);
@@ -910,6 +955,7 @@ int nww_run_windows_host(nww_engine* e, const int16_t* pcm_host, int64_t n, floa
         NWW_CUDA(cudaEventRecord(e->ev_done[slot], e->stream));
     }
     NWW_CUDA(cudaMemcpyAsync(scores_host, e->d_scores, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    NWW_CUDA(order_leave(e, e->stream));
     NWW_CUDA(cudaStreamSynchronize(e->stream));
     return NWW_OK;
 }
@@ -920,7 +966,7 @@ int nww_stream_open(nww_engine* e, int64_t n_streams) {
     if (!e || n_streams <= 0) return fail(NWW_EINVAL, "nww_stream_open: need an engine and n_streams > 0");
     std::lock_guard<std::mutex> lock(e->mu);
     NWW_CUDA(cudaSetDevice(e->device));
-    NWW_CUDA(cudaStreamSynchronize(e->stream));
+    NWW_CUDA(cudaDeviceSynchronize());          // pushes may be in flight on any caller stream
     stream_free(e);
     StreamState st{};
     st.n_streams = n_streams;
@@ -987,7 +1033,11 @@ int nww_stream_push(nww_engine* e, const int16_t* chunks_dev, int32_t chunk_len,
     std::lock_guard<std::mutex> lock(e->mu);
     if (!e->streams.ring) return fail(NWW_EINVAL, "nww_stream_push: no streams are open (call nww_stream_open)");
     NWW_CUDA(cudaSetDevice(e->device));
-    return stream_push_locked(e, chunks_dev, chunk_len, scores_dev, static_cast<cudaStream_t>(stream));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    NWW_CUDA(order_enter(e, st));
+    int rc = stream_push_locked(e, chunks_dev, chunk_len, scores_dev, st);
+    NWW_CUDA(order_leave(e, st));
+    return rc;
 }
 
 int nww_stream_push_host(nww_engine* e, const int16_t* chunks_host, int32_t chunk_len, float* scores_host) {
@@ -1010,10 +1060,12 @@ int nww_stream_push_host(nww_engine* e, const int16_t* chunks_host, int32_t chun
         NWW_CUDA(cudaMalloc(&e->d_scores, (size_t)n * sizeof(float)));
         e->scores_cap = n;
     }
+    NWW_CUDA(order_enter(e, e->stream));
     NWW_CUDA(cudaMemcpyAsync(e->d_chunk, chunks_host, bytes, cudaMemcpyHostToDevice, e->stream));
     int rc = stream_push_locked(e, e->d_chunk, chunk_len, e->d_scores, e->stream);
     if (rc) return rc;
     NWW_CUDA(cudaMemcpyAsync(scores_host, e->d_scores, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    NWW_CUDA(order_leave(e, e->stream));
     NWW_CUDA(cudaStreamSynchronize(e->stream));
     return NWW_OK;
 }
@@ -1024,6 +1076,7 @@ int nww_stream_reset(nww_engine* e, const int64_t* ids_host, int64_t n_ids) {
     if (!e->streams.ring) return fail(NWW_EINVAL, "nww_stream_reset: no streams are open");
     NWW_CUDA(cudaSetDevice(e->device));
     const StreamState& S = e->streams;
+    NWW_CUDA(order_enter(e, e->stream));        // after the pushes, whichever stream they were enqueued on
     if (!ids_host) {
         if (e->d_mel_ring) e->mel_inc = true;      // all counters return to 0: frame numbering restarts
         stream_reset_kernel<<<(unsigned)S.n_streams, 256, 0, e->stream>>>(S, nullptr, S.n_streams);
@@ -1043,6 +1096,7 @@ int nww_stream_reset(nww_engine* e, const int64_t* ids_host, int64_t n_ids) {
     }
     e->launches++;
     NWW_CUDA(cudaGetLastError());
+    NWW_CUDA(order_leave(e, e->stream));
     NWW_CUDA(cudaStreamSynchronize(e->stream));
     return NWW_OK;
 }

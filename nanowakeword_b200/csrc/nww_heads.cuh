@@ -114,7 +114,12 @@ template <typename G>
 static int launch_frontend_f64(const FrontendTables<double>& tab, int sm_count, WindowSource pcm, long long n, float* mel,
                                int time_major, cudaStream_t st, int64_t* launches, std::string* err, int frame_lo = 0) {
     const int grid = (int)std::min<long long>(n, sm_count);
-    if constexpr (std::is_same<G, GeoNS40x98>::value) {
+    if (pcm.fbase != nullptr) {
+        // float feed: generic FP64 front end reading float32 samples straight from global memory (all frames)
+        auto k = frontend_f32_kernel<double, G, kNfb64, kStageNT>;
+        NWW_HCUDA(set_smem(k, FrontendSmem<double, G, kNfb64>::kWork));
+        k<<<grid, kStageNT, FrontendSmem<double, G, kNfb64>::kWork, st>>>(pcm.fbase, n, tab, mel, time_major);
+    } else if constexpr (std::is_same<G, GeoNS40x98>::value) {
         NWW_HCUDA(set_smem(frontend3_kernel, Fe3KernelSmem::kTotal));
         frontend3_kernel<<<grid, Fe3::NT, Fe3KernelSmem::kTotal, st>>>(pcm, n, tab, mel, time_major, frame_lo);
     } else {
@@ -614,7 +619,6 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
         return launch_quartznet_blocks(hw, mel, F, n, p, feat, sm_count, st, launches, err);
     }
     if (!mel_ready && !conv2_nhwc && (rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel, 0, st, launches, err))) return rc;
-    if (mel_dump && !conv2_nhwc)    if (!mel_ready && !conv2_nhwc && (rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel, 0, st, launches, err))) return rc;
     if (mel_dump && !conv2_nhwc) NWW_HCUDA(cudaMemcpyAsync(mel_dump, mel, (size_t)n * F * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
 
     if (hw.arch == NWW_ARCH_TCN) {

@@ -670,12 +670,21 @@ raw_pcm_kernel(WindowSource src, long long n, float* __restrict__ p, int len, in
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n * q4; i += (long long)gridDim.x * blockDim.x) {
         const long long w = i / q4;
         const int i0 = (int)(i - w * q4) * 4;
-        const int16_t* x = src.at(w);
         float v[4];
+        if (src.fbase != nullptr) {                       // float feed: the samples are already x / 32768
+            const float* xf = src.atf(w);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int j = i0 + e - pad;
-            v[e] = (j >= 0 && j < src.clip) ? (float)x[j] * (1.0f / 32768.0f) : 0.0f;
+            for (int e = 0; e < 4; ++e) {
+                const int j = i0 + e - pad;
+                v[e] = (j >= 0 && j < src.clip) ? xf[j] : 0.0f;
+            }
+        } else {
+            const int16_t* x = src.at(w);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = i0 + e - pad;
+                v[e] = (j >= 0 && j < src.clip) ? (float)x[j] * (1.0f / 32768.0f) : 0.0f;
+            }
         }
         *reinterpret_cast<float4*>(p + w * len + i0) = make_float4(v[0], v[1], v[2], v[3]);
     }

@@ -56,9 +56,14 @@ struct WindowSource {
     const int16_t* base;
     const long long* offsets;     // nullable
     int clip;
+    // Float feeds (nww_run_windows_f32): densely packed float32 windows already scaled to [-1, 1) the way the
+    // reference scales them (nanointerpreter.py:750); base is null then.  Only the launchers look at this field:
+    // they pick the float front end (frontend_f32_kernel) / the float raw-audio loader.
+    const float* fbase = nullptr;
     __device__ __forceinline__ const int16_t* at(long long w) const {
         return base + (offsets ? offsets[w] : w * (long long)clip);
     }
+    __device__ __forceinline__ const float* atf(long long w) const { return fbase + w * (long long)clip; }
 };
 
 // ----------------------------------------------------------------------------------------

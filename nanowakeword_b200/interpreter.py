@@ -19,10 +19,11 @@ from __future__ import annotations
 import logging
 import os
 import threading
+import time
 import wave
 from collections import defaultdict, deque
 from functools import partial
-from typing import Dict, List, Optional, Union
+from typing import Callable, Dict, List, Optional, Union
 
 import numpy as np
 
@@ -75,9 +76,12 @@ class DetectionResult:
 
 
 class _PcmRing:
-    """Last ``maxlen`` int16 samples of a stream — the role of the reference's
-    ``deque(maxlen=clip_samples)`` of Python floats (nanointerpreter.py:176-183, 751, 756),
-    kept as int16 so a window can go to the device without a float round trip."""
+    """Last ``maxlen`` samples of a stream — the role of the reference's
+    ``deque(maxlen=clip_samples)`` of Python floats (nanointerpreter.py:176-183, 751, 756).
+    Kept as int16 (a window then goes to the device without a float round trip) for as long as
+    every sample the caller gave is an integer in the int16 range — which ``predict`` documents;
+    the first chunk that is not switches the ring to the reference's own representation,
+    ``float32(x) / 32768``, for good (until ``clear``)."""
 
     def __init__(self, maxlen: int):
         self.maxlen = maxlen
@@ -85,7 +89,22 @@ class _PcmRing:
         self.filled = 0
 
     def extend(self, x: np.ndarray):
+        x = np.asarray(x).ravel()
+        if x.dtype != np.int16:
+            xf = x.astype(np.float32) / np.float32(32768.0)            # nanointerpreter.py:750, verbatim
+            y = xf.astype(np.float64) * 32768.0
+            if self.data.dtype == np.int16 and np.array_equal(y, np.rint(y)) and \
+                    (y.size == 0 or (y.min() >= -32768.0 and y.max() <= 32767.0)):
+                x = y.astype(np.int16)
+            else:
+                if self.data.dtype == np.int16:
+                    self.data = self.data.astype(np.float32) / np.float32(32768.0)
+                x = xf
+        elif self.data.dtype != np.int16:
+            x = x.astype(np.float32) / np.float32(32768.0)
         n = len(x)
+        if n == 0:                 # deque.extend([]) is a no-op in the reference
+            return
         if n >= self.maxlen:
             self.data[:] = x[-self.maxlen:]
             self.filled = self.maxlen
@@ -95,7 +114,7 @@ class _PcmRing:
         self.filled = min(self.maxlen, self.filled + n)
 
     def clear(self):
-        self.data[:] = 0
+        self.data = np.zeros(self.maxlen, dtype=np.int16)
         self.filled = 0
 
     def __len__(self):
@@ -296,11 +315,10 @@ class NanoInterpreter:
 
     def _predict_e2e(self, x, patience={}, threshold={}, debounce_time=0.0) -> DetectionResult:
         current: Dict[str, float] = {}
-        x16 = x if x.dtype == np.int16 else x.astype(np.int16)
         for name, session in self.models.items():
             clip = self.e2e_clip_samples[name]
             ring = self.e2e_buffer[name]
-            ring.extend(x16.ravel())
+            ring.extend(x)
             self.e2e_buffer_samples[name] += len(x)       # cumulative, cleared only by reset() (:752-753)
             if self.e2e_buffer_samples[name] >= clip:
                 if self.cascade_config and name == self.cascade_config["verifier"]:
@@ -354,32 +372,55 @@ class NanoInterpreter:
             raise TypeError("`clip` must be a file path (string) or a numpy array.")
         return [self.predict(data, **kwargs)]              # e2e: one call on the whole clip (:828-830)
 
-    def listen(self, on_detect=None, threshold: float = 0.9, chunk_size: int = 1280, blocking: bool = True, **kwargs):
-        """Microphone loop (reference :835-945).  Needs pyaudio, like the reference."""
+    def listen(self, on_detection: Optional[Callable[[str, float], None]] = None, threshold: float = 0.5,
+               cooldown: float = 1.0, chunk_size: int = 1280, on_score: Optional[Callable[[float, float], None]] = None,
+               on_audio: Optional[Callable[[np.ndarray], None]] = None, blocking: bool = True) -> None:
+        """Microphone loop with the reference's signature and callback contract (nanointerpreter.py:835-945):
+        every ``chunk_size`` frames ``on_audio(audio)``, ``predict(audio)``, ``on_score(verifier_score, gate_score)``;
+        when the verifier score exceeds ``threshold`` and more than ``cooldown`` seconds passed since the last
+        detection, ``on_detection(model_name, score)`` fires and the interpreter is ``reset()``.  Needs PyAudio,
+        like the reference; ``blocking=False`` runs the loop on a daemon thread until ``stop()``."""
         try:
             import pyaudio
         except ImportError:
-            raise ImportError("PyAudio is not installed. Please run `pip install pyaudio`.")
-        self._stop_event = threading.Event()
+            raise ImportError("PyAudio is required for listen(). Install it with: pip install pyaudio")
 
-        def loop():
+        if on_detection is None:
+            def on_detection(name: str, score: float) -> None:
+                print(f"\nDetected '{name}'!  (score: {score:.5f})")
+
+        def _loop():
             pa = pyaudio.PyAudio()
             stream = pa.open(format=pyaudio.paInt16, channels=1, rate=16000, input=True, frames_per_buffer=chunk_size)
+            last_detection = 0.0
+            stop_event = self._stop_event
             try:
-                while not self._stop_event.is_set():
-                    chunk = np.frombuffer(stream.read(chunk_size, exception_on_overflow=False), dtype=np.int16)
-                    res = self.predict(chunk, **kwargs)
-                    if res.score >= threshold and on_detect is not None:
-                        on_detect(res)
+                while not (stop_event and stop_event.is_set()):
+                    audio = np.frombuffer(stream.read(chunk_size, exception_on_overflow=False), dtype=np.int16)
+                    if on_audio is not None:
+                        on_audio(audio)
+                    self.predict(audio)
+                    v_score = self.verifier_score
+                    g_score = self.gate_score
+                    if on_score is not None:
+                        on_score(v_score, g_score)
+                    now = time.monotonic()
+                    if v_score > threshold and (now - last_detection) > cooldown:
+                        on_detection(self.model_name, v_score)
+                        last_detection = now
+                        self.reset()
+            except KeyboardInterrupt:
+                pass
             finally:
                 stream.stop_stream()
                 stream.close()
                 pa.terminate()
 
         if blocking:
-            loop()
+            _loop()
         else:
-            self._listen_thread = threading.Thread(target=loop, daemon=True)
+            self._stop_event = threading.Event()
+            self._listen_thread = threading.Thread(target=_loop, daemon=True)
             self._listen_thread.start()
 
     def _reduce_noise(self, x: np.ndarray) -> np.ndarray:

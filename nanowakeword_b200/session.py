@@ -112,7 +112,7 @@ class Engine:
             raise ValueError(f"pcm must have shape (B, {self.clip_samples})")
         n = pcm.shape[0]
         dev = pcm.device
-        scores = out if out is not None else torch.empty(n, dtype=torch.float32, device=dev)
+        scores = self._check_out(out, n, dev)
         extra = {}
         mel = logits = emb = None
         if want_mel:
@@ -126,10 +126,38 @@ class Engine:
         _lib.check(self._lib, rc, "nww_run_windows")
         return (scores, extra) if extra else scores
 
+    def score_device_f32(self, pcm, out=None, want_mel=False, stream=None):
+        """pcm: CUDA float32 tensor (B, clip_samples) holding what the reference feeds its session
+        (``int16 / 32768``, nanointerpreter.py:750) — or any other float audio: the samples are used
+        as they are, not re-quantised.  Returns scores (B,) float32 on the device."""
+        torch = _torch()
+        if pcm.dtype != torch.float32 or not pcm.is_cuda or not pcm.is_contiguous():
+            raise ValueError("pcm must be a contiguous CUDA float32 tensor")
+        if pcm.dim() != 2 or pcm.shape[1] != self.clip_samples:
+            raise ValueError(f"pcm must have shape (B, {self.clip_samples})")
+        n = pcm.shape[0]
+        scores = self._check_out(out, n, pcm.device)
+        mel = torch.empty((n, self.n_mels, self.n_frames), dtype=torch.float32, device=pcm.device) if want_mel else None
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        rc = self._lib.nww_run_windows_f32(self._h, p(pcm), n, p(scores), p(mel), None, None, self._stream_ptr(stream))
+        _lib.check(self._lib, rc, "nww_run_windows_f32")
+        return (scores, {"mel": mel}) if want_mel else scores
+
+    def _check_out(self, out, n, device):
+        torch = _torch()
+        if out is None:
+            return torch.empty(n, dtype=torch.float32, device=device)
+        if (not isinstance(out, torch.Tensor) or out.dtype != torch.float32 or out.device != device
+                or not out.is_contiguous() or out.numel() < n):
+            raise ValueError(f"out must be a contiguous float32 tensor on {device} with at least {n} elements")
+        return out
+
     def logmel_device(self, pcm, time_major=False, stream=None):
         torch = _torch()
         if pcm.dtype != torch.int16 or not pcm.is_cuda or not pcm.is_contiguous():
             raise ValueError("pcm must be a contiguous CUDA int16 tensor")
+        if pcm.dim() != 2 or pcm.shape[1] != self.clip_samples:
+            raise ValueError(f"pcm must have shape (B, {self.clip_samples})")
         n = pcm.shape[0]
         shape = (n, self.n_frames, self.n_mels) if time_major else (n, self.n_mels, self.n_frames)
         mel = torch.empty(shape, dtype=torch.float32, device=pcm.device)
@@ -299,6 +327,17 @@ class B200Session:
         if x.ndim != 2 or x.shape[1] != n:
             raise ValueError(f"Got invalid dimensions for input: expected (batch, {n}), got {tuple(x.shape)}")
         if x.dtype != np.int16:
-            x = np.clip(np.rint(x.astype(np.float64) * 32768.0), -32768, 32767).astype(np.int16)
+            # Float feed.  What the reference's interpreter produces (int16 / 32768, nanointerpreter.py:750) sits on
+            # the int16 grid: x * 32768 is then exact and the window takes the int16 path (half the bytes over PCIe,
+            # bit-identical arithmetic).  Anything else is NOT re-quantised: it goes through the engine's float path.
+            xf = np.ascontiguousarray(x, dtype=np.float32)
+            y = xf.astype(np.float64) * 32768.0
+            if np.array_equal(y, np.rint(y)) and (y.size == 0 or (y.min() >= -32768.0 and y.max() <= 32767.0)):
+                x = y.astype(np.int16)
+            else:
+                torch = _torch()
+                dev = torch.device("cuda", self.engine.device)
+                scores = self.engine.score_device_f32(torch.from_numpy(xf).to(dev))
+                return [scores.cpu().numpy().reshape(-1, 1, 1)]
         scores = self.engine.score_host(x)
         return [scores.reshape(-1, 1, 1)]

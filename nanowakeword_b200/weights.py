@@ -145,6 +145,19 @@ def pack_tensors(sd: dict, cfg: dict) -> dict[str, np.ndarray]:
             out[f"crnn.conv{i}.w"] = _conv3x3_ic_tap_oc(w).astype(np.float32)       # (Cin, 9, Cout)
             out[f"crnn.conv{i}.b"] = b.astype(np.float32)
             i += 1
+        # CRNNModel builds its recurrent part with num_layers = n_blocks and rnn_type from crnn_rnn_type
+        # (architectures.py:243-262, default 'lstm'); the engine holds ONE bidirectional GRU layer.  Refuse anything
+        # else here instead of packing layer 0 only (silently wrong scores) or failing on an opaque size mismatch.
+        if "model.rnn.weight_ih_l1" in sd:
+            raise ValueError("crnn: only a single recurrent layer (n_blocks = 1) is built into the B200 engine")
+        if str(cfg.get("crnn_rnn_type", "gru")).lower() != "gru":
+            raise ValueError(f"crnn: crnn_rnn_type '{cfg.get('crnn_rnn_type')}' is not built into the B200 engine (gru only)")
+        w_hh0 = _f64(sd, "model.rnn.weight_hh_l0")
+        if w_hh0.shape[0] != 3 * w_hh0.shape[1]:
+            raise ValueError(f"crnn: model.rnn.weight_hh_l0 has shape {w_hh0.shape}; a GRU layer has (3H, H) "
+                             "(an LSTM checkpoint has (4H, H): crnn_rnn_type must be 'gru')")
+        if "model.rnn.weight_ih_l0_reverse" not in sd:
+            raise ValueError("crnn: the B200 engine builds the bidirectional GRU of CRNNModel only")
         for sfx, tag in (("", "fwd"), ("_reverse", "bwd")):
             out[f"crnn.gru.{tag}.w_ih_nk"] = _f64(sd, "model.rnn.weight_ih_l0" + sfx).astype(np.float32)  # (3H, In), dense-kernel layout
             out[f"crnn.gru.{tag}.w_ih_kn"] = np.ascontiguousarray(_f64(sd, "model.rnn.weight_ih_l0" + sfx).T).astype(np.float32)  # (In, 3H), row-GEMM layout

@@ -424,10 +424,13 @@ def embedding_from_features(x, sd, cfg, dtype=np.float64):
 
 def forward_logits(pcm, sd, cfg, frontend: FrontendSpec | str | None = None, dtype=np.float64,
                    return_mel=False):
-    """int16 PCM (B, N) -> logits (B, 1): front end + backbone + classifier."""
+    """int16 PCM (B, N) — or float PCM already scaled by 1/32768, as the session is fed — -> logits (B, 1):
+    front end + backbone + classifier."""
     if cfg["model_type"] in RAW_AUDIO_HEADS:
         sd = _cast_sd(sd, dtype)
-        x = np.asarray(pcm).astype(dtype) / dtype(32768.0)
+        pcm = np.asarray(pcm)
+        # int16 -> x / 32768 (nanointerpreter.py:750); float input is what the session is fed: already scaled
+        x = pcm.astype(dtype) / dtype(32768.0) if pcm.dtype == np.int16 else pcm.astype(dtype)
         logits = classifier(_BACKBONES[cfg["model_type"]](x, sd, cfg), sd, cfg)
         return (logits, None) if return_mel else logits
     if frontend is None:

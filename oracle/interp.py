@@ -22,8 +22,9 @@ class OracleInterpreter:
         self.clip = clip_samples
         if score_fn is None:
             def score_fn(clip_f32):
-                pcm = np.rint(clip_f32.astype(np.float64) * 32768.0).astype(np.int16)
-                return float(forward_scores(pcm[None, :], sd, cfg).item())
+                # the float clip goes to the model as it is (nanointerpreter.py:771-783); for int16 input
+                # float32(x) / 32768 is exact, so this equals scoring the int16 window
+                return float(forward_scores(clip_f32[None, :], sd, cfg).item())
         self.score_fn = score_fn
         self.reset()
 

@@ -1,0 +1,170 @@
+"""GPU parity, round 2: the float feed (no re-quantisation), cross-stream ordering, predict_clip /
+predict_batch on the real engine.  Same tolerances as tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+from nanowakeword_b200.synth import default_config, make_state_dict, synth_pcm
+
+pytestmark = pytest.mark.gpu
+
+SCORE_TOL = 1e-3
+MEL_TOL = 1e-4
+RAW_HEADS = ("e2e_quartznet", "e2e_cnn")
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+def _engine(mt, **kw):
+    from nanowakeword_b200 import Engine
+    cfg = default_config(mt)
+    sd = make_state_dict(cfg, seed=0)
+    return Engine(sd, cfg, device=0, **kw), sd, cfg
+
+
+def _off_grid_audio(n, seed):
+    """Quiet float audio that is NOT int16 / 32768: a few tens of LSB in amplitude scaled by an irrational-ish gain,
+    so rounding it to the int16 grid changes the log-mel by far more than the tolerance; one sample at exactly
+    +1.0 (which int16 cannot hold) and one beyond full scale."""
+    q = (synth_pcm(n, seed=seed, kind="gauss") // 64).astype(np.float32) / np.float32(32768.0)
+    x = (q * np.float32(0.7310586)).astype(np.float32)
+    x[:, 5000] = 1.0
+    x[:, 9000] = -1.25
+    return x
+
+
+@pytest.mark.parametrize("mt", ["cnn", "dnn", "tcn", "bcresnet", "crnn", "e2e_dnn", "gru", "quartznet", "e2e_quartznet", "e2e_cnn"])
+def test_float_feed_is_not_requantised(torch_cuda, mt):
+    """nww_run_windows_f32 (through Engine.score_device_f32): the reference's session takes float32 audio
+    (nanointerpreter.py:750, 771-783).  On the int16 grid the float path must agree with the int16 path; off
+    the grid it must follow the oracle fed the SAME floats, not their int16 rounding."""
+    from oracle.heads import forward_scores
+    eng, sd, cfg = _engine(mt)
+    geom = "REF64x101" if mt == "e2e_dnn" else "NS40x98"
+    # (1) on the grid
+    pcm = np.concatenate([synth_pcm(20, seed=61, kind="gauss"), synth_pcm(12, seed=62, kind="uniform")])
+    xf = pcm.astype(np.float32) / np.float32(32768.0)
+    s_i16 = eng.score_device(torch_cuda.from_numpy(pcm).cuda()).cpu().numpy()
+    s_f32 = eng.score_device_f32(torch_cuda.from_numpy(xf).cuda()).cpu().numpy()
+    ref = forward_scores(pcm, sd, cfg).ravel()
+    assert np.abs(s_f32 - ref).max() < SCORE_TOL
+    assert np.abs(s_f32 - s_i16).max() < 1e-4
+    # (2) off the grid
+    x = _off_grid_audio(24, seed=63)
+    ref_f, mel_f = forward_scores(x, sd, cfg, return_mel=True)
+    if mt in RAW_HEADS:
+        got = eng.score_device_f32(torch_cuda.from_numpy(x).cuda())
+    else:
+        got, extra = eng.score_device_f32(torch_cuda.from_numpy(x).cuda(), want_mel=True)
+        mel = extra["mel"].cpu().numpy()
+        assert np.abs(mel - mel_f).max() < MEL_TOL
+        # and the int16 rounding of the same audio is a different signal at this tolerance
+        from oracle.frontend import GEOMETRIES, log_mel
+        xq = np.clip(np.rint(x.astype(np.float64) * 32768.0), -32768, 32767).astype(np.int16)
+        assert np.abs(log_mel(xq, GEOMETRIES[geom]) - mel_f).max() > 100 * MEL_TOL
+    assert np.abs(got.cpu().numpy() - ref_f.ravel()).max() < SCORE_TOL
+
+
+def test_session_run_float_feeds(torch_cuda):
+    """B200Session.run: float32 (B, N) / (B, 1, N) on the grid takes the int16 path (bit-identical to int16 input),
+    off the grid takes the float path; '+1.0' is not clipped."""
+    from nanowakeword_b200 import B200Session
+    from oracle.heads import forward_scores
+    cfg = default_config("cnn")
+    sd = make_state_dict(cfg, seed=0)
+    sess = B200Session(state_dict=sd, cfg=cfg, device=0)
+    pcm = synth_pcm(9, seed=71, kind="gauss")
+    a = sess.run(None, {"input": pcm})[0]
+    b = sess.run(None, {"input": pcm.astype(np.float32) / 32768.0})[0]
+    c = sess.run(None, {"input": (pcm.astype(np.float32) / 32768.0)[:, None, :]})[0]
+    assert a.shape == (9, 1, 1) and np.array_equal(a, b) and np.array_equal(a, c)
+    x = _off_grid_audio(7, seed=72)
+    d = sess.run(None, {"audio": x})[0]
+    assert d.shape == (7, 1, 1) and d.dtype == np.float32
+    assert np.abs(d.ravel() - forward_scores(x, sd, cfg).ravel()).max() < SCORE_TOL
+    with pytest.raises(ValueError):
+        sess.run(None, {"input": x[:, :100]})
+    with pytest.raises(ValueError):
+        sess.run(None, {"wrong": x})
+
+
+def test_calls_on_different_cuda_streams_are_ordered(torch_cuda):
+    """the engine's workspaces are shared between calls; calls enqueued on different CUDA streams (and the
+    host-path calls on the engine's private stream) must behave as if issued on one stream."""
+    torch = torch_cuda
+    eng, sd, cfg = _engine("cnn")
+    pcm_a = torch.from_numpy(synth_pcm(1500, seed=81, kind="gauss")).cuda()
+    pcm_b = torch.from_numpy(synth_pcm(1500, seed=82, kind="uniform")).cuda()
+    ref_a = eng.score_device(pcm_a).cpu().numpy()
+    ref_b = eng.score_device(pcm_b).cpu().numpy()
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(3):
+        out_a = eng.score_device(pcm_a, stream=s1)
+        out_b = eng.score_device(pcm_b, stream=s2)             # no synchronisation in between
+        host_b = eng.score_host(pcm_b.cpu().numpy()[:700])      # private stream, right behind
+        out_a2 = eng.score_device(pcm_a, stream=s2)
+        torch.cuda.synchronize()
+        assert np.array_equal(out_a.cpu().numpy(), ref_a)
+        assert np.array_equal(out_b.cpu().numpy(), ref_b)
+        assert np.array_equal(host_b, ref_b[:700])
+        assert np.array_equal(out_a2.cpu().numpy(), ref_a)
+    # stream rings: pushes on a caller stream, reset on the engine's stream, pushes again
+    n = 64
+    eng.stream_open(n)
+    chunks = torch.from_numpy(synth_pcm(n, seed=83, kind="gauss")).cuda()
+    for rep in range(2):
+        for s in range(0, 16000, 1600):
+            sc = eng.stream_push_device(chunks[:, s:s + 1600].contiguous(), stream=s1 if s % 3200 else s2)
+        torch.cuda.synchronize()
+        assert np.array_equal(sc.cpu().numpy(), eng.score_device(chunks).cpu().numpy())
+        eng.stream_reset()                                      # no sync needed before the next pushes
+    eng.stream_close()
+    with pytest.raises(ValueError):
+        eng.score_device(pcm_a, out=torch.empty(10, device="cuda"))
+    with pytest.raises(ValueError):
+        eng.logmel_device(pcm_a[:, :100].contiguous())
+
+
+def test_predict_clip_and_predict_batch_on_the_engine(torch_cuda, tmp_path, golden_frontend):
+    """predict_clip (nanointerpreter.py:816-833) on the reference's example recordings (the first four golden
+    windows are its example WAVs cropped / padded to one second), as WAV files and as arrays; predict_batch against
+    the oracle."""
+    import wave
+    from nanowakeword_b200 import NanoInterpreter, save_model
+    from oracle.heads import forward_scores
+    from oracle.interp import OracleInterpreter
+    cfg = default_config("cnn")
+    sd = make_state_dict(cfg, seed=0)
+    interp = NanoInterpreter.load_model(save_model(str(tmp_path / "wake.pt"), sd, cfg))
+    g = golden_frontend["pcm"]
+    ref = forward_scores(g, sd, cfg).ravel()
+    for i in range(4):
+        clip = np.concatenate([g[i], g[(i + 1) % 4][:3375]])           # 19 375 samples, like the positive example
+        path = str(tmp_path / f"ex{i}.wav")
+        with wave.open(path, "wb") as f:
+            f.setnchannels(1); f.setsampwidth(2); f.setframerate(16000)
+            f.writeframes(clip.tobytes())
+        orc = OracleInterpreter(sd, cfg, name="wake")
+        want = orc.predict(clip)["wake"]
+        for arg in (path, clip):
+            interp.reset()
+            out = interp.predict_clip(arg)
+            assert len(out) == 1 and abs(out[0].score - want) < SCORE_TOL
+            assert abs(interp.raw_scores["wake"] - orc.raw_scores["wake"]) < SCORE_TOL
+            assert interp.raw_scores["wake"] > 0.0 and out[0].score == 0.0   # scored, but still inside the warm-up
+    got = interp.predict_batch(g)
+    assert got.shape == (len(g),) and np.abs(got - ref).max() < SCORE_TOL
+    # a float chunk that is off the int16 grid goes through the float ring and the float path
+    interp.reset()
+    x = _off_grid_audio(1, seed=91)[0] * np.float32(32768.0)            # predict() scales by 1/32768 itself
+    orc = OracleInterpreter(sd, cfg, name="wake")
+    interp.predict(x)
+    orc.predict(x)
+    assert interp.e2e_buffer["wake"].data.dtype == np.float32
+    assert abs(interp.raw_scores["wake"] - orc.raw_scores["wake"]) < SCORE_TOL

@@ -331,3 +331,186 @@ def test_cascade_bank_matches_cascade_interpreters():
             skipped += r.gate_score < thr
             passed += r.gate_score >= thr
     assert skipped > 10 and passed > 10          # both branches exercised
+
+
+# ---------------------------------------------------------------------------------------------- round 2: boundary
+class _FloatAwareSession(_FakeSession):
+    """Accepts what the interpreter hands over: int16, or float32 once the ring went float."""
+
+    def run(self, _, feed):
+        self.calls += 1
+        x = np.asarray(feed["input"])
+        self.last_dtype = x.dtype
+        pcm = x if x.dtype == np.int16 else x.astype(np.float64) * 32768.0
+        return [self.fn(pcm).reshape(-1, 1, 1)]
+
+
+def test_pcm_ring_empty_chunk_and_float_switch():
+    """deque.extend([]) is a no-op; non-int16 input follows nanointerpreter.py:750 verbatim."""
+    it = NanoInterpreter(["/nonexistent/wake.pt"], sessions={"wake": _FloatAwareSession()})
+    r = it.predict(np.zeros(0, np.int16))
+    assert r.score == 0.0 and it.e2e_buffer_samples["wake"] == 0
+    rng = np.random.default_rng(3)
+    a = np.clip(rng.normal(0, 3000, 16000), -32768, 32767).astype(np.int16)
+    it.predict(a)
+    assert it.e2e_buffer["wake"].data.dtype == np.int16 and it.models["wake"].last_dtype == np.int16
+    it.predict(a[:1280].astype(np.float64))                      # integers in a float array stay on the int16 path
+    assert it.e2e_buffer["wake"].data.dtype == np.int16
+    off = a[:1280].astype(np.float32) + 0.25                     # off the int16 grid: the ring goes float for good
+    it.predict(off)
+    ring = it.e2e_buffer["wake"].data
+    assert ring.dtype == np.float32 and it.models["wake"].last_dtype == np.float32
+    assert np.array_equal(ring[-1280:], off / np.float32(32768.0))
+    assert np.array_equal(ring[-2560:-1280], a[:1280].astype(np.float32) / np.float32(32768.0))
+    it.predict(a[:640])                                          # int16 chunks are scaled into the float ring
+    assert np.array_equal(it.e2e_buffer["wake"].data[-640:], a[:640].astype(np.float32) / np.float32(32768.0))
+    it.reset()
+    assert it.e2e_buffer["wake"].data.dtype == np.int16 and len(it.e2e_buffer["wake"]) == 0
+
+
+def test_predict_clip_wav_and_array(tmp_path):
+    """predict_clip (nanointerpreter.py:816-833): WAV path or ndarray, ONE predict() on the whole clip in e2e mode."""
+    import wave
+    rng = np.random.default_rng(5)
+    audio = np.clip(rng.normal(0, 4000, 19375), -32768, 32767).astype(np.int16)
+    path = str(tmp_path / "clip.wav")
+    with wave.open(path, "wb") as f:
+        f.setnchannels(1); f.setsampwidth(2); f.setframerate(16000)
+        f.writeframes(audio.tobytes())
+    it, orc = _make_interp(), _oracle()
+    out = it.predict_clip(path)
+    assert isinstance(out, list) and len(out) == 1 and isinstance(out[0], DetectionResult)
+    assert it.models["wake"].calls == 1
+    assert it.raw_scores["wake"] == pytest.approx(orc.predict(audio) and orc.raw_scores["wake"], abs=1e-7)
+    it2 = _make_interp()
+    out2 = it2.predict_clip(audio)
+    assert it2.raw_scores["wake"] == it.raw_scores["wake"] and out2[0].score == out[0].score
+    bad = str(tmp_path / "bad.wav")
+    with wave.open(bad, "wb") as f:
+        f.setnchannels(1); f.setsampwidth(2); f.setframerate(8000)
+        f.writeframes(audio.tobytes())
+    with pytest.raises(ValueError, match="16kHz, 16-bit, single-channel"):
+        it.predict_clip(bad)
+    with pytest.raises(TypeError):
+        it.predict_clip(12345)
+
+
+class _FakePyAudio:
+    """Stand-in for the pyaudio module: serves prepared int16 audio chunk by chunk, then raises KeyboardInterrupt
+    (what Ctrl+C does to the reference's blocking loop, nanointerpreter.py:928-929)."""
+    paInt16 = 8
+
+    def __init__(self, audio, raise_at_end=True):
+        self.audio, self.pos, self.raise_at_end = audio, 0, raise_at_end
+        self.opened = self.closed = self.terminated = 0
+        self.open_kwargs = None
+
+    def PyAudio(self):
+        return self
+
+    def open(self, **kw):
+        self.opened += 1
+        self.open_kwargs = kw
+        return self
+
+    def read(self, n, exception_on_overflow=True):
+        assert exception_on_overflow is False
+        if self.pos + n > len(self.audio):
+            if self.raise_at_end:
+                raise KeyboardInterrupt
+            self.pos = 0
+        out = self.audio[self.pos:self.pos + n]
+        self.pos += n
+        return out.tobytes()
+
+    def stop_stream(self):
+        pass
+
+    def close(self):
+        self.closed += 1
+
+    def terminate(self):
+        self.terminated += 1
+
+
+def test_listen_signature_and_callback_contract(monkeypatch):
+    """listen() as the reference defines it (nanointerpreter.py:835-945): same parameters, on_audio -> predict ->
+    on_score(verifier, gate) every chunk, on_detection(name, score) above threshold outside the cooldown, reset()
+    after a detection."""
+    import inspect
+    import sys
+    sig = inspect.signature(NanoInterpreter.listen)
+    assert list(sig.parameters) == ["self", "on_detection", "threshold", "cooldown", "chunk_size", "on_score", "on_audio", "blocking"]
+    assert [sig.parameters[k].default for k in ("threshold", "cooldown", "chunk_size", "blocking")] == [0.5, 1.0, 1280, True]
+
+    rng = np.random.default_rng(9)
+    loud = np.clip(rng.normal(0, 9000, 1280 * 40), -32768, 32767).astype(np.int16)     # fake model fires on loud audio
+    fake = _FakePyAudio(loud)
+    monkeypatch.setitem(sys.modules, "pyaudio", fake)
+    it = _make_interp()
+    resets, audio_chunks, scores, dets = [], [], [], []
+    orig_reset = it.reset
+    it.reset = lambda: (resets.append(len(scores)), orig_reset())[1]
+    it.listen(on_detection=lambda name, s: dets.append((name, s, len(scores))), threshold=0.5, cooldown=0.0,
+              on_score=lambda v, g: scores.append((v, g)), on_audio=lambda a: audio_chunks.append(a.copy()))
+    assert fake.open_kwargs == dict(format=fake.paInt16, channels=1, rate=16000, input=True, frames_per_buffer=1280)
+    assert fake.closed == 1 and fake.terminated == 1
+    assert len(audio_chunks) == 40 and all(a.dtype == np.int16 and a.shape == (1280,) for a in audio_chunks)
+    assert len(scores) == 40 and all(g == 0.0 for _, g in scores)
+    # same chunks through an oracle interpreter that is reset after each detection -> same detections
+    orc, expect = _oracle(), []
+    for i in range(40):
+        v = orc.predict(loud[i * 1280:(i + 1) * 1280])["wake"]
+        assert scores[i][0] == pytest.approx(v, abs=1e-7)
+        if v > 0.5:
+            expect.append(i + 1)
+            orc.reset()
+    assert [d[2] for d in dets] == expect and len(expect) >= 1
+    assert all(d[0] == "wake" and d[1] > 0.5 for d in dets)
+    assert resets == expect                                          # reset() right after every detection
+    # 13 chunks of 1280 fill the 16000-sample ring (the five warm-up zeros are spent on calls 1..5, which score 0
+    # anyway): the first detection is the 13th call, and after every reset() it takes 13 calls again
+    assert expect == [13, 26, 39]
+
+    # cooldown: one detection only when the cooldown outlasts the audio
+    fake2 = _FakePyAudio(loud)
+    monkeypatch.setitem(sys.modules, "pyaudio", fake2)
+    it2, dets2 = _make_interp(), []
+    it2.listen(on_detection=lambda n, s: dets2.append(n), threshold=0.5, cooldown=3600.0)
+    assert dets2 == ["wake"]
+
+    # default on_detection prints; non-blocking mode runs on a daemon thread until stop()
+    fake3 = _FakePyAudio(loud, raise_at_end=False)
+    monkeypatch.setitem(sys.modules, "pyaudio", fake3)
+    it3, seen = _make_interp(), []
+    it3.listen(threshold=2.0, on_score=lambda v, g: seen.append(v), blocking=False)
+    import time
+    t0 = time.time()
+    while len(seen) < 5 and time.time() - t0 < 10:
+        time.sleep(0.01)
+    assert it3._listen_thread is not None and it3._listen_thread.daemon
+    it3.stop()
+    assert it3._listen_thread is None and len(seen) >= 5 and fake3.terminated == 1
+
+
+def test_listen_without_pyaudio_raises_import_error(monkeypatch):
+    import sys
+    monkeypatch.setitem(sys.modules, "pyaudio", None)
+    with pytest.raises(ImportError, match="PyAudio is required for listen"):
+        _make_interp().listen()
+
+
+def test_crnn_packer_refuses_what_the_engine_does_not_build():
+    """multi-layer or LSTM CRNN checkpoints must be refused, not packed as layer 0 / opaque size errors."""
+    cfg = default_config("crnn")
+    sd = make_state_dict(cfg, 0)
+    deep = dict(sd)
+    deep["model.rnn.weight_ih_l1"] = np.zeros((384, 256), np.float32)
+    with pytest.raises(ValueError, match="single recurrent layer"):
+        pack_tensors(deep, cfg)
+    with pytest.raises(ValueError, match="crnn_rnn_type"):
+        pack_tensors(sd, dict(cfg, crnn_rnn_type="lstm"))
+    lstm = dict(sd)
+    lstm["model.rnn.weight_hh_l0"] = np.zeros((512, 128), np.float32)
+    with pytest.raises(ValueError, match=r"\(4H, H\)"):
+        pack_tensors(lstm, cfg)
