@@ -16,6 +16,7 @@
 #include "nww_blob.h"
 #include "nww_cnn.cuh"
 #include "nww_cnn2.cuh"
+#include "nww_cnn3.cuh"
 #include "nww_gemm_tc.cuh"
 #include "nww_heads.cuh"
 #include "nww_stage.cuh"
@@ -389,6 +390,27 @@ static int launch_tail(nww_engine* e, const float* feat, int64_t n, float* score
     return NWW_OK;
 }
 
+// The fused CNN stage (PCM or log-mel -> conv1 -> tcgen05 conv2 -> feature rows): v3 = warp-specialised pipeline
+// (nww_cnn3.cuh, default), v2 = the phase-serial kernel it replaces (nww_cnn2.cuh; reserved[0] bit 3, A/B measurements).
+static int launch_cnn_stage(nww_engine* e, WindowSource pcm, Cnn2MelSource ms, int64_t n, float* feat_hi, float* feat_lo, float* mel,
+                            cudaStream_t st) {
+    const int act = e->spec.activation;
+    if (e->spec.reserved[0] & 8) {
+        auto k = act == NWW_ACT_RELU ? cnn2_stage_kernel<ACT_RELU> : act == NWW_ACT_GELU ? cnn2_stage_kernel<ACT_GELU>
+                                                                                           : cnn2_stage_kernel<ACT_SILU>;
+        NWW_CUDA(set_smem(k, Cnn2::kTotal));
+        k<<<grid_for(e, n), Cnn2::NT, Cnn2::kTotal, st>>>(pcm, ms, n, e->tab64, e->cnn2, feat_hi, feat_lo, mel);
+    } else {
+        auto k = act == NWW_ACT_RELU ? cnn3_stage_kernel<ACT_RELU> : act == NWW_ACT_GELU ? cnn3_stage_kernel<ACT_GELU>
+                                                                                           : cnn3_stage_kernel<ACT_SILU>;
+        NWW_CUDA(set_smem(k, Cnn3::kTotal));
+        k<<<grid_for(e, n), Cnn3::NT, Cnn3::kTotal, st>>>(pcm, ms, n, e->tab64, e->cnn2, feat_hi, feat_lo, mel);
+    }
+    e->launches++;
+    NWW_CUDA(cudaGetLastError());
+    return NWW_OK;
+}
+
 // Stage A for one chunk: PCM (int16, device) -> feature rows in e->d_feat.
 // stream_s0 >= 0: stream mode, the log-mel of window i is that of stream stream_s0 + i in the mel ring.
 static int launch_stage_a(nww_engine* e, WindowSource pcm, int64_t n, float* mel, cudaStream_t st, int64_t stream_s0 = -1) {
@@ -427,14 +449,8 @@ static int launch_stage_a(nww_engine* e, WindowSource pcm, int64_t n, float* mel
         case NWW_ARCH_CNN: {
             using G = GeoNS40x98;
             if (e->cnn2_enabled) {
-                auto k = e->spec.activation == NWW_ACT_RELU   ? cnn2_stage_kernel<ACT_RELU>
-                         : e->spec.activation == NWW_ACT_GELU ? cnn2_stage_kernel<ACT_GELU>
-                                                              : cnn2_stage_kernel<ACT_SILU>;
-                NWW_CUDA(set_smem(k, Cnn2::kTotal));
-                k<<<grid_for(e, n), Cnn2::NT, Cnn2::kTotal, st>>>(pcm, cnn2_src, n, e->tab64, e->cnn2, e->d_feat_hi, e->d_feat_lo, mel);
-                e->launches++;
-                NWW_CUDA(cudaGetLastError());
-                return NWW_OK;
+                int rc = launch_cnn_stage(e, pcm, cnn2_src, n, e->d_feat_hi, e->d_feat_lo, mel, st);
+                return rc;
             }
             if (pcm.fbase != nullptr) return fail(NWW_EUNSUPPORTED, "float feeds need the default (v2) CNN stage");
             auto k = cnn_stage_kernel<double, G, kNfb64, kStageNT>;
@@ -447,13 +463,8 @@ static int launch_stage_a(nww_engine* e, WindowSource pcm, int64_t n, float* mel
         }
         case NWW_ARCH_CRNN_GRU:
             if (e->crnn_cnn2) {
-                auto k = e->spec.activation == NWW_ACT_RELU   ? cnn2_stage_kernel<ACT_RELU>
-                         : e->spec.activation == NWW_ACT_GELU ? cnn2_stage_kernel<ACT_GELU>
-                                                              : cnn2_stage_kernel<ACT_SILU>;
-                NWW_CUDA(set_smem(k, Cnn2::kTotal));
-                k<<<grid_for(e, n), Cnn2::NT, Cnn2::kTotal, st>>>(pcm, cnn2_src, n, e->tab64, e->cnn2, e->d_nhwc, nullptr, mel);
-                e->launches++;
-                NWW_CUDA(cudaGetLastError());
+                int rc = launch_cnn_stage(e, pcm, cnn2_src, n, e->d_nhwc, nullptr, mel, st);
+                if (rc) return rc;
                 return launch_head_stage_a(e->heads, e->tab64, e->spec.activation, e->sm_count, pcm, n, e->d_feat, e->d_scratch,
                                            nullptr, st, &e->launches, &g_last_error, true, e->d_nhwc);
             }

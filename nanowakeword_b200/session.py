@@ -53,10 +53,16 @@ class Engine:
         spec.chunk_windows = int(chunk_windows)
         # reserved[0] bit 0: keep the first dense layer on CUDA cores; bit 1: CNN head on the v1
         # (CUDA-core conv2) stage kernel instead of the tcgen05 one (A/B measurements)
-        if cnn_stage not in ("v1", "v2"):
-            raise ValueError("cnn_stage must be 'v1' or 'v2'")
+        if cnn_stage in ("v2", "v3"):
+            cnn_stage, pipelined = "v2", cnn_stage == "v3"
+        elif cnn_stage == "v1":
+            pipelined = False
+        else:
+            raise ValueError("cnn_stage must be 'v1', 'v2' or 'v3'")
         # bit 2: streams always re-run the front end on the whole window (no incremental mel ring)
-        spec.reserved[0] = (0 if tensor_cores else 1) | (2 if cnn_stage == "v1" else 0) | (0 if stream_incremental else 4)
+        # bit 3: the phase-serial tcgen05 CNN stage (nww_cnn2.cuh) instead of the warp-specialised pipeline (nww_cnn3.cuh)
+        spec.reserved[0] = ((0 if tensor_cores else 1) | (2 if cnn_stage == "v1" else 0) | (0 if stream_incremental else 4)
+                            | (0 if pipelined else 8))
         self._blob = (C.c_char * len(blob)).from_buffer_copy(blob)
         handle = C.c_void_p()
         rc = self._lib.nww_create(C.byref(spec), C.cast(self._blob, C.c_void_p), len(blob), int(device), C.byref(handle))

@@ -119,8 +119,10 @@ def test_calls_on_different_cuda_streams_are_ordered(torch_cuda):
     eng.stream_open(n)
     chunks = torch.from_numpy(synth_pcm(n, seed=83, kind="gauss")).cuda()
     for rep in range(2):
-        for s in range(0, 16000, 1600):
-            sc = eng.stream_push_device(chunks[:, s:s + 1600].contiguous(), stream=s1 if s % 3200 else s2)
+        pieces = [chunks[:, s:s + 1600].contiguous() for s in range(0, 16000, 1600)]
+        torch.cuda.synchronize()                                # the slices were made on torch's current stream
+        for i, piece in enumerate(pieces):
+            sc = eng.stream_push_device(piece, stream=s1 if i & 1 else s2)
         torch.cuda.synchronize()
         assert np.array_equal(sc.cpu().numpy(), eng.score_device(chunks).cpu().numpy())
         eng.stream_reset()                                      # no sync needed before the next pushes
