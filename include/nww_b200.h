@@ -151,6 +151,11 @@ typedef struct nww_profile_t {
 int nww_set_profiling(nww_engine* e, int enable);
 int nww_get_profile(nww_engine* e, nww_profile_t* out);
 
+/* Pipe micro-benchmark on `device`: kind 0 = FP32 FFMA, 1 = FP64 DFMA; *tflops receives the measured peak
+ * (independent FMA chains, CUDA events, best of 5; 1 FMA = 2 flop).  bench.py quotes the stage kernel's FP32 /
+ * FP64 work against these measured roofs ("FP32 CUDA-core peak: builder to measure"). */
+int nww_microbench(int device, int kind, double* tflops);
+
 /* Block until everything enqueued on the engine's own streams has finished. */
 int nww_synchronize(nww_engine* e);
 

@@ -64,6 +64,7 @@ SIGNATURES = {
     "nww_set_profiling": (C.c_int, [_P, C.c_int]),
     "nww_get_profile": (C.c_int, [_P, C.POINTER(NwwProfile)]),
     "nww_synchronize": (C.c_int, [_P]),
+    "nww_microbench": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
 }
 
 _lib = None

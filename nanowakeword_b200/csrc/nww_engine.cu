@@ -527,6 +527,23 @@ static void stream_free(nww_engine* e) {
     e->streams = StreamState{};
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters) {
+    // 16 independent accumulator chains per thread: enough ILP to saturate the pipe at 8 resident warps per scheduler
+    T a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = (T)(threadIdx.x + i) * (T)1e-3;
+    const T x = (T)1.0000001, y = (T)1e-7;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = a[i] * x + y;
+    }
+    T s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    if (s == (T)-1.0) out[0] = s;           // never true: keeps the chains alive
+}
+
 // ------------------------------------------------------------------------------ C ABI
 extern "C" {
 
@@ -1138,6 +1155,38 @@ int nww_get_profile(nww_engine* e, nww_profile_t* out) {
         e->event_pool.push_back(e->spans[i].b);
     }
     e->spans.clear();
+    return NWW_OK;
+}
+
+// ---- pipe micro-benchmarks: the on-chip roofs bench.py quotes next to the HBM / tensor peaks ----------------------
+int nww_microbench(int device, int kind, double* tflops) {
+    // kind 0: FP32 FFMA, 1: FP64 DFMA.  Measured with CUDA events, best of 5; result in TFLOP/s (1 FMA = 2 flop).
+    if (!tflops || (kind != 0 && kind != 1)) return fail(NWW_EINVAL, "nww_microbench: bad argument");
+    NWW_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    NWW_CUDA(cudaGetDeviceProperties(&prop, device));
+    void* d = nullptr;
+    NWW_CUDA(cudaMalloc(&d, 64));
+    cudaEvent_t a, b;
+    NWW_CUDA(cudaEventCreate(&a));
+    NWW_CUDA(cudaEventCreate(&b));
+    const int grid = prop.multiProcessorCount * 8, iters = kind == 0 ? 8192 : 2048;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        NWW_CUDA(cudaEventRecord(a, 0));
+        if (kind == 0) fma_peak_kernel<float><<<grid, 256>>>(static_cast<float*>(d), iters);
+        else fma_peak_kernel<double><<<grid, 256>>>(static_cast<double*>(d), iters);
+        NWW_CUDA(cudaEventRecord(b, 0));
+        NWW_CUDA(cudaEventSynchronize(b));
+        float ms = 0.f;
+        NWW_CUDA(cudaEventElapsedTime(&ms, a, b));
+        const double fl = 2.0 * 16.0 * iters * 256.0 * grid;
+        if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);     // first launch = warm-up
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d);
+    *tflops = best;
     return NWW_OK;
 }
 

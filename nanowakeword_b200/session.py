@@ -63,6 +63,7 @@ class Engine:
         # bit 3: the phase-serial tcgen05 CNN stage (nww_cnn2.cuh) instead of the warp-specialised pipeline (nww_cnn3.cuh)
         spec.reserved[0] = ((0 if tensor_cores else 1) | (2 if cnn_stage == "v1" else 0) | (0 if stream_incremental else 4)
                             | (0 if pipelined else 8))
+        self.cnn_stage = "v3" if (pipelined and cnn_stage == "v2") else cnn_stage
         self._blob = (C.c_char * len(blob)).from_buffer_copy(blob)
         handle = C.c_void_p()
         rc = self._lib.nww_create(C.byref(spec), C.cast(self._blob, C.c_void_p), len(blob), int(device), C.byref(handle))

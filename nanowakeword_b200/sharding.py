@@ -33,19 +33,21 @@ def scatter_windows(pcm_root, n_total: int, clip_samples: int, rank: int, world:
     if world == 1:
         local.copy_(pcm_root[start:start + count])
         return local
+    # ONE grouped NCCL call (ncclGroupStart / End around every send): the per-destination transfers run concurrently
+    # over NVSwitch instead of being serialised as independent point-to-point operations.
+    ops = []
     if rank == src:
-        reqs = []
         for r in range(world):
             s, c = partition(n_total, world, r)
             if r == src:
                 local.copy_(pcm_root[s:s + c])
             elif c:
                 # NCCL has no int16: ship the rows as raw bytes
-                reqs.append(dist.isend(pcm_root[s:s + c].contiguous().view(torch.uint8), dst=r))
-        for q in reqs:
-            q.wait()
+                ops.append(dist.P2POp(dist.isend, pcm_root[s:s + c].contiguous().view(torch.uint8), r))
     elif count:
-        dist.recv(local.view(torch.uint8), src=src)
+        ops.append(dist.P2POp(dist.irecv, local.view(torch.uint8), src))
+    for q in (dist.batch_isend_irecv(ops) if ops else []):
+        q.wait()
     return local
 
 

@@ -170,3 +170,103 @@ def test_predict_clip_and_predict_batch_on_the_engine(torch_cuda, tmp_path, gold
     orc.predict(x)
     assert interp.e2e_buffer["wake"].data.dtype == np.float32
     assert abs(interp.raw_scores["wake"] - orc.raw_scores["wake"]) < SCORE_TOL
+
+
+# ------------------------------------------------------------------------ BASELINE configs #3, #4, #5 at their stated sizes
+def _device_pcm(torch, n, seed):
+    """Full-scale uniform int16 windows generated on the device (n x 32 kB would take minutes through numpy)."""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    out = torch.empty((n, 16000), dtype=torch.int16, device="cuda")
+    for o in range(0, n, 16384):
+        out[o:o + 16384] = torch.randint(-32768, 32768, (min(16384, n - o), 16000), generator=g, device="cuda",
+                                         dtype=torch.int32).to(torch.int16)
+    return out
+
+
+@pytest.mark.parametrize("mt,n", [("bcresnet", 65536), ("crnn", 131072)])
+def test_configs_4_and_5_per_gpu_batch_sizes(torch_cuda, mt, n):
+    """BASELINE configs #4 (262 144 windows / 4 GPUs, BcResNet) and #5 (1 048 576 / 8 GPUs, CRNN-GRU) at the number of
+    windows ONE GPU owns: every launch chunk of the batch is scored; a strided sample is held to the oracle and the
+    size-independent properties of a per-window map are checked on the full result."""
+    from oracle.heads import forward_scores
+    torch = torch_cuda
+    eng, sd, cfg = _engine(mt)
+    pcm = _device_pcm(torch, n, seed=100 + n % 97)
+    # plant known windows across chunk boundaries: duplicates must score identically wherever they land
+    chunk = eng.info["chunk_windows"]
+    plants = [0, 1, chunk - 1, chunk, 3 * chunk + 7, n // 2, n - chunk - 1, n - 1]
+    for p in plants[1:]:
+        pcm[p] = pcm[0]
+    s = eng.score_device(pcm)
+    torch.cuda.synchronize()
+    assert s.shape == (n,) and bool(torch.isfinite(s).all()) and float(s.min()) >= 0.0 and float(s.max()) <= 1.0
+    sp = s[torch.tensor(plants, device="cuda")].cpu().numpy()
+    assert np.all(sp == sp[0])
+    idx = np.arange(5, n, n // 24)[:24]
+    ref = forward_scores(pcm[torch.from_numpy(idx).cuda()].cpu().numpy(), sd, cfg).ravel()
+    assert np.abs(s.cpu().numpy()[idx] - ref).max() < SCORE_TOL
+    # the same windows in a small batch give the same bits (no dependence on batch size / chunking)
+    small = eng.score_device(pcm[torch.from_numpy(idx).cuda()].contiguous()).cpu().numpy()
+    assert np.array_equal(small, s.cpu().numpy()[idx])
+    del pcm
+    torch.cuda.empty_cache()
+
+
+def test_config_3_65536_streams_tcn(torch_cuda):
+    """BASELINE config #3: 65 536 streams x 1280-sample steps, TCN head.  Every stream is pushed through the ring /
+    incremental-mel path; a strided sample of streams is checked step by step against its own oracle interpreter
+    (nanointerpreter.py:735-814), and the whole bank against batch scoring of the ring contents."""
+    from nanowakeword_b200 import StreamBank
+    from oracle.interp import OracleInterpreter
+    torch = torch_cuda
+    eng, sd, cfg = _engine("tcn")
+    n, L, steps = 65536, 1280, 16
+    rng = np.random.default_rng(33)
+    base = np.clip(rng.normal(0, 3000, (257, L * steps)), -32768, 32767).astype(np.int16)     # 257 distinct streams, tiled
+    audio = np.tile(base, (n // 257 + 1, 1))[:n]
+    sample = [0, 1, 256, 257, 4143, 4144, 30000, n - 1]
+    oracles = {i: OracleInterpreter(sd, cfg, name="m") for i in sample}
+    bank = StreamBank(eng, n)
+    for s in range(steps):
+        chunks = np.ascontiguousarray(audio[:, s * L:(s + 1) * L])
+        got = bank.push(chunks)
+        assert got.shape == (n,)
+        for i in sample:
+            want = oracles[i].predict(chunks[i])["m"]
+            assert abs(got[i] - want) < SCORE_TOL, (s, i, got[i], want)
+            assert abs(bank.raw_scores[i] - oracles[i].raw_scores["m"]) < SCORE_TOL
+        # streams fed the same audio give the same bits, wherever they sit in the bank
+        assert np.array_equal(bank.raw_scores[:257], bank.raw_scores[257:514])
+    assert (bank.raw_scores > 0).all()
+    # ring contents == last 16000 samples: batch scoring of those windows agrees with the stream path
+    tail = np.ascontiguousarray(audio[:4096, steps * L - 16000:steps * L])
+    assert np.abs(eng.score_host(tail) - bank.raw_scores[:4096]).max() < 1e-5
+    bank.close()
+
+
+@pytest.mark.parametrize("mt,chunk_len", [("bcresnet", 1280), ("crnn", 1280), ("gru", 1280), ("lstm", 960), ("rnn", 1280),
+                                          ("quartznet", 1280), ("e2e_cnn", 1600)])
+def test_stream_rings_match_oracle_interpreters_other_heads(torch_cuda, golden_frontend, mt, chunk_len):
+    """Stream-vs-reference-interpreter parity for the heads round 1 only checked incremental-vs-full against themselves."""
+    from nanowakeword_b200 import StreamBank
+    from oracle.interp import OracleInterpreter
+    eng, sd, cfg = _engine(mt)
+    n = 3
+    g = golden_frontend["pcm"]
+    audio = np.stack([np.concatenate([g[(i + k) % len(g)] for k in range(2)]) for i in range(n)])   # (n, 32000)
+    bank = StreamBank(eng, n)
+    oracles = [OracleInterpreter(sd, cfg, name="m") for _ in range(n)]
+    n_steps = audio.shape[1] // chunk_len
+    for s in range(n_steps):
+        chunks = np.ascontiguousarray(audio[:, s * chunk_len:(s + 1) * chunk_len])
+        if s == n_steps - 6:
+            bank.reset([1])
+            oracles[1].reset()
+        got = bank.push(chunks)
+        for i, o in enumerate(oracles):
+            want = o.predict(chunks[i])["m"]
+            assert abs(got[i] - want) < SCORE_TOL, (s, i, got[i], want)
+            assert abs(bank.raw_scores[i] - o.raw_scores["m"]) < SCORE_TOL
+    assert (bank.raw_scores[[0, 2]] > 0).all()
+    bank.close()

@@ -75,7 +75,33 @@ def full(rep, out):
                     f.write(f"{k:90s} {d[hdr.index(k)]:>18s} {units[hdr.index(k)]}\n")
 
 
+def traffic_digest(rep, tag, windows_per_launch, path="profiles/ncu_traffic.json"):
+    """dram bytes of the largest captured launch of each kernel -> profiles/ncu_traffic.json (read by bench.py)."""
+    import json, os
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    def val(d, k):
+        i = hdr.index(k)
+        v = float(d[i].replace(",", ""))
+        return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[units[i]]
+    digest = json.load(open(path)) if os.path.exists(path) else {}
+    best = {}
+    for d in data:
+        name = d[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").split("<")[0].split("::")[-1]
+        tot = val(d, "dram__bytes_read.sum") + val(d, "dram__bytes_write.sum")
+        if name not in best or tot > best[name][0]:
+            best[name] = (tot, val(d, "dram__bytes_read.sum"), val(d, "dram__bytes_write.sum"))
+    for name, (tot, rd, wr) in best.items():
+        digest[name] = {"dram_bytes_per_launch": tot, "dram_bytes_read": rd, "dram_bytes_write": wr,
+                        "windows_per_launch": windows_per_launch, "dram_bytes_per_window": tot / windows_per_launch,
+                        "source": f"{tag}_ncu_full.txt (ncu --set full, largest captured launch)"}
+    json.dump(digest, open(path, "w"), indent=1)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 4:          # ... <windows_per_launch>: also refresh profiles/ncu_traffic.json
+        traffic_digest(sys.argv[2], sys.argv[3], float(sys.argv[4]))
     launches(sys.argv[1], sys.argv[3] + "_launches.txt")
     if sys.argv[2] != "-":
         full(sys.argv[2], sys.argv[3] + "_ncu_full.txt")
