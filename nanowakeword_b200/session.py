@@ -251,18 +251,30 @@ def save_model(path: str, state_dict: dict, cfg: dict) -> str:
 
 
 def load_artifacts(path: str):
-    """Resolve a model path to (state_dict as numpy, cfg).  Accepts ``x.pt`` or ``x.onnx``
-    (the reference always writes both, trainer.py:476-535); the weights are read from the
-    ``.pt`` and the architecture from the ``.json`` sidecar.  Parsing ``.onnx`` graphs is a
-    follow-up."""
+    """Resolve a model path to (state_dict as numpy, cfg).
+
+    * ``x.onnx`` as the reference's trainer writes it (trainer.py:474-511, _export/onnx.py:157-221): the graph itself is
+      read and pattern-matched onto the e2e architectures the engine builds (``onnx_reader``) — no sidecar needed, so
+      ``load_model("x.onnx")`` and ``load_model("x.onnx", cascade=True)`` (which looks for ``x_lite.onnx``,
+      nanointerpreter.py:476-487) work on exactly the files a training run leaves behind;
+    * ``x.pt`` (``torch.save(state_dict)``, _export/pytorch.py:26-46) plus the ``x.json`` sidecar written by
+      :func:`save_model` — a state_dict alone does not say which architecture it belongs to.  When both the sidecar pair
+      and an ``.onnx`` exist, the sidecar pair wins for a ``.pt`` path and the graph wins for an ``.onnx`` path.
+    """
     stem, ext = os.path.splitext(path)
     if not os.path.exists(path):
         raise FileNotFoundError(f"Model file not found: {path}")
+    if ext.lower() == ".onnx":
+        from .onnx_reader import load_onnx
+        return load_onnx(path)
     pt, js = stem + ".pt", stem + ".json"
     if not os.path.exists(pt) or not os.path.exists(js):
+        if os.path.exists(stem + ".onnx"):
+            from .onnx_reader import load_onnx
+            return load_onnx(stem + ".onnx")
         raise NotImplementedError(
-            f"{path}: the B200 engine needs the PyTorch state_dict '{pt}' and the spec sidecar '{js}' "
-            "next to the model (ONNX graph ingestion is not implemented)")
+            f"{path}: a bare state_dict does not identify its architecture; the B200 engine needs the spec sidecar "
+            f"'{js}' next to '{pt}' (written by save_model), or the '.onnx' file the reference's trainer exports")
     torch = _torch()
     sd = torch.load(pt, map_location="cpu", weights_only=True)
     with open(js) as f:
@@ -300,6 +312,7 @@ class B200Session:
         self.engine = Engine(state_dict, cfg, device=device, **engine_kwargs)
         self.cfg = cfg
         n = self.engine.clip_samples
+        input_ndim = int(cfg.get("input_ndim", input_ndim))       # an .onnx graph says what its input looks like
         shape = ["batch_size", n] if input_ndim == 2 else ["batch_size", 1, n]
         self._inputs = [_NodeArg("input", shape)]
         self._outputs = [_NodeArg("output", ["batch_size", 1, 1])]

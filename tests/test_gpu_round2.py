@@ -270,3 +270,45 @@ def test_stream_rings_match_oracle_interpreters_other_heads(torch_cuda, golden_f
             assert abs(bank.raw_scores[i] - o.raw_scores["m"]) < SCORE_TOL
     assert (bank.raw_scores[[0, 2]] > 0).all()
     bank.close()
+
+
+def test_load_model_from_onnx_with_cascade(torch_cuda, tmp_path, golden_frontend):
+    """The files a reference training run leaves behind (trainer.py:474-535: <name>.onnx, <name>_lite.onnx, no sidecar)
+    load as a cascade (nanointerpreter.py:458-501) and stream like two oracle interpreters gated per call (:758-769)."""
+    import sys
+    from conftest import GOLDEN
+    sys.path.insert(0, GOLDEN)
+    from onnx_writer import write_e2e_model
+    from nanowakeword_b200 import NanoInterpreter
+    from oracle.interp import OracleInterpreter
+    cfg_v, cfg_g = default_config("e2e_dnn"), default_config("e2e_quartznet")
+    sd_v, sd_g = make_state_dict(cfg_v, seed=0), make_state_dict(cfg_g, seed=0)
+    stem = str(tmp_path / "hey")
+    write_e2e_model(stem + ".onnx", sd_v, cfg_v, style="folded")
+    write_e2e_model(stem + "_lite.onnx", sd_g, cfg_g, style="explicit")
+    # pick a gate threshold that actually splits the calls
+    gate_thr = 0.9
+    interp = NanoInterpreter.load_model(stem + ".onnx", cascade=True, gate_threshold=gate_thr)
+    assert interp.is_cascade and interp.gate_name == "hey_lite" and interp.model_name == "hey"
+    assert list(interp.models) == ["hey_lite", "hey"]
+    assert interp.models["hey"].get_inputs()[0].shape == ["batch_size", 1, 16000] and interp.e2e_input_ndim["hey"] == 3
+    og, ov = OracleInterpreter(sd_g, cfg_g, name="g"), OracleInterpreter(sd_v, cfg_v, name="v")
+    g = golden_frontend["pcm"]
+    stream = np.concatenate([g[0], g[4], g[1], g[5]])
+    passed = skipped = 0
+    for i in range(0, len(stream), 1280):
+        chunk = stream[i:i + 1280]
+        r = interp.predict(chunk)
+        gs = og.predict(chunk)["g"]
+        assert abs(r.gate_score - gs) < SCORE_TOL
+        if og.buf_samples >= 16000 and gs < gate_thr:            # verifier skipped: 0.0, raw score 0.0, buffer still fed
+            ov.buf.extend((chunk.astype(np.float32) / 32768.0).tolist())
+            ov.buf_samples += len(chunk)
+            ov.prediction_buffer.append(0.0)
+            want, skipped = 0.0, skipped + 1
+            assert interp.raw_scores["hey"] == 0.0
+        else:
+            want = ov.predict(chunk)["v"]
+            passed += og.buf_samples >= 16000
+        assert abs(r.score - want) < SCORE_TOL, (i, r.score, want)
+    assert passed > 0 or skipped > 0
