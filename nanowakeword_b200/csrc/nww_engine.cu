@@ -647,6 +647,61 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
                     e->heads.tcn_umma = true;
                 }
             }
+            if (spec->arch == NWW_ARCH_TCN && e->heads.tcn_cone && !(spec->reserved[0] & 1) && !(spec->reserved[0] & 16)) {
+                // the cone as one tcgen05 row GEMM per layer over all windows of a launch group (reserved[0] bit 4 keeps
+                // the per-tile cone kernel): layer program + weights as K-chunked operand streams
+                const TcnConeParams& C = e->heads.tcn_plan;
+                HeadWeights& H = e->heads;
+                int li = 0;
+                bool ok = true;
+                auto add = [&](const float* w_host, const float* bias_dev, int Cin, int taps, int Cout, int a_in_mel, long long a_off,
+                               int a_rs, int n_pos, int o_in_feat, long long o_off, int act, int pre_relu, int has_res, long long r_off,
+                               int r_rs) -> int {
+                    if (li >= 12 || Cout % 64 || Cout > 512 || Cin % 4) { ok = false; return NWW_OK; }
+                    const int K = taps * Cin, Kp = (K + kKcKC - 1) / kKcKC * kKcKC;
+                    std::vector<float> wp((size_t)Kp * Cout, 0.0f);
+                    memcpy(wp.data(), w_host, (size_t)K * Cout * sizeof(float));
+                    std::vector<uint16_t> wq;
+                    rowgemm_kc_pack(wp.data(), Kp, Cout, &wq);
+                    void* d = nullptr;
+                    NWW_CUDA(cudaMalloc(&d, wq.size() * sizeof(uint16_t)));
+                    e->d_extra.push_back(d);
+                    NWW_CUDA(cudaMemcpy(d, wq.data(), wq.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+                    H.tcn_row[li++] = HeadWeights::TcnRowLayer{a_off, o_off, r_off, a_in_mel, o_in_feat, has_res, a_rs, r_rs, n_pos, Kp, K,
+                                                               Cout, act, pre_relu, reinterpret_cast<const uint4*>(d), bias_dev};
+                    return NWW_OK;
+                };
+                int cin = C.c_in;
+                long long x_off = (long long)(C.T - C.n_in) * C.c_in;       // level 0 reads the time-major log-mel itself
+                int x_in_mel = 1;
+                for (int l = 0; l < C.levels && ok; ++l) {
+                    const std::string p = "tcn." + std::to_string(l);
+                    const int Cc = C.ch[l];
+                    const bool last = l + 1 == C.levels;
+                    rc = add(e->blob.f32(p + ".conv1.w"), H.tcn_c1[l].b, cin, 3, Cc, x_in_mel, x_off, cin, C.n_mid[l], 0, C.off_mid[l], 1, 0,
+                             0, 0, 0);
+                    if (rc) return rc;
+                    long long r_off = x_off + 4ll * cin;                     // identity residual of output p = block input 2 p + 4
+                    int r_rs = 2 * cin;
+                    if (cin != Cc) {
+                        rc = add(e->blob.f32(p + ".down.w"), H.tcn_down[l].b, cin, 1, Cc, x_in_mel, x_off + 4ll * cin, 2 * cin, C.n_out[l], 0,
+                                 C.off_res, 0, 0, 0, 0, 0);
+                        if (rc) return rc;
+                        r_off = C.off_res;
+                        r_rs = Cc;
+                    } else if (x_in_mel) {
+                        ok = false;                                          // an identity residual straight from the log-mel: not built
+                    }
+                    rc = add(e->blob.f32(p + ".conv2.w"), H.tcn_c2[l].b, Cc, 3, Cc, 0, C.off_mid[l], 2 * Cc, C.n_out[l], last ? 1 : 0,
+                             last ? 0 : C.off_out[l], 1, 1, 1, r_off, r_rs);
+                    if (rc) return rc;
+                    x_off = C.off_out[l];
+                    x_in_mel = 0;
+                    cin = Cc;
+                }
+                H.tcn_n_row_layers = li;
+                H.tcn_rows = ok;
+            }
             if (spec->arch == NWW_ARCH_CRNN_GRU && e->heads.gru_hidden == kGruTcH && e->heads.gru_wih_f_kn &&
                 !(spec->reserved[0] & 1)) {
                 std::vector<uint16_t> wq;                         // blob w_hh is (H, 3H) = [k][n]
@@ -756,7 +811,11 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
         const size_t per_window = (size_t)e->feat_dim * sizeof(float) * 3 + e->scratch_per_window;
         // the recurrent heads work on 128-window tiles, one per SM: two waves of those per chunk
         const bool rnn = spec->arch == NWW_ARCH_GRU || spec->arch == NWW_ARCH_LSTM;
-        int mult = (int)std::max<size_t>(1, std::min<size_t>(rnn ? 2 * kRnnTM : 28, ((size_t)2 << 30) / (per_window * e->sm_count)));
+        // the TCN's row-GEMM layers are per-launch-group kernels over (window, position) rows: one group should hold a whole
+        // bank of streams (BASELINE config #3: 65 536), within a 3 GB workspace
+        const bool tcn_rows = spec->arch == NWW_ARCH_TCN && e->heads.tcn_rows;
+        int mult = (int)std::max<size_t>(1, std::min<size_t>(rnn ? 2 * kRnnTM : tcn_rows ? 448 : 28,
+                                                              ((size_t)(tcn_rows ? 3 : 2) << 30) / (per_window * e->sm_count)));
         e->chunk = spec->chunk_windows > 0 ? spec->chunk_windows : e->sm_count * mult;
     }
     NWW_CUDA(cudaMalloc(&e->d_feat, (size_t)e->chunk * e->feat_dim * sizeof(float)));

@@ -37,6 +37,19 @@ struct HeadWeights {
     bool crnn_cnn2 = false;           // conv1 + conv2 through cnn2_stage_kernel (default channel counts 16, 32, 32)
     bool tcn_cone = false;            // fused dependency-cone kernel (nww_tcn.cuh) instead of the layer kernels
     TcnConeParams tcn_plan{};
+    // the cone as one K-chunked tcgen05 row GEMM per layer over ALL windows of a launch group (nww_rowgemm.cuh): the
+    // weights of a layer stream from L2 once per 128-row tile instead of once per 4 windows, activations go through a
+    // per-window scratch in global memory (L2).  Default for the TCN head; tcn_umma / the FP32 cone are the A/B variants.
+    struct TcnRowLayer {
+        long long a_off, o_off, r_off;            // float offsets: A / out / residual base inside mel (level 0 input) or act scratch
+        int a_in_mel, o_in_feat, has_res;
+        int a_row_stride, r_row_stride, n_pos, K, k_valid, N, act, pre_relu;
+        const uint4* wq;
+        const float* bias;
+    };
+    bool tcn_rows = false;
+    int tcn_n_row_layers = 0;
+    TcnRowLayer tcn_row[12];
     bool tcn_umma = false;            // ... with the layer GEMMs on tcgen05 (nww_tcn_umma.cuh)
     TcnUmmaParams tcn_uplan{};
     const uint4* tcn_wq = nullptr;
@@ -188,7 +201,8 @@ inline int setup_head_weights(int arch, int geometry, const BlobLookup& get, con
             cone_ok = tcn_plan(&P);
         }
         hw->tcn_cone = cone_ok;
-        if (cone_ok) hw->scratch_floats = (size_t)GeoNS40x98::N_FRAMES * hw->tcn_in;      // only the (T, F) log-mel goes through HBM
+        // the (T, F) log-mel + (row-GEMM layers) the cone's activations of one window
+        if (cone_ok) hw->scratch_floats = (size_t)GeoNS40x98::N_FRAMES * hw->tcn_in + hw->tcn_plan.per_window;
     } else if (arch == NWW_ARCH_BCRESNET) {
         if (geometry != NWW_GEOM_NS40X98) { *err = "bcresnet head is built for the NS40x98 geometry"; return NWW_EUNSUPPORTED; }
         hw->bc_init = {need("bc.init.w", 32 * 9), need("bc.init.b", 32)};
@@ -581,6 +595,30 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
         const int frame_lo = (T - P.n_in) & ~1;
         if (!mel_ready && (rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel, 1, st, launches, err, frame_lo))) return rc;
         if (mel_dump && (rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel_dump, 0, st, launches, err))) return rc;
+        if (hw.tcn_rows) {
+            // stream mode: the cone's frames out of the mel ring, time-major, into the same place the front end writes them
+            if (ring.ring != nullptr) {
+                stream_mel_tail_kernel<<<ew_grid(n * P.n_in * F, sm_count), 256, 0, st>>>(ring, n, mel, T - P.n_in, P.n_in);
+                if ((rc = done())) return rc;
+            }
+            float* act = take((size_t)P.per_window);
+            NWW_HCUDA(set_smem(rowgemm_kc_umma_kernel<true>, rowgemm_kc_smem_bytes()));
+            NWW_HCUDA(cudaFuncSetAttribute(rowgemm_kc_umma_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            for (int li = 0; li < hw.tcn_n_row_layers; ++li) {
+                const HeadWeights::TcnRowLayer& L = hw.tcn_row[li];
+                const long long rows = n * L.n_pos;
+                const long long a_ws = L.a_in_mel ? (long long)F * T : P.per_window, o_ws = L.o_in_feat ? L.N : P.per_window;
+                const float* A = (L.a_in_mel ? mel : act) + L.a_off;
+                float* O = (L.o_in_feat ? feat : act) + L.o_off;
+                const KcLaunch kl = rowgemm_kc_launch(rows, L.N, sm_count);
+                rowgemm_kc_umma_kernel<true><<<kl.grid, kKcNT, kl.smem, st>>>(
+                    A, kc_seq(L.n_pos, a_ws, L.a_row_stride, 0), kc_one_seg(L.k_valid), L.K, L.wq, L.bias,
+                    L.has_res ? act + L.r_off : nullptr, O, kc_seq(L.n_pos, o_ws, L.N, 0), rows, L.N, L.N, L.act, kl.ring,
+                    kc_seq(L.n_pos, P.per_window, L.r_row_stride, 0), L.pre_relu);
+                if ((rc = done())) return rc;
+            }
+            return NWW_OK;
+        }
         if (hw.tcn_umma) {
             const size_t usm = tcn_umma_smem_bytes(hw.tcn_uplan);
             NWW_HCUDA(set_smem(tcn_cone_umma_kernel, usm));

@@ -481,7 +481,9 @@ template <bool VIEWS>
 __global__ void __launch_bounds__(kKcNT, VIEWS ? 2 : 1)
 rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, KcSegs sg, int K, const uint4* __restrict__ wq,
                        const float* __restrict__ bias, const float* __restrict__ res, float* __restrict__ out, KcView ov, long long rows,
-                       int N, int n_valid, int act, int ring) {
+                       int N, int n_valid, int act, int ring,
+                       KcView rv = KcView{0, 0, 0, 0, 0, 0} /* where the residual row of GEMM row r lives; rpw == 0: res + r * N */,
+                       int pre_relu = 0 /* ReLU before the residual is added: TemporalBlock's relu(relu(conv2) + res) */) {
     NWW_DYN_SMEM(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned char* a_s = smem;                                         // two chunk buffers
@@ -602,12 +604,13 @@ rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, KcSegs sg, int K,
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
                 if (r < rows) {
                     float4* dst = reinterpret_cast<float4*>(out + o_at + c0);
-                    const float4* rs = res ? reinterpret_cast<const float4*>(res + r * N + c0) : nullptr;
+                    const float4* rs = res ? reinterpret_cast<const float4*>(res + (VIEWS && rv.rpw ? rv.at(r) : r * N) + c0) : nullptr;
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
                         if (VIEWS && c0 + 4 * j4 >= n_valid) break;
                         float4 o = make_float4(v[4 * j4] + __ldg(bias + c0 + 4 * j4), v[4 * j4 + 1] + __ldg(bias + c0 + 4 * j4 + 1),
                                                v[4 * j4 + 2] + __ldg(bias + c0 + 4 * j4 + 2), v[4 * j4 + 3] + __ldg(bias + c0 + 4 * j4 + 3));
+                        if (VIEWS && pre_relu) { o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f); }
                         if (rs) {
                             const float4 t = __ldg(rs + j4);
                             o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;

@@ -98,4 +98,20 @@ stream_mel_gather_kernel(StreamState st, const float* __restrict__ mel_ring, flo
     }
 }
 
+// The last n_tail frames of every stream's current window out of the mel ring, TIME-major, at the place a time-major
+// (n, T, F) log-mel buffer holds them: out[s][(t0 + pos) * F + m].  Feeds the TCN's row-GEMM layers in stream mode.
+__global__ void __launch_bounds__(256)
+stream_mel_tail_kernel(MelRingRef ring, long long n, float* __restrict__ out, int t0, int n_tail) {
+    const long long total = n * (long long)(n_tail * SMel::F);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long w = i / (n_tail * SMel::F);
+        const int r = (int)(i - w * (n_tail * SMel::F));
+        const int m = r / n_tail, pos = r - m * n_tail;            // reads run along time inside a mel row of the ring
+        const long long s = ring.s0 + w;
+        const int head = smel_slot(ring.count[s] / SMel::HOP - 3 + 1);
+        out[w * (long long)(SMel::F * SMel::T) + (long long)(t0 + pos) * SMel::F + m] =
+            ring.ring[s * SMel::STREAM_FLOATS + m * SMel::ROW + head + t0 + pos];
+    }
+}
+
 }  // namespace nww
