@@ -1091,12 +1091,26 @@ int nww_stream_close(nww_engine* e) {
 
 static int stream_push_locked(nww_engine* e, const int16_t* chunks_dev, int chunk_len, float* scores_dev, cudaStream_t st) {
     const StreamState& S = e->streams;
-    stream_append_kernel<<<(unsigned)S.n_streams, 256, 0, st>>>(S, chunks_dev, chunk_len);
-    e->launches++;
-    NWW_CUDA(cudaGetLastError());
     const int n_new = chunk_len / SMel::HOP;
     if (e->mel_inc && (chunk_len % SMel::HOP != 0 || n_new > SMel::MAX_NEW)) e->mel_inc = false;   // until the next full reset
     int rc;
+    if (e->mel_inc && !(e->spec.reserved[0] & 32) && (reinterpret_cast<uintptr_t>(chunks_dev) & 15) == 0) {
+        // fused ingest: ring append + the frames the chunk completes, one warp per stream (reserved[0] bit 5: the two-kernel form)
+        NWW_CUDA(set_smem(stream_push_mel_kernel, SPush::kTotal));
+        const int64_t groups = (S.n_streams + SPush::NW - 1) / SPush::NW;
+        stream_push_mel_kernel<<<grid_for(e, groups), SPush::NT, SPush::kTotal, st>>>(S, chunks_dev, chunk_len, e->d_mel_ring, e->tab64);
+        e->launches++;
+        NWW_CUDA(cudaGetLastError());
+        rc = run_device(e, S.ring, S.n_streams, scores_dev, nullptr, nullptr, nullptr, st, S.win_off, true);
+        if (rc) return rc;
+        stream_mask_kernel<<<(unsigned)((S.n_streams + 255) / 256), 256, 0, st>>>(S, scores_dev);
+        e->launches++;
+        NWW_CUDA(cudaGetLastError());
+        return NWW_OK;
+    }
+    stream_append_kernel<<<(unsigned)S.n_streams, 256, 0, st>>>(S, chunks_dev, chunk_len);
+    e->launches++;
+    NWW_CUDA(cudaGetLastError());
     if (e->mel_inc) {
         NWW_CUDA(set_smem(stream_mel_update_kernel, SMel::kTotal));
         const int64_t groups = (S.n_streams + SMel::SPB - 1) / SMel::SPB;

@@ -598,7 +598,9 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
         if (hw.tcn_rows) {
             // stream mode: the cone's frames out of the mel ring, time-major, into the same place the front end writes them
             if (ring.ring != nullptr) {
-                stream_mel_tail_kernel<<<ew_grid(n * P.n_in * F, sm_count), 256, 0, st>>>(ring, n, mel, T - P.n_in, P.n_in);
+                if (P.n_in > kMelTailMax) { *err = "tcn: dependency cone longer than 32 frames is not built for stream mode"; return NWW_EUNSUPPORTED; }
+                stream_mel_tail_kernel<<<(int)std::min<long long>((n + kMelTailWarps - 1) / kMelTailWarps, (long long)sm_count * 8),
+                                         kMelTailWarps * 32, 0, st>>>(ring, n, mel, T - P.n_in, P.n_in);
                 if ((rc = done())) return rc;
             }
             float* act = take((size_t)P.per_window);

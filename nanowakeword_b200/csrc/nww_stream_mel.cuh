@@ -15,7 +15,7 @@
 // full-window path otherwise.
 #pragma once
 
-#include "nww_fe2.cuh"
+#include "nww_fe3.cuh"
 #include "nww_stream.cuh"
 
 namespace nww {
@@ -99,18 +99,100 @@ stream_mel_gather_kernel(StreamState st, const float* __restrict__ mel_ring, flo
 }
 
 // The last n_tail frames of every stream's current window out of the mel ring, TIME-major, at the place a time-major
-// (n, T, F) log-mel buffer holds them: out[s][(t0 + pos) * F + m].  Feeds the TCN's row-GEMM layers in stream mode.
-__global__ void __launch_bounds__(256)
+// (n, T, F) log-mel buffer holds them: out[s][(t0 + pos) * F + m] — one contiguous run of n_tail * F floats per stream.
+// One warp per stream: reads run along time inside the ring's mel rows, a padded shared tile transposes, writes are
+// coalesced.  Feeds the TCN's row-GEMM layers in stream mode.
+constexpr int kMelTailWarps = 8, kMelTailMax = 32;       // n_tail <= 32
+__global__ void __launch_bounds__(kMelTailWarps * 32)
 stream_mel_tail_kernel(MelRingRef ring, long long n, float* __restrict__ out, int t0, int n_tail) {
-    const long long total = n * (long long)(n_tail * SMel::F);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long w = i / (n_tail * SMel::F);
-        const int r = (int)(i - w * (n_tail * SMel::F));
-        const int m = r / n_tail, pos = r - m * n_tail;            // reads run along time inside a mel row of the ring
+    __shared__ float tile[kMelTailWarps][kMelTailMax][SMel::F + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (long long w = (long long)blockIdx.x * kMelTailWarps + warp; w < n; w += (long long)gridDim.x * kMelTailWarps) {
         const long long s = ring.s0 + w;
         const int head = smel_slot(ring.count[s] / SMel::HOP - 3 + 1);
-        out[w * (long long)(SMel::F * SMel::T) + (long long)(t0 + pos) * SMel::F + m] =
-            ring.ring[s * SMel::STREAM_FLOATS + m * SMel::ROW + head + t0 + pos];
+        const float* src = ring.ring + s * SMel::STREAM_FLOATS + head + t0;
+        if (lane < n_tail)
+            for (int m = 0; m < SMel::F; ++m) tile[warp][lane][m] = src[m * SMel::ROW + lane];
+        __syncwarp();
+        float* dst = out + w * (long long)(SMel::F * SMel::T) + (long long)t0 * SMel::F;
+        for (int i = lane; i < n_tail * SMel::F; i += 32) dst[i] = tile[warp][i / SMel::F][i % SMel::F];
+        __syncwarp();
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// K9 ingest step, fused: append the chunk to the PCM ring AND compute the log-mel frames it completes, one launch.
+// One WARP per stream (persistent CTAs of 14 warps): the warp stages [320 samples before the chunk | the chunk] in its
+// shared slot — the 320 older samples are one contiguous run of the mirrored ring, the chunk comes straight from the
+// caller's buffer and is written to both copies of the ring on the way —, then runs ceil(n_new / 2) warp-private packed
+// FFTs (fe3_warp_fft: the arithmetic of the batch front end, so the ring stays bit-identical to recomputing windows) and
+// writes the dB frames to both copies of the mel ring.  Replaces stream_append_kernel + stream_mel_update_kernel when
+// every chunk is a multiple of the hop (<= 16 frames).
+// ----------------------------------------------------------------------------------------
+struct SPush {
+    static constexpr int NW = 14, NT = NW * 32;
+    static constexpr int OLD = 2 * SMel::HOP;                                   // samples before the chunk that the new frames reach back to
+    static constexpr int PCM_SLOT = OLD + SMel::HOP * SMel::MAX_NEW + SMel::HOP;   // + one hop: the dummy second frame of an odd count
+    static constexpr size_t kWork = (size_t)NW * Fe3::NPAD * sizeof(cplx<double>);
+    static constexpr size_t kPcm = ((size_t)NW * PCM_SLOT * sizeof(int16_t) + 127) / 128 * 128;
+    static constexpr size_t kTotal = kWork + Fe3::kTwBytes + Fe3::kWinBytes + kPcm;
+};
+
+__global__ void __launch_bounds__(SPush::NT, 1)
+stream_push_mel_kernel(StreamState st, const int16_t* __restrict__ chunks, int chunk_len, float* __restrict__ mel_ring,
+                       FrontendTables<double> tab) {
+    NWW_DYN_SMEM(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    cplx<double>* wb = reinterpret_cast<cplx<double>*>(smem) + (size_t)warp * Fe3::NPAD;
+    cplx<double>* tw = reinterpret_cast<cplx<double>*>(smem + SPush::kWork);
+    double* win_s = reinterpret_cast<double*>(smem + SPush::kWork + Fe3::kTwBytes);
+    int16_t* slot = reinterpret_cast<int16_t*>(smem + SPush::kWork + Fe3::kTwBytes + Fe3::kWinBytes) + (size_t)warp * SPush::PCM_SLOT;
+    fe2_build_tables(tw, tab, tid, SPush::NT);
+    fe3_build_window(win_s, tab.window, tid, SPush::NT);
+    for (int i = lane; i < SPush::PCM_SLOT; i += 32) slot[i] = 0;              // whatever the dummy frame reads is finite
+    __syncthreads();
+    const int R = st.R, n_new = chunk_len / SMel::HOP;
+    for (long long s = (long long)blockIdx.x * SPush::NW + warp; s < st.n_streams; s += (long long)gridDim.x * SPush::NW) {
+        int16_t* ring = st.ring + s * st.pitch();
+        const int wp = st.wpos[s];                                              // a multiple of the hop: 16-byte aligned
+        const long long cnt = st.count[s] + chunk_len;
+        // the 320 samples before the write position: contiguous in the mirrored ring
+        const int16_t* old = ring + (wp >= SPush::OLD ? wp - SPush::OLD : wp - SPush::OLD + R);
+        for (int i = lane * 8; i < SPush::OLD; i += 32 * 8)
+            *reinterpret_cast<uint4*>(slot + i) = *reinterpret_cast<const uint4*>(old + i);
+        const int16_t* src = chunks + s * (long long)chunk_len;
+        for (int i = lane * 8; i < chunk_len; i += 32 * 8) {
+            const uint4 v = *reinterpret_cast<const uint4*>(src + i);
+            *reinterpret_cast<uint4*>(slot + SPush::OLD + i) = v;
+            int p = wp + i;
+            if (p >= R) p -= R;
+            *reinterpret_cast<uint4*>(ring + p) = v;
+            *reinterpret_cast<uint4*>(ring + p + R) = v;
+        }
+        __syncwarp();
+        const long long a0 = cnt / SMel::HOP - 3 - (n_new - 1);                 // absolute number of the first new frame
+        float* mrow = mel_ring + s * SMel::STREAM_FLOATS;
+#pragma unroll 1
+        for (int f = 0; 2 * f < n_new; ++f) {
+            const int sa = smel_slot(a0 + 2 * f), sb = smel_slot(a0 + 2 * f + 1);
+            const bool has_b = 2 * f + 1 < n_new;
+            fe3_warp_fft(slot + 2 * f * SMel::HOP, wb, win_s, tw, tab,
+                         [&](int fr, int m, float db) {
+                             if (fr && !has_b) return;
+                             float* row = mrow + m * SMel::ROW + (fr ? sb : sa);
+                             row[0] = db;
+                             row[SMel::T] = db;
+                         },
+                         lane);
+        }
+        if (lane == 0) {
+            int nw = wp + chunk_len;
+            if (nw >= R) nw -= R;
+            st.wpos[s] = nw;
+            st.count[s] = cnt;
+            st.win_off[s] = s * st.pitch() + nw;
+        }
+        __syncwarp();
     }
 }
 

@@ -32,7 +32,7 @@ class Engine:
 
     def __init__(self, state_dict: dict, cfg: dict, device: int = 0, frontend_precision: str = "fp64",
                  chunk_windows: int = 0, tensor_cores: bool = True, cnn_stage: str = "v2",
-                 stream_incremental: bool = True, tcn_layers: str = "rows"):
+                 stream_incremental: bool = True, tcn_layers: str = "rows", stream_ingest: str = "fused"):
         self._lib = _lib.load_library()
         self.cfg = dict(cfg)
         self.geometry = geometry_for(cfg)
@@ -65,7 +65,8 @@ class Engine:
             raise ValueError("tcn_layers must be 'rows' or 'cone'")
         # bit 3: the phase-serial tcgen05 CNN stage (nww_cnn2.cuh) instead of the warp-specialised pipeline (nww_cnn3.cuh)
         spec.reserved[0] = ((0 if tensor_cores else 1) | (2 if cnn_stage == "v1" else 0) | (0 if stream_incremental else 4)
-                            | (0 if pipelined else 8) | (0 if tcn_layers == "rows" else 16))
+                            | (0 if pipelined else 8) | (0 if tcn_layers == "rows" else 16)
+                            | (0 if stream_ingest == "fused" else 32))       # bit 5: ring append and mel update as two kernels
         self.cnn_stage = "v3" if (pipelined and cnn_stage == "v2") else cnn_stage
         self._blob = (C.c_char * len(blob)).from_buffer_copy(blob)
         handle = C.c_void_p()
