@@ -30,6 +30,10 @@
 
 #include "nww_cnn2.cuh"
 
+#ifndef NWW_EXP
+#define NWW_EXP 0        // developer experiments: 1 = conv warps skip conv1 + MMAs, 2 = skip the MMAs only
+#endif
+
 namespace nww {
 
 struct Cnn3 {
@@ -43,6 +47,7 @@ struct Cnn3 {
     static constexpr int MEL_P = 104, MEL_ROWS = 42;           // 2 * MEL_P = 16 (mod 32): pooled rows y, y + 1 hit different banks
     static constexpr int CONV_ROUNDS = (D::CONV1_TASKS + CONV_NT - 1) / CONV_NT;   // 8
     static constexpr int BAR_CONV = 1;                         // named barrier of the 256 conv threads
+    static constexpr int BAR_FE = 2;                           // named barrier of the 224 front-end threads
 
     static constexpr size_t oWork = 0;
     static constexpr size_t kWork = (size_t)N_FE_WARPS * Fe3::NPAD * sizeof(cplx<double>);            // 58240
@@ -70,6 +75,22 @@ __host__ __device__ constexpr int cnn3_task_end(int r) {     // tasks in slots <
 #ifndef NWW_CPUSIM
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Wait that yields the issue slots: the consumer warps of the pipeline spend most of a window waiting for the front end,
+// and a tight try_wait loop on 8 warps takes issue cycles from the 7 warps that are the critical path.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return;
+        __nanosleep(ns);
+    }
 }
 #endif
 
@@ -159,6 +180,9 @@ cnn3_stage_kernel(WindowSource src, Cnn2MelSource msrc, long long n_windows, Fro
                 if (r == 0) mbar_wait(&full_pcm[0], par);
                 if (r < 6) mbar_wait(&full_pcm[r + 1], par);                    // the round's last FFTs reach 240 samples into it
                 if (it > 0) mbar_wait(&done[r < 6 ? r + 1 : 6], par ^ 1u);      // conv1 of the previous window is past this slot
+                // the seven warps start every round together: their instruction streams (64 KB of straight-line FFT code)
+                // then stay within a few cache lines of each other instead of spreading over the whole instruction cache
+                named_bar_sync(P::BAR_FE, P::N_FE_WARPS * 32);
                 float* mf = melp + P::MEL_P + 1 + 2 * f;
                 fe3_warp_fft(x + 2 * f * D::G::HOP, wb, win_s, tw, tab,
                              [&](int fr, int m, float db) {
@@ -192,7 +216,7 @@ cnn3_stage_kernel(WindowSource src, Cnn2MelSource msrc, long long n_windows, Fro
                 const long long wn = w + gridDim.x;
                 if (wn >= n_windows) break;
                 for (int s = 0; s < P::N_SLOTS; ++s) {
-                    mbar_wait(&consumed[s], (uint32_t)(it & 1));
+                    mbar_wait_backoff(&consumed[s], (uint32_t)(it & 1), 500);
                     issue_segment(wn, s);
                 }
             }
@@ -204,9 +228,11 @@ cnn3_stage_kernel(WindowSource src, Cnn2MelSource msrc, long long n_windows, Fro
         constexpr uint32_t kIdesc = umma_idesc_bf16(128, 32);
         const uint64_t da_base = umma_desc_noswz(a1_addr, D::KG_BYTES, 128);
         const uint64_t db_base = umma_desc_noswz(w2_addr, 512, 128);
+        // (the tile / quad loops stay rolled: the pipeline's three roles share one instruction cache, and 216 unrolled
+        //  MMAs with their descriptor arithmetic are 17 KB of code that one thread walks once per window)
         auto issue_tile = [&](int tile) {                                       // see nww_cnn2.cuh
             const uint64_t da_t = da_base + (uint64_t)(tile * 128);
-#pragma unroll
+#pragma unroll 1
             for (int quad = 0; quad < 4; ++quad) {
                 const int dy = quad >> 1, dx = quad & 1;
                 const uint32_t d_tmem = tmem_base + (uint32_t)((tile * 4 + quad) * 32);
@@ -216,8 +242,8 @@ cnn3_stage_kernel(WindowSource src, Cnn2MelSource msrc, long long n_windows, Fro
                     for (int c = 0; c < 3; ++c) {
                         const int ry = dy + r - 1, cx = dx + c - 1;
                         const int plane = ((ry & 1) << 1) | (cx & 1);
-                        const int s0 = 26 + 25 * (ry >> 1) + (cx >> 1);
-                        const uint64_t da_hi = da_t + (uint64_t)((plane * 2 * D::PLANE_BYTES) / 16 + s0);
+                        const int s0 = 26 + 25 * (ry >> 1) + (cx >> 1);       // >> is arithmetic: ry, cx = -1 .. 2
+                        const uint64_t da_hi = da_t + (uint64_t)(long long)((plane * 2 * D::PLANE_BYTES) / 16 + s0);
                         const uint64_t da_lo = da_hi + (uint64_t)(D::PLANE_BYTES / 16);
                         const uint64_t db_hi = db_base + (uint64_t)(((r * 3 + c) * 2 * D::W2_TAP_BYTES) / 16);
                         const uint64_t db_lo = db_hi + (uint64_t)(D::W2_TAP_BYTES / 16);
@@ -281,45 +307,40 @@ cnn3_stage_kernel(WindowSource src, Cnn2MelSource msrc, long long n_windows, Fro
                                                                          cnn2_pack_bf16(lb[4], lb[5]), cnn2_pack_bf16(lb[6], lb[7]));
         };
 
-        // this thread's eight conv1 tasks (the same for every window): task T = ctid + 256 i in slot order;
-        // inside slot r: (row y, column, channel group) with the column fastest, so a warp reads runs of mel columns.
-        // packed: slot << 12 | y << 7 | x << 1 | cg; -1 = no task.  wait_slot[i] / next_slot[i] are warp-uniform.
-        int task[P::CONV_ROUNDS];
-        int wait_slot = 0, next_slot = 0;                                       // 8 x 3-bit fields each
+        // conv1 tasks in slot order: task T = ctid + 256 i; inside slot r: (row y, column, channel group) with the column
+        // fastest, so a warp reads runs of mel columns.  Decoded on the fly in a ROLLED loop (one copy of the 450-instruction
+        // task body: see the instruction-cache note above).
         auto slot_of = [](int T) {
             int r = 0;
-            while (r < 6 && T >= cnn3_task_end(r)) ++r;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) r += T >= cnn3_task_end(q) ? 1 : 0;
             return r;
         };
-#pragma unroll
-        for (int i = 0; i < P::CONV_ROUNDS; ++i) {
-            const int T = ctid + P::CONV_NT * i;
-            if (T < D::CONV1_TASKS) {
-                const int r = slot_of(T);
-                const int local = T - (r ? cnn3_task_end(r - 1) : 0);
-                const int nc2 = 2 * cnn3_ncols(r);
-                const int y = local / nc2, rem = local - y * nc2;
-                task[i] = (r << 12) | (y << 7) | ((cnn3_x0(r) + (rem >> 1)) << 1) | (rem & 1);
-            } else {
-                task[i] = -1;
-            }
-            const int t_hi = min(cw * 32 + 31 + P::CONV_NT * i, D::CONV1_TASKS - 1);    // the warp's last task of round i
-            const int t_nx = cw * 32 + P::CONV_NT * (i + 1);                            // its first task of round i + 1
-            wait_slot |= slot_of(t_hi) << (3 * i);
-            next_slot |= ((i + 1 < P::CONV_ROUNDS && t_nx < D::CONV1_TASKS) ? slot_of(t_nx) : 7) << (3 * i);
-        }
 
         int it = 0;
         for (long long w = blockIdx.x; w < n_windows; w += gridDim.x, ++it) {
             const uint32_t par = (uint32_t)(it & 1);
             int arrived = 0;                                                    // done[r] signalled for r < arrived
-#pragma unroll
+#pragma unroll 1
             for (int i = 0; i < P::CONV_ROUNDS; ++i) {
+                const int T = ctid + P::CONV_NT * i;
                 if (cw * 32 + P::CONV_NT * i < D::CONV1_TASKS) {
-                    mbar_wait(&full_mel[(wait_slot >> (3 * i)) & 7], par);
-                    if (task[i] >= 0) conv1_task((task[i] >> 7) & 31, (task[i] >> 1) & 63, task[i] & 1);
+                    // the warp waits for the slot of its LAST task of the round (slots complete in order)
+                    mbar_wait_backoff(&full_mel[slot_of(min(cw * 32 + 31 + P::CONV_NT * i, D::CONV1_TASKS - 1))], par, 200);
+                    if (T < D::CONV1_TASKS) {
+                        const int r = slot_of(T);
+                        const int local = T - (r ? 40 * cnn3_x0(r) : 0);          // tasks before slot r = 40 per column
+                        const int nc2 = r == 0 ? 12 : (r == 6 ? 16 : 14);
+                        const int y = r == 0 ? local / 12 : (r == 6 ? local >> 4 : local / 14);
+                        const int rem = local - y * nc2;
+#if NWW_EXP != 1
+                        conv1_task(y, cnn3_x0(r) + (rem >> 1), rem & 1);
+#endif
+                    }
                 }
-                const int upto = (next_slot >> (3 * i)) & 7;                    // slots below this are finished by this warp
+                // slots below the one of the warp's first task of the next round are finished by this warp
+                const int t_nx = cw * 32 + P::CONV_NT * (i + 1);
+                const int upto = (i + 1 < P::CONV_ROUNDS && t_nx < D::CONV1_TASKS) ? slot_of(t_nx) : 7;
                 __syncwarp();
                 if (lane == 0)
                     for (; arrived < upto; ++arrived) mbar_arrive(&done[arrived]);
@@ -328,15 +349,19 @@ cnn3_stage_kernel(WindowSource src, Cnn2MelSource msrc, long long n_windows, Fro
             // ---- conv2: all planes written -> 2 x 108 MMAs by one thread --------------------------------------
             fence_proxy_async();
             named_bar_sync(P::BAR_CONV, P::CONV_NT);
+#if NWW_EXP == 1 || NWW_EXP == 2
+            if (ctid == 0) { umma_commit(&mma_bar[0]); umma_commit(&mma_bar[1]); }
+#else
             if (ctid == 0) {
                 tc_fence_after();
-                issue_tile(0);
-                issue_tile(1);
+#pragma unroll 1
+                for (int tile = 0; tile < 2; ++tile) issue_tile(tile);
             }
+#endif
             // ---- epilogue: warp -> (TMEM lane quarter, M tile), both channel halves ------------------------------
             {
                 const int q = cw & 3, tile = cw >> 2;
-                mbar_wait(&mma_bar[tile], par);
+                mbar_wait_backoff(&mma_bar[tile], par, 100);
                 tc_fence_after();
                 const int m = tile * 128 + q * 32 + lane;
                 const int ph = m / D::PITCH, pw = m - ph * D::PITCH;
