@@ -127,10 +127,19 @@ int nww_run_windows_host(nww_engine* e, const int16_t* pcm_host, int64_t n_windo
  *                    fewer than clip_samples since it was opened / reset.  Ordered on `stream`.
  * nww_stream_push_host  same with host buffers (H2D of the chunks, D2H of the scores; synchronous).
  * nww_stream_reset   ids_host == NULL resets every stream, else the n_ids listed streams.
+ * nww_stream_push_select[_host]  like nww_stream_push[_host], but only the n_ids streams listed in ids (distinct
+ *                    indices, any order) are SCORED: every stream still receives its chunk (PCM ring and log-mel ring
+ *                    advance), the streams not listed report 0.  This is the cascade's verifier stage
+ *                    (nanointerpreter.py:758-769: the verifier is skipped, score 0.0, when the gate score is below
+ *                    gate_threshold) for many streams: a gated-off stream costs the ingest step only.
  */
 int nww_stream_open(nww_engine* e, int64_t n_streams);
 int nww_stream_push(nww_engine* e, const int16_t* chunks_dev, int32_t chunk_len, float* scores_dev, void* stream);
 int nww_stream_push_host(nww_engine* e, const int16_t* chunks_host, int32_t chunk_len, float* scores_host);
+int nww_stream_push_select(nww_engine* e, const int16_t* chunks_dev, int32_t chunk_len, const int64_t* ids_dev, int64_t n_ids,
+                           float* scores_dev, void* stream);
+int nww_stream_push_select_host(nww_engine* e, const int16_t* chunks_host, int32_t chunk_len, const int64_t* ids_host, int64_t n_ids,
+                                float* scores_host);
 int nww_stream_reset(nww_engine* e, const int64_t* ids_host, int64_t n_ids);
 int nww_stream_close(nww_engine* e);
 

@@ -59,6 +59,8 @@ SIGNATURES = {
     "nww_stream_open": (C.c_int, [_P, C.c_int64]),
     "nww_stream_push": (C.c_int, [_P, _P, C.c_int32, _P, _P]),
     "nww_stream_push_host": (C.c_int, [_P, _P, C.c_int32, _P]),
+    "nww_stream_push_select": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int64, _P, _P]),
+    "nww_stream_push_select_host": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int64, _P]),
     "nww_stream_reset": (C.c_int, [_P, _P, C.c_int64]),
     "nww_stream_close": (C.c_int, [_P]),
     "nww_set_profiling": (C.c_int, [_P, C.c_int]),

@@ -219,7 +219,7 @@ cnn2_stage_kernel(WindowSource src, Cnn2MelSource msrc, long long n_windows, Fro
         if (from_mel) {
             // ---- stream mode: the window's 98 frames are contiguous per mel row in the mirrored ring ---------
             // (count == nullptr: a plain (n, F, T) log-mel buffer — float feeds, nww_run_windows_f32)
-            const long long s = msrc.s0 + w;
+            const long long s = msrc.count ? msrc.stream(w) : msrc.s0 + w;
             const bool plain = msrc.count == nullptr;
             const int row = plain ? D::TT : SMel::ROW;
             const float* ring = plain ? msrc.ring + s * (long long)(D::F * D::TT)

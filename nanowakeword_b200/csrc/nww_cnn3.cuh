@@ -155,7 +155,7 @@ cnn3_stage_kernel(WindowSource src, Cnn2MelSource msrc, long long n_windows, Fro
         for (long long w = blockIdx.x; w < n_windows; w += gridDim.x, ++it) {
             const uint32_t par = (uint32_t)(it & 1);
             if (from_mel) {
-                const long long s = msrc.s0 + w;
+                const long long s = msrc.count ? msrc.stream(w) : msrc.s0 + w;
                 const bool plain = msrc.count == nullptr;
                 const int row = plain ? D::TT : SMel::ROW;
                 const float* ring = plain ? msrc.ring + s * (long long)(D::F * D::TT)

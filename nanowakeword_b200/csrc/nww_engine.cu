@@ -113,6 +113,12 @@ struct nww_engine {
     bool last_valid = false;
     cudaStream_t last_stream = nullptr;
     float* d_melf = nullptr;             // [chunk][F][T] log-mel of float feeds for the stage kernels that start from mel
+    // selective push (nww_stream_push_select): the streams to score, their window offsets and compact scores
+    const long long* sel_ids = nullptr;  // non-null only while a selective push is being enqueued
+    long long* d_sel_ids = nullptr;      // staging for the host variant
+    long long* d_sel_off = nullptr;
+    float* d_sel_scores = nullptr;
+    int64_t sel_cap = 0;
 
     // multi-stream mode (nww_stream_*): mirrored int16 rings in HBM
     StreamState streams{};
@@ -415,27 +421,23 @@ static int launch_cnn_stage(nww_engine* e, WindowSource pcm, Cnn2MelSource ms, i
 // stream_s0 >= 0: stream mode, the log-mel of window i is that of stream stream_s0 + i in the mel ring.
 static int launch_stage_a(nww_engine* e, WindowSource pcm, int64_t n, float* mel, cudaStream_t st, int64_t stream_s0 = -1) {
     const bool from_ring = stream_s0 >= 0;
-    StreamState sub = e->streams;                 // view of streams [stream_s0, stream_s0 + n) for the gather kernel
-    if (from_ring) {
-        sub.count += stream_s0;
-        sub.n_streams = n;
-    }
-    const float* ring0 = from_ring ? e->d_mel_ring + stream_s0 * (int64_t)SMel::STREAM_FLOATS : nullptr;
+    // window i of this launch group is stream stream_s0 + i of the bank, or, in a selective push, stream sel_ids[stream_s0 + i]
+    const MelRingRef ring_ref{from_ring ? e->d_mel_ring : nullptr, e->streams.count, from_ring ? stream_s0 : 0, e->sel_ids};
     // Float feed into a stage kernel that stages int16 PCM itself (cnn2_stage_kernel): log-mel by the float front end
     // into d_melf first, then the kernel starts from that plain (n, F, T) buffer (count == nullptr marks the layout).
-    Cnn2MelSource cnn2_src{from_ring ? e->d_mel_ring : nullptr, e->streams.count, from_ring ? stream_s0 : 0};
+    Cnn2MelSource cnn2_src = ring_ref;
     if (pcm.fbase != nullptr && (e->cnn2_enabled || e->crnn_cnn2)) {
         if (!e->d_melf) NWW_CUDA(cudaMalloc(&e->d_melf, (size_t)e->chunk * e->n_mels * e->n_frames * sizeof(float)));
         int rc = launch_frontend<GeoNS40x98>(e, pcm, n, e->d_melf, 0, st);
         if (rc) return rc;
         if (mel) NWW_CUDA(cudaMemcpyAsync(mel, e->d_melf, (size_t)n * e->n_mels * e->n_frames * sizeof(float), cudaMemcpyDeviceToDevice, st));
         mel = nullptr;
-        cnn2_src = Cnn2MelSource{e->d_melf, nullptr, 0};
+        cnn2_src = Cnn2MelSource{e->d_melf, nullptr, 0, nullptr};
     }
     switch (e->spec.arch) {
         case NWW_ARCH_DNN: {
             if (from_ring) {
-                stream_mel_gather_kernel<<<ew_grid(n * 3920, e->sm_count), 256, 0, st>>>(sub, ring0, e->d_feat, 1);
+                stream_mel_gather_kernel<<<ew_grid(n * 3920, e->sm_count), 256, 0, st>>>(ring_ref, n, e->d_feat, 1);
                 e->launches++;
                 NWW_CUDA(cudaGetLastError());
                 return NWW_OK;
@@ -473,11 +475,11 @@ static int launch_stage_a(nww_engine* e, WindowSource pcm, int64_t n, float* mel
             if (from_ring && e->spec.arch == NWW_ARCH_TCN && e->heads.tcn_cone)     // the cone kernel reads the ring itself
                 return launch_head_stage_a(e->heads, e->tab64, e->spec.activation, e->sm_count, pcm, n, e->d_feat, e->d_scratch,
                                            mel, st, &e->launches, &g_last_error, true, nullptr,
-                                           MelRingRef{e->d_mel_ring, e->streams.count, stream_s0});
+                                           ring_ref);
             if (from_ring) {
                 const int tm = e->spec.arch == NWW_ARCH_GRU || e->spec.arch == NWW_ARCH_LSTM ||
                                e->spec.arch == NWW_ARCH_QUARTZNET;                               // sequence heads read (T, F)
-                stream_mel_gather_kernel<<<ew_grid(n * 3920, e->sm_count), 256, 0, st>>>(sub, ring0, e->d_scratch, tm);
+                stream_mel_gather_kernel<<<ew_grid(n * 3920, e->sm_count), 256, 0, st>>>(ring_ref, n, e->d_scratch, tm);
                 e->launches++;
                 NWW_CUDA(cudaGetLastError());
             }
@@ -913,6 +915,9 @@ void nww_destroy(nww_engine* e) {
 nww_engine::~nww_engine() {
     nww_engine* e = this;
     cudaFree(e->d_melf);
+    cudaFree(e->d_sel_ids);
+    cudaFree(e->d_sel_off);
+    cudaFree(e->d_sel_scores);
     if (e->ev_last) cudaEventDestroy(e->ev_last);
     cudaFree(e->d_blob);
     cudaFree(e->arena.dev);
@@ -1089,11 +1094,50 @@ int nww_stream_close(nww_engine* e) {
     return NWW_OK;
 }
 
-static int stream_push_locked(nww_engine* e, const int16_t* chunks_dev, int chunk_len, float* scores_dev, cudaStream_t st) {
+// Score the streams of the bank after an ingest step: all of them, or (ids_dev != nullptr) only the n_ids listed ones —
+// the others report 0 and cost nothing beyond the ingest.
+static int stream_score_locked(nww_engine* e, float* scores_dev, cudaStream_t st, bool from_mel, const long long* ids_dev, int64_t n_ids) {
+    const StreamState& S = e->streams;
+    int rc;
+    if (ids_dev == nullptr) {
+        rc = run_device(e, S.ring, S.n_streams, scores_dev, nullptr, nullptr, nullptr, st, S.win_off, from_mel);
+        if (rc) return rc;
+        stream_mask_kernel<<<(unsigned)((S.n_streams + 255) / 256), 256, 0, st>>>(S, scores_dev);
+        e->launches++;
+        NWW_CUDA(cudaGetLastError());
+        return NWW_OK;
+    }
+    NWW_CUDA(cudaMemsetAsync(scores_dev, 0, (size_t)S.n_streams * sizeof(float), st));
+    if (n_ids == 0) return NWW_OK;
+    if (e->sel_cap < n_ids) {
+        cudaFree(e->d_sel_off);
+        cudaFree(e->d_sel_scores);
+        e->d_sel_off = nullptr;
+        e->d_sel_scores = nullptr;
+        e->sel_cap = 0;
+        NWW_CUDA(cudaMalloc(&e->d_sel_off, (size_t)S.n_streams * sizeof(long long)));
+        NWW_CUDA(cudaMalloc(&e->d_sel_scores, (size_t)S.n_streams * sizeof(float)));
+        e->sel_cap = S.n_streams;
+    }
+    const unsigned g = (unsigned)((n_ids + 255) / 256);
+    stream_select_offsets_kernel<<<g, 256, 0, st>>>(S, ids_dev, n_ids, e->d_sel_off);
+    e->launches++;
+    NWW_CUDA(cudaGetLastError());
+    e->sel_ids = ids_dev;
+    rc = run_device(e, S.ring, n_ids, e->d_sel_scores, nullptr, nullptr, nullptr, st, e->d_sel_off, from_mel);
+    e->sel_ids = nullptr;
+    if (rc) return rc;
+    stream_select_scatter_kernel<<<g, 256, 0, st>>>(S, ids_dev, n_ids, e->d_sel_scores, scores_dev);
+    e->launches++;
+    NWW_CUDA(cudaGetLastError());
+    return NWW_OK;
+}
+
+static int stream_push_locked(nww_engine* e, const int16_t* chunks_dev, int chunk_len, float* scores_dev, cudaStream_t st,
+                              const long long* ids_dev = nullptr, int64_t n_ids = 0) {
     const StreamState& S = e->streams;
     const int n_new = chunk_len / SMel::HOP;
     if (e->mel_inc && (chunk_len % SMel::HOP != 0 || n_new > SMel::MAX_NEW)) e->mel_inc = false;   // until the next full reset
-    int rc;
     if (e->mel_inc && !(e->spec.reserved[0] & 32) && (reinterpret_cast<uintptr_t>(chunks_dev) & 15) == 0) {
         // fused ingest: ring append + the frames the chunk completes, one warp per stream (reserved[0] bit 5: the two-kernel form)
         NWW_CUDA(set_smem(stream_push_mel_kernel, SPush::kTotal));
@@ -1101,12 +1145,7 @@ static int stream_push_locked(nww_engine* e, const int16_t* chunks_dev, int chun
         stream_push_mel_kernel<<<grid_for(e, groups), SPush::NT, SPush::kTotal, st>>>(S, chunks_dev, chunk_len, e->d_mel_ring, e->tab64);
         e->launches++;
         NWW_CUDA(cudaGetLastError());
-        rc = run_device(e, S.ring, S.n_streams, scores_dev, nullptr, nullptr, nullptr, st, S.win_off, true);
-        if (rc) return rc;
-        stream_mask_kernel<<<(unsigned)((S.n_streams + 255) / 256), 256, 0, st>>>(S, scores_dev);
-        e->launches++;
-        NWW_CUDA(cudaGetLastError());
-        return NWW_OK;
+        return stream_score_locked(e, scores_dev, st, true, ids_dev, n_ids);
     }
     stream_append_kernel<<<(unsigned)S.n_streams, 256, 0, st>>>(S, chunks_dev, chunk_len);
     e->launches++;
@@ -1117,15 +1156,9 @@ static int stream_push_locked(nww_engine* e, const int16_t* chunks_dev, int chun
         stream_mel_update_kernel<<<grid_for(e, groups), Fe2::NT, SMel::kTotal, st>>>(S, e->d_mel_ring, e->tab64, n_new);
         e->launches++;
         NWW_CUDA(cudaGetLastError());
-        rc = run_device(e, S.ring, S.n_streams, scores_dev, nullptr, nullptr, nullptr, st, S.win_off, true);
-    } else {
-        rc = run_device(e, S.ring, S.n_streams, scores_dev, nullptr, nullptr, nullptr, st, S.win_off);
+        return stream_score_locked(e, scores_dev, st, true, ids_dev, n_ids);
     }
-    if (rc) return rc;
-    stream_mask_kernel<<<(unsigned)((S.n_streams + 255) / 256), 256, 0, st>>>(S, scores_dev);
-    e->launches++;
-    NWW_CUDA(cudaGetLastError());
-    return NWW_OK;
+    return stream_score_locked(e, scores_dev, st, false, ids_dev, n_ids);
 }
 
 int nww_stream_push(nww_engine* e, const int16_t* chunks_dev, int32_t chunk_len, float* scores_dev, void* stream) {
@@ -1164,6 +1197,60 @@ int nww_stream_push_host(nww_engine* e, const int16_t* chunks_host, int32_t chun
     NWW_CUDA(order_enter(e, e->stream));
     NWW_CUDA(cudaMemcpyAsync(e->d_chunk, chunks_host, bytes, cudaMemcpyHostToDevice, e->stream));
     int rc = stream_push_locked(e, e->d_chunk, chunk_len, e->d_scores, e->stream);
+    if (rc) return rc;
+    NWW_CUDA(cudaMemcpyAsync(scores_host, e->d_scores, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    NWW_CUDA(order_leave(e, e->stream));
+    NWW_CUDA(cudaStreamSynchronize(e->stream));
+    return NWW_OK;
+}
+
+int nww_stream_push_select(nww_engine* e, const int16_t* chunks_dev, int32_t chunk_len, const int64_t* ids_dev, int64_t n_ids,
+                           float* scores_dev, void* stream) {
+    if (!e || !chunks_dev || !scores_dev || (n_ids > 0 && !ids_dev)) return fail(NWW_EINVAL, "nww_stream_push_select: null argument");
+    if (chunk_len <= 0 || n_ids < 0) return fail(NWW_EINVAL, "nww_stream_push_select: chunk_len must be positive, n_ids >= 0");
+    std::lock_guard<std::mutex> lock(e->mu);
+    if (!e->streams.ring) return fail(NWW_EINVAL, "nww_stream_push_select: no streams are open (call nww_stream_open)");
+    if (n_ids > e->streams.n_streams) return fail(NWW_EINVAL, "nww_stream_push_select: more ids than streams");
+    NWW_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static_assert(sizeof(long long) == sizeof(int64_t), "id width");
+    static const long long kNone = 0;
+    NWW_CUDA(order_enter(e, st));
+    int rc = stream_push_locked(e, chunks_dev, chunk_len, scores_dev, st, n_ids ? reinterpret_cast<const long long*>(ids_dev) : &kNone, n_ids);
+    NWW_CUDA(order_leave(e, st));
+    return rc;
+}
+
+int nww_stream_push_select_host(nww_engine* e, const int16_t* chunks_host, int32_t chunk_len, const int64_t* ids_host, int64_t n_ids,
+                                float* scores_host) {
+    if (!e || !chunks_host || !scores_host || (n_ids > 0 && !ids_host)) return fail(NWW_EINVAL, "nww_stream_push_select_host: null argument");
+    if (chunk_len <= 0 || n_ids < 0) return fail(NWW_EINVAL, "nww_stream_push_select_host: chunk_len must be positive, n_ids >= 0");
+    std::lock_guard<std::mutex> lock(e->mu);
+    if (!e->streams.ring) return fail(NWW_EINVAL, "nww_stream_push_select_host: no streams are open (call nww_stream_open)");
+    const int64_t n = e->streams.n_streams;
+    for (int64_t i = 0; i < n_ids; ++i)
+        if (ids_host[i] < 0 || ids_host[i] >= n) return fail(NWW_EINVAL, "nww_stream_push_select_host: stream id out of range");
+    if (n_ids > n) return fail(NWW_EINVAL, "nww_stream_push_select_host: more ids than streams");
+    NWW_CUDA(cudaSetDevice(e->device));
+    const size_t bytes = (size_t)n * chunk_len * sizeof(int16_t);
+    if (e->chunk_cap < bytes) {
+        cudaFree(e->d_chunk);
+        e->d_chunk = nullptr;
+        NWW_CUDA(cudaMalloc(&e->d_chunk, bytes));
+        e->chunk_cap = bytes;
+    }
+    if (e->scores_cap < n) {
+        cudaFree(e->d_scores);
+        e->d_scores = nullptr;
+        NWW_CUDA(cudaMalloc(&e->d_scores, (size_t)n * sizeof(float)));
+        e->scores_cap = n;
+    }
+    if (!e->d_sel_ids) NWW_CUDA(cudaMalloc(&e->d_sel_ids, (size_t)n * sizeof(long long)));
+    static const long long kNone = 0;
+    NWW_CUDA(order_enter(e, e->stream));
+    NWW_CUDA(cudaMemcpyAsync(e->d_chunk, chunks_host, bytes, cudaMemcpyHostToDevice, e->stream));
+    if (n_ids) NWW_CUDA(cudaMemcpyAsync(e->d_sel_ids, ids_host, (size_t)n_ids * sizeof(int64_t), cudaMemcpyHostToDevice, e->stream));
+    int rc = stream_push_locked(e, e->d_chunk, chunk_len, e->d_scores, e->stream, n_ids ? e->d_sel_ids : &kNone, n_ids);
     if (rc) return rc;
     NWW_CUDA(cudaMemcpyAsync(scores_host, e->d_scores, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     NWW_CUDA(order_leave(e, e->stream));

@@ -85,6 +85,22 @@ stream_reset_kernel(StreamState st, const long long* __restrict__ ids, long long
     }
 }
 
+// Selective scoring: window offsets of the listed streams, and their scores back to the per-stream array.
+__global__ void __launch_bounds__(256)
+stream_select_offsets_kernel(StreamState st, const long long* __restrict__ ids, long long n_ids, long long* __restrict__ off) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_ids) off[i] = st.win_off[ids[i]];
+}
+__global__ void __launch_bounds__(256)
+stream_select_scatter_kernel(StreamState st, const long long* __restrict__ ids, long long n_ids, const float* __restrict__ sel,
+                             float* __restrict__ scores) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_ids) {
+        const long long s = ids[i];
+        scores[s] = st.count[s] < st.R ? 0.0f : sel[i];          // nanointerpreter.py:755: no score before clip_samples arrived
+    }
+}
+
 // A stream that has not yet received clip_samples reports 0 (nanointerpreter.py:755, 785-786).
 __global__ void __launch_bounds__(256)
 stream_mask_kernel(StreamState st, float* __restrict__ scores) {

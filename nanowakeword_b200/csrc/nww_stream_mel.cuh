@@ -39,6 +39,10 @@ struct MelRingRef {
     const float* ring;
     const long long* count;     // per-stream sample counters (position of the window in the ring)
     long long s0;
+    // Selective scoring (nww_stream_push_select: the cascade's verifier scores only the streams its gate let through,
+    // nanointerpreter.py:758-769): window s0 + w of the launch is stream ids[s0 + w] instead of stream s0 + w.
+    const long long* ids = nullptr;
+    __device__ __forceinline__ long long stream(long long w) const { return ids ? ids[s0 + w] : s0 + w; }
 };
 
 __device__ __forceinline__ int smel_slot(long long a) {
@@ -86,15 +90,16 @@ stream_mel_update_kernel(StreamState st, float* __restrict__ mel_ring, FrontendT
 
 // Current window of every stream out of the mel ring: (n, F, T) or, time_major, (n, T, F).
 __global__ void __launch_bounds__(256)
-stream_mel_gather_kernel(StreamState st, const float* __restrict__ mel_ring, float* __restrict__ out, int time_major) {
-    const long long total = st.n_streams * (long long)(SMel::F * SMel::T);
+stream_mel_gather_kernel(MelRingRef ring, long long n, float* __restrict__ out, int time_major) {
+    const long long total = n * (long long)(SMel::F * SMel::T);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long s = i / (SMel::F * SMel::T);
-        const int r = (int)(i - s * (SMel::F * SMel::T));
+        const long long w = i / (SMel::F * SMel::T);
+        const int r = (int)(i - w * (SMel::F * SMel::T));
         const int m = r / SMel::T, t = r - m * SMel::T;             // reads are contiguous along t
-        const int head = smel_slot(st.count[s] / SMel::HOP - 3 + 1);
-        const float v = mel_ring[s * SMel::STREAM_FLOATS + m * SMel::ROW + head + t];
-        out[s * (long long)(SMel::F * SMel::T) + (time_major ? t * SMel::F + m : r)] = v;
+        const long long s = ring.stream(w);
+        const int head = smel_slot(ring.count[s] / SMel::HOP - 3 + 1);
+        const float v = ring.ring[s * SMel::STREAM_FLOATS + m * SMel::ROW + head + t];
+        out[w * (long long)(SMel::F * SMel::T) + (time_major ? t * SMel::F + m : r)] = v;
     }
 }
 
@@ -108,7 +113,7 @@ stream_mel_tail_kernel(MelRingRef ring, long long n, float* __restrict__ out, in
     __shared__ float tile[kMelTailWarps][kMelTailMax][SMel::F + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (long long w = (long long)blockIdx.x * kMelTailWarps + warp; w < n; w += (long long)gridDim.x * kMelTailWarps) {
-        const long long s = ring.s0 + w;
+        const long long s = ring.stream(w);
         const int head = smel_slot(ring.count[s] / SMel::HOP - 3 + 1);
         const float* src = ring.ring + s * SMel::STREAM_FLOATS + head + t0;
         if (lane < n_tail)

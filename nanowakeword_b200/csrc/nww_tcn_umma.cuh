@@ -157,7 +157,7 @@ tcn_cone_umma_kernel(const float* __restrict__ mel_tm, long long mel_win_stride,
             for (int i = tid; i < nw * n_in_f; i += kTuNT) {
                 const int w = i / n_in_f, r = i - w * n_in_f;
                 const int pos = r % P.n_in, m = r / P.n_in;
-                const long long s = ring.s0 + w0 + w;
+                const long long s = ring.stream(w0 + w);
                 const int head = smel_slot(ring.count[s] / SMel::HOP - 3 + 1);
                 act[(size_t)w * pw + P.off_in + pos * P.c_in + m] =
                     ring.ring[s * SMel::STREAM_FLOATS + m * SMel::ROW + head + (P.T - P.n_in) + pos];

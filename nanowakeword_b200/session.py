@@ -228,16 +228,43 @@ class Engine:
         _lib.check(self._lib, rc, "nww_stream_push")
         return scores
 
-    def stream_push_host(self, chunks: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+    def stream_push_host(self, chunks: np.ndarray, out: Optional[np.ndarray] = None, select=None) -> np.ndarray:
+        """``select``: None = score every stream; else the indices of the streams to score (the others still receive
+        their chunk and report 0) — the cascade's verifier stage, nww_stream_push_select_host."""
         if not isinstance(chunks, np.ndarray) or chunks.dtype != np.int16 or chunks.ndim != 2:
             raise ValueError("chunks must be an int16 numpy array (n_streams, chunk_len)")
         if chunks.shape[0] != getattr(self, "n_streams", 0):
             raise ValueError(f"chunks must have one row per open stream ({getattr(self, 'n_streams', 0)})")
         chunks = np.ascontiguousarray(chunks)
         scores = out if out is not None else np.empty(chunks.shape[0], dtype=np.float32)
-        rc = self._lib.nww_stream_push_host(self._h, chunks.ctypes.data_as(C.c_void_p), int(chunks.shape[1]),
-                                            scores.ctypes.data_as(C.c_void_p))
-        _lib.check(self._lib, rc, "nww_stream_push_host")
+        if select is None:
+            rc = self._lib.nww_stream_push_host(self._h, chunks.ctypes.data_as(C.c_void_p), int(chunks.shape[1]),
+                                                scores.ctypes.data_as(C.c_void_p))
+            _lib.check(self._lib, rc, "nww_stream_push_host")
+            return scores
+        ids = np.ascontiguousarray(np.asarray(select, dtype=np.int64).ravel())
+        if ids.size and np.unique(ids).size != ids.size:
+            raise ValueError("select must list distinct stream indices")
+        rc = self._lib.nww_stream_push_select_host(self._h, chunks.ctypes.data_as(C.c_void_p), int(chunks.shape[1]),
+                                                   ids.ctypes.data_as(C.c_void_p) if ids.size else None, int(ids.size),
+                                                   scores.ctypes.data_as(C.c_void_p))
+        _lib.check(self._lib, rc, "nww_stream_push_select_host")
+        return scores
+
+    def stream_push_select_device(self, chunks, ids, out=None, stream=None):
+        """Device form of the selective push: ``ids`` is a CUDA int64 tensor of distinct stream indices."""
+        torch = _torch()
+        if chunks.dtype != torch.int16 or not chunks.is_cuda or not chunks.is_contiguous() or chunks.dim() != 2:
+            raise ValueError("chunks must be a contiguous CUDA int16 tensor (n_streams, chunk_len)")
+        if chunks.shape[0] != getattr(self, "n_streams", 0):
+            raise ValueError(f"chunks must have one row per open stream ({getattr(self, 'n_streams', 0)})")
+        if ids.dtype != torch.int64 or not ids.is_cuda or not ids.is_contiguous():
+            raise ValueError("ids must be a contiguous CUDA int64 tensor")
+        scores = self._check_out(out, chunks.shape[0], chunks.device)
+        rc = self._lib.nww_stream_push_select(self._h, C.c_void_p(chunks.data_ptr()), int(chunks.shape[1]),
+                                              C.c_void_p(ids.data_ptr()) if ids.numel() else None, int(ids.numel()),
+                                              C.c_void_p(scores.data_ptr()), self._stream_ptr(stream))
+        _lib.check(self._lib, rc, "nww_stream_push_select")
         return scores
 
 

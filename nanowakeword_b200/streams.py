@@ -106,11 +106,14 @@ class CascadeBank:
     gate's own warm-up zeroing, is below ``gate_threshold``.  ``push`` returns the verifier's post-processed scores,
     like ``DetectionResult.score``; ``gate_scores`` holds the gate's (``DetectionResult.gate_score``).
 
-    The verifier engine still scores every stream (the rings must advance anyway); skipping the gated-off ones
-    inside the engine is a throughput optimisation this class leaves open.
+    The verifier engine receives every chunk (its rings must advance) but SCORES only the streams whose gate fired
+    (``nww_stream_push_select_host``): a gated-off stream costs the verifier one ingest step, so the bank's throughput
+    scales with the gate's pass rate.  ``select_in_engine=False`` keeps the round-1 form (score everything, zero on
+    the host) for A/B measurements.
     """
 
-    def __init__(self, gate_engine, verifier_engine, n_streams: int, gate_threshold: float = 0.3):
+    def __init__(self, gate_engine, verifier_engine, n_streams: int, gate_threshold: float = 0.3, select_in_engine: bool = True):
+        self.select_in_engine = bool(select_in_engine)
         self.gate = StreamBank(gate_engine, n_streams)
         self.verifier = StreamBank(verifier_engine, n_streams)
         self.n = int(n_streams)
@@ -131,8 +134,13 @@ class CascadeBank:
         gcur = graw.astype(np.float32, copy=True)
         gcur[g._hist_len < WARMUP] = 0.0                      # what `current[gate]` holds when the verifier is reached
         self.gate_scores = g._finish(graw, chunks.shape[1], 0, 0.0, 0.0)   # filters are keyed by the verifier's name
-        vraw = self.verifier.engine.stream_push_host(chunks).astype(np.float32, copy=True)
-        vraw[gcur < self.gate_threshold] = 0.0                # skipped: score and raw score are 0.0 (:760-766)
+        if self.select_in_engine:
+            passed = np.flatnonzero(gcur >= self.gate_threshold)
+            vraw = self.verifier.engine.stream_push_host(chunks, select=passed).astype(np.float32, copy=True)
+            self.last_pass_rate = passed.size / max(1, self.n)
+        else:
+            vraw = self.verifier.engine.stream_push_host(chunks).astype(np.float32, copy=True)
+            vraw[gcur < self.gate_threshold] = 0.0            # skipped: score and raw score are 0.0 (:760-766)
         return self.verifier._finish(vraw, chunks.shape[1], patience, threshold, debounce_time)
 
     @property

@@ -312,3 +312,66 @@ def test_load_model_from_onnx_with_cascade(torch_cuda, tmp_path, golden_frontend
             passed += og.buf_samples >= 16000
         assert abs(r.score - want) < SCORE_TOL, (i, r.score, want)
     assert passed > 0 or skipped > 0
+
+
+@pytest.mark.parametrize("mt", ["cnn", "tcn", "crnn", "dnn", "e2e_quartznet"])
+def test_selective_stream_push_scores_only_the_listed_streams(torch_cuda, mt):
+    """nww_stream_push_select[_host]: every stream ingests its chunk, only the listed ones are scored — and they get
+    exactly the score a full push gives them (bit-identical), in any order of ids, across launch-chunk boundaries."""
+    from nanowakeword_b200 import Engine
+    cfg = default_config(mt)
+    sd = make_state_dict(cfg, seed=0)
+    full = Engine(sd, cfg, device=0, chunk_windows=37)
+    sel = Engine(sd, cfg, device=0, chunk_windows=37)
+    n, L = 101, 1280
+    full.stream_open(n)
+    sel.stream_open(n)
+    rng = np.random.default_rng(17)
+    for step in range(17):
+        chunks = np.clip(rng.normal(0, 3000, (n, L)), -32768, 32767).astype(np.int16)
+        ids = rng.permutation(n)[:rng.integers(0, n + 1)] if step % 5 else np.arange(0)
+        a = full.stream_push_host(chunks)
+        if step % 2:
+            b = sel.stream_push_host(chunks, select=ids)
+        else:
+            b = sel.stream_push_select_device(torch_cuda.from_numpy(chunks).cuda(),
+                                              torch_cuda.from_numpy(ids.astype(np.int64)).cuda()).cpu().numpy()
+        want = np.zeros(n, np.float32)
+        want[ids] = a[ids]
+        assert np.array_equal(b, want), (mt, step, np.abs(b - want).max())
+    assert (a != 0).any()
+    with pytest.raises(ValueError):
+        sel.stream_push_host(chunks, select=[0, 0])
+    with pytest.raises(ValueError):
+        sel.stream_push_host(chunks, select=[n])
+    full.stream_close()
+    sel.stream_close()
+
+
+def test_cascade_bank_on_engines_scales_with_the_gate(torch_cuda):
+    """CascadeBank on two real engines: identical results with and without in-engine selection, and the verifier's
+    kernel launches drop when the gate lets nothing through."""
+    from nanowakeword_b200 import CascadeBank, Engine
+    cfg_g, cfg_v = default_config("dnn"), default_config("cnn")
+    sd_g, sd_v = make_state_dict(cfg_g, seed=0), make_state_dict(cfg_v, seed=0)
+    n, L = 64, 1280
+    rng = np.random.default_rng(23)
+    audio = np.clip(rng.normal(0, 3000, (n, L * 20)), -32768, 32767).astype(np.int16)
+    outs = {}
+    for mode in (True, False):
+        bank = CascadeBank(Engine(sd_g, cfg_g, device=0), Engine(sd_v, cfg_v, device=0), n, gate_threshold=0.2,
+                           select_in_engine=mode)
+        res = [bank.push(np.ascontiguousarray(audio[:, s * L:(s + 1) * L])).copy() for s in range(20)]
+        outs[mode] = (np.stack(res), bank.raw_scores.copy(), bank.gate_scores.copy())
+        bank.close()
+    for a, b in zip(outs[True], outs[False]):
+        assert np.array_equal(a, b)
+    assert (outs[True][0] > 0).any() and (outs[True][0][-1] == 0).any()      # some streams pass the gate, some do not
+    bank = CascadeBank(Engine(sd_g, cfg_g, device=0), Engine(sd_v, cfg_v, device=0), n, gate_threshold=2.0)   # nothing passes
+    for s in range(15):
+        bank.push(np.ascontiguousarray(audio[:, s * L:(s + 1) * L]))
+    l0 = bank.verifier.engine.info["kernel_launches"]
+    bank.push(np.ascontiguousarray(audio[:, 15 * L:16 * L]))
+    assert bank.verifier.engine.info["kernel_launches"] - l0 == 1            # the fused ingest kernel only
+    assert np.all(bank.raw_scores == 0.0)
+    bank.close()

@@ -162,7 +162,7 @@ def test_load_model_errors(tmp_path):
         NanoInterpreter.load_model("x.onnx", remote_pipeline="bogus")
     p = tmp_path / "m.onnx"
     p.write_bytes(b"\x08\x07")
-    with pytest.raises(NotImplementedError):          # .onnx without its .pt/.json siblings
+    with pytest.raises(ValueError, match="no GraphProto"):      # an .onnx path is parsed (round 2): this one has no graph
         NanoInterpreter.load_model(str(p))
 
 
@@ -199,11 +199,17 @@ class _FakeStreamEngine:
         self.rings[sel] = 0
         self.count[sel] = 0
 
-    def stream_push_host(self, chunks):
+    scored = 0                        # streams actually scored (the selective push skips the others)
+
+    def stream_push_host(self, chunks, select=None):
         L = chunks.shape[1]
         self.rings = np.concatenate([self.rings, chunks], axis=1)[:, -self.clip:]
         self.count += L
-        out = np.array([self.score_fn(r) for r in self.rings], np.float32)
+        ids = range(len(self.rings)) if select is None else [int(i) for i in select]
+        out = np.zeros(len(self.rings), np.float32)
+        for i in ids:
+            out[i] = self.score_fn(self.rings[i])
+        self.scored += len(ids)
         out[self.count < self.clip] = 0.0
         return out
 
@@ -331,6 +337,8 @@ def test_cascade_bank_matches_cascade_interpreters():
             skipped += r.gate_score < thr
             passed += r.gate_score >= thr
     assert skipped > 10 and passed > 10          # both branches exercised
+    # the verifier engine scored only the streams whose gate fired (nww_stream_push_select_host), the gate all of them
+    assert gate_eng.scored == 30 * n and ver_eng.scored == passed
 
 
 # ---------------------------------------------------------------------------------------------- round 2: boundary
