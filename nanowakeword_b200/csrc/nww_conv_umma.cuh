@@ -30,7 +30,7 @@
 
 namespace nww {
 
-constexpr int kCuNT = 256;
+constexpr int kCuNT = 512;            // 16 warps: the load / convert phase is latency-bound, the epilogue has (tile, chunk) tasks for all
 
 struct ConvUmmaPlan {
     int H, W, Cin, Cout, pool;
@@ -129,30 +129,46 @@ conv3x3_umma_kernel(const float* __restrict__ in, const uint4* __restrict__ wq, 
     for (long long w = blockIdx.x; w < n_windows; w += gridDim.x) {
         // ---- input window -> bf16 hi / lo position lists ------------------------------------------------------------
         const float* src = in + w * (long long)P.H * P.W * P.Cin;
-        for (int i = tid; i < P.H * P.W * P.kg; i += kCuNT) {
-            const int g = i % P.kg, pix = i / P.kg;
-            const int y = pix / P.W, x = pix - y * P.W;
-            const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + (size_t)pix * P.Cin + 8 * g));
-            const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + (size_t)pix * P.Cin + 8 * g) + 1);
-            const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-            uint32_t h[8], l[8];
+        // (four cells per thread and trip, all eight 128-bit loads issued before the first conversion)
+        const int n_cells = P.H * P.W * P.kg;
+        for (int i0 = tid; i0 < n_cells; i0 += 4 * kCuNT) {
+            float4 v0[4], v1[4];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                h[k] = float_to_bf16_bits(v[k]);
-                l[k] = float_to_bf16_bits(v[k] - bf16_bits_to_float(h[k]));
+            for (int j = 0; j < 4; ++j) {
+                const int i = i0 + j * kCuNT;
+                if (i < n_cells) {
+                    const int g = i % P.kg, pix = i / P.kg;
+                    const float4* p4 = reinterpret_cast<const float4*>(src + (size_t)pix * P.Cin + 8 * g);
+                    v0[j] = __ldg(p4);
+                    v1[j] = __ldg(p4 + 1);
+                }
             }
-            int plane, s;
-            if (P.pool) {
-                plane = ((y & 1) << 1) | (x & 1);
-                s = ((y >> 1) + 1) * P.P + (x >> 1) + 1;
-            } else {
-                plane = 0;
-                s = (y + 1) * P.P + x + 1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = i0 + j * kCuNT;
+                if (i >= n_cells) break;
+                const int g = i % P.kg, pix = i / P.kg;
+                const int y = pix / P.W, x = pix - y * P.W;
+                const float v[8] = {v0[j].x, v0[j].y, v0[j].z, v0[j].w, v1[j].x, v1[j].y, v1[j].z, v1[j].w};
+                uint32_t h[8], l[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    h[k] = float_to_bf16_bits(v[k]);
+                    l[k] = float_to_bf16_bits(v[k] - bf16_bits_to_float(h[k]));
+                }
+                int plane, s;
+                if (P.pool) {
+                    plane = ((y & 1) << 1) | (x & 1);
+                    s = ((y >> 1) + 1) * P.P + (x >> 1) + 1;
+                } else {
+                    plane = 0;
+                    s = (y + 1) * P.P + x + 1;
+                }
+                unsigned char* dst = a_s + (size_t)plane * 2 * plane_bytes + (size_t)g * lbo_a + (size_t)s * 16;
+                *reinterpret_cast<uint4*>(dst) = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+                *reinterpret_cast<uint4*>(dst + plane_bytes) =
+                    make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
             }
-            unsigned char* dst = a_s + (size_t)plane * 2 * plane_bytes + (size_t)g * lbo_a + (size_t)s * 16;
-            *reinterpret_cast<uint4*>(dst) = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
-            *reinterpret_cast<uint4*>(dst + plane_bytes) =
-                make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
         }
         fence_proxy_async();
         tc_fence_before();
@@ -198,10 +214,10 @@ conv3x3_umma_kernel(const float* __restrict__ in, const uint4* __restrict__ wq, 
         tc_fence_after();
         // ---- epilogue: warp -> TMEM lane quarter; tasks (tile, 16-column chunk) dealt to the two warps of a quarter ----
         {
-            const int q = warp & 3, sub = warp >> 2;                 // 8 warps: two per quarter
+            const int q = warp & 3, sub = warp >> 2;                 // 16 warps: four per quarter
             const int chunks = P.Cout / 16;
             float* dst_w = out + w * (long long)Ho * Wo * P.Cout;
-            for (int task = sub; task < P.tiles * chunks; task += 2) {
+            for (int task = sub; task < P.tiles * chunks; task += kCuNT / 128) {
                 const int t = task / chunks, ch = task - t * chunks;
                 uint32_t r[4][16];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * quads * P.Cout + ch * 16);

@@ -325,9 +325,9 @@ static int launch_frontend(nww_engine* e, WindowSource pcm, int64_t n, float* me
         NWW_CUDA(set_smem(frontend3_kernel, Fe3KernelSmem::kTotal));
         frontend3_kernel<<<grid_for(e, n), Fe3::NT, Fe3KernelSmem::kTotal, st>>>(pcm, n, e->tab64, mel, time_major, 0);
     } else {
-        auto k = frontend_kernel<double, G, kNfb64, kStageNT>;
-        NWW_CUDA(set_smem(k, FrontendSmem<double, G, kNfb64>::kTotal));
-        k<<<grid_for(e, n), kStageNT, FrontendSmem<double, G, kNfb64>::kTotal, st>>>(pcm, n, e->tab64, mel, time_major);
+        auto k = frontend_kernel<double, G, kNfbRef, kStageNT>;
+        NWW_CUDA(set_smem(k, FrontendSmem<double, G, kNfbRef>::kTotal));
+        k<<<grid_for(e, n), kStageNT, FrontendSmem<double, G, kNfbRef>::kTotal, st>>>(pcm, n, e->tab64, mel, time_major);
     }
     e->launches++;
     NWW_CUDA(cudaGetLastError());

@@ -24,6 +24,10 @@ namespace nww {
 
 constexpr int kStageNT = 512;       // threads per stage-A CTA
 constexpr int kNfb64 = 7;           // FFTs per batch, double
+// REF64x101 (51 packed FFT-400 per window, radix 5 x 5 x 4 x 4): a pass has 80 (radix 5) or 100 (radix 4) butterflies per
+// FFT, so 7 FFTs per batch leave 512 threads 55 % / 68 % busy in their second round; 17 FFTs per batch = exactly three
+// batches per window, 89 % / 83 % busy, a third of the CTA barriers (109 KB of work buffer).
+constexpr int kNfbRef = 17;
 constexpr int kNfb32 = 13;          // FFTs per batch, float
 
 struct ConvW { const float* w = nullptr; const float* b = nullptr; };
@@ -129,16 +133,17 @@ static int launch_frontend_f64(const FrontendTables<double>& tab, int sm_count, 
     const int grid = (int)std::min<long long>(n, sm_count);
     if (pcm.fbase != nullptr) {
         // float feed: generic FP64 front end reading float32 samples straight from global memory (all frames)
-        auto k = frontend_f32_kernel<double, G, kNfb64, kStageNT>;
-        NWW_HCUDA(set_smem(k, FrontendSmem<double, G, kNfb64>::kWork));
-        k<<<grid, kStageNT, FrontendSmem<double, G, kNfb64>::kWork, st>>>(pcm.fbase, n, tab, mel, time_major);
+        constexpr int NFB = std::is_same<G, GeoNS40x98>::value ? kNfb64 : kNfbRef;
+        auto k = frontend_f32_kernel<double, G, NFB, kStageNT>;
+        NWW_HCUDA(set_smem(k, FrontendSmem<double, G, NFB>::kWork));
+        k<<<grid, kStageNT, FrontendSmem<double, G, NFB>::kWork, st>>>(pcm.fbase, n, tab, mel, time_major);
     } else if constexpr (std::is_same<G, GeoNS40x98>::value) {
         NWW_HCUDA(set_smem(frontend3_kernel, Fe3KernelSmem::kTotal));
         frontend3_kernel<<<grid, Fe3::NT, Fe3KernelSmem::kTotal, st>>>(pcm, n, tab, mel, time_major, frame_lo);
     } else {
-        auto k = frontend_kernel<double, G, kNfb64, kStageNT>;
-        NWW_HCUDA(set_smem(k, FrontendSmem<double, G, kNfb64>::kTotal));
-        k<<<grid, kStageNT, FrontendSmem<double, G, kNfb64>::kTotal, st>>>(pcm, n, tab, mel, time_major);
+        auto k = frontend_kernel<double, G, kNfbRef, kStageNT>;
+        NWW_HCUDA(set_smem(k, FrontendSmem<double, G, kNfbRef>::kTotal));
+        k<<<grid, kStageNT, FrontendSmem<double, G, kNfbRef>::kTotal, st>>>(pcm, n, tab, mel, time_major);
     }
     (*launches)++;
     NWW_HCUDA(cudaGetLastError());

@@ -531,20 +531,39 @@ rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, KcSegs sg, int K,
             const uint32_t buf = g & 1u;
             if (g >= 2) mbar_wait(bar_afree + buf, ((g >> 1) - 1u) & 1u);   // chunk g - 2's MMAs have read this buffer
             unsigned char* ab = a_s + (size_t)buf * kKcABuf;
-            for (int i = tid; i < kKcRows * (kKcKC / 8); i += kKcNT) {
+            // every thread owns kPer (row, K group) cells of the chunk: ALL their global loads are issued before the first
+            // conversion, so a thread has 2 * kPer 128-bit loads in flight instead of 2 (the operand producer was
+            // latency-bound on L2: profiles/r02_rowgemm_tcn_before.txt, long-scoreboard 57 % of the samples)
+            constexpr int kPer = kKcRows * (kKcKC / 8) / kKcNT;
+            float4 v0[kPer], v1[kPer];
+            int k8s[kPer];
+#pragma unroll
+            for (int j = 0; j < kPer; ++j) {
+                const int i = tid + j * kKcNT;
                 const int gq = i / kKcRows, r = i - gq * kKcRows;
-                uint4 hv = make_uint4(0, 0, 0, 0), lv = hv;
                 const int k8 = kc * kKcKC + 8 * gq;
                 const long long ra = VIEWS ? row_at[r] : (r0 + r < rows ? (r0 + r) * (long long)K : -1);
+                k8s[j] = -1;
+                v0[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                v1[j] = v0[j];
                 if (ra >= 0 && (!VIEWS || k8 < sg.k_valid)) {
                     const int seg = VIEWS ? k8 / sg.seg_len : 0;
                     const float4* p = reinterpret_cast<const float4*>(A + ra + (VIEWS ? seg * sg.seg_stride + (k8 - seg * sg.seg_len) : k8));
-                    const float4 v0 = __ldg(p), v1 = __ldg(p + 1);
-                    float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-                    if (VIEWS && k8 + 8 > sg.k_valid) {                // the group straddles the end of the valid columns
+                    v0[j] = __ldg(p);
+                    v1[j] = __ldg(p + 1);
+                    k8s[j] = k8;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kPer; ++j) {
+                const int i = tid + j * kKcNT;
+                uint4 hv = make_uint4(0, 0, 0, 0), lv = hv;
+                if (k8s[j] >= 0) {
+                    float v[8] = {v0[j].x, v0[j].y, v0[j].z, v0[j].w, v1[j].x, v1[j].y, v1[j].z, v1[j].w};
+                    if (VIEWS && k8s[j] + 8 > sg.k_valid) {            // the group straddles the end of the valid columns
 #pragma unroll
                         for (int e = 0; e < 8; ++e)
-                            if (k8 + e >= sg.k_valid) v[e] = 0.0f;
+                            if (k8s[j] + e >= sg.k_valid) v[e] = 0.0f;
                     }
                     uint32_t h[8], l[8];
 #pragma unroll
