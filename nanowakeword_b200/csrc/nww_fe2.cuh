@@ -122,6 +122,49 @@ __device__ __forceinline__ float fe2_mel_dot(const float* __restrict__ prow, int
     return acc0 + acc1;
 }
 
+// Both frames of a packed FFT for one filter: the weights are loaded once for the two dot products, and every load of
+// a step is issued before the first multiply (the filter length is a run-time value, so the plain loop above exposes one
+// shared-memory round trip per four bins — tools/probe/fft_probe.cu: 42 % of a lone warp's time per FFT).  Same
+// operations in the same order per (filter, frame) as fe2_mel_dot: bit-identical results.
+__device__ __forceinline__ void fe2_mel_dot2(const float* __restrict__ prow_a, const float* __restrict__ prow_b, int m,
+                                             const cplx<double>* __restrict__ tw_smem, const FrontendTables<double>& tab,
+                                             float* __restrict__ out_a, float* __restrict__ out_b) {
+    if (!tab.mel_vec_ok) {
+        *out_a = fe2_mel_dot(prow_a, m, tw_smem, tab);
+        *out_b = fe2_mel_dot(prow_b, m, tw_smem, tab);
+        return;
+    }
+    const float* wpad = reinterpret_cast<const float*>(tw_smem + Fe2::N_TW);
+    const int2 mt = reinterpret_cast<const int2*>(wpad + Fe2::MEL_MAX * Fe2::MEL_ROW)[m];
+    const int k0 = mt.x, n4 = mt.y;
+    const float4* __restrict__ pa4 = reinterpret_cast<const float4*>(prow_a + k0);
+    const float4* __restrict__ pb4 = reinterpret_cast<const float4*>(prow_b + k0);
+    const float4* __restrict__ w4 = reinterpret_cast<const float4*>(wpad + m * Fe2::MEL_ROW);
+    constexpr int MAXG = Fe2::MEL_ROW / 4;                     // 9 groups of four bins
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f, b0 = 0.0f, b1 = 0.0f, b2 = 0.0f, b3 = 0.0f;
+#pragma unroll
+    for (int g0 = 0; g0 < MAXG; g0 += 3) {                      // three groups (nine 128-bit loads) in flight at a time
+        float4 pa[3], pb[3], w[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            if (g0 + j < n4) {
+                w[j] = w4[g0 + j];
+                pa[j] = pa4[g0 + j];
+                pb[j] = pb4[g0 + j];
+            }
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            if (g0 + j < n4) {
+                a0 = fmaf(w[j].x, pa[j].x, a0); a1 = fmaf(w[j].y, pa[j].y, a1);
+                a2 = fmaf(w[j].z, pa[j].z, a2); a3 = fmaf(w[j].w, pa[j].w, a3);
+                b0 = fmaf(w[j].x, pb[j].x, b0); b1 = fmaf(w[j].y, pb[j].y, b1);
+                b2 = fmaf(w[j].z, pb[j].z, b2); b3 = fmaf(w[j].w, pb[j].w, b3);
+            }
+    }
+    *out_a = (a0 + a1) + (a2 + a3);
+    *out_b = (b0 + b1) + (b2 + b3);
+}
+
 // A batch = up to four consecutive frames (hop 160) = two packed FFTs.  `x` points at sample 0 of the
 // batch's first frame in shared memory; frames beyond `nframes` are computed on whatever follows in
 // shared memory (it must be readable up to x + 3 * 160 + 448) and dropped.

@@ -135,15 +135,17 @@ __device__ __forceinline__ void fe3_warp_fft(const int16_t* __restrict__ x, cplx
         pwb[256 + lane] = 0.0f;
     }
     __syncwarp();
-    // ---- mel + dB: 40 filters x 2 frames over 32 lanes, widest filters first -------------------------------------
-#pragma unroll 1
-    for (int r = 0; r < 3; ++r) {
-        const int slot = (lane >> 1) + 16 * r;
-        if (slot >= GeoNS40x98::N_MELS) break;
-        const int fr = lane & 1;
-        const int m = GeoNS40x98::N_MELS - 1 - slot;
-        const float pm = fe2_mel_dot(pwa + fr * Fe2::PW_PITCH, m, tw_smem, tab);
-        store(fr, m, (pm <= tab.amin) ? tab.floor_db : 10.0f * log10f(pm));
+    // ---- mel + dB: a lane owns one filter for BOTH frames (the weights are read once), the 32 widest filters first ---
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int slot = lane + 32 * r;
+        if (slot < GeoNS40x98::N_MELS) {
+            const int m = GeoNS40x98::N_MELS - 1 - slot;
+            float pm_a, pm_b;
+            fe2_mel_dot2(pwa, pwb, m, tw_smem, tab, &pm_a, &pm_b);
+            store(0, m, (pm_a <= tab.amin) ? tab.floor_db : 10.0f * log10f(pm_a));
+            store(1, m, (pm_b <= tab.amin) ? tab.floor_db : 10.0f * log10f(pm_b));
+        }
     }
     __syncwarp();                                                // the buffer is free for the warp's next FFT
 }
