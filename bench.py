@@ -509,9 +509,20 @@ def run_gpu_arm(args, rank, world, local_rank):
                      "frac": fp32_tflops / max(1e-9, pipe_peaks["fp32_fma_tflops"]),
                      "what": "conv1 + sparse mel + log (1.33 MFLOP/window), peak = nww_microbench FFMA"},
         },
-        "note": "no single pipe binds this kernel: it is latency / issue bound (profiles/r02_*: issue slots 44 % busy); "
-                "fractions per pipe are given so the distance to each roof is explicit",
+        "note": "the kernel alternates between a front-end phase that sits on the SM's shared-memory data pipe (16 warp-private "
+                "FP64 FFTs: 580 cycles per FFT against ~550 shared-memory wavefronts, tools/probe/fft_probe.cu) and a conv phase bound "
+                "by barriers and tensor-core operand fetch; fractions per pipe are given so the distance to each roof is explicit",
     }
+    if traffic and traffic.get("smem_wavefronts_per_window"):
+        # one wavefront per cycle per SM is the shared-memory data pipe's roof (ncu l1tex__data_pipe_lsu_wavefronts_mem_shared)
+        roofline["pipes"]["shared_memory"] = {
+            "wavefronts_per_window": traffic["smem_wavefronts_per_window"], "cycles_per_window": cyc_per_window,
+            "frac": traffic["smem_wavefronts_per_window"] / cyc_per_window,
+            "what": "ncu digest (profiles/ncu_traffic.json) / live cycles per window; ~27 k of the wavefronts belong to the FFT phase, "
+                    "which runs at ~95 % of this roof while it lasts"}
+        roofline["pipes"]["issue"] = {"warp_instructions_per_window": traffic.get("warp_instructions_per_window"),
+                                      "frac": (traffic.get("warp_instructions_per_window") or 0) / 4.0 / cyc_per_window,
+                                      "what": "4 issue slots per cycle per SM"}
 
     # ---- secondary: the other model types the engine builds, same 4096-window batch resident in HBM -----------------
     other = None

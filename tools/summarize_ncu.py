@@ -90,11 +90,20 @@ def traffic_digest(rep, tag, windows_per_launch, path="profiles/ncu_traffic.json
     for d in data:
         name = d[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").split("<")[0].split("::")[-1]
         tot = val(d, "dram__bytes_read.sum") + val(d, "dram__bytes_write.sum")
+        def num(k):
+            return float(d[hdr.index(k)].replace(",", "")) if k in hdr and d[hdr.index(k)] not in ("", "n/a") else None
         if name not in best or tot > best[name][0]:
-            best[name] = (tot, val(d, "dram__bytes_read.sum"), val(d, "dram__bytes_write.sum"))
-    for name, (tot, rd, wr) in best.items():
+            best[name] = (tot, val(d, "dram__bytes_read.sum"), val(d, "dram__bytes_write.sum"),
+                          num("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"), num("smsp__inst_executed.sum"),
+                          num("sm__cycles_elapsed.max"), num("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+                          num("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+                          num("smsp__issue_active.avg.pct_of_peak_sustained_active"))
+    for name, (tot, rd, wr, wav, inst, cyc, fp64, tens, issue) in best.items():
         digest[name] = {"dram_bytes_per_launch": tot, "dram_bytes_read": rd, "dram_bytes_write": wr,
                         "windows_per_launch": windows_per_launch, "dram_bytes_per_window": tot / windows_per_launch,
+                        "smem_wavefronts_per_window": wav / windows_per_launch if wav else None,
+                        "warp_instructions_per_window": inst / windows_per_launch if inst else None,
+                        "sm_cycles_elapsed": cyc, "fp64_pipe_pct": fp64, "tensor_pipe_pct": tens, "issue_active_pct": issue,
                         "source": f"{tag}_ncu_full.txt (ncu --set full, largest captured launch)"}
     json.dump(digest, open(path, "w"), indent=1)
 
