@@ -17,6 +17,7 @@
 #include "nww_cnn.cuh"
 #include "nww_cnn2.cuh"
 #include "nww_cnn3.cuh"
+#include "nww_cnn4.cuh"
 #include "nww_gemm_tc.cuh"
 #include "nww_heads.cuh"
 #include "nww_stage.cuh"
@@ -94,6 +95,7 @@ struct nww_engine {
     TailParams tail_rest{};                           // layers 1.. (after the tensor-core layer)
 
     int chunk = 0;
+    int split_per_sm = 4;            // windows per SM and sub-chunk of the split CNN stage (reserved[1] overrides)
     float* d_feat = nullptr;         // [chunk][feat_dim]
     float* d_scratch = nullptr;      // per-head scratch (e.g. CRNN sequence), may be null
     size_t scratch_per_window = 0;
@@ -113,6 +115,10 @@ struct nww_engine {
     bool last_valid = false;
     cudaStream_t last_stream = nullptr;
     float* d_melf = nullptr;             // [chunk][F][T] log-mel of float feeds for the stage kernels that start from mel
+    // split CNN stage (nww_cnn4.cuh): the front-end kernel runs on its own stream beside the convolution kernel
+    cudaStream_t fe_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr;
+    std::vector<cudaEvent_t> ev_fe;
     // selective push (nww_stream_push_select): the streams to score, their window offsets and compact scores
     const long long* sel_ids = nullptr;  // non-null only while a selective push is being enqueued
     long long* d_sel_ids = nullptr;      // staging for the host variant
@@ -401,6 +407,44 @@ static int launch_tail(nww_engine* e, const float* feat, int64_t n, float* score
 static int launch_cnn_stage(nww_engine* e, WindowSource pcm, Cnn2MelSource ms, int64_t n, float* feat_hi, float* feat_lo, float* mel,
                             cudaStream_t st) {
     const int act = e->spec.activation;
+    if ((e->spec.reserved[0] & 64) && pcm.base != nullptr && pcm.offsets == nullptr && pcm.fbase == nullptr && ms.ring == nullptr) {
+        // two co-resident kernels: front end of sub-chunk k + 1 on the engine's front-end stream beside the convolution of
+        // sub-chunk k on the caller's stream; the log-mel goes through a (n, F, T) buffer in L2
+        const int64_t fe_floats = (int64_t)e->n_mels * e->n_frames;
+        if (!mel && !e->d_melf) NWW_CUDA(cudaMalloc(&e->d_melf, (size_t)e->chunk * fe_floats * sizeof(float)));
+        float* melbuf = mel ? mel : e->d_melf;
+        if (!e->fe_stream) {
+            NWW_CUDA(cudaStreamCreateWithFlags(&e->fe_stream, cudaStreamNonBlocking));
+            NWW_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+        }
+        const int64_t S = (int64_t)e->sm_count * e->split_per_sm;
+        const int n_sub = (int)((n + S - 1) / S);
+        while ((int)e->ev_fe.size() < n_sub) {
+            cudaEvent_t ev = nullptr;
+            NWW_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            e->ev_fe.push_back(ev);
+        }
+        auto kc = act == NWW_ACT_RELU ? conv4_mel_kernel<ACT_RELU> : act == NWW_ACT_GELU ? conv4_mel_kernel<ACT_GELU>
+                                                                                           : conv4_mel_kernel<ACT_SILU>;
+        NWW_CUDA(set_smem(fe4_mel_kernel, Fe4::kTotal));
+        NWW_CUDA(set_smem(kc, Conv4::kTotal));
+        NWW_CUDA(cudaFuncSetAttribute(fe4_mel_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        NWW_CUDA(cudaFuncSetAttribute(kc, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        NWW_CUDA(cudaEventRecord(e->ev_fork, st));                          // inputs ready, workspaces free: in the caller's stream order
+        NWW_CUDA(cudaStreamWaitEvent(e->fe_stream, e->ev_fork, 0));
+        for (int k = 0; k < n_sub; ++k) {
+            const int64_t w0 = k * S, m = std::min<int64_t>(S, n - w0);
+            fe4_mel_kernel<<<grid_for(e, m), Fe4::NT, Fe4::kTotal, e->fe_stream>>>(pcm.base + w0 * e->clip, m, e->tab64, melbuf + w0 * fe_floats);
+            NWW_CUDA(cudaGetLastError());
+            NWW_CUDA(cudaEventRecord(e->ev_fe[k], e->fe_stream));
+            NWW_CUDA(cudaStreamWaitEvent(st, e->ev_fe[k], 0));
+            kc<<<grid_for(e, m), Conv4::NT, Conv4::kTotal, st>>>(melbuf + w0 * fe_floats, m, e->cnn2, feat_hi + w0 * Cnn2::FEAT,
+                                                                 feat_lo ? feat_lo + w0 * Cnn2::FEAT : nullptr);
+            NWW_CUDA(cudaGetLastError());
+            e->launches += 2;
+        }
+        return NWW_OK;
+    }
     if (e->spec.reserved[0] & 8) {
         auto k = act == NWW_ACT_RELU ? cnn2_stage_kernel<ACT_RELU> : act == NWW_ACT_GELU ? cnn2_stage_kernel<ACT_GELU>
                                                                                            : cnn2_stage_kernel<ACT_SILU>;
@@ -571,6 +615,7 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
     e->device = device;
     e->sm_count = prop.multiProcessorCount;
     e->spec = *spec;
+    if (spec->reserved[1] > 0) e->split_per_sm = spec->reserved[1];
     e->blob_host.assign(static_cast<const unsigned char*>(weights), static_cast<const unsigned char*>(weights) + weights_size);
     std::string err;
     if (!parse_blob(e->blob_host.data(), e->blob_host.size(), &e->blob, &err)) return fail(NWW_EINVAL, err);
@@ -915,6 +960,9 @@ void nww_destroy(nww_engine* e) {
 nww_engine::~nww_engine() {
     nww_engine* e = this;
     cudaFree(e->d_melf);
+    if (e->fe_stream) cudaStreamDestroy(e->fe_stream);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    for (auto ev : e->ev_fe) cudaEventDestroy(ev);
     cudaFree(e->d_sel_ids);
     cudaFree(e->d_sel_off);
     cudaFree(e->d_sel_scores);

@@ -32,7 +32,7 @@ class Engine:
 
     def __init__(self, state_dict: dict, cfg: dict, device: int = 0, frontend_precision: str = "fp64",
                  chunk_windows: int = 0, tensor_cores: bool = True, cnn_stage: str = "v2",
-                 stream_incremental: bool = True, tcn_layers: str = "rows", stream_ingest: str = "fused"):
+                 stream_incremental: bool = True, tcn_layers: str = "rows", stream_ingest: str = "fused", split_per_sm: int = 0):
         self._lib = _lib.load_library()
         self.cfg = dict(cfg)
         self.geometry = geometry_for(cfg)
@@ -53,12 +53,13 @@ class Engine:
         spec.chunk_windows = int(chunk_windows)
         # reserved[0] bit 0: keep the first dense layer on CUDA cores; bit 1: CNN head on the v1
         # (CUDA-core conv2) stage kernel instead of the tcgen05 one (A/B measurements)
-        if cnn_stage in ("v2", "v3"):
+        split = cnn_stage == "v4"          # two co-resident kernels (nww_cnn4.cuh): front end beside the convolution
+        if cnn_stage in ("v2", "v3", "v4"):
             cnn_stage, pipelined = "v2", cnn_stage == "v3"
         elif cnn_stage == "v1":
             pipelined = False
         else:
-            raise ValueError("cnn_stage must be 'v1', 'v2' or 'v3'")
+            raise ValueError("cnn_stage must be 'v1', 'v2', 'v3' or 'v4'")
         # bit 2: streams always re-run the front end on the whole window (no incremental mel ring)
         # bit 4: TCN cone as the per-tile kernel (nww_tcn_umma.cuh) instead of one row GEMM per layer over the launch group
         if tcn_layers not in ("rows", "cone"):
@@ -66,8 +67,10 @@ class Engine:
         # bit 3: the phase-serial tcgen05 CNN stage (nww_cnn2.cuh) instead of the warp-specialised pipeline (nww_cnn3.cuh)
         spec.reserved[0] = ((0 if tensor_cores else 1) | (2 if cnn_stage == "v1" else 0) | (0 if stream_incremental else 4)
                             | (0 if pipelined else 8) | (0 if tcn_layers == "rows" else 16)
-                            | (0 if stream_ingest == "fused" else 32))       # bit 5: ring append and mel update as two kernels
-        self.cnn_stage = "v3" if (pipelined and cnn_stage == "v2") else cnn_stage
+                            | (0 if stream_ingest == "fused" else 32)        # bit 5: ring append and mel update as two kernels
+                            | (64 if split else 0))                           # bit 6: split CNN stage (front-end + conv kernels)
+        spec.reserved[1] = int(split_per_sm)                                  # windows per SM and sub-chunk of the split stage (0 = default)
+        self.cnn_stage = "v4" if split else "v3" if (pipelined and cnn_stage == "v2") else cnn_stage
         self._blob = (C.c_char * len(blob)).from_buffer_copy(blob)
         handle = C.c_void_p()
         rc = self._lib.nww_create(C.byref(spec), C.cast(self._blob, C.c_void_p), len(blob), int(device), C.byref(handle))

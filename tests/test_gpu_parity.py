@@ -235,6 +235,8 @@ def test_incremental_stream_mel_is_bit_identical_to_full_recompute(torch_cuda, m
 
 
 @pytest.mark.parametrize("mt,kw", [("cnn", dict(tensor_cores=False)), ("cnn", dict(cnn_stage="v1")),
+                                   ("cnn", dict(cnn_stage="v3")), ("cnn", dict(cnn_stage="v4")), ("crnn", dict(cnn_stage="v4")),
+                                   ("tcn", dict(tcn_layers="cone")), ("cnn", dict(stream_ingest="two_kernels")),
                                    ("dnn", dict(tensor_cores=False)), ("bcresnet", dict(tensor_cores=False)),
                                    ("crnn", dict(tensor_cores=False)), ("e2e_dnn", dict(tensor_cores=False)),
                                    ("tcn", dict(tensor_cores=False))])

@@ -1,4 +1,4 @@
-"""Dev probe (GPU box): the pipelined CNN stage (v3) against the phase-serial one (v2): bit-identity and timing."""
+"""Dev probe (GPU box): the CNN stage variants against the phase-serial one (v2): bit-identity and timing."""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -6,12 +6,14 @@ from nanowakeword_b200 import Engine
 from nanowakeword_b200.synth import default_config, make_state_dict, synth_pcm
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+variants = sys.argv[3].split(",") if len(sys.argv) > 3 else ["v2", "v4"]
 for mt in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["cnn", "crnn"]):
     cfg = default_config(mt); sd = make_state_dict(cfg, 0)
     pcm = torch.from_numpy(synth_pcm(B, seed=1234)).cuda()
     res = {}
-    for v in ("v2", "v3"):
-        eng = Engine(sd, cfg, cnn_stage=v)
+    for v in variants:
+        name, _, per = v.partition(":")
+        eng = Engine(sd, cfg, cnn_stage=name, split_per_sm=int(per or 0))
         out = torch.empty(B, dtype=torch.float32, device="cuda")
         small, ex = eng.score_device(pcm[:300].contiguous(), want_mel=True)
         torch.cuda.synchronize()
@@ -25,6 +27,8 @@ for mt in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["cnn", "crnn"]):
         res[v] = (out.cpu().numpy().copy(), small.cpu().numpy().copy(), ex["mel"].cpu().numpy().copy())
         print(f"{mt} {v}: {ms:.3f} ms  {B / ms * 1e3 / 1e6:.3f} Mwin/s", flush=True)
         eng.close()
-    for i, nm in enumerate(("scores", "scores[:300]", "mel[:300]")):
-        d = np.abs(res["v2"][i] - res["v3"][i]).max()
-        print(f"  {nm}: max |v2 - v3| = {d:.3e}  identical={np.array_equal(res['v2'][i], res['v3'][i])}")
+    ref = variants[0]
+    for v in variants[1:]:
+        same = [np.array_equal(res[ref][i], res[v][i]) for i in range(3)]
+        d = [float(np.abs(res[ref][i] - res[v][i]).max()) for i in range(3)]
+        print(f"  {v} vs {ref}: scores / scores[:300] / mel[:300] identical = {same}  max diff = {d}")
