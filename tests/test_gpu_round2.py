@@ -314,8 +314,9 @@ def test_load_model_from_onnx_with_cascade(torch_cuda, tmp_path, golden_frontend
     assert passed > 0 or skipped > 0
 
 
-@pytest.mark.parametrize("mt", ["cnn", "tcn", "crnn", "dnn", "e2e_quartznet"])
-def test_selective_stream_push_scores_only_the_listed_streams(torch_cuda, mt):
+@pytest.mark.parametrize("mt,L", [("cnn", 1280), ("tcn", 1280), ("crnn", 1280), ("dnn", 1280), ("e2e_quartznet", 1280),
+                                  ("cnn", 1000), ("tcn", 777), ("gru", 1280)])
+def test_selective_stream_push_scores_only_the_listed_streams(torch_cuda, mt, L):
     """nww_stream_push_select[_host]: every stream ingests its chunk, only the listed ones are scored — and they get
     exactly the score a full push gives them (bit-identical), in any order of ids, across launch-chunk boundaries."""
     from nanowakeword_b200 import Engine
@@ -323,11 +324,11 @@ def test_selective_stream_push_scores_only_the_listed_streams(torch_cuda, mt):
     sd = make_state_dict(cfg, seed=0)
     full = Engine(sd, cfg, device=0, chunk_windows=37)
     sel = Engine(sd, cfg, device=0, chunk_windows=37)
-    n, L = 101, 1280
+    n = 101                                  # L = 1280: incremental mel ring; 1000 / 777: full windows out of the PCM ring
     full.stream_open(n)
     sel.stream_open(n)
     rng = np.random.default_rng(17)
-    for step in range(17):
+    for step in range(17 if L >= 1000 else 25):
         chunks = np.clip(rng.normal(0, 3000, (n, L)), -32768, 32767).astype(np.int16)
         ids = rng.permutation(n)[:rng.integers(0, n + 1)] if step % 5 else np.arange(0)
         a = full.stream_push_host(chunks)
