@@ -522,3 +522,14 @@ def test_crnn_packer_refuses_what_the_engine_does_not_build():
     lstm["model.rnn.weight_hh_l0"] = np.zeros((512, 128), np.float32)
     with pytest.raises(ValueError, match=r"\(4H, H\)"):
         pack_tensors(lstm, cfg)
+
+
+def test_package_exports_match_the_reference():
+    """nanowakeword/__init__.py:1-5 exports NanoInterpreter, VAD, AudioFeatures: the names import; the two that are out
+    of scope say so when constructed."""
+    import nanowakeword_b200 as pkg
+    for name in ("NanoInterpreter", "VAD", "AudioFeatures"):
+        assert hasattr(pkg, name) and name in pkg.__all__
+    for cls in (pkg.VAD, pkg.AudioFeatures):
+        with pytest.raises(NotImplementedError, match="outside the B200 hot path"):
+            cls()
