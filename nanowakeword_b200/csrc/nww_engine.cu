@@ -732,9 +732,9 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
                     int r_rs = 2 * cin;
                     if (cin != Cc) {
                         rc = add(e->blob.f32(p + ".down.w"), H.tcn_down[l].b, cin, 1, Cc, x_in_mel, x_off + 4ll * cin, 2 * cin, C.n_out[l], 0,
-                                 C.off_res, 0, 0, 0, 0, 0);
+                                 H.tcn_res_off[l], 0, 0, 0, 0, 0);
                         if (rc) return rc;
-                        r_off = C.off_res;
+                        r_off = H.tcn_res_off[l];
                         r_rs = Cc;
                     } else if (x_in_mel) {
                         ok = false;                                          // an identity residual straight from the log-mel: not built
@@ -748,6 +748,10 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
                 }
                 H.tcn_n_row_layers = li;
                 H.tcn_rows = ok;
+                // bit 7: all layers (+ the stream-mode gather) in ONE cooperative launch.  Measured 15 % slower than one launch
+                // per layer (14.7 vs 18.2 M stream-steps/s at 65 536 streams: the grid barriers cost more than the launches
+                // they replace), so it is opt-in: 4 launches per push instead of 12
+                H.tcn_fused = (spec->reserved[0] & 128) != 0;
             }
             if (spec->arch == NWW_ARCH_CRNN_GRU && e->heads.gru_hidden == kGruTcH && e->heads.gru_wih_f_kn &&
                 !(spec->reserved[0] & 1)) {

@@ -51,7 +51,10 @@ struct HeadWeights {
         const uint4* wq;
         const float* bias;
     };
+    int tcn_rows_pw = 0;              // floats of activation scratch per window in the row-GEMM form (cone + per-level residuals)
+    int tcn_res_off[8] = {0};
     bool tcn_rows = false;
+    bool tcn_fused = false;           // all layers (and the stream-mode gather) in one cooperative launch (opt-in)
     int tcn_n_row_layers = 0;
     TcnRowLayer tcn_row[12];
     bool tcn_umma = false;            // ... with the layer GEMMs on tcgen05 (nww_tcn_umma.cuh)
@@ -207,7 +210,22 @@ inline int setup_head_weights(int arch, int geometry, const BlobLookup& get, con
         }
         hw->tcn_cone = cone_ok;
         // the (T, F) log-mel + (row-GEMM layers) the cone's activations of one window
-        if (cone_ok) hw->scratch_floats = (size_t)GeoNS40x98::N_FRAMES * hw->tcn_in + hw->tcn_plan.per_window;
+        if (cone_ok) {
+            // row-GEMM layers: every level that has a 1x1 downsample gets its OWN residual buffer behind the cone's
+            // activations (a buffer written twice in one launch could be stale in another SM's L1 in the fused kernel)
+            int pw = hw->tcn_plan.per_window;
+            int cin_l = hw->tcn_in;
+            for (int i = 0; i < lv; ++i) {
+                hw->tcn_res_off[i] = -1;
+                if (cin_l != hw->tcn_ch[i]) {
+                    hw->tcn_res_off[i] = pw;
+                    pw += hw->tcn_plan.n_out[i] * hw->tcn_ch[i];
+                }
+                cin_l = hw->tcn_ch[i];
+            }
+            hw->tcn_rows_pw = (pw + 3) & ~3;
+            hw->scratch_floats = (size_t)GeoNS40x98::N_FRAMES * hw->tcn_in + hw->tcn_rows_pw;
+        }
     } else if (arch == NWW_ARCH_BCRESNET) {
         if (geometry != NWW_GEOM_NS40X98) { *err = "bcresnet head is built for the NS40x98 geometry"; return NWW_EUNSUPPORTED; }
         hw->bc_init = {need("bc.init.w", 32 * 9), need("bc.init.b", 32)};
@@ -600,6 +618,43 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
         const int frame_lo = (T - P.n_in) & ~1;
         if (!mel_ready && (rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel, 1, st, launches, err, frame_lo))) return rc;
         if (mel_dump && (rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel_dump, 0, st, launches, err))) return rc;
+        if (hw.tcn_rows && hw.tcn_fused && hw.tcn_n_row_layers <= kTcnFusedMaxLayers && P.n_in <= kMelTailMax) {
+            // ONE cooperative launch: [gather of the cone's frames out of the mel ring] + all layers, grid barriers in between
+            float* act = take((size_t)hw.tcn_rows_pw);
+            TcnFusedParams FP{};
+            FP.n_layers = hw.tcn_n_row_layers;
+            FP.ring = ring;
+            FP.n = n;
+            FP.mel = mel;
+            FP.t0 = T - P.n_in;
+            FP.n_tail = P.n_in;
+            for (int li = 0; li < hw.tcn_n_row_layers; ++li) {
+                const HeadWeights::TcnRowLayer& L = hw.tcn_row[li];
+                const long long a_ws = L.a_in_mel ? (long long)F * T : hw.tcn_rows_pw, o_ws = L.o_in_feat ? L.N : hw.tcn_rows_pw;
+                TcnFusedLayer& D = FP.L[li];
+                D.A = (L.a_in_mel ? mel : act) + L.a_off;
+                D.av = kc_seq(L.n_pos, a_ws, L.a_row_stride, 0);
+                D.k_valid = L.k_valid; D.K = L.K; D.wq = L.wq; D.bias = L.bias;
+                D.res = L.has_res ? act + L.r_off : nullptr;
+                D.rv = kc_seq(L.n_pos, hw.tcn_rows_pw, L.r_row_stride, 0);
+                D.out = (L.o_in_feat ? feat : act) + L.o_off;
+                D.ov = kc_seq(L.n_pos, o_ws, L.N, 0);
+                D.rows = n * L.n_pos; D.N = L.N; D.act = L.act; D.pre_relu = L.pre_relu;
+            }
+            const size_t smem = rowgemm_kc_smem_bytes(2);
+            NWW_HCUDA(set_smem(tcn_rows_fused_kernel, smem));
+            NWW_HCUDA(cudaFuncSetAttribute(tcn_rows_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            int per_sm = 0;
+            NWW_HCUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tcn_rows_fused_kernel, kKcNT, smem));
+            if (per_sm >= 1) {
+                const long long tiles0 = (n * hw.tcn_row[0].n_pos + kKcRows - 1) / kKcRows;
+                const int grid = (int)std::min<long long>(std::max<long long>(tiles0, 1), (long long)sm_count * std::min(per_sm, 2));
+                void* args[] = {(void*)&FP};
+                NWW_HCUDA(cudaLaunchCooperativeKernel((const void*)tcn_rows_fused_kernel, dim3(grid), dim3(kKcNT), args, smem, st));
+                return done();
+            }
+            p -= (size_t)hw.tcn_rows_pw * (size_t)n;        // no co-residency: fall through to one launch per layer
+        }
         if (hw.tcn_rows) {
             // stream mode: the cone's frames out of the mel ring, time-major, into the same place the front end writes them
             if (ring.ring != nullptr) {
@@ -608,20 +663,20 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
                                          kMelTailWarps * 32, 0, st>>>(ring, n, mel, T - P.n_in, P.n_in);
                 if ((rc = done())) return rc;
             }
-            float* act = take((size_t)P.per_window);
+            float* act = take((size_t)hw.tcn_rows_pw);
             NWW_HCUDA(set_smem(rowgemm_kc_umma_kernel<true>, rowgemm_kc_smem_bytes()));
             NWW_HCUDA(cudaFuncSetAttribute(rowgemm_kc_umma_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             for (int li = 0; li < hw.tcn_n_row_layers; ++li) {
                 const HeadWeights::TcnRowLayer& L = hw.tcn_row[li];
                 const long long rows = n * L.n_pos;
-                const long long a_ws = L.a_in_mel ? (long long)F * T : P.per_window, o_ws = L.o_in_feat ? L.N : P.per_window;
+                const long long a_ws = L.a_in_mel ? (long long)F * T : hw.tcn_rows_pw, o_ws = L.o_in_feat ? L.N : hw.tcn_rows_pw;
                 const float* A = (L.a_in_mel ? mel : act) + L.a_off;
                 float* O = (L.o_in_feat ? feat : act) + L.o_off;
                 const KcLaunch kl = rowgemm_kc_launch(rows, L.N, sm_count);
                 rowgemm_kc_umma_kernel<true><<<kl.grid, kKcNT, kl.smem, st>>>(
                     A, kc_seq(L.n_pos, a_ws, L.a_row_stride, 0), kc_one_seg(L.k_valid), L.K, L.wq, L.bias,
                     L.has_res ? act + L.r_off : nullptr, O, kc_seq(L.n_pos, o_ws, L.N, 0), rows, L.N, L.N, L.act, kl.ring,
-                    kc_seq(L.n_pos, P.per_window, L.r_row_stride, 0), L.pre_relu);
+                    kc_seq(L.n_pos, hw.tcn_rows_pw, L.r_row_stride, 0), L.pre_relu);
                 if ((rc = done())) return rc;
             }
             return NWW_OK;

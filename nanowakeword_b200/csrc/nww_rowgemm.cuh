@@ -5,6 +5,10 @@
 // product h W_hh^T of every step.
 #pragma once
 
+#ifndef NWW_CPUSIM
+#include <cooperative_groups.h>
+#endif
+
 #include <string.h>
 #include <vector>
 
@@ -477,40 +481,38 @@ inline KcSegs kc_one_seg(int k_valid) { return KcSegs{1 << 30, 0, k_valid}; }
 // act: 0 none, 1 ReLU, 2 GELU, 3 SiLU (apply_act codes + 1)
 // VIEWS = false is the fast path for plain matrices (A = [rows][K], out = [rows][N], all columns stored, act 0 / 1):
 // no per-row address table, no segment arithmetic, no column masks.
-template <bool VIEWS>
-__global__ void __launch_bounds__(kKcNT, VIEWS ? 2 : 1)
-rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, KcSegs sg, int K, const uint4* __restrict__ wq,
-                       const float* __restrict__ bias, const float* __restrict__ res, float* __restrict__ out, KcView ov, long long rows,
-                       int N, int n_valid, int act, int ring,
-                       KcView rv = KcView{0, 0, 0, 0, 0, 0} /* where the residual row of GEMM row r lives; rpw == 0: res + r * N */,
-                       int pre_relu = 0 /* ReLU before the residual is added: TemporalBlock's relu(relu(conv2) + res) */) {
-    NWW_DYN_SMEM(smem);
+// Read path of the operand / residual loads: the read-only (non-coherent) path for a launch per layer; plain cached loads
+// inside the fused multi-layer kernel, where a layer reads what OTHER SMs wrote earlier in the same launch.  That is safe
+// because every activation buffer of the cone is written exactly once per launch, before its first read (the layer
+// program gives each level its own residual buffer), so no SM can hold a stale L1 line; L2-only loads (ld.global.cg)
+// were measured 40 % slower — the rows of a layer overlap (three taps) and want L1.
+template <bool COHERENT> __device__ __forceinline__ float4 kc_ld(const float4* p) {
+#ifndef NWW_CPUSIM
+    if (COHERENT) return *p;
+#endif
+    return __ldg(p);
+}
+
+// mbarrier / ring bookkeeping that lives across tiles (and, in the fused kernel, across layers)
+struct KcState { uint32_t c_slot = 0, c_par = 0, p_slot = 0, done_phase = 0, g = 0; };
+
+// All tiles of one row GEMM for this CTA (see rowgemm_kc_umma_kernel for the arguments); shared-memory carve-up, barriers
+// and TMEM were set up by the caller.
+template <bool VIEWS, bool COHERENT>
+__device__ __forceinline__ void rowgemm_kc_run(const float* __restrict__ A, const KcView& av, const KcSegs& sg, int K,
+                                               const uint4* __restrict__ wq, const float* __restrict__ bias,
+                                               const float* __restrict__ res, float* __restrict__ out, const KcView& ov, long long rows,
+                                               int N, int n_valid, int act, int ring, const KcView& rv, int pre_relu, KcState& S,
+                                               unsigned char* a_s, unsigned char* b_s, uint64_t* bar_full, uint64_t* bar_empty,
+                                               uint64_t* bar_afree, uint64_t* bar_done, long long* row_at, uint32_t tmem_base) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    unsigned char* a_s = smem;                                         // two chunk buffers
-    unsigned char* b_s = smem + 2 * kKcABuf;                           // weight ring
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(b_s + ring * kKcSub);
-    uint64_t* bar_empty = bar_full + kKcRing;
-    uint64_t* bar_afree = bar_full + 2 * kKcRing;                      // [2]: the MMAs that read chunk buffer b are done
-    uint64_t* bar_done = bar_full + 2 * kKcRing + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + 2 * kKcRing + 3);
-    long long* row_at = reinterpret_cast<long long*>(b_s + ring * kKcSub + 256);   // A offsets of the tile's rows
-    const uint32_t tmem_cols = N <= 64 ? 64u : N <= 128 ? 128u : N <= 256 ? 256u : 512u;
-    if (tid == 0) {
-        for (int i = 0; i < 2 * kKcRing + 3; ++i) mbar_init(bar_full + i, 1);
-        fence_mbar_init();
-    }
-    if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
     const uint32_t idesc = umma_idesc_bf16(128, kKcNC);
     const uint64_t da_buf0 = umma_desc_noswz(smem_u32(a_s), kKcRows * 16, 128);
     const uint64_t db_ring = umma_desc_noswz(smem_u32(b_s), kKcNC * 16, 128);
     const int n_kc = K / kKcKC, n_nc = N / kKcNC, total = n_kc * n_nc;
-    uint32_t c_slot = 0, c_par = 0, p_slot = 0, done_phase = 0;
-    uint32_t g = 0;                                                    // chunks converted so far: buffer g & 1
-    for (long long r0 = (long long)blockIdx.x * kKcRows; r0 < rows; r0 += (long long)gridDim.x * kKcRows) {
+    uint32_t& c_slot = S.c_slot; uint32_t& c_par = S.c_par; uint32_t& p_slot = S.p_slot; uint32_t& done_phase = S.done_phase;
+    uint32_t& g = S.g;                                                 // chunks converted so far: buffer g & 1
+    for (long long r0 = (long long)blockIdx.x * kKcRows; r0 < rows; r0 += (long long)gridDim.x * kKcRows) {   // persistent over the launch's tiles
         int p_pos = 0, prev_slot = -1;
         uint32_t prev_par = 0;
         auto produce = [&]() {                                         // thread 0: next sub-block of the tile's stream
@@ -549,8 +551,8 @@ rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, KcSegs sg, int K,
                 if (ra >= 0 && (!VIEWS || k8 < sg.k_valid)) {
                     const int seg = VIEWS ? k8 / sg.seg_len : 0;
                     const float4* p = reinterpret_cast<const float4*>(A + ra + (VIEWS ? seg * sg.seg_stride + (k8 - seg * sg.seg_len) : k8));
-                    v0[j] = __ldg(p);
-                    v1[j] = __ldg(p + 1);
+                    v0[j] = kc_ld<COHERENT>(p);
+                    v1[j] = kc_ld<COHERENT>(p + 1);
                     k8s[j] = k8;
                 }
             }
@@ -631,7 +633,7 @@ rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, KcSegs sg, int K,
                                                v[4 * j4 + 2] + __ldg(bias + c0 + 4 * j4 + 2), v[4 * j4 + 3] + __ldg(bias + c0 + 4 * j4 + 3));
                         if (VIEWS && pre_relu) { o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f); }
                         if (rs) {
-                            const float4 t = __ldg(rs + j4);
+                            const float4 t = kc_ld<COHERENT>(rs + j4);
                             o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
                         }
                         if (!VIEWS) {
@@ -647,6 +649,38 @@ rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, KcSegs sg, int K,
         tc_fence_before();
         __syncthreads();
     }
+}
+
+template <bool VIEWS>
+__global__ void __launch_bounds__(kKcNT, VIEWS ? 2 : 1)
+rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, KcSegs sg, int K, const uint4* __restrict__ wq,
+                       const float* __restrict__ bias, const float* __restrict__ res, float* __restrict__ out, KcView ov, long long rows,
+                       int N, int n_valid, int act, int ring,
+                       KcView rv = KcView{0, 0, 0, 0, 0, 0} /* where the residual row of GEMM row r lives; rpw == 0: res + r * N */,
+                       int pre_relu = 0 /* ReLU before the residual is added: TemporalBlock's relu(relu(conv2) + res) */) {
+    NWW_DYN_SMEM(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned char* a_s = smem;                                         // two chunk buffers
+    unsigned char* b_s = smem + 2 * kKcABuf;                           // weight ring
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(b_s + ring * kKcSub);
+    uint64_t* bar_empty = bar_full + kKcRing;
+    uint64_t* bar_afree = bar_full + 2 * kKcRing;                      // [2]: the MMAs that read chunk buffer b are done
+    uint64_t* bar_done = bar_full + 2 * kKcRing + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + 2 * kKcRing + 3);
+    long long* row_at = reinterpret_cast<long long*>(b_s + ring * kKcSub + 256);   // A offsets of the tile's rows
+    const uint32_t tmem_cols = N <= 64 ? 64u : N <= 128 ? 128u : N <= 256 ? 256u : 512u;
+    if (tid == 0) {
+        for (int i = 0; i < 2 * kKcRing + 3; ++i) mbar_init(bar_full + i, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    KcState S;
+    rowgemm_kc_run<VIEWS, false>(A, av, sg, K, wq, bias, res, out, ov, rows, N, n_valid, act, ring, rv, pre_relu, S, a_s, b_s, bar_full,
+                                 bar_empty, bar_afree, bar_done, row_at, tmem_base);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -654,6 +688,94 @@ rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, KcSegs sg, int K,
         tmem_dealloc(tmem_base, tmem_cols);
     }
 }
+
+#ifndef NWW_CPUSIM
+// ---------------------------------------------------------------------------------------
+// The TCN dependency cone (nww_tcn.cuh) as ONE cooperative launch: every layer is the row GEMM above over all windows
+// of the launch group, with a grid-wide barrier between layers (layer l + 1 reads what other CTAs wrote in layer l, so
+// its operand / residual loads go to L2: kc_ld<true>).  In stream mode the launch starts with the gather of the cone's
+// frames out of the mel ring (stream_mel_tail_kernel's job: one warp per stream, transposed through shared memory).
+// Replaces 9 launches per push (tail gather + 8 layers) by one; same tiles, same order: bit-identical.
+// ---------------------------------------------------------------------------------------
+struct TcnFusedLayer {
+    const float* A; KcView av; int k_valid, K;
+    const uint4* wq; const float* bias;
+    const float* res; KcView rv;
+    float* out; KcView ov;
+    long long rows; int N, act, pre_relu;
+};
+constexpr int kTcnFusedMaxLayers = 9;
+struct TcnFusedParams {
+    int n_layers;
+    TcnFusedLayer L[kTcnFusedMaxLayers];
+    MelRingRef ring;            // ring.ring != nullptr: gather first
+    long long n;                // windows (streams) of the launch group
+    float* mel;                 // time-major (n, T, F) log-mel buffer the first layer reads
+    int t0, n_tail;
+};
+
+__global__ void __maxnreg__(96)          // two CTAs of 256 threads per SM with room to spare (registers come in groups of four warps)
+tcn_rows_fused_kernel(const __grid_constant__ TcnFusedParams P) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    NWW_DYN_SMEM(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int ring = 2;
+    unsigned char* a_s = smem;
+    unsigned char* b_s = smem + 2 * kKcABuf;
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(b_s + ring * kKcSub);
+    uint64_t* bar_empty = bar_full + kKcRing;
+    uint64_t* bar_afree = bar_full + 2 * kKcRing;
+    uint64_t* bar_done = bar_full + 2 * kKcRing + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + 2 * kKcRing + 3);
+    long long* row_at = reinterpret_cast<long long*>(b_s + ring * kKcSub + 256);
+    constexpr uint32_t tmem_cols = 128;                                // every layer of the cone has N <= 128
+    if (tid == 0) {
+        for (int i = 0; i < 2 * kKcRing + 3; ++i) mbar_init(bar_full + i, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (P.ring.ring != nullptr) {
+        // the cone's n_tail frames of every stream, time-major, where the batch front end would have written them
+        float* tile = reinterpret_cast<float*>(a_s) + (size_t)warp * (kMelTailMax * (SMel::F + 1));
+        const int nw = kKcNT / 32;
+        for (long long w = (long long)blockIdx.x * nw + warp; w < P.n; w += (long long)gridDim.x * nw) {
+            const long long s = P.ring.stream(w);
+            const int head = smel_slot(P.ring.count[s] / SMel::HOP - 3 + 1);
+            const float* src = P.ring.ring + s * SMel::STREAM_FLOATS + head + P.t0;
+            if (lane < P.n_tail)
+                for (int m = 0; m < SMel::F; ++m) tile[lane * (SMel::F + 1) + m] = src[m * SMel::ROW + lane];
+            __syncwarp();
+            float* dst = P.mel + w * (long long)(SMel::F * SMel::T) + (long long)P.t0 * SMel::F;
+            for (int i = lane; i < P.n_tail * SMel::F; i += 32) dst[i] = tile[(i / SMel::F) * (SMel::F + 1) + i % SMel::F];
+            __syncwarp();
+        }
+        __threadfence();
+        grid.sync();
+    }
+    KcState S;
+    for (int l = 0; l < P.n_layers; ++l) {
+        const TcnFusedLayer& L = P.L[l];
+        rowgemm_kc_run<true, true>(L.A, L.av, KcSegs{1 << 30, 0, L.k_valid}, L.K, L.wq, L.bias, L.res, L.out, L.ov, L.rows, L.N, L.N, L.act, ring,
+                                   L.rv, L.pre_relu, S, a_s, b_s, bar_full, bar_empty, bar_afree, bar_done, row_at, tmem_base);
+        if (l + 1 < P.n_layers) {
+            __threadfence();
+            grid.sync();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+#endif
 
 // QuartzNet depthwise Conv1d (padding 'same', no bias: it is folded into the pointwise bias) on channel-last rows.
 // x [n][T][in_pitch] (first C channels used), dw [k][Cp];  a [n * T][K]: columns [0, Cp) = depthwise output

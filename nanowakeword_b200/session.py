@@ -62,11 +62,11 @@ class Engine:
             raise ValueError("cnn_stage must be 'v1', 'v2', 'v3' or 'v4'")
         # bit 2: streams always re-run the front end on the whole window (no incremental mel ring)
         # bit 4: TCN cone as the per-tile kernel (nww_tcn_umma.cuh) instead of one row GEMM per layer over the launch group
-        if tcn_layers not in ("rows", "cone"):
-            raise ValueError("tcn_layers must be 'rows' or 'cone'")
+        if tcn_layers not in ("rows", "rows_fused", "cone"):
+            raise ValueError("tcn_layers must be 'rows', 'rows_fused' or 'cone'")
         # bit 3: the phase-serial tcgen05 CNN stage (nww_cnn2.cuh) instead of the warp-specialised pipeline (nww_cnn3.cuh)
         spec.reserved[0] = ((0 if tensor_cores else 1) | (2 if cnn_stage == "v1" else 0) | (0 if stream_incremental else 4)
-                            | (0 if pipelined else 8) | (0 if tcn_layers == "rows" else 16)
+                            | (0 if pipelined else 8) | (16 if tcn_layers == "cone" else 0) | (128 if tcn_layers == "rows_fused" else 0)   # bit 7: the cone's layers in one cooperative launch
                             | (0 if stream_ingest == "fused" else 32)        # bit 5: ring append and mel update as two kernels
                             | (64 if split else 0))                           # bit 6: split CNN stage (front-end + conv kernels)
         spec.reserved[1] = int(split_per_sm)                                  # windows per SM and sub-chunk of the split stage (0 = default)

@@ -376,3 +376,27 @@ def test_cascade_bank_on_engines_scales_with_the_gate(torch_cuda):
     assert bank.verifier.engine.info["kernel_launches"] - l0 == 1            # the fused ingest kernel only
     assert np.all(bank.raw_scores == 0.0)
     bank.close()
+
+
+def test_tcn_fused_cone_launch_is_bit_identical_to_per_layer_launches(torch_cuda):
+    """The cooperative single-launch form of the TCN's row-GEMM layers (grid barriers between layers, L2 loads, the
+    stream-mode gather inside) against one launch per layer: same bits in batch mode (ragged chunks) and stream mode."""
+    from nanowakeword_b200 import Engine
+    cfg = default_config("tcn")
+    sd = make_state_dict(cfg, seed=0)
+    a = Engine(sd, cfg, device=0, tcn_layers="rows_fused")
+    b = Engine(sd, cfg, device=0)
+    pcm = np.concatenate([synth_pcm(700, seed=5, kind="gauss"), synth_pcm(337, seed=6, kind="uniform")])
+    dev = torch_cuda.from_numpy(pcm).cuda()
+    assert np.array_equal(a.score_device(dev).cpu().numpy(), b.score_device(dev).cpu().numpy())
+    n, L = 333, 1280
+    a.stream_open(n)
+    b.stream_open(n)
+    rng = np.random.default_rng(3)
+    la = a.info["kernel_launches"]
+    for step in range(15):
+        chunks = np.clip(rng.normal(0, 3000, (n, L)), -32768, 32767).astype(np.int16)
+        assert np.array_equal(a.stream_push_host(chunks), b.stream_push_host(chunks)), step
+    assert (a.info["kernel_launches"] - la) == 15 * 4          # ingest, fused cone, dense tail, mask
+    a.stream_close()
+    b.stream_close()
