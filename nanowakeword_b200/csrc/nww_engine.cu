@@ -571,6 +571,14 @@ static void stream_free(nww_engine* e) {
     e->d_mel_ring = nullptr;
     e->mel_inc = false;
     e->streams = StreamState{};
+    // the selective-push staging is sized by the bank: a re-opened (larger) bank allocates it again
+    cudaFree(e->d_sel_ids);
+    cudaFree(e->d_sel_off);
+    cudaFree(e->d_sel_scores);
+    e->d_sel_ids = nullptr;
+    e->d_sel_off = nullptr;
+    e->d_sel_scores = nullptr;
+    e->sel_cap = 0;
 }
 
 template <typename T>

@@ -341,6 +341,12 @@ def test_selective_stream_push_scores_only_the_listed_streams(torch_cuda, mt, L)
         want[ids] = a[ids]
         assert np.array_equal(b, want), (mt, step, np.abs(b - want).max())
     assert (a != 0).any()
+    # a re-opened, larger bank re-allocates the selection staging
+    sel.stream_open(4 * n)
+    big = np.tile(chunks, (4, 1))
+    got = sel.stream_push_host(big, select=np.arange(4 * n - 1, -1, -1))
+    assert got.shape == (4 * n,) and np.all(got == 0.0)          # rings not full yet: every score is masked
+    sel.stream_open(n)
     with pytest.raises(ValueError):
         sel.stream_push_host(chunks, select=[0, 0])
     with pytest.raises(ValueError):
