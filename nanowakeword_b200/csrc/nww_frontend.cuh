@@ -48,7 +48,7 @@ template <typename T> struct FrontendTables {
     const float* mel_w;         // packed filter weights (float32 values of the reference's fb)
     float amin;                 // 1e-10
     float floor_db;             // 10*log10(amin)
-    int mel_vec_ok;             // every filter fits the 32-bin padded row of the vectorised mel (nww_fe2.cuh)
+    int mel_vec_ok;             // every filter fits the padded row of the vectorised mel (nww_fe2.cuh: 32 bins; nww_fe5.cuh: 20)
 };
 
 // --------------------------------------------------------------------------- small DFTs

@@ -11,6 +11,7 @@
 #include "../../include/nww_b200.h"
 #include "nww_layers.cuh"
 #include "nww_fe3.cuh"
+#include "nww_fe5.cuh"
 #include "nww_stage.cuh"
 #include "nww_tail.cuh"
 #include "nww_tcn.cuh"
@@ -143,6 +144,9 @@ static int launch_frontend_f64(const FrontendTables<double>& tab, int sm_count, 
     } else if constexpr (std::is_same<G, GeoNS40x98>::value) {
         NWW_HCUDA(set_smem(frontend3_kernel, Fe3KernelSmem::kTotal));
         frontend3_kernel<<<grid, Fe3::NT, Fe3KernelSmem::kTotal, st>>>(pcm, n, tab, mel, time_major, frame_lo);
+    } else if (tab.mel_vec_ok) {
+        NWW_HCUDA(set_smem(frontend5_kernel, Fe5::kTotal));
+        frontend5_kernel<<<grid, Fe5::NT, Fe5::kTotal, st>>>(pcm, n, tab, mel, time_major);
     } else {
         auto k = frontend_kernel<double, G, kNfbRef, kStageNT>;
         NWW_HCUDA(set_smem(k, FrontendSmem<double, G, kNfbRef>::kTotal));

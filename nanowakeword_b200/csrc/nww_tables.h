@@ -21,7 +21,7 @@ struct HostFrontendTables {
     std::vector<uint16_t> binpos;
     std::vector<int> mel_start, mel_count, mel_woff;
     std::vector<float> mel_w;
-    int mel_vec_ok = 0;                    // all filters: (start % 4) + count <= 32 (and <= 40 filters)
+    int mel_vec_ok = 0;                    // all filters fit the padded row of the vectorised mel (see below)
 };
 
 // radices[] lists the DIF pass radices in execution order; their product must be n_fft.
@@ -82,9 +82,12 @@ inline bool build_frontend_tables(int n_fft, int win, int n_mels, const int* rad
         out->mel_count[m] = last - first + 1;
         for (int k = first; k <= last; ++k) out->mel_w.push_back(fb_f32[(size_t)k * n_mels + m]);
     }
-    out->mel_vec_ok = n_mels <= 40;
+    // the padded-row mel of the warp-private front ends: 40 filters x 32 bins (nww_fe2.cuh, n_fft 512) or
+    // 64 filters x 20 bins (nww_fe5.cuh, n_fft 400); other tables take the generic front end
+    const int row = (n_fft == 400) ? 20 : 32;
+    out->mel_vec_ok = (n_fft == 400) ? (n_mels == 64) : (n_mels <= 40);
     for (int m = 0; m < n_mels; ++m)
-        if ((out->mel_start[m] & 3) + out->mel_count[m] > 32) out->mel_vec_ok = 0;
+        if ((out->mel_start[m] & 3) + out->mel_count[m] > row) out->mel_vec_ok = 0;
     return true;
 }
 
