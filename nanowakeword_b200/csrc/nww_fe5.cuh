@@ -27,7 +27,7 @@ namespace nww {
 
 struct Fe5 {
     using G = GeoREF64x101;
-    static constexpr int NT = 512, NWARP = 16;
+    static constexpr int NT = 384, NWARP = 12;                  // 168 registers per thread: the radix-20 butterflies do not spill
     static constexpr int N_PACKED = (G::N_FRAMES + 1) / 2;      // 51 packed FFTs per window
     static constexpr int P = 21;                                // pitch (complex) of a pass-1 output row: odd, so that
                                                                 // lanes reading different rows hit different 16-byte banks
