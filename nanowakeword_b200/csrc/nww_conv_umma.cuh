@@ -18,6 +18,7 @@
 #pragma once
 
 #include <string.h>
+#include <algorithm>
 #include <vector>
 
 #include "nww_tc.cuh"
@@ -42,6 +43,10 @@ struct ConvUmmaPlan {
     int kg;           // Cin / 8
     int tmem_cols;    // power of two >= tiles * quads * Cout
     size_t a_bytes, b_bytes, smem_bytes;
+    // fused first layer (conv_umma_plan_front1): the loader computes Conv2d(1, Cin, 3, pad 1) + act + MaxPool2d(2) from the
+    // log-mel (Hm x Wm per window) straight into the position lists, so that layer's activations never exist in HBM
+    int f1_hm = 0, f1_wm = 0, f1_pitch = 0;
+    size_t f1_tile = 0, f1_stage = 0, f1_w = 0;      // shared-memory offsets: zero-bordered mel tile | raw mel (TMA target) | weights + bias
 };
 
 inline bool conv_umma_plan(int H, int W, int Cin, int Cout, int pool, ConvUmmaPlan* p) {
@@ -61,6 +66,24 @@ inline bool conv_umma_plan(int H, int W, int Cin, int Cout, int pool, ConvUmmaPl
     p->b_bytes = (size_t)9 * 2 * p->kg * Cout * 16;
     p->smem_bytes = p->a_bytes + p->b_bytes + Cout * sizeof(float) + 128;
     return p->smem_bytes <= 220 * 1024;
+}
+
+// Adds the fused first layer to a plan: mel (Hm, Wm) -> conv 3x3 (1 -> Cin = 16) -> pool -> (H, W) = (Hm / 2, Wm / 2).
+inline bool conv_umma_plan_front1(ConvUmmaPlan* plan, int Hm, int Wm) {
+    ConvUmmaPlan q = *plan;                                               // the plan changes only if everything fits
+    ConvUmmaPlan* p = &q;
+    if (!p->pool || p->Cin != 16 || p->H != Hm / 2 || p->W != Wm / 2 || (Hm * Wm) % 4) return false;
+    p->f1_hm = Hm; p->f1_wm = Wm;
+    p->f1_pitch = (std::max(Wm + 2, 2 * p->W + 4) + 3) / 4 * 4;           // even: the 4 x 4 patches are read as float2
+    size_t off = (p->smem_bytes + 127) / 128 * 128;
+    p->f1_tile = off;  off += (size_t)(Hm + 2) * p->f1_pitch * sizeof(float);
+    off = (off + 127) / 128 * 128;
+    p->f1_stage = off; off += (size_t)Hm * Wm * sizeof(float);
+    p->f1_w = off;     off += (size_t)(9 * 16 + 16) * sizeof(float) + 16;  // + the mel mbarrier
+    p->smem_bytes = off;
+    if (p->smem_bytes > 227 * 1024) return false;
+    *plan = q;
+    return true;
 }
 
 // host: folded (Cin, 9, Cout) FP32 weights -> [tap][hi|lo][K group][Cout][8] bf16
@@ -91,9 +114,13 @@ inline void conv_umma_pack_weights(const float* w, int Cin, int Cout, std::vecto
 }
 
 // in [n][H*W][Cin] -> out [n][Ho*Wo][Cout]  (Ho, Wo = H/2, W/2 with pool)
+// FRONT1: `in` is the log-mel [n][Hm][Wm]; w1 [9][16] (tap-major) and b1 [16] are the first layer's folded weights (the
+// arithmetic of bc_init_conv_kernel, FMA for FMA, so both routes give the same activations).
+template <bool FRONT1>
 __global__ void __launch_bounds__(kCuNT, 1)
 conv3x3_umma_kernel(const float* __restrict__ in, const uint4* __restrict__ wq, const float* __restrict__ bias,
-                    float* __restrict__ out, long long n_windows, ConvUmmaPlan P, int act) {
+                    float* __restrict__ out, long long n_windows, ConvUmmaPlan P, int act,
+                    const float* __restrict__ w1 = nullptr, const float* __restrict__ b1 = nullptr) {
     NWW_DYN_SMEM(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned char* a_s = smem;
@@ -112,9 +139,28 @@ conv3x3_umma_kernel(const float* __restrict__ in, const uint4* __restrict__ wq, 
     for (int i = tid; i < (int)(P.a_bytes / 16); i += kCuNT) reinterpret_cast<uint4*>(a_s)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < (int)(P.b_bytes / 16); i += kCuNT) reinterpret_cast<uint4*>(b_s)[i] = __ldg(wq + i);
     for (int i = tid; i < P.Cout; i += kCuNT) bias_s[i] = bias[i];
+    float* tile1 = reinterpret_cast<float*>(smem + P.f1_tile);
+    float* stage1 = reinterpret_cast<float*>(smem + P.f1_stage);
+    float* w1s = reinterpret_cast<float*>(smem + P.f1_w);                  // [9][16] | bias [16]
+    uint64_t* mel_bar = reinterpret_cast<uint64_t*>(smem + P.f1_w + (9 * 16 + 16) * sizeof(float));
+    const uint32_t mel_bytes = (uint32_t)(P.f1_hm * P.f1_wm) * (uint32_t)sizeof(float);
+    if (FRONT1) {
+        for (int i = tid; i < (P.f1_hm + 2) * P.f1_pitch; i += kCuNT) tile1[i] = 0.0f;     // the border stays zero
+        for (int i = tid; i < 9 * 16; i += kCuNT) w1s[i] = w1[i];
+        for (int i = tid; i < 16; i += kCuNT) w1s[9 * 16 + i] = b1[i];
+        if (tid == 0) {
+            mbar_init(mel_bar, 1);
+            fence_mbar_init();
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (FRONT1 && tid == 0 && (long long)blockIdx.x < n_windows) {
+        mbar_expect_tx(mel_bar, mel_bytes);
+        bulk_g2s(stage1, in + (long long)blockIdx.x * (P.f1_hm * P.f1_wm), mel_bytes, mel_bar);
+    }
+    uint32_t mel_phase = 0;
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t lbo_a = (uint32_t)P.npos * 16, lbo_b = (uint32_t)P.Cout * 16;
     const uint32_t plane_bytes = (uint32_t)P.kg * lbo_a;            // one (plane, hi|lo)
@@ -127,6 +173,69 @@ conv3x3_umma_kernel(const float* __restrict__ in, const uint4* __restrict__ wq, 
     uint32_t phase = 0;
 
     for (long long w = blockIdx.x; w < n_windows; w += gridDim.x) {
+        if (FRONT1) {
+            // ---- log-mel (TMA, fetched behind the previous window) -> zero-bordered tile; next window's fetch starts ----
+            mbar_wait(mel_bar, mel_phase);
+            mel_phase ^= 1;
+            for (int i = tid; i < P.f1_hm * P.f1_wm; i += kCuNT) {
+                const int r = i / P.f1_wm, c = i - r * P.f1_wm;
+                tile1[(r + 1) * P.f1_pitch + c + 1] = stage1[i];
+            }
+            __syncthreads();
+            if (tid == 0 && w + gridDim.x < n_windows) {
+                fence_proxy_async();
+                mbar_expect_tx(mel_bar, mel_bytes);
+                bulk_g2s(stage1, in + (w + gridDim.x) * (long long)(P.f1_hm * P.f1_wm), mel_bytes, mel_bar);
+            }
+            // ---- first layer: task = (pooled pixel, 8 channels) -> bf16 hi / lo rows of the parity planes -------------
+            for (int T = tid; T < P.H * P.W * 2; T += kCuNT) {
+                const int pix = T >> 1, cg = T & 1;
+                const int y = pix / P.W, x = pix - y * P.W;
+                float pin[4][4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float2 lo = *reinterpret_cast<const float2*>(tile1 + (2 * y + r) * P.f1_pitch + 2 * x);
+                    const float2 hi = *reinterpret_cast<const float2*>(tile1 + (2 * y + r) * P.f1_pitch + 2 * x + 2);
+                    pin[r][0] = lo.x; pin[r][1] = lo.y; pin[r][2] = hi.x; pin[r][3] = hi.y;
+                }
+                float acc[8][4];
+#pragma unroll
+                for (int o = 0; o < 8; ++o) {
+                    const float bv = w1s[9 * 16 + cg * 8 + o];
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) acc[o][q4] = bv;
+                }
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float4 wa = *reinterpret_cast<const float4*>(w1s + (r * 3 + c) * 16 + cg * 8);
+                        const float4 wb = *reinterpret_cast<const float4*>(w1s + (r * 3 + c) * 16 + cg * 8 + 4);
+                        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                        for (int o = 0; o < 8; ++o) {
+                            acc[o][0] = fmaf(pin[r][c], wv[o], acc[o][0]);
+                            acc[o][1] = fmaf(pin[r][c + 1], wv[o], acc[o][1]);
+                            acc[o][2] = fmaf(pin[r + 1][c], wv[o], acc[o][2]);
+                            acc[o][3] = fmaf(pin[r + 1][c + 1], wv[o], acc[o][3]);
+                        }
+                    }
+                uint32_t h[8], l[8];
+#pragma unroll
+                for (int o = 0; o < 8; ++o) {
+                    const float best = fmaxf(fmaxf(apply_act(acc[o][0], act), apply_act(acc[o][1], act)),
+                                             fmaxf(apply_act(acc[o][2], act), apply_act(acc[o][3], act)));
+                    h[o] = float_to_bf16_bits(best);
+                    l[o] = float_to_bf16_bits(best - bf16_bits_to_float(h[o]));
+                }
+                const int plane = ((y & 1) << 1) | (x & 1);
+                const int s = ((y >> 1) + 1) * P.P + (x >> 1) + 1;
+                unsigned char* dst = a_s + (size_t)plane * 2 * plane_bytes + (size_t)cg * lbo_a + (size_t)s * 16;
+                *reinterpret_cast<uint4*>(dst) = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+                *reinterpret_cast<uint4*>(dst + plane_bytes) =
+                    make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
+            }
+        } else {
         // ---- input window -> bf16 hi / lo position lists ------------------------------------------------------------
         const float* src = in + w * (long long)P.H * P.W * P.Cin;
         // (four cells per thread and trip, all eight 128-bit loads issued before the first conversion)
@@ -169,6 +278,7 @@ conv3x3_umma_kernel(const float* __restrict__ in, const uint4* __restrict__ wq, 
                 *reinterpret_cast<uint4*>(dst + plane_bytes) =
                     make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
             }
+        }
         }
         fence_proxy_async();
         tc_fence_before();

@@ -837,6 +837,7 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
                 const int cin[3] = {1, 16, 32}, cout[3] = {16, 32, 64}, hh[3] = {64, 32, 16}, ww[3] = {101, 50, 25}, pool[3] = {1, 1, 0};
                 bool ok = true;
                 for (int j = 1; j <= 2; ++j) ok = ok && conv_umma_plan(hh[j], ww[j], cin[j], cout[j], pool[j], &e->heads.e2e_plan[j]);
+                if (ok && !(spec->reserved[0] & 256)) conv_umma_plan_front1(&e->heads.e2e_plan[1], hh[0], ww[0]);   // bit 8: keep conv1 a kernel of its own
                 for (int j = 1; j <= 2 && ok; ++j) {
                     std::vector<uint16_t> wq;
                     conv_umma_pack_weights(e->blob.f32("e2e.conv" + std::to_string(j) + ".w"), cin[j], cout[j], &wq);

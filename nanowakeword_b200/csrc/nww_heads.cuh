@@ -588,12 +588,22 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
         if ((rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel, 0, st, launches, err))) return rc;
         if (hw.e2e_wq[1] && hw.e2e_wq[2]) {
             // channel-last pipeline: conv1 (FP32, pool) -> conv2 (tcgen05, pool) -> conv3 (tcgen05) -> avg pool
-            bc_init_conv_kernel<<<ew_grid(n * 2 * 32 * 50, sm_count), 256, 0, st>>>(mel, hw.e2e_conv[0].w, hw.e2e_conv[0].b, a1, n, 64, 101, 16, act);
-            if ((rc = done())) return rc;
-            for (int j = 1; j <= 2; ++j) {
+            const int grid = (int)std::min<long long>(n, sm_count);
+            if (hw.e2e_plan[1].f1_hm) {
+                // conv1 inside conv2's loader: the (16, 32, 50) activations never exist in HBM
+                const ConvUmmaPlan& P = hw.e2e_plan[1];
+                NWW_HCUDA(set_smem(conv3x3_umma_kernel<true>, P.smem_bytes));
+                conv3x3_umma_kernel<true><<<grid, kCuNT, P.smem_bytes, st>>>(mel, hw.e2e_wq[1], hw.e2e_conv[1].b, a2, n, P, act,
+                                                                              hw.e2e_conv[0].w, hw.e2e_conv[0].b);
+                if ((rc = done())) return rc;
+            } else {
+                bc_init_conv_kernel<<<ew_grid(n * 2 * 32 * 50, sm_count), 256, 0, st>>>(mel, hw.e2e_conv[0].w, hw.e2e_conv[0].b, a1, n, 64, 101, 16, act);
+                if ((rc = done())) return rc;
+            }
+            for (int j = hw.e2e_plan[1].f1_hm ? 2 : 1; j <= 2; ++j) {
                 const ConvUmmaPlan& P = hw.e2e_plan[j];
-                NWW_HCUDA(set_smem(conv3x3_umma_kernel, P.smem_bytes));
-                conv3x3_umma_kernel<<<(int)std::min<long long>(n, sm_count), kCuNT, P.smem_bytes, st>>>(
+                NWW_HCUDA(set_smem(conv3x3_umma_kernel<false>, P.smem_bytes));
+                conv3x3_umma_kernel<false><<<grid, kCuNT, P.smem_bytes, st>>>(
                     j == 1 ? a1 : a2, hw.e2e_wq[j], hw.e2e_conv[j].b, j == 1 ? a2 : a3, n, P, act);
                 if ((rc = done())) return rc;
             }
@@ -806,8 +816,8 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
                 // third conv on tcgen05 (nww_conv_umma.cuh), then the (c, h) -> feature repack
                 float* a3 = take((size_t)S0 * In0);
                 const ConvUmmaPlan& P = hw.crnn_plan3;
-                NWW_HCUDA(set_smem(conv3x3_umma_kernel, P.smem_bytes));
-                conv3x3_umma_kernel<<<(int)std::min<long long>(n, sm_count), kCuNT, P.smem_bytes, st>>>(
+                NWW_HCUDA(set_smem(conv3x3_umma_kernel<false>, P.smem_bytes));
+                conv3x3_umma_kernel<false><<<(int)std::min<long long>(n, sm_count), kCuNT, P.smem_bytes, st>>>(
                     conv2_nhwc, hw.crnn_wq3, hw.crnn_conv[2].b, a3, n, P, act);
                 if ((rc = done())) return rc;
                 seq_pack_nhwc_kernel<<<ew_grid(n * S0 * In0, sm_count), 256, 0, st>>>(a3, seq_direct, n, hw.crnn_ch[2], 5, 12);
