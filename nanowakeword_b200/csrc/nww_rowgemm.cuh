@@ -414,7 +414,10 @@ rowgemm_umma_kernel(const float* __restrict__ A, long long a_row_mul, long long 
 constexpr int kKcRows = 128, kKcNT = 256, kKcKC = 64, kKcNC = 64, kKcRing = 4;
 constexpr int kKcABuf = 2 * (kKcKC / 8) * kKcRows * 16;           // hi | lo of one chunk: 32 KB
 constexpr int kKcSub = 2 * (kKcKC / 8) * kKcNC * 16;              // one weight sub-block: 16 KB
-inline size_t rowgemm_kc_smem_bytes(int ring = kKcRing) { return (size_t)2 * kKcABuf + (size_t)ring * kKcSub + 256 + kKcRows * sizeof(long long); }
+constexpr int kKcKoff = 256;                                       // K groups (of 8 columns) whose offsets are tabulated: K <= 2048
+inline size_t rowgemm_kc_smem_bytes(int ring = kKcRing) {
+    return (size_t)2 * kKcABuf + (size_t)ring * kKcSub + 256 + (kKcRows + kKcKoff) * sizeof(long long);
+}
 // Narrow outputs (N <= 128) leave a tile little MMA work between its operand conversion and its epilogue: a two-slot
 // weight ring makes the CTA small enough (97 KB, <= 128 TMEM columns) for two CTAs per SM to overlap those phases.
 struct KcLaunch { int ring, grid; size_t smem; };
@@ -512,6 +515,17 @@ __device__ __forceinline__ void rowgemm_kc_run(const float* __restrict__ A, cons
     const int n_kc = K / kKcKC, n_nc = N / kKcNC, total = n_kc * n_nc;
     uint32_t& c_slot = S.c_slot; uint32_t& c_par = S.c_par; uint32_t& p_slot = S.p_slot; uint32_t& done_phase = S.done_phase;
     uint32_t& g = S.g;                                                 // chunks converted so far: buffer g & 1
+    // where K group k8 / 8 of an A row starts relative to the row (segments resolved once per launch instead of a
+    // division per cell: the operand producer spent a quarter of its instructions on this address arithmetic); -1 = all padding
+    long long* koff = row_at + kKcRows;
+    const bool tab = VIEWS && K / 8 <= kKcKoff;
+    if (tab) {
+        __syncthreads();                                               // (fused kernel) the previous layer's last conversion has read the table
+        for (int g8 = tid; g8 < K / 8; g8 += kKcNT) {
+            const int k8 = 8 * g8, seg = k8 / sg.seg_len;
+            koff[g8] = k8 < sg.k_valid ? seg * sg.seg_stride + (k8 - seg * sg.seg_len) : -1;
+        }
+    }
     for (long long r0 = (long long)blockIdx.x * kKcRows; r0 < rows; r0 += (long long)gridDim.x * kKcRows) {   // persistent over the launch's tiles
         int p_pos = 0, prev_slot = -1;
         uint32_t prev_par = 0;
@@ -541,16 +555,27 @@ __device__ __forceinline__ void rowgemm_kc_run(const float* __restrict__ A, cons
             int k8s[kPer];
 #pragma unroll
             for (int j = 0; j < kPer; ++j) {
-                const int i = tid + j * kKcNT;
-                const int gq = i / kKcRows, r = i - gq * kKcRows;
+                // a warp instruction covers 8 rows x 4 K groups (128 contiguous bytes per row: 8 cache lines per request; one
+                // row per lane was 32 lines per request and the L1 tag stage showed it) at the price of 4-way conflicts on the
+                // operand stores, which the shared-memory pipe (8 % busy) does not notice
+                const int cw = warp + (kKcNT / 32) * j;
+                const int gq = (cw & 1) * 4 + (lane & 3), r = (cw >> 1) * 8 + (lane >> 2);
                 const int k8 = kc * kKcKC + 8 * gq;
                 const long long ra = VIEWS ? row_at[r] : (r0 + r < rows ? (r0 + r) * (long long)K : -1);
                 k8s[j] = -1;
                 v0[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 v1[j] = v0[j];
-                if (ra >= 0 && (!VIEWS || k8 < sg.k_valid)) {
-                    const int seg = VIEWS ? k8 / sg.seg_len : 0;
-                    const float4* p = reinterpret_cast<const float4*>(A + ra + (VIEWS ? seg * sg.seg_stride + (k8 - seg * sg.seg_len) : k8));
+                long long ko = k8;
+                if (VIEWS) {
+                    if (tab) {
+                        ko = koff[k8 >> 3];
+                    } else {
+                        const int seg = k8 / sg.seg_len;
+                        ko = k8 < sg.k_valid ? seg * sg.seg_stride + (k8 - seg * sg.seg_len) : -1;
+                    }
+                }
+                if (ra >= 0 && ko >= 0) {
+                    const float4* p = reinterpret_cast<const float4*>(A + ra + ko);
                     v0[j] = kc_ld<COHERENT>(p);
                     v1[j] = kc_ld<COHERENT>(p + 1);
                     k8s[j] = k8;
@@ -558,7 +583,8 @@ __device__ __forceinline__ void rowgemm_kc_run(const float* __restrict__ A, cons
             }
 #pragma unroll
             for (int j = 0; j < kPer; ++j) {
-                const int i = tid + j * kKcNT;
+                const int cw = warp + (kKcNT / 32) * j;
+                const int i = ((cw & 1) * 4 + (lane & 3)) * kKcRows + (cw >> 1) * 8 + (lane >> 2);     // [K group][row]
                 uint4 hv = make_uint4(0, 0, 0, 0), lv = hv;
                 if (k8s[j] >= 0) {
                     float v[8] = {v0[j].x, v0[j].y, v0[j].z, v0[j].w, v1[j].x, v1[j].y, v1[j].z, v1[j].w};
