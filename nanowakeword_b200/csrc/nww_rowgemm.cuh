@@ -648,6 +648,10 @@ __device__ __forceinline__ void rowgemm_kc_run(const float* __restrict__ A, cons
             const long long o_at = r < rows ? (VIEWS ? ov.at(r) : r * (long long)N) : 0;
             for (int c0 = hcol * (N / 2); c0 < (hcol + 1) * (N / 2) && c0 < n_valid; c0 += 32) {
                 float v[32];
+                float4 bq[8];                                          // the bias of these 32 columns: eight 128-bit loads in flight
+#pragma unroll                                                         // behind the TMEM load (32 scalar loads stalled the epilogue)
+                for (int j4 = 0; j4 < 8; ++j4)
+                    bq[j4] = c0 + 4 * j4 < n_valid ? __ldg(reinterpret_cast<const float4*>(bias + c0) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
                 if (r < rows) {
                     float4* dst = reinterpret_cast<float4*>(out + o_at + c0);
@@ -655,8 +659,7 @@ __device__ __forceinline__ void rowgemm_kc_run(const float* __restrict__ A, cons
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
                         if (VIEWS && c0 + 4 * j4 >= n_valid) break;
-                        float4 o = make_float4(v[4 * j4] + __ldg(bias + c0 + 4 * j4), v[4 * j4 + 1] + __ldg(bias + c0 + 4 * j4 + 1),
-                                               v[4 * j4 + 2] + __ldg(bias + c0 + 4 * j4 + 2), v[4 * j4 + 3] + __ldg(bias + c0 + 4 * j4 + 3));
+                        float4 o = make_float4(v[4 * j4] + bq[j4].x, v[4 * j4 + 1] + bq[j4].y, v[4 * j4 + 2] + bq[j4].z, v[4 * j4 + 3] + bq[j4].w);
                         if (VIEWS && pre_relu) { o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f); }
                         if (rs) {
                             const float4 t = kc_ld<COHERENT>(rs + j4);
