@@ -21,6 +21,9 @@
 
 #include "nww_tc.cuh"
 #include "nww_tcn.cuh"
+#ifndef NWW_CPUSIM
+#include "nww_fe3.cuh"
+#endif
 
 namespace nww {
 
@@ -77,6 +80,126 @@ bc_init_conv_kernel(const float* __restrict__ mel, const float* __restrict__ w, 
         dst[1] = make_float4(v[4], v[5], v[6], v[7]);
     }
 }
+
+// ---------------------------------------------------------------------------------------
+// Stage kernel of the BcResNet head (batch mode, int16 PCM): PCM -> log-mel (the warp-private FP64 front end of
+// nww_fe3.cuh, into a zero-bordered shared-memory plane) -> init conv + folded BN + act + 2x2 max pool -> channel-last
+// activations [n][20 * 49][32], one window per CTA iteration.  The (40, 98) log-mel never goes to HBM and back, and the
+// front end's shared-memory-bound phase and the conv's FMA-bound phase run in one launch.  Same arithmetic, FMA for
+// FMA, as frontend3_kernel + bc_init_conv_kernel (which the stream / float-feed paths keep using): bit-identical.
+// Shared memory as in cnn2_stage_kernel: FFT scratch | twiddles + Hann | mel plane | weights | one PCM slot (the next
+// window's PCM is fetched by TMA as soon as the FFT phase has consumed this one).
+// ---------------------------------------------------------------------------------------
+#ifndef NWW_CPUSIM
+struct BcStage {
+    using G = GeoNS40x98;
+    static constexpr int NT = 512, F = 40, TT = 98, C0 = 32, H1 = 20, W1 = 49;
+    static constexpr int MEL_P = 100, MEL_ROWS = 42;
+    static constexpr size_t oTw = align_up(Fe3::kWorkBytes, 1024);
+    static constexpr size_t oMel = oTw + Fe3::kTwBytes + Fe3::kWinBytes;
+    static constexpr size_t oW = oMel + align_up(sizeof(float) * MEL_ROWS * MEL_P, 128);
+    static constexpr size_t oPcm = oW + align_up(sizeof(float) * (9 * C0 + C0), 128);
+    using Stager = PcmStager<G::CLIP, 1>;
+    static constexpr size_t kTotal = oPcm + Stager::kBytes;
+};
+
+// The conv phase of bc_stage_kernel as a function of its own (not inlined: inside the kernel the register allocator kept
+// the front end's loop-invariant values live through this loop and spilled ~20 values per task — 15 % of the kernel's
+// stall samples, profiles/r02_bc_stage_*; here the loop has the whole register file to itself).
+template <int ACT>
+__device__ __noinline__ void bc_stage_conv(const float* __restrict__ melp, const float* __restrict__ ws, const float* __restrict__ bs,
+                                           float* __restrict__ ow, int tid) {
+    using D = BcStage;
+    // task = (pooled pixel, 8 channels): the 4 x 4 log-mel patch, 9 taps x 8 channels x 4 conv outputs, act, max
+#pragma unroll 1
+    for (int T = tid; T < D::H1 * D::W1 * (D::C0 / 8); T += D::NT) {
+        const int pix = T >> 2, g = T & 3;
+        const int y = pix / D::W1, xx = pix - y * D::W1;
+        float in[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float2 lo = *reinterpret_cast<const float2*>(melp + (2 * y + r) * D::MEL_P + 2 * xx);
+            const float2 hi = *reinterpret_cast<const float2*>(melp + (2 * y + r) * D::MEL_P + 2 * xx + 2);
+            in[r][0] = lo.x; in[r][1] = lo.y; in[r][2] = hi.x; in[r][3] = hi.y;
+        }
+        // packed FP32 FMAs (FFMA2: two IEEE FMAs per instruction — channels o, o + 1 of one conv output — so the 288
+        // FMAs of a task cost 144 issue slots; results are bit-identical to the scalar form)
+        float2 acc[4][4];                                          // [channel pair][pooling quad]
+#pragma unroll
+        for (int o2 = 0; o2 < 4; ++o2) {
+            const float2 bv = *reinterpret_cast<const float2*>(bs + g * 8 + 2 * o2);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[o2][q] = bv;
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float4 wa = *reinterpret_cast<const float4*>(ws + (r * 3 + c) * D::C0 + g * 8);
+                const float4 wb = *reinterpret_cast<const float4*>(ws + (r * 3 + c) * D::C0 + g * 8 + 4);
+                const float2 wv[4] = {make_float2(wa.x, wa.y), make_float2(wa.z, wa.w), make_float2(wb.x, wb.y), make_float2(wb.z, wb.w)};
+                const float2 p00 = make_float2(in[r][c], in[r][c]), p01 = make_float2(in[r][c + 1], in[r][c + 1]);
+                const float2 p10 = make_float2(in[r + 1][c], in[r + 1][c]), p11 = make_float2(in[r + 1][c + 1], in[r + 1][c + 1]);
+#pragma unroll
+                for (int o2 = 0; o2 < 4; ++o2) {
+                    acc[o2][0] = __ffma2_rn(p00, wv[o2], acc[o2][0]);
+                    acc[o2][1] = __ffma2_rn(p01, wv[o2], acc[o2][1]);
+                    acc[o2][2] = __ffma2_rn(p10, wv[o2], acc[o2][2]);
+                    acc[o2][3] = __ffma2_rn(p11, wv[o2], acc[o2][3]);
+                }
+            }
+        float v[8];
+#pragma unroll
+        for (int o2 = 0; o2 < 4; ++o2) {
+            v[2 * o2] = fmaxf(fmaxf(apply_act(acc[o2][0].x, ACT), apply_act(acc[o2][1].x, ACT)),
+                              fmaxf(apply_act(acc[o2][2].x, ACT), apply_act(acc[o2][3].x, ACT)));
+            v[2 * o2 + 1] = fmaxf(fmaxf(apply_act(acc[o2][0].y, ACT), apply_act(acc[o2][1].y, ACT)),
+                                  fmaxf(apply_act(acc[o2][2].y, ACT), apply_act(acc[o2][3].y, ACT)));
+        }
+        float4* dst = reinterpret_cast<float4*>(ow + (size_t)pix * D::C0 + g * 8);
+        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(BcStage::NT, 1)
+bc_stage_kernel(WindowSource src, long long n_windows, FrontendTables<double> tab, const float* __restrict__ w /* [9][32] */,
+                const float* __restrict__ bias, float* __restrict__ out, float* __restrict__ mel_dump /* nullable, (F, T) */) {
+    using D = BcStage;
+    NWW_DYN_SMEM(smem);
+    const int tid = threadIdx.x;
+    cplx<double>* tw = reinterpret_cast<cplx<double>*>(smem + D::oTw);
+    double* win_s = reinterpret_cast<double*>(smem + D::oTw + Fe3::kTwBytes);
+    float* melp = reinterpret_cast<float*>(smem + D::oMel);
+    float* ws = reinterpret_cast<float*>(smem + D::oW);
+    float* bs = ws + 9 * D::C0;
+    typename D::Stager stager;
+    stager.carve(smem + D::oPcm);
+    stager.init(tid);
+    fe2_build_tables(tw, tab, tid, D::NT);
+    fe3_build_window(win_s, tab.window, tid, D::NT);
+    for (int i = tid; i < 9 * D::C0; i += D::NT) ws[i] = w[i];
+    for (int i = tid; i < D::C0; i += D::NT) bs[i] = bias[i];
+    for (int i = tid; i < D::MEL_ROWS * D::MEL_P; i += D::NT) melp[i] = 0.0f;    // zero border, written once
+    __syncthreads();
+
+    long long wi = blockIdx.x;
+    if (wi < n_windows) stager.issue(0, src.at(wi), tid);
+    for (int it = 0; wi < n_windows; wi += gridDim.x, ++it) {
+        const int16_t* x = stager.wait(0, it & 1, src.at(wi));
+        fe3_logmel_window(x, smem, win_s, tw, tab, melp + D::MEL_P + 1, D::MEL_P, 1, tid);       // ends with a CTA barrier
+        const long long wn = wi + gridDim.x;
+        if (wn < n_windows) stager.issue(0, src.at(wn), tid);
+        if (mel_dump != nullptr) {
+            float* md = mel_dump + wi * (long long)(D::F * D::TT);
+            for (int i = tid; i < D::F * D::TT; i += D::NT) md[i] = melp[(i / D::TT + 1) * D::MEL_P + (i % D::TT) + 1];
+        }
+        bc_stage_conv<ACT>(melp, ws, bs, out + wi * (long long)(D::H1 * D::W1 * D::C0), tid);
+        __syncthreads();                 // the mel plane and the FFT scratch are free for the next window
+    }
+}
+#endif
 
 // depthwise 3x3, stride (sh, sw), pad 1, no bias / activation, channel-last.  w [C][9].
 // in [n][H*W][C] -> dwo [n][Ho*Wo][C] and ctr [n][Ho*Wo][C] = in at (sh y, sw x) (the shortcut's input).

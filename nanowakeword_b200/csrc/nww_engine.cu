@@ -846,6 +846,7 @@ int nww_create(const nww_spec* spec, const void* weights, size_t weights_size, i
                     e->heads.e2e_wq[j] = reinterpret_cast<const uint4*>(e->d_conv_wq[j]);
                 }
             }
+            if (spec->arch == NWW_ARCH_BCRESNET) e->heads.bc_stage = !(spec->reserved[0] & 512);
             if (spec->arch == NWW_ARCH_BCRESNET && !(spec->reserved[0] & 1)) {
                 // pointwise + shortcut weights as pre-split bf16 UMMA operands (reserved[0] bit 0 keeps the FP32 row GEMM)
                 const int ch[4] = {32, 64, 128, 256};

@@ -78,6 +78,7 @@ struct HeadWeights {
     ConvW e2e_conv[3];
     const uint4* e2e_wq[3] = {nullptr, nullptr, nullptr};    // conv2 / conv3 weights as bf16 UMMA operands (index 1, 2)
     ConvUmmaPlan e2e_plan[3];
+    bool bc_stage = true;             // BcResNet batch path: front end + init conv as one stage kernel (reserved[0] bit 9 clears it)
     // CRNN conv3 on the same kernel
     const uint4* crnn_wq3 = nullptr;
     ConvUmmaPlan crnn_plan3;
@@ -732,8 +733,12 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
         if (mel_dump && (rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel_dump, 0, st, launches, err))) return rc;
         return launch_quartznet_blocks(hw, mel, F, n, p, feat, sm_count, st, launches, err);
     }
-    if (!mel_ready && !conv2_nhwc && (rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel, 0, st, launches, err))) return rc;
-    if (mel_dump && !conv2_nhwc) NWW_HCUDA(cudaMemcpyAsync(mel_dump, mel, (size_t)n * F * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    // BcResNet from int16 PCM: front end + init conv in one stage kernel (the log-mel stays in shared memory)
+    const bool bc_stage = hw.arch == NWW_ARCH_BCRESNET && hw.bc_stage && !mel_ready && pcm.fbase == nullptr;
+    if (!bc_stage) {
+        if (!mel_ready && !conv2_nhwc && (rc = launch_frontend_f64<G>(tab, sm_count, pcm, n, mel, 0, st, launches, err))) return rc;
+        if (mel_dump && !conv2_nhwc) NWW_HCUDA(cudaMemcpyAsync(mel_dump, mel, (size_t)n * F * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
 
     if (hw.arch == NWW_ARCH_TCN) {
         // positions each layer output must cover so that the final step (T-1) is exact
@@ -771,7 +776,13 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
     if (hw.arch == NWW_ARCH_BCRESNET) {
         // channel-last pipeline (nww_bc.cuh): init conv -> 3 x (depthwise + centre tap, pointwise/shortcut row GEMMs) -> GAP
         float* a0 = take(32 * 20 * 49);
-        bc_init_conv_kernel<<<ew_grid(n * 4 * 20 * 49, sm_count), 256, 0, st>>>(mel, hw.bc_init.w, hw.bc_init.b, a0, n, F, T, 32, act);
+        if (bc_stage) {
+            auto k = act == ACT_RELU ? bc_stage_kernel<ACT_RELU> : act == ACT_GELU ? bc_stage_kernel<ACT_GELU> : bc_stage_kernel<ACT_SILU>;
+            NWW_HCUDA(set_smem(k, BcStage::kTotal));
+            k<<<(int)std::min<long long>(n, sm_count), BcStage::NT, BcStage::kTotal, st>>>(pcm, n, tab, hw.bc_init.w, hw.bc_init.b, a0, mel_dump);
+        } else {
+            bc_init_conv_kernel<<<ew_grid(n * 4 * 20 * 49, sm_count), 256, 0, st>>>(mel, hw.bc_init.w, hw.bc_init.b, a0, n, F, T, 32, act);
+        }
         if ((rc = done())) return rc;
         const int ch[4] = {32, 64, 128, 256};
         const int sh[3] = {2, 2, 2}, sw[3] = {2, 2, 1};
