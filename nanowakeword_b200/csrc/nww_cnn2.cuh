@@ -169,15 +169,14 @@ cnn2_stage_kernel(WindowSource src, Cnn2MelSource msrc, long long n_windows, Fro
             const float2 hi = *reinterpret_cast<const float2*>(melp + (2 * y + r) * D::MEL_P + 2 * x + 2);
             in[r][0] = lo.x; in[r][1] = lo.y; in[r][2] = hi.x; in[r][3] = hi.y;
         }
-        float acc[8][4];
-        {
-            const float4 ba = *reinterpret_cast<const float4*>(b1s + cg * 8);
-            const float4 bb = *reinterpret_cast<const float4*>(b1s + cg * 8 + 4);
-            const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+        // packed FP32 FMAs (FFMA2: two IEEE FMAs per instruction — channels o, o + 1 of one conv output): the 288 FMAs of
+        // a task take 144 issue slots, and this phase is issue-bound; bit-identical to the scalar form
+        float2 acc[4][4];                                              // [channel pair][pooling quad]
 #pragma unroll
-            for (int o = 0; o < 8; ++o)
+        for (int o2 = 0; o2 < 4; ++o2) {
+            const float2 bv = *reinterpret_cast<const float2*>(b1s + cg * 8 + 2 * o2);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) acc[o][q] = bv[o];
+            for (int q = 0; q < 4; ++q) acc[o2][q] = bv;
         }
         const float* wk = w1s + cg * 72;
 #pragma unroll
@@ -186,20 +185,23 @@ cnn2_stage_kernel(WindowSource src, Cnn2MelSource msrc, long long n_windows, Fro
             for (int c = 0; c < 3; ++c) {
                 const float4 wa = *reinterpret_cast<const float4*>(wk + (r * 3 + c) * 8);
                 const float4 wb = *reinterpret_cast<const float4*>(wk + (r * 3 + c) * 8 + 4);
-                const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+                const float2 wv[4] = {make_float2(wa.x, wa.y), make_float2(wa.z, wa.w), make_float2(wb.x, wb.y), make_float2(wb.z, wb.w)};
+                const float2 p00 = make_float2(in[r][c], in[r][c]), p01 = make_float2(in[r][c + 1], in[r][c + 1]);
+                const float2 p10 = make_float2(in[r + 1][c], in[r + 1][c]), p11 = make_float2(in[r + 1][c + 1], in[r + 1][c + 1]);
 #pragma unroll
-                for (int o = 0; o < 8; ++o) {
-                    acc[o][0] = fmaf(in[r][c], wv[o], acc[o][0]);
-                    acc[o][1] = fmaf(in[r][c + 1], wv[o], acc[o][1]);
-                    acc[o][2] = fmaf(in[r + 1][c], wv[o], acc[o][2]);
-                    acc[o][3] = fmaf(in[r + 1][c + 1], wv[o], acc[o][3]);
+                for (int o2 = 0; o2 < 4; ++o2) {
+                    acc[o2][0] = __ffma2_rn(p00, wv[o2], acc[o2][0]);
+                    acc[o2][1] = __ffma2_rn(p01, wv[o2], acc[o2][1]);
+                    acc[o2][2] = __ffma2_rn(p10, wv[o2], acc[o2][2]);
+                    acc[o2][3] = __ffma2_rn(p11, wv[o2], acc[o2][3]);
                 }
             }
         uint32_t hb[8], lb[8];
 #pragma unroll
         for (int o = 0; o < 8; ++o) {
-            const float best = fmaxf(fmaxf(cnn2_act<ACT>(acc[o][0]), cnn2_act<ACT>(acc[o][1])),
-                                     fmaxf(cnn2_act<ACT>(acc[o][2]), cnn2_act<ACT>(acc[o][3])));
+            const float a0 = (o & 1) ? acc[o >> 1][0].y : acc[o >> 1][0].x, a1 = (o & 1) ? acc[o >> 1][1].y : acc[o >> 1][1].x;
+            const float a2 = (o & 1) ? acc[o >> 1][2].y : acc[o >> 1][2].x, a3 = (o & 1) ? acc[o >> 1][3].y : acc[o >> 1][3].x;
+            const float best = fmaxf(fmaxf(cnn2_act<ACT>(a0), cnn2_act<ACT>(a1)), fmaxf(cnn2_act<ACT>(a2), cnn2_act<ACT>(a3)));
             hb[o] = float_to_bf16_bits(best);
             lb[o] = float_to_bf16_bits(best - bf16_bits_to_float(hb[o]));
         }
