@@ -544,6 +544,35 @@ def run_gpu_arm(args, rank, world, local_rank):
         other = {"workload": f"batch={WINDOWS_PER_GPU} windows resident in HBM, full path per model type (reference model_type names)",
                  "unit": UNIT, "values": other}
 
+    # ---- secondary: the verifier of a cascade (nanointerpreter.py:758-769) scores only the streams whose gate fired ------
+    # every stream ingests its chunk; the table shows how the verifier's push rate follows the gate's pass rate
+    cascade = None
+    if world == 1 and not args.no_streams:
+        try:
+            ns, L = 16384, 1280
+            cfg_v = default_config("cnn")
+            eng_v = Engine(make_state_dict(cfg_v, 0), cfg_v, device=local_rank)
+            rng = np.random.default_rng(11)
+            ch = torch.from_numpy(np.clip(rng.normal(0, 3000, (ns, L)), -32768, 32767).astype(np.int16)).to(dev)
+            out_v = torch.empty(ns, dtype=torch.float32, device=dev)
+            eng_v.stream_open(ns)
+            for _ in range(14):
+                eng_v.stream_push_device(ch, out=out_v)
+            rates = {}
+            for frac in (0.0, 0.01, 0.1, 0.5, 1.0):
+                k = int(round(frac * ns))
+                ids = torch.from_numpy(np.sort(rng.choice(ns, size=k, replace=False)).astype(np.int64)).to(dev)
+                for _ in range(2):
+                    eng_v.stream_push_select_device(ch, ids, out=out_v)
+                ms = time_device(torch, lambda i: eng_v.stream_push_select_device(ch, ids, out=out_v), 10)
+                rates[f"{frac:g}"] = round(ns / (ms * 1e-3), 1)
+            eng_v.stream_close()
+            eng_v.close()
+            cascade = {"workload": f"{ns} streams x {L}-sample steps through nww_stream_push_select on the verifier (CNN head): all streams "
+                                   "ingest, the listed fraction is scored", "unit": "stream-steps/s", "by_pass_rate": rates}
+        except Exception as ex:
+            cascade = {"error": repr(ex)}
+
     cores = os.cpu_count() or 1
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -569,7 +598,8 @@ def run_gpu_arm(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_total * CLIP * 2, "d2h_bytes_per_step": n_total * 4,
                 "api": "B200Session.run(None, {'input': int16 (4096,16000) pinned host array}) per rank", "host_link": h2d},
         "gpu_launches": int(launches), "clocks": clocks, "sustained": sustained, "roofline": roofline, "cpu_baseline": cpu,
-        "parity": parity, "streams_cfg3": streams, "root_ingest": root_ingest, "other_models": other,
+        "parity": parity, "streams_cfg3": streams, "cascade_verifier": cascade, "root_ingest": root_ingest,
+        "other_models": other,
     }
     emit(line)
     if world > 1:
