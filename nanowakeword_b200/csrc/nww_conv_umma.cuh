@@ -41,7 +41,10 @@ struct ConvUmmaPlan {
     int npos;         // positions allocated per plane and K group
     int planes;       // 1 or 4
     int kg;           // Cin / 8
-    int tmem_cols;    // power of two >= tiles * quads * Cout
+    int tmem_cols;    // power of two >= nbuf * tiles * quads * Cout
+    int acc_cols;     // tiles * quads * Cout: one set of accumulators
+    int nbuf;         // 2: two sets of position lists AND two sets of accumulators: window i + 1's MMAs run under window i's
+                      // epilogue and window i + 2's loads / conversions (the tensor pipe is the only thing that is not overlapped)
     size_t a_bytes, b_bytes, smem_bytes;
     // fused first layer (conv_umma_plan_front1): the loader computes Conv2d(1, Cin, 3, pad 1) + act + MaxPool2d(2) from the
     // log-mel (Hm x Wm per window) straight into the position lists, so that layer's activations never exist in HBM
@@ -61,11 +64,14 @@ inline bool conv_umma_plan(int H, int W, int Cin, int Cout, int pool, ConvUmmaPl
     p->npos = p->tiles * 128 + 2 * p->P + 8;
     const int cols = p->tiles * (pool ? 4 : 1) * Cout;
     if (cols > 512) return false;
-    p->tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+    p->acc_cols = cols;
     p->a_bytes = (size_t)p->planes * 2 * p->kg * p->npos * 16;
     p->b_bytes = (size_t)9 * 2 * p->kg * Cout * 16;
-    p->smem_bytes = p->a_bytes + p->b_bytes + Cout * sizeof(float) + 128;
-    return p->smem_bytes <= 220 * 1024;
+    p->nbuf = (2 * cols <= 512 && 2 * p->a_bytes + p->b_bytes + Cout * sizeof(float) + 128 <= 226 * 1024) ? 2 : 1;
+    const int tc = p->nbuf * cols;
+    p->tmem_cols = tc <= 32 ? 32 : tc <= 64 ? 64 : tc <= 128 ? 128 : tc <= 256 ? 256 : 512;
+    p->smem_bytes = p->nbuf * p->a_bytes + p->b_bytes + Cout * sizeof(float) + 128;
+    return p->smem_bytes <= 226 * 1024;
 }
 
 // Adds the fused first layer to a plan: mel (Hm, Wm) -> conv 3x3 (1 -> Cin = 16) -> pool -> (H, W) = (Hm / 2, Wm / 2).
@@ -73,6 +79,11 @@ inline bool conv_umma_plan_front1(ConvUmmaPlan* plan, int Hm, int Wm) {
     ConvUmmaPlan q = *plan;                                               // the plan changes only if everything fits
     ConvUmmaPlan* p = &q;
     if (!p->pool || p->Cin != 16 || p->H != Hm / 2 || p->W != Wm / 2 || (Hm * Wm) % 4) return false;
+    if (p->nbuf == 2) {                                                    // the fused first layer works on one set of position lists
+        p->nbuf = 1;
+        p->smem_bytes -= p->a_bytes;
+        p->tmem_cols = p->acc_cols <= 32 ? 32 : p->acc_cols <= 64 ? 64 : p->acc_cols <= 128 ? 128 : p->acc_cols <= 256 ? 256 : 512;
+    }
     p->f1_hm = Hm; p->f1_wm = Wm;
     p->f1_pitch = (std::max(Wm + 2, 2 * p->W + 4) + 3) / 4 * 4;           // even: the 4 x 4 patches are read as float2
     size_t off = (p->smem_bytes + 127) / 128 * 128;
@@ -123,20 +134,22 @@ conv3x3_umma_kernel(const float* __restrict__ in, const uint4* __restrict__ wq, 
                     const float* __restrict__ w1 = nullptr, const float* __restrict__ b1 = nullptr) {
     NWW_DYN_SMEM(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    unsigned char* a_s = smem;
-    unsigned char* b_s = smem + P.a_bytes;
-    float* bias_s = reinterpret_cast<float*>(smem + P.a_bytes + P.b_bytes);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + P.a_bytes + P.b_bytes + P.Cout * sizeof(float));
+    unsigned char* a_s = smem;                                     // P.nbuf sets of position lists
+    const size_t a_all = (size_t)P.nbuf * P.a_bytes;
+    unsigned char* b_s = smem + a_all;
+    float* bias_s = reinterpret_cast<float*>(smem + a_all + P.b_bytes);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + a_all + P.b_bytes + P.Cout * sizeof(float));
     bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bar) + 7) & ~(uintptr_t)7);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);    // bar[2]: one per accumulator set
     const int n_acc = P.tiles * (P.pool ? 4 : 1);                  // accumulators = (tile, quad) pairs
     const int n_issuers = n_acc < 4 ? n_acc : 4;                   // lane 0 of warps 0..3 each issue the MMAs of their accumulators
     if (tid == 0) {
         mbar_init(bar, (uint32_t)n_issuers);
+        mbar_init(bar + 1, (uint32_t)n_issuers);
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
-    for (int i = tid; i < (int)(P.a_bytes / 16); i += kCuNT) reinterpret_cast<uint4*>(a_s)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < (int)(a_all / 16); i += kCuNT) reinterpret_cast<uint4*>(a_s)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < (int)(P.b_bytes / 16); i += kCuNT) reinterpret_cast<uint4*>(b_s)[i] = __ldg(wq + i);
     for (int i = tid; i < P.Cout; i += kCuNT) bias_s[i] = bias[i];
     float* tile1 = reinterpret_cast<float*>(smem + P.f1_tile);
@@ -170,72 +183,9 @@ conv3x3_umma_kernel(const float* __restrict__ in, const uint4* __restrict__ wq, 
     const uint32_t idesc = umma_idesc_bf16(128, P.Cout);
     const int quads = P.pool ? 4 : 1;
     const int Ho = P.pool ? P.H / 2 : P.H, Wo = P.pool ? P.W / 2 : P.W;
-    uint32_t phase = 0;
 
-    for (long long w = blockIdx.x; w < n_windows; w += gridDim.x) {
-        if (FRONT1) {
-            // ---- log-mel (TMA, fetched behind the previous window) -> zero-bordered tile; next window's fetch starts ----
-            mbar_wait(mel_bar, mel_phase);
-            mel_phase ^= 1;
-            for (int i = tid; i < P.f1_hm * P.f1_wm; i += kCuNT) {
-                const int r = i / P.f1_wm, c = i - r * P.f1_wm;
-                tile1[(r + 1) * P.f1_pitch + c + 1] = stage1[i];
-            }
-            __syncthreads();
-            if (tid == 0 && w + gridDim.x < n_windows) {
-                fence_proxy_async();
-                mbar_expect_tx(mel_bar, mel_bytes);
-                bulk_g2s(stage1, in + (w + gridDim.x) * (long long)(P.f1_hm * P.f1_wm), mel_bytes, mel_bar);
-            }
-            // ---- first layer: task = (pooled pixel, 8 channels) -> bf16 hi / lo rows of the parity planes -------------
-            for (int T = tid; T < P.H * P.W * 2; T += kCuNT) {
-                const int pix = T >> 1, cg = T & 1;
-                const int y = pix / P.W, x = pix - y * P.W;
-                float pin[4][4];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const float2 lo = *reinterpret_cast<const float2*>(tile1 + (2 * y + r) * P.f1_pitch + 2 * x);
-                    const float2 hi = *reinterpret_cast<const float2*>(tile1 + (2 * y + r) * P.f1_pitch + 2 * x + 2);
-                    pin[r][0] = lo.x; pin[r][1] = lo.y; pin[r][2] = hi.x; pin[r][3] = hi.y;
-                }
-                float acc[8][4];
-#pragma unroll
-                for (int o = 0; o < 8; ++o) {
-                    const float bv = w1s[9 * 16 + cg * 8 + o];
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) acc[o][q4] = bv;
-                }
-#pragma unroll
-                for (int r = 0; r < 3; ++r)
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const float4 wa = *reinterpret_cast<const float4*>(w1s + (r * 3 + c) * 16 + cg * 8);
-                        const float4 wb = *reinterpret_cast<const float4*>(w1s + (r * 3 + c) * 16 + cg * 8 + 4);
-                        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-                        for (int o = 0; o < 8; ++o) {
-                            acc[o][0] = fmaf(pin[r][c], wv[o], acc[o][0]);
-                            acc[o][1] = fmaf(pin[r][c + 1], wv[o], acc[o][1]);
-                            acc[o][2] = fmaf(pin[r + 1][c], wv[o], acc[o][2]);
-                            acc[o][3] = fmaf(pin[r + 1][c + 1], wv[o], acc[o][3]);
-                        }
-                    }
-                uint32_t h[8], l[8];
-#pragma unroll
-                for (int o = 0; o < 8; ++o) {
-                    const float best = fmaxf(fmaxf(apply_act(acc[o][0], act), apply_act(acc[o][1], act)),
-                                             fmaxf(apply_act(acc[o][2], act), apply_act(acc[o][3], act)));
-                    h[o] = float_to_bf16_bits(best);
-                    l[o] = float_to_bf16_bits(best - bf16_bits_to_float(h[o]));
-                }
-                const int plane = ((y & 1) << 1) | (x & 1);
-                const int s = ((y >> 1) + 1) * P.P + (x >> 1) + 1;
-                unsigned char* dst = a_s + (size_t)plane * 2 * plane_bytes + (size_t)cg * lbo_a + (size_t)s * 16;
-                *reinterpret_cast<uint4*>(dst) = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
-                *reinterpret_cast<uint4*>(dst + plane_bytes) =
-                    make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
-            }
-        } else {
+    // input window w (channel-last FP32) -> bf16 hi / lo position lists at ab
+    auto load_window = [&](long long w, unsigned char* ab) {
         // ---- input window -> bf16 hi / lo position lists ------------------------------------------------------------
         const float* src = in + w * (long long)P.H * P.W * P.Cin;
         // (four cells per thread and trip, all eight 128-bit loads issued before the first conversion)
@@ -273,24 +223,23 @@ conv3x3_umma_kernel(const float* __restrict__ in, const uint4* __restrict__ wq, 
                     plane = 0;
                     s = (y + 1) * P.P + x + 1;
                 }
-                unsigned char* dst = a_s + (size_t)plane * 2 * plane_bytes + (size_t)g * lbo_a + (size_t)s * 16;
+                unsigned char* dst = ab + (size_t)plane * 2 * plane_bytes + (size_t)g * lbo_a + (size_t)s * 16;
                 *reinterpret_cast<uint4*>(dst) = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
                 *reinterpret_cast<uint4*>(dst + plane_bytes) =
                     make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
             }
         }
-        }
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-        // ---- MMAs ----------------------------------------------------------------------------------------------------
+    };
+
+    // one elected lane of warps 0..3: this window's MMAs from the position lists at descriptor da_win into accumulator set tm_off
+    auto issue_mmas = [&](uint64_t da_win, uint32_t tm_off, uint64_t* bar_set) {
         if (lane == 0 && warp < n_issuers) {
             tc_fence_after();
             for (int acc = warp; acc < n_acc; acc += n_issuers) {
                 const int t = acc / quads, quad = acc - t * quads;
                 {
                     const int dy = quad >> 1, dx = quad & 1;
-                    const uint32_t d_tmem = tmem_base + (uint32_t)((t * quads + quad) * P.Cout);
+                    const uint32_t d_tmem = tmem_base + tm_off + (uint32_t)((t * quads + quad) * P.Cout);
                     bool first = true;
                     for (int r = 0; r < 3; ++r)
                         for (int c = 0; c < 3; ++c) {
@@ -303,7 +252,7 @@ conv3x3_umma_kernel(const float* __restrict__ in, const uint4* __restrict__ wq, 
                                 plane = 0;
                                 s0 = t * 128 + r * P.P + c;
                             }
-                            const uint64_t a_hi = da_base + (uint64_t)(((size_t)plane * 2 * plane_bytes) / 16 + s0);
+                            const uint64_t a_hi = da_win + (uint64_t)(((size_t)plane * 2 * plane_bytes) / 16 + s0);
                             const uint64_t a_lo = a_hi + (uint64_t)(plane_bytes / 16);
                             const uint64_t b_hi = db_base + (uint64_t)(((size_t)(r * 3 + c) * 2 * bop_bytes) / 16);
                             const uint64_t b_lo = b_hi + (uint64_t)(bop_bytes / 16);
@@ -317,11 +266,11 @@ conv3x3_umma_kernel(const float* __restrict__ in, const uint4* __restrict__ wq, 
                         }
                 }
             }
-            umma_commit(bar);
+            umma_commit(bar_set);
         }
-        mbar_wait(bar, phase);
-        phase ^= 1;
-        tc_fence_after();
+    };
+    // bias, activation (+ max over the pooling quads), channel-last FP32 store of window w from accumulator set tm_off
+    auto epilogue = [&](long long w, uint32_t tm_off) {
         // ---- epilogue: warp -> TMEM lane quarter; tasks (tile, 16-column chunk) dealt to the two warps of a quarter ----
         {
             const int q = warp & 3, sub = warp >> 2;                 // 16 warps: four per quarter
@@ -330,7 +279,7 @@ conv3x3_umma_kernel(const float* __restrict__ in, const uint4* __restrict__ wq, 
             for (int task = sub; task < P.tiles * chunks; task += kCuNT / 128) {
                 const int t = task / chunks, ch = task - t * chunks;
                 uint32_t r[4][16];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * quads * P.Cout + ch * 16);
+                const uint32_t taddr = tmem_base + tm_off + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * quads * P.Cout + ch * 16);
                 tmem_ld_32x32b_x16_nowait(taddr, r[0]);
                 if (P.pool) {
                     tmem_ld_32x32b_x16_nowait(taddr + P.Cout, r[1]);
@@ -360,7 +309,116 @@ conv3x3_umma_kernel(const float* __restrict__ in, const uint4* __restrict__ wq, 
             }
             tc_fence_before();
         }
-        __syncthreads();          // TMEM and the position lists are free again
+    };
+
+    if (!FRONT1 && P.nbuf == 2) {
+        // ---- pipelined schedule: iteration i issues MMAs(i), then does epilogue(i - 1) and the loads of window i + 1 -------------
+        uint32_t ph[2] = {0, 0};
+        long long w = blockIdx.x, prev_w = -1;
+        if (w < n_windows) load_window(w, a_s);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        int it = 0;
+        for (; w < n_windows; w += gridDim.x, ++it) {
+            const int set = it & 1;
+            issue_mmas(da_base + (uint64_t)(((size_t)set * P.a_bytes) >> 4), (uint32_t)(set * P.acc_cols), bar + set);
+            if (it > 0) {
+                mbar_wait(bar + (set ^ 1), ph[set ^ 1]);             // MMAs(i - 1): their accumulators are complete, their position lists free
+                ph[set ^ 1] ^= 1u;
+                tc_fence_after();
+                epilogue(prev_w, (uint32_t)((set ^ 1) * P.acc_cols));
+            }
+            if (w + gridDim.x < n_windows) load_window(w + gridDim.x, a_s + (size_t)(set ^ 1) * P.a_bytes);
+            fence_proxy_async();
+            tc_fence_before();
+            __syncthreads();          // accumulator set (i - 1) & 1 and the position lists of window i + 1 are ready for iteration i + 1
+            prev_w = w;
+        }
+        if (it > 0) {
+            const int set = (it - 1) & 1;
+            mbar_wait(bar + set, ph[set]);
+            tc_fence_after();
+            epilogue(prev_w, (uint32_t)(set * P.acc_cols));
+        }
+    } else {
+        uint32_t phase = 0;
+        for (long long w = blockIdx.x; w < n_windows; w += gridDim.x) {
+            if (FRONT1) {
+                // ---- log-mel (TMA, fetched behind the previous window) -> zero-bordered tile; next window's fetch starts ----
+                mbar_wait(mel_bar, mel_phase);
+                mel_phase ^= 1;
+                for (int i = tid; i < P.f1_hm * P.f1_wm; i += kCuNT) {
+                    const int r = i / P.f1_wm, c = i - r * P.f1_wm;
+                    tile1[(r + 1) * P.f1_pitch + c + 1] = stage1[i];
+                }
+                __syncthreads();
+                if (tid == 0 && w + gridDim.x < n_windows) {
+                    fence_proxy_async();
+                    mbar_expect_tx(mel_bar, mel_bytes);
+                    bulk_g2s(stage1, in + (w + gridDim.x) * (long long)(P.f1_hm * P.f1_wm), mel_bytes, mel_bar);
+                }
+                // ---- first layer: task = (pooled pixel, 8 channels) -> bf16 hi / lo rows of the parity planes -------------
+                for (int T = tid; T < P.H * P.W * 2; T += kCuNT) {
+                    const int pix = T >> 1, cg = T & 1;
+                    const int y = pix / P.W, x = pix - y * P.W;
+                    float pin[4][4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const float2 lo = *reinterpret_cast<const float2*>(tile1 + (2 * y + r) * P.f1_pitch + 2 * x);
+                        const float2 hi = *reinterpret_cast<const float2*>(tile1 + (2 * y + r) * P.f1_pitch + 2 * x + 2);
+                        pin[r][0] = lo.x; pin[r][1] = lo.y; pin[r][2] = hi.x; pin[r][3] = hi.y;
+                    }
+                    float acc[8][4];
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) {
+                        const float bv = w1s[9 * 16 + cg * 8 + o];
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) acc[o][q4] = bv;
+                    }
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const float4 wa = *reinterpret_cast<const float4*>(w1s + (r * 3 + c) * 16 + cg * 8);
+                            const float4 wb = *reinterpret_cast<const float4*>(w1s + (r * 3 + c) * 16 + cg * 8 + 4);
+                            const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                            for (int o = 0; o < 8; ++o) {
+                                acc[o][0] = fmaf(pin[r][c], wv[o], acc[o][0]);
+                                acc[o][1] = fmaf(pin[r][c + 1], wv[o], acc[o][1]);
+                                acc[o][2] = fmaf(pin[r + 1][c], wv[o], acc[o][2]);
+                                acc[o][3] = fmaf(pin[r + 1][c + 1], wv[o], acc[o][3]);
+                            }
+                        }
+                    uint32_t h[8], l[8];
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) {
+                        const float best = fmaxf(fmaxf(apply_act(acc[o][0], act), apply_act(acc[o][1], act)),
+                                                 fmaxf(apply_act(acc[o][2], act), apply_act(acc[o][3], act)));
+                        h[o] = float_to_bf16_bits(best);
+                        l[o] = float_to_bf16_bits(best - bf16_bits_to_float(h[o]));
+                    }
+                    const int plane = ((y & 1) << 1) | (x & 1);
+                    const int s = ((y >> 1) + 1) * P.P + (x >> 1) + 1;
+                    unsigned char* dst = a_s + (size_t)plane * 2 * plane_bytes + (size_t)cg * lbo_a + (size_t)s * 16;
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+                    *reinterpret_cast<uint4*>(dst + plane_bytes) =
+                        make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
+                }
+            } else {
+                load_window(w, a_s);
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncthreads();
+            issue_mmas(da_base, 0u, bar);
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            tc_fence_after();
+            epilogue(w, 0u);
+            __syncthreads();          // TMEM and the position lists are free again
+        }
     }
     tc_fence_before();
     __syncthreads();
