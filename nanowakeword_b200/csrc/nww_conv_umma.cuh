@@ -430,19 +430,40 @@ conv3x3_umma_kernel(const float* __restrict__ in, const uint4* __restrict__ wq, 
 
 // AdaptiveAvgPool2d((1, OW)) in its deployed AvgPool2d form (_export/onnx.py:139-147) on channel-last input:
 // in [B][H*W][C] -> out [B][C*OW]  (feature index c * OW + j, the reference's flatten of (C, 1, OW))
+// One thread = one (window, channel quad): it streams its four channels' H x W activations once as 128-bit loads (a warp
+// reads two pixels' 256 contiguous bytes per instruction, a whole image row of W loads in flight) and adds each pixel to
+// the bins that contain its column — rows outer, columns inner, the order a per-bin loop uses.  W and OW are
+// compile-time so that the bin tests fold away and the row loop is fully unrolled.
+template <int W, int OW>
 __global__ void __launch_bounds__(256)
-avgpool_row_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, long long B, int C, int H, int W, int OW) {
-    const int sw = W / OW, kw = W - (OW - 1) * sw;
-    const long long total = B * C * OW;
+avgpool_row_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, long long B, int C, int H) {
+    constexpr int sw = W / OW, kw = W - (OW - 1) * sw;
+    const int c4n = C / 4;
+    const long long total = B * c4n;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(t % C);
-        const int j = (int)((t / C) % OW);
-        const long long b = t / ((long long)C * OW);
-        const float* src = in + b * (long long)H * W * C + c;
-        float s = 0.0f;
-        for (int y = 0; y < H; ++y)
-            for (int x = 0; x < kw; ++x) s += __ldg(src + ((long long)y * W + j * sw + x) * C);
-        out[b * (long long)C * OW + c * OW + j] = s / (float)(H * kw);
+        const int c4 = (int)(t % c4n);
+        const long long b = t / c4n;
+        const float4* src = reinterpret_cast<const float4*>(in + b * (long long)H * W * C) + c4;
+        float4 s[OW];
+#pragma unroll
+        for (int j = 0; j < OW; ++j) s[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int y = 0; y < H; ++y) {
+            const float4* row = src + (long long)y * W * c4n;
+            float4 v[W];
+#pragma unroll
+            for (int x = 0; x < W; ++x) v[x] = __ldg(row + (long long)x * c4n);
+#pragma unroll
+            for (int x = 0; x < W; ++x)
+#pragma unroll
+                for (int j = 0; j < OW; ++j)
+                    if (x >= j * sw && x < j * sw + kw) { s[j].x += v[x].x; s[j].y += v[x].y; s[j].z += v[x].z; s[j].w += v[x].w; }
+        }
+        float* o = out + b * (long long)C * OW + (long long)(4 * c4) * OW;
+#pragma unroll
+        for (int j = 0; j < OW; ++j) {
+            o[j] = s[j].x / (float)(H * kw); o[OW + j] = s[j].y / (float)(H * kw);
+            o[2 * OW + j] = s[j].z / (float)(H * kw); o[3 * OW + j] = s[j].w / (float)(H * kw);
+        }
     }
 }
 

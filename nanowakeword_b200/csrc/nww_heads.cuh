@@ -608,7 +608,7 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
                     j == 1 ? a1 : a2, hw.e2e_wq[j], hw.e2e_conv[j].b, j == 1 ? a2 : a3, n, P, act);
                 if ((rc = done())) return rc;
             }
-            avgpool_row_nhwc_kernel<<<ew_grid(n * 64, sm_count), 256, 0, st>>>(a3, feat, n, 64, 16, 25, 4);
+            avgpool_row_nhwc_kernel<25, 4><<<ew_grid(n * 16, sm_count), 256, 0, st>>>(a3, feat, n, 64, 16);
             if ((rc = done())) return rc;
             if (mel_dump) NWW_HCUDA(cudaMemcpyAsync(mel_dump, mel, (size_t)n * 64 * 101 * sizeof(float), cudaMemcpyDeviceToDevice, st));
             return NWW_OK;
