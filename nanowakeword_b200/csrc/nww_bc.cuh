@@ -442,16 +442,29 @@ inline void bcu_pack_weights(const float* pw, const float* sc, int Cin, int Cout
         }
 }
 
-// global average pool, channel-last: in [n][P][C] -> out [n][C]
+// global average pool, channel-last: in [n][P][C] -> out [n][C]   (C % 4 == 0)
+// One thread = one (window, channel quad), eight 128-bit loads in flight; pixels are added in order.
 __global__ void __launch_bounds__(256) bc_gap_kernel(const float* __restrict__ in, float* __restrict__ out, long long n, int P, int C) {
-    const long long total = n * C;
+    const int c4n = C / 4;
+    const long long total = n * c4n;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const long long b = t / C;
-        const int c = (int)(t - b * C);
-        const float* src = in + b * (long long)P * C + c;
-        float s = 0.0f;
-        for (int p = 0; p < P; ++p) s += __ldg(src + (long long)p * C);
-        out[t] = s / (float)P;
+        const long long b = t / c4n;
+        const int c4 = (int)(t - b * c4n);
+        const float4* src = reinterpret_cast<const float4*>(in + b * (long long)P * C) + c4;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        int p = 0;
+        for (; p + 8 <= P; p += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __ldg(src + (long long)(p + i) * c4n);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s.x += v[i].x; s.y += v[i].y; s.z += v[i].z; s.w += v[i].w; }
+        }
+        for (; p < P; ++p) {
+            const float4 v = __ldg(src + (long long)p * c4n);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        reinterpret_cast<float4*>(out + b * C)[c4] = make_float4(s.x / (float)P, s.y / (float)P, s.z / (float)P, s.w / (float)P);
     }
 }
 

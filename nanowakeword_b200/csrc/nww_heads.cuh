@@ -449,7 +449,7 @@ inline int launch_quartznet_blocks(const HeadWeights& hw, const float* x, int pi
         x = y;
         pitch = B.N;
     }
-    bc_gap_kernel<<<ew_grid(n * pitch, sm_count), 256, 0, st>>>(x, feat, n, T, pitch);
+    bc_gap_kernel<<<ew_grid(n * (pitch / 4), sm_count), 256, 0, st>>>(x, feat, n, T, pitch);
     return done();
 }
 
@@ -552,7 +552,7 @@ inline int launch_raw_cnn(const HeadWeights& hw, int act, int sm_count, WindowSo
         img = out;
         C = L.cout; H = L.Hout; W = L.Wout;
     }
-    bc_gap_kernel<<<ew_grid(n * C, sm_count), 256, 0, st>>>(img, feat, n, H * W, C);
+    bc_gap_kernel<<<ew_grid(n * (C / 4), sm_count), 256, 0, st>>>(img, feat, n, H * W, C);
     return done();
 }
 
@@ -812,7 +812,7 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
             if ((rc = done())) return rc;
             x = out; H = Ho; W = Wo;
         }
-        bc_gap_kernel<<<ew_grid(n * 256, sm_count), 256, 0, st>>>(x, feat, n, H * W, 256);
+        bc_gap_kernel<<<ew_grid(n * 64, sm_count), 256, 0, st>>>(x, feat, n, H * W, 256);
         return done();
     }
     if (hw.arch == NWW_ARCH_CRNN_GRU) {
