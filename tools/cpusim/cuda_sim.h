@@ -3,6 +3,9 @@
 // nanowakeword_b200/csrc/*.cuh can be exercised for indexing/numerics triage in a container
 // without a GPU.  It is not part of the product, the tests, the bench or smoke().
 #pragma once
+#ifndef __shared__
+#define __shared__ static      // one block runs at a time in the host model
+#endif
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
@@ -86,6 +89,7 @@ template <typename T> inline T __shfl_down_sync(unsigned, T v, int d) {
 }
 template <typename T> inline T __ldg(const T* p) { return *p; }
 inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return {fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }   // FFMA2: two IEEE FMAs
 inline float __fdividef(float a, float b) { return a / b; }
 inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }

@@ -8,7 +8,6 @@
 #include <random>
 #include <vector>
 #include "cuda_sim.h"
-#define __shared__ static      // one block runs at a time in the host model
 #include "../../nanowakeword_b200/csrc/nww_rowgemm.cuh"
 using namespace nww;
 
