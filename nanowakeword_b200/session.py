@@ -32,7 +32,8 @@ class Engine:
 
     def __init__(self, state_dict: dict, cfg: dict, device: int = 0, frontend_precision: str = "fp64",
                  chunk_windows: int = 0, tensor_cores: bool = True, cnn_stage: str = "v2",
-                 stream_incremental: bool = True, tcn_layers: str = "rows", stream_ingest: str = "fused", split_per_sm: int = 0):
+                 stream_incremental: bool = True, tcn_layers: str = "rows", stream_ingest: str = "fused", split_per_sm: int = 0,
+                 fused_first_conv: bool = True):
         self._lib = _lib.load_library()
         self.cfg = dict(cfg)
         self.geometry = geometry_for(cfg)
@@ -68,7 +69,10 @@ class Engine:
         spec.reserved[0] = ((0 if tensor_cores else 1) | (2 if cnn_stage == "v1" else 0) | (0 if stream_incremental else 4)
                             | (0 if pipelined else 8) | (16 if tcn_layers == "cone" else 0) | (128 if tcn_layers == "rows_fused" else 0)   # bit 7: the cone's layers in one cooperative launch
                             | (0 if stream_ingest == "fused" else 32)        # bit 5: ring append and mel update as two kernels
-                            | (64 if split else 0))                           # bit 6: split CNN stage (front-end + conv kernels)
+                            | (64 if split else 0)                            # bit 6: split CNN stage (front-end + conv kernels)
+                            # bits 8 / 9 (A/B): the first convolution as a kernel of its own instead of inside conv2's loader
+                            # (e2e_dnn) / behind the front end in one stage kernel (bcresnet); bit-identical either way
+                            | (0 if fused_first_conv else 256 | 512))
         spec.reserved[1] = int(split_per_sm)                                  # windows per SM and sub-chunk of the split stage (0 = default)
         self.cnn_stage = "v4" if split else "v3" if (pipelined and cnn_stage == "v2") else cnn_stage
         self._blob = (C.c_char * len(blob)).from_buffer_copy(blob)

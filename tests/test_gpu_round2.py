@@ -406,3 +406,19 @@ def test_tcn_fused_cone_launch_is_bit_identical_to_per_layer_launches(torch_cuda
     assert (a.info["kernel_launches"] - la) == 15 * 4          # ingest, fused cone, dense tail, mask
     a.stream_close()
     b.stream_close()
+
+
+@pytest.mark.parametrize("mt", ["e2e_dnn", "bcresnet"])
+def test_fused_first_conv_is_bit_identical(torch_cuda, mt):
+    """e2e_dnn: conv1 inside conv2's loader (conv3x3_umma_kernel<true>); bcresnet: front end + init conv in one stage kernel
+    (bc_stage_kernel).  Both repeat the stand-alone kernels' arithmetic FMA for FMA, so scores and log-mel are identical."""
+    torch = torch_cuda
+    pcm = torch.from_numpy(synth_pcm(333, seed=21, kind="gauss")).cuda()
+    res = []
+    for fused in (True, False):
+        eng, _, _ = _engine(mt, fused_first_conv=fused)
+        s, extra = eng.score_device(pcm, want_mel=True)
+        res.append((s.cpu().numpy().copy(), extra["mel"].cpu().numpy().copy()))
+        eng.close()
+    assert np.array_equal(res[0][0], res[1][0])
+    assert np.array_equal(res[0][1], res[1][1])
