@@ -384,7 +384,9 @@ static int launch_tail_tc(nww_engine* e, int64_t n, float* scores, float* logits
 static int launch_tail(nww_engine* e, const float* feat, int64_t n, float* scores, float* logits, float* emb,
                        cudaStream_t st) {
     if (e->tc_enabled) return launch_tail_tc(e, n, scores, logits, emb, st);
-    if ((size_t)e->tail.layers[0].K * e->tail.layers[0].N <= 65536) {      // small layers only: favour CTA count
+    // small layers only: favour CTA count — until the launch has enough rows to fill the GPU with 32-window tiles too
+    // (a stream bank of 65 536 rows: the weights are then fetched by a quarter of the CTAs)
+    if ((size_t)e->tail.layers[0].K * e->tail.layers[0].N <= 65536 && n < (int64_t)kTailTM * 4 * e->sm_count) {
         const size_t smem = tail_smem_bytes(e->tail.max_width, kTailTMSmall);
         NWW_CUDA(set_smem(tail_kernel_t<kTailTMSmall>, smem));
         const int64_t tiles = (n + kTailTMSmall - 1) / kTailTMSmall;
