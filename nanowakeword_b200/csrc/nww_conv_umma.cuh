@@ -311,114 +311,101 @@ conv3x3_umma_kernel(const float* __restrict__ in, const uint4* __restrict__ wq, 
         }
     };
 
-    if (!FRONT1 && P.nbuf == 2) {
-        // ---- pipelined schedule: iteration i issues MMAs(i), then does epilogue(i - 1) and the loads of window i + 1 -------------
-        uint32_t ph[2] = {0, 0};
-        long long w = blockIdx.x, prev_w = -1;
-        if (w < n_windows) load_window(w, a_s);
+    // the first layer's loader (FRONT1): window w's log-mel -> conv1 + act + pool -> the position lists at a_s
+    auto load_front1 = [&](long long w) {
+        // ---- log-mel (TMA, fetched behind the previous window) -> zero-bordered tile; next window's fetch starts ----
+        mbar_wait(mel_bar, mel_phase);
+        mel_phase ^= 1;
+        for (int i = tid; i < P.f1_hm * P.f1_wm; i += kCuNT) {
+            const int r = i / P.f1_wm, c = i - r * P.f1_wm;
+            tile1[(r + 1) * P.f1_pitch + c + 1] = stage1[i];
+        }
+        __syncthreads();
+        if (tid == 0 && w + gridDim.x < n_windows) {
+            fence_proxy_async();
+            mbar_expect_tx(mel_bar, mel_bytes);
+            bulk_g2s(stage1, in + (w + gridDim.x) * (long long)(P.f1_hm * P.f1_wm), mel_bytes, mel_bar);
+        }
+        // ---- first layer: task = (pooled pixel, 8 channels) -> bf16 hi / lo rows of the parity planes -------------
+        for (int T = tid; T < P.H * P.W * 2; T += kCuNT) {
+            const int pix = T >> 1, cg = T & 1;
+            const int y = pix / P.W, x = pix - y * P.W;
+            float pin[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float2 lo = *reinterpret_cast<const float2*>(tile1 + (2 * y + r) * P.f1_pitch + 2 * x);
+                const float2 hi = *reinterpret_cast<const float2*>(tile1 + (2 * y + r) * P.f1_pitch + 2 * x + 2);
+                pin[r][0] = lo.x; pin[r][1] = lo.y; pin[r][2] = hi.x; pin[r][3] = hi.y;
+            }
+            float acc[8][4];
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                const float bv = w1s[9 * 16 + cg * 8 + o];
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) acc[o][q4] = bv;
+            }
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float4 wa = *reinterpret_cast<const float4*>(w1s + (r * 3 + c) * 16 + cg * 8);
+                    const float4 wb = *reinterpret_cast<const float4*>(w1s + (r * 3 + c) * 16 + cg * 8 + 4);
+                    const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) {
+                        acc[o][0] = fmaf(pin[r][c], wv[o], acc[o][0]);
+                        acc[o][1] = fmaf(pin[r][c + 1], wv[o], acc[o][1]);
+                        acc[o][2] = fmaf(pin[r + 1][c], wv[o], acc[o][2]);
+                        acc[o][3] = fmaf(pin[r + 1][c + 1], wv[o], acc[o][3]);
+                    }
+                }
+            uint32_t h[8], l[8];
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                const float best = fmaxf(fmaxf(apply_act(acc[o][0], act), apply_act(acc[o][1], act)),
+                                         fmaxf(apply_act(acc[o][2], act), apply_act(acc[o][3], act)));
+                h[o] = float_to_bf16_bits(best);
+                l[o] = float_to_bf16_bits(best - bf16_bits_to_float(h[o]));
+            }
+            const int plane = ((y & 1) << 1) | (x & 1);
+            const int s = ((y >> 1) + 1) * P.P + (x >> 1) + 1;
+            unsigned char* dst = a_s + (size_t)plane * 2 * plane_bytes + (size_t)cg * lbo_a + (size_t)s * 16;
+            *reinterpret_cast<uint4*>(dst) = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+            *reinterpret_cast<uint4*>(dst + plane_bytes) =
+                make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
+        }
+    };
+
+    // One schedule for every configuration, one call site per phase (the kernel is instruction-cache sized, so the phases
+    // must not be duplicated).  Iteration i (i = -1 .. n_it):
+    //   issue MMAs(i)  ->  [wait] epilogue(e)  ->  load window i + 1  ->  CTA barrier
+    // with e = i - 1 when there are two sets of position lists / accumulators (MMAs(i) run under epilogue(i - 1) and the loads of
+    // window i + 1; the buffer those loads overwrite was last read by MMAs(i - 1), which the wait has seen complete) and
+    // e = i with one set (the loads of window i + 1 follow the wait for MMAs(i)).
+    const int n_it = (long long)blockIdx.x < n_windows ? (int)((n_windows - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    const int lag = P.nbuf == 2 ? 1 : 0;
+    uint32_t ph[2] = {0, 0};
+    for (int it = -1; it < n_it + lag; ++it) {
+        if (it >= 0 && it < n_it) {
+            const int set = it & (P.nbuf - 1);
+            issue_mmas(da_base + (uint64_t)(((size_t)set * P.a_bytes) >> 4), (uint32_t)(set * P.acc_cols), bar + set);
+        }
+        const int e = it - lag;
+        if (e >= 0 && e < n_it) {
+            const int set = e & (P.nbuf - 1);
+            mbar_wait(bar + set, ph[set]);
+            ph[set] ^= 1u;
+            tc_fence_after();
+            epilogue((long long)blockIdx.x + (long long)e * gridDim.x, (uint32_t)(set * P.acc_cols));
+        }
+        if (it + 1 < n_it) {
+            const long long wn = (long long)blockIdx.x + (long long)(it + 1) * gridDim.x;
+            if (FRONT1) load_front1(wn);
+            else load_window(wn, a_s + (size_t)((it + 1) & (P.nbuf - 1)) * P.a_bytes);
+        }
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
-        int it = 0;
-        for (; w < n_windows; w += gridDim.x, ++it) {
-            const int set = it & 1;
-            issue_mmas(da_base + (uint64_t)(((size_t)set * P.a_bytes) >> 4), (uint32_t)(set * P.acc_cols), bar + set);
-            if (it > 0) {
-                mbar_wait(bar + (set ^ 1), ph[set ^ 1]);             // MMAs(i - 1): their accumulators are complete, their position lists free
-                ph[set ^ 1] ^= 1u;
-                tc_fence_after();
-                epilogue(prev_w, (uint32_t)((set ^ 1) * P.acc_cols));
-            }
-            if (w + gridDim.x < n_windows) load_window(w + gridDim.x, a_s + (size_t)(set ^ 1) * P.a_bytes);
-            fence_proxy_async();
-            tc_fence_before();
-            __syncthreads();          // accumulator set (i - 1) & 1 and the position lists of window i + 1 are ready for iteration i + 1
-            prev_w = w;
-        }
-        if (it > 0) {
-            const int set = (it - 1) & 1;
-            mbar_wait(bar + set, ph[set]);
-            tc_fence_after();
-            epilogue(prev_w, (uint32_t)(set * P.acc_cols));
-        }
-    } else {
-        uint32_t phase = 0;
-        for (long long w = blockIdx.x; w < n_windows; w += gridDim.x) {
-            if (FRONT1) {
-                // ---- log-mel (TMA, fetched behind the previous window) -> zero-bordered tile; next window's fetch starts ----
-                mbar_wait(mel_bar, mel_phase);
-                mel_phase ^= 1;
-                for (int i = tid; i < P.f1_hm * P.f1_wm; i += kCuNT) {
-                    const int r = i / P.f1_wm, c = i - r * P.f1_wm;
-                    tile1[(r + 1) * P.f1_pitch + c + 1] = stage1[i];
-                }
-                __syncthreads();
-                if (tid == 0 && w + gridDim.x < n_windows) {
-                    fence_proxy_async();
-                    mbar_expect_tx(mel_bar, mel_bytes);
-                    bulk_g2s(stage1, in + (w + gridDim.x) * (long long)(P.f1_hm * P.f1_wm), mel_bytes, mel_bar);
-                }
-                // ---- first layer: task = (pooled pixel, 8 channels) -> bf16 hi / lo rows of the parity planes -------------
-                for (int T = tid; T < P.H * P.W * 2; T += kCuNT) {
-                    const int pix = T >> 1, cg = T & 1;
-                    const int y = pix / P.W, x = pix - y * P.W;
-                    float pin[4][4];
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const float2 lo = *reinterpret_cast<const float2*>(tile1 + (2 * y + r) * P.f1_pitch + 2 * x);
-                        const float2 hi = *reinterpret_cast<const float2*>(tile1 + (2 * y + r) * P.f1_pitch + 2 * x + 2);
-                        pin[r][0] = lo.x; pin[r][1] = lo.y; pin[r][2] = hi.x; pin[r][3] = hi.y;
-                    }
-                    float acc[8][4];
-#pragma unroll
-                    for (int o = 0; o < 8; ++o) {
-                        const float bv = w1s[9 * 16 + cg * 8 + o];
-#pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4) acc[o][q4] = bv;
-                    }
-#pragma unroll
-                    for (int r = 0; r < 3; ++r)
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            const float4 wa = *reinterpret_cast<const float4*>(w1s + (r * 3 + c) * 16 + cg * 8);
-                            const float4 wb = *reinterpret_cast<const float4*>(w1s + (r * 3 + c) * 16 + cg * 8 + 4);
-                            const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-                            for (int o = 0; o < 8; ++o) {
-                                acc[o][0] = fmaf(pin[r][c], wv[o], acc[o][0]);
-                                acc[o][1] = fmaf(pin[r][c + 1], wv[o], acc[o][1]);
-                                acc[o][2] = fmaf(pin[r + 1][c], wv[o], acc[o][2]);
-                                acc[o][3] = fmaf(pin[r + 1][c + 1], wv[o], acc[o][3]);
-                            }
-                        }
-                    uint32_t h[8], l[8];
-#pragma unroll
-                    for (int o = 0; o < 8; ++o) {
-                        const float best = fmaxf(fmaxf(apply_act(acc[o][0], act), apply_act(acc[o][1], act)),
-                                                 fmaxf(apply_act(acc[o][2], act), apply_act(acc[o][3], act)));
-                        h[o] = float_to_bf16_bits(best);
-                        l[o] = float_to_bf16_bits(best - bf16_bits_to_float(h[o]));
-                    }
-                    const int plane = ((y & 1) << 1) | (x & 1);
-                    const int s = ((y >> 1) + 1) * P.P + (x >> 1) + 1;
-                    unsigned char* dst = a_s + (size_t)plane * 2 * plane_bytes + (size_t)cg * lbo_a + (size_t)s * 16;
-                    *reinterpret_cast<uint4*>(dst) = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
-                    *reinterpret_cast<uint4*>(dst + plane_bytes) =
-                        make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
-                }
-            } else {
-                load_window(w, a_s);
-            }
-            fence_proxy_async();
-            tc_fence_before();
-            __syncthreads();
-            issue_mmas(da_base, 0u, bar);
-            mbar_wait(bar, phase);
-            phase ^= 1;
-            tc_fence_after();
-            epilogue(w, 0u);
-            __syncthreads();          // TMEM and the position lists are free again
-        }
     }
     tc_fence_before();
     __syncthreads();
