@@ -127,7 +127,7 @@ stream_mel_tail_kernel(MelRingRef ring, long long n, float* __restrict__ out, in
 
 // ----------------------------------------------------------------------------------------
 // K9 ingest step, fused: append the chunk to the PCM ring AND compute the log-mel frames it completes, one launch.
-// One WARP per stream (persistent CTAs of 14 warps): the warp stages [320 samples before the chunk | the chunk] in its
+// One WARP per stream (persistent CTAs of 12 warps): the warp stages [320 samples before the chunk | the chunk] in its
 // shared slot — the 320 older samples are one contiguous run of the mirrored ring, the chunk comes straight from the
 // caller's buffer and is written to both copies of the ring on the way —, then runs ceil(n_new / 2) warp-private packed
 // FFTs (fe3_warp_fft: the arithmetic of the batch front end, so the ring stays bit-identical to recomputing windows) and
@@ -135,7 +135,7 @@ stream_mel_tail_kernel(MelRingRef ring, long long n, float* __restrict__ out, in
 // every chunk is a multiple of the hop (<= 16 frames).
 // ----------------------------------------------------------------------------------------
 struct SPush {
-    static constexpr int NW = 14, NT = NW * 32;
+    static constexpr int NW = 12, NT = NW * 32;          // 12 warps x 168 registers: at 14 x 128 the FFT loop spilled and its reloads (long scoreboard) were 22 % of the samples
     static constexpr int OLD = 2 * SMel::HOP;                                   // samples before the chunk that the new frames reach back to
     static constexpr int PCM_SLOT = OLD + SMel::HOP * SMel::MAX_NEW + SMel::HOP;   // + one hop: the dummy second frame of an odd count
     static constexpr size_t kWork = (size_t)NW * Fe3::NPAD * sizeof(cplx<double>);
