@@ -125,7 +125,8 @@ int nww_run_windows_host(nww_engine* e, const int16_t* pcm_host, int64_t n_windo
  *                    chunk_len new samples (any positive length); scores_dev (n_streams) receives the
  *                    probability of each stream's last clip_samples, or 0 while a stream has received
  *                    fewer than clip_samples since it was opened / reset.  Ordered on `stream`.
- * nww_stream_push_host  same with host buffers (H2D of the chunks, D2H of the scores; synchronous).
+ * nww_stream_push_host  same with host buffers (H2D of the chunks, D2H of the scores; synchronous).  Large banks are cut
+ *                       into up to four pieces so that a piece's copy runs behind the previous piece's kernels.
  * nww_stream_reset   ids_host == NULL resets every stream, else the n_ids listed streams.
  * nww_stream_push_select[_host]  like nww_stream_push[_host], but only the n_ids streams listed in ids (distinct
  *                    indices, any order) are SCORED: every stream still receives its chunk (PCM ring and log-mel ring

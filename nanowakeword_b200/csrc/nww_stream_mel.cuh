@@ -145,7 +145,7 @@ struct SPush {
 
 __global__ void __launch_bounds__(SPush::NT, 1)
 stream_push_mel_kernel(StreamState st, const int16_t* __restrict__ chunks, int chunk_len, float* __restrict__ mel_ring,
-                       FrontendTables<double> tab) {
+                       FrontendTables<double> tab, long long s_begin, long long s_end /* streams [s_begin, s_end) of the bank */) {
     NWW_DYN_SMEM(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     cplx<double>* wb = reinterpret_cast<cplx<double>*>(smem) + (size_t)warp * Fe3::NPAD;
@@ -157,7 +157,7 @@ stream_push_mel_kernel(StreamState st, const int16_t* __restrict__ chunks, int c
     for (int i = lane; i < SPush::PCM_SLOT; i += 32) slot[i] = 0;              // whatever the dummy frame reads is finite
     __syncthreads();
     const int R = st.R, n_new = chunk_len / SMel::HOP;
-    for (long long s = (long long)blockIdx.x * SPush::NW + warp; s < st.n_streams; s += (long long)gridDim.x * SPush::NW) {
+    for (long long s = s_begin + (long long)blockIdx.x * SPush::NW + warp; s < s_end; s += (long long)gridDim.x * SPush::NW) {
         int16_t* ring = st.ring + s * st.pitch();
         const int wp = st.wpos[s];                                              // a multiple of the hop: 16-byte aligned
         const long long cnt = st.count[s] + chunk_len;

@@ -33,7 +33,7 @@ class Engine:
     def __init__(self, state_dict: dict, cfg: dict, device: int = 0, frontend_precision: str = "fp64",
                  chunk_windows: int = 0, tensor_cores: bool = True, cnn_stage: str = "v2",
                  stream_incremental: bool = True, tcn_layers: str = "rows", stream_ingest: str = "fused", split_per_sm: int = 0,
-                 fused_first_conv: bool = True):
+                 fused_first_conv: bool = True, push_pieces: int = 0):
         self._lib = _lib.load_library()
         self.cfg = dict(cfg)
         self.geometry = geometry_for(cfg)
@@ -73,6 +73,7 @@ class Engine:
                             # bits 8 / 9 (A/B): the first convolution as a kernel of its own instead of inside conv2's loader
                             # (e2e_dnn) / behind the front end in one stage kernel (bcresnet); bit-identical either way
                             | (0 if fused_first_conv else 256 | 512))
+        spec.reserved[2] = int(push_pieces)                                   # pieces of a bank per host push (0 = default of 4, up to 8)
         spec.reserved[1] = int(split_per_sm)                                  # windows per SM and sub-chunk of the split stage (0 = default)
         self.cnn_stage = "v4" if split else "v3" if (pipelined and cnn_stage == "v2") else cnn_stage
         self._blob = (C.c_char * len(blob)).from_buffer_copy(blob)

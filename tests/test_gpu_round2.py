@@ -422,3 +422,22 @@ def test_fused_first_conv_is_bit_identical(torch_cuda, mt):
         eng.close()
     assert np.array_equal(res[0][0], res[1][0])
     assert np.array_equal(res[0][1], res[1][1])
+
+
+def test_piecewise_host_push_matches_single_piece(torch_cuda):
+    """nww_stream_push_host cuts a large bank into pieces (copy of piece p + 1 behind the kernels of piece p); a stream's
+    scores do not depend on how the bank was cut."""
+    n = 9000                                                   # >= 2 x 4096: the piecewise path; not a multiple of the piece count
+    rng = np.random.default_rng(5)
+    one, _, _ = _engine("tcn", push_pieces=1)
+    many, _, _ = _engine("tcn", push_pieces=3)
+    one.stream_open(n)
+    many.stream_open(n)
+    for i in range(15):
+        chunks = np.clip(rng.normal(0, 3000, (n, 1280)), -32768, 32767).astype(np.int16)
+        a = one.stream_push_host(chunks)
+        b = many.stream_push_host(chunks)
+        assert np.array_equal(a, b), i
+    assert a.max() > 0.0
+    one.close()
+    many.close()
