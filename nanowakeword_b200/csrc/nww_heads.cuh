@@ -29,6 +29,7 @@ constexpr int kNfb64 = 7;           // FFTs per batch, double
 // FFT, so 7 FFTs per batch leave 512 threads 55 % / 68 % busy in their second round; 17 FFTs per batch = exactly three
 // batches per window, 89 % / 83 % busy, a third of the CTA barriers (109 KB of work buffer).
 constexpr int kNfbRef = 17;
+constexpr long long kTcnRowsMinWindows = 2048;     // TCN: windows per launch from which one row GEMM per layer beats the cone kernel
 constexpr int kNfb32 = 13;          // FFTs per batch, float
 
 struct ConvW { const float* w = nullptr; const float* b = nullptr; };
@@ -670,7 +671,10 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
             }
             p -= (size_t)hw.tcn_rows_pw * (size_t)n;        // no co-residency: fall through to one launch per layer
         }
-        if (hw.tcn_rows) {
+        // Small launches take the per-tile cone kernel (one launch, weights re-read per 4 windows: 86 us for one window against
+        // 150 us for the eight row-GEMM launches, 256 vs 335 us for 256); from a couple of thousand windows on the row GEMMs over
+        // the whole launch group win.  Same operand splits and accumulation order: the two routes are bit-identical.
+        if (hw.tcn_rows && (n >= kTcnRowsMinWindows || !hw.tcn_umma)) {
             // stream mode: the cone's frames out of the mel ring, time-major, into the same place the front end writes them
             if (ring.ring != nullptr) {
                 if (P.n_in > kMelTailMax) { *err = "tcn: dependency cone longer than 32 frames is not built for stream mode"; return NWW_EUNSUPPORTED; }
