@@ -573,6 +573,27 @@ def run_gpu_arm(args, rank, world, local_rank):
         except Exception as ex:
             cascade = {"error": repr(ex)}
 
+    # ---- secondary: BASELINE configs[0] — one window, DNN head, through host buffers (what one predict() call costs) ----------
+    latency = None
+    if world == 1 and not args.no_streams:
+        try:
+            cfg_l = default_config("dnn")
+            eng_l = Engine(make_state_dict(cfg_l, 0), cfg_l, device=local_rank)
+            one = torch.from_numpy(synth_pcm(1, seed=3)).pin_memory().numpy()
+            for _ in range(50):
+                eng_l.score_host(one)
+            ts = []
+            for _ in range(400):
+                t0 = time.perf_counter()
+                eng_l.score_host(one)
+                ts.append(time.perf_counter() - t0)
+            ts = np.sort(np.asarray(ts)) * 1e6
+            eng_l.close()
+            latency = {"workload": "configs[0]: batch=1, DNN head, Engine.score_host (pinned int16 window in, score out, synchronous)",
+                       "p50_us": round(float(ts[200]), 1), "p99_us": round(float(ts[395]), 1), "calls": 400}
+        except Exception as ex:
+            latency = {"error": repr(ex)}
+
     cores = os.cpu_count() or 1
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -598,7 +619,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_total * CLIP * 2, "d2h_bytes_per_step": n_total * 4,
                 "api": "B200Session.run(None, {'input': int16 (4096,16000) pinned host array}) per rank", "host_link": h2d},
         "gpu_launches": int(launches), "clocks": clocks, "sustained": sustained, "roofline": roofline, "cpu_baseline": cpu,
-        "parity": parity, "streams_cfg3": streams, "cascade_verifier": cascade, "root_ingest": root_ingest,
+        "parity": parity, "streams_cfg3": streams, "cascade_verifier": cascade, "latency_cfg1": latency, "root_ingest": root_ingest,
         "other_models": other,
     }
     emit(line)
