@@ -288,7 +288,7 @@ inline size_t bcu_smem_bytes(int Cin) {
     return (size_t)4 * kBcuRows * Cin * 2 /* A: dw, ctr x hi, lo */ + (size_t)4 * kBcuNC * Cin * 2 /* B chunk */ + 128;
 }
 
-__global__ void __launch_bounds__(kBcuNT, 1)
+__global__ void __launch_bounds__(kBcuNT, 3)
 bc_block_umma_kernel(const float* __restrict__ dwo, const float* __restrict__ ctr, const uint4* __restrict__ wq /* see above */,
                      const float* __restrict__ bpw, const float* __restrict__ bsc, float* __restrict__ out, long long rows,
                      int Cin, int Cout, int act) {

@@ -804,7 +804,10 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
                 const size_t smem = bcu_smem_bytes(ch[j]);
                 NWW_HCUDA(set_smem(bc_block_umma_kernel, smem));
                 const long long tiles = (rows + kBcuRows - 1) / kBcuRows;
-                bc_block_umma_kernel<<<(int)std::min<long long>(tiles, (long long)sm_count), kBcuNT, smem, st>>>(
+                // two CTAs per SM where they fit (Cin <= 64: <= 98 KB of shared memory, 102 registers, 128 TMEM columns each):
+                // one CTA's operand conversion / epilogue runs under the other's MMAs
+                const int per_sm = smem <= 70 * 1024 ? 3 : smem <= 110 * 1024 ? 2 : 1;
+                bc_block_umma_kernel<<<(int)std::min<long long>(tiles, (long long)sm_count * per_sm), kBcuNT, smem, st>>>(
                     dwo, ctr, hw.bc_wq[j], hw.bc_pw[j].b, hw.bc_sc[j].b, out, rows, ch[j], ch[j + 1], act);
             } else {
                 const size_t smem = bc_block_smem_bytes(ch[j]);
