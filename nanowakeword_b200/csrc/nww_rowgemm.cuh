@@ -418,13 +418,14 @@ constexpr int kKcKoff = 256;                                       // K groups (
 inline size_t rowgemm_kc_smem_bytes(int ring = kKcRing) {
     return (size_t)2 * kKcABuf + (size_t)ring * kKcSub + 256 + (kKcRows + kKcKoff) * sizeof(long long);
 }
-// Narrow outputs (N <= 128) leave a tile little MMA work between its operand conversion and its epilogue: a two-slot
-// weight ring makes the CTA small enough (97 KB, <= 128 TMEM columns) for two CTAs per SM to overlap those phases.
+// Outputs up to 256 columns leave a tile little MMA work between its operand conversion and its epilogue: a two-slot
+// weight ring makes the CTA small enough (101 KB, <= 256 TMEM columns, 128 registers) for two CTAs per SM to overlap
+// those phases (N <= 128: +39 % on the raw-audio models; N = 256: +4 % on QuartzNet).
 struct KcLaunch { int ring, grid; size_t smem; };
 inline KcLaunch rowgemm_kc_launch(long long rows, int N, int sm_count) {
-    const int ring = N <= 128 ? 2 : kKcRing;
+    const int ring = N <= 256 ? 2 : kKcRing;                          // (N <= 256: two CTAs share the SM's 512 TMEM columns)
     const long long tiles = (rows + kKcRows - 1) / kKcRows;
-    const long long cap = (long long)sm_count * (N <= 128 ? 2 : 1);
+    const long long cap = (long long)sm_count * (N <= 256 ? 2 : 1);
     return KcLaunch{ring, (int)(tiles < cap ? tiles : cap), rowgemm_kc_smem_bytes(ring)};
 }
 
@@ -681,7 +682,7 @@ __device__ __forceinline__ void rowgemm_kc_run(const float* __restrict__ A, cons
 }
 
 template <bool VIEWS>
-__global__ void __launch_bounds__(kKcNT, VIEWS ? 2 : 1)
+__global__ void __launch_bounds__(kKcNT, 2)
 rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, KcSegs sg, int K, const uint4* __restrict__ wq,
                        const float* __restrict__ bias, const float* __restrict__ res, float* __restrict__ out, KcView ov, long long rows,
                        int N, int n_valid, int act, int ring,
