@@ -443,10 +443,16 @@ inline int launch_quartznet_blocks(const HeadWeights& hw, const float* x, int pi
         }
         if ((rc = done())) return rc;
         float* y = plane[i & 1];
-        const KcLaunch kl = rowgemm_kc_launch(rows, B.N, sm_count);
-        rowgemm_kc_umma_kernel<false><<<kl.grid, kKcNT, kl.smem, st>>>(
-            a, kc_plain(rows, B.K), kc_one_seg(B.K), B.K, B.wq, B.b, B.has_res ? nullptr : x, y, kc_plain(rows, B.N), rows, B.N, B.N, 1, kl.ring);
-        if ((rc = done())) return rc;
+        // layers wider than 256 columns run as 256-column slices: a slice leaves room for two CTAs per SM (512 TMEM columns,
+        // 101 KB of shared memory each), whose operand conversion / MMA / epilogue phases then overlap
+        const int n_slice = B.N > 256 && B.N % 256 == 0 ? 256 : B.N;
+        const KcLaunch kl = rowgemm_kc_launch(rows, n_slice, sm_count);
+        for (int n_off = 0; n_off < B.N; n_off += n_slice) {
+            rowgemm_kc_umma_kernel<false><<<kl.grid, kKcNT, kl.smem, st>>>(
+                a, kc_plain(rows, B.K), kc_one_seg(B.K), B.K, B.wq, B.b, B.has_res ? nullptr : x, y, kc_plain(rows, B.N), rows, n_slice, n_slice, 1,
+                kl.ring, KcView{0, 0, 0, 0, 0, 0}, 0, n_off, B.N);
+            if ((rc = done())) return rc;
+        }
         x = y;
         pitch = B.N;
     }

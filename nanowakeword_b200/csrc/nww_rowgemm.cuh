@@ -507,6 +507,7 @@ __device__ __forceinline__ void rowgemm_kc_run(const float* __restrict__ A, cons
                                                const uint4* __restrict__ wq, const float* __restrict__ bias,
                                                const float* __restrict__ res, float* __restrict__ out, const KcView& ov, long long rows,
                                                int N, int n_valid, int act, int ring, const KcView& rv, int pre_relu, KcState& S,
+                                               int n_off, int n_pitch /* this launch computes columns [n_off, n_off + N) of n_pitch */,
                                                unsigned char* a_s, unsigned char* b_s, uint64_t* bar_full, uint64_t* bar_empty,
                                                uint64_t* bar_afree, uint64_t* bar_done, long long* row_at, uint32_t tmem_base) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -514,6 +515,7 @@ __device__ __forceinline__ void rowgemm_kc_run(const float* __restrict__ A, cons
     const uint64_t da_buf0 = umma_desc_noswz(smem_u32(a_s), kKcRows * 16, 128);
     const uint64_t db_ring = umma_desc_noswz(smem_u32(b_s), kKcNC * 16, 128);
     const int n_kc = K / kKcKC, n_nc = N / kKcNC, total = n_kc * n_nc;
+    const int nc_total = n_pitch / kKcNC, nc_off = n_off / kKcNC;      // the weight stream holds every 64-column group of every K chunk
     uint32_t& c_slot = S.c_slot; uint32_t& c_par = S.c_par; uint32_t& p_slot = S.p_slot; uint32_t& done_phase = S.done_phase;
     uint32_t& g = S.g;                                                 // chunks converted so far: buffer g & 1
     // where K group k8 / 8 of an A row starts relative to the row (segments resolved once per launch instead of a
@@ -532,7 +534,8 @@ __device__ __forceinline__ void rowgemm_kc_run(const float* __restrict__ A, cons
         uint32_t prev_par = 0;
         auto produce = [&]() {                                         // thread 0: next sub-block of the tile's stream
             mbar_expect_tx(bar_full + p_slot, kKcSub);
-            bulk_g2s(b_s + (size_t)p_slot * kKcSub, reinterpret_cast<const unsigned char*>(wq) + (size_t)p_pos * kKcSub, kKcSub,
+            bulk_g2s(b_s + (size_t)p_slot * kKcSub,
+                     reinterpret_cast<const unsigned char*>(wq) + (size_t)((p_pos / n_nc) * nc_total + nc_off + p_pos % n_nc) * kKcSub, kKcSub,
                      bar_full + p_slot);
             p_slot = (int)p_slot + 1 == ring ? 0 : p_slot + 1;
             ++p_pos;
@@ -646,17 +649,17 @@ __device__ __forceinline__ void rowgemm_kc_run(const float* __restrict__ A, cons
         {
             const int q = warp & 3, hcol = warp >> 2;
             const long long r = r0 + q * 32 + lane;
-            const long long o_at = r < rows ? (VIEWS ? ov.at(r) : r * (long long)N) : 0;
+            const long long o_at = r < rows ? (VIEWS ? ov.at(r) : r * (long long)n_pitch) + n_off : 0;
             for (int c0 = hcol * (N / 2); c0 < (hcol + 1) * (N / 2) && c0 < n_valid; c0 += 32) {
                 float v[32];
                 float4 bq[8];                                          // the bias of these 32 columns: eight 128-bit loads in flight
 #pragma unroll                                                         // behind the TMEM load (32 scalar loads stalled the epilogue)
                 for (int j4 = 0; j4 < 8; ++j4)
-                    bq[j4] = c0 + 4 * j4 < n_valid ? __ldg(reinterpret_cast<const float4*>(bias + c0) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    bq[j4] = c0 + 4 * j4 < n_valid ? __ldg(reinterpret_cast<const float4*>(bias + n_off + c0) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
                 if (r < rows) {
                     float4* dst = reinterpret_cast<float4*>(out + o_at + c0);
-                    const float4* rs = res ? reinterpret_cast<const float4*>(res + (VIEWS && rv.rpw ? rv.at(r) : r * N) + c0) : nullptr;
+                    const float4* rs = res ? reinterpret_cast<const float4*>(res + (VIEWS && rv.rpw ? rv.at(r) : r * (long long)n_pitch) + n_off + c0) : nullptr;
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
                         if (VIEWS && c0 + 4 * j4 >= n_valid) break;
@@ -687,7 +690,8 @@ rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, KcSegs sg, int K,
                        const float* __restrict__ bias, const float* __restrict__ res, float* __restrict__ out, KcView ov, long long rows,
                        int N, int n_valid, int act, int ring,
                        KcView rv = KcView{0, 0, 0, 0, 0, 0} /* where the residual row of GEMM row r lives; rpw == 0: res + r * N */,
-                       int pre_relu = 0 /* ReLU before the residual is added: TemporalBlock's relu(relu(conv2) + res) */) {
+                       int pre_relu = 0 /* ReLU before the residual is added: TemporalBlock's relu(relu(conv2) + res) */,
+                       int n_off = 0, int n_pitch = 0 /* columns [n_off, n_off + N) of an n_pitch-wide layer (0: N); plain matrices only */) {
     NWW_DYN_SMEM(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned char* a_s = smem;                                         // two chunk buffers
@@ -709,7 +713,7 @@ rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, KcSegs sg, int K,
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     KcState S;
-    rowgemm_kc_run<VIEWS, false>(A, av, sg, K, wq, bias, res, out, ov, rows, N, n_valid, act, ring, rv, pre_relu, S, a_s, b_s, bar_full,
+    rowgemm_kc_run<VIEWS, false>(A, av, sg, K, wq, bias, res, out, ov, rows, N, n_valid, act, ring, rv, pre_relu, S, n_off, n_pitch ? n_pitch : N, a_s, b_s, bar_full,
                                  bar_empty, bar_afree, bar_done, row_at, tmem_base);
     tc_fence_before();
     __syncthreads();
@@ -792,7 +796,7 @@ tcn_rows_fused_kernel(const __grid_constant__ TcnFusedParams P) {
     for (int l = 0; l < P.n_layers; ++l) {
         const TcnFusedLayer& L = P.L[l];
         rowgemm_kc_run<true, true>(L.A, L.av, KcSegs{1 << 30, 0, L.k_valid}, L.K, L.wq, L.bias, L.res, L.out, L.ov, L.rows, L.N, L.N, L.act, ring,
-                                   L.rv, L.pre_relu, S, a_s, b_s, bar_full, bar_empty, bar_afree, bar_done, row_at, tmem_base);
+                                   L.rv, L.pre_relu, S, 0, L.N, a_s, b_s, bar_full, bar_empty, bar_afree, bar_done, row_at, tmem_base);
         if (l + 1 < P.n_layers) {
             __threadfence();
             grid.sync();
