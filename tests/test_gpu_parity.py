@@ -150,7 +150,8 @@ def test_session_duck_type_and_interpreter(torch_cuda, tmp_path, golden_frontend
     assert interp.score == 0.0 and interp.e2e_buffer_samples["hey_b200"] == 0
 
 
-@pytest.mark.parametrize("mt,chunk_len", [("cnn", 1280), ("cnn", 1000), ("dnn", 1280), ("tcn", 777), ("e2e_quartznet", 1001)])
+@pytest.mark.parametrize("mt,chunk_len", [("cnn", 1280), ("cnn", 1000), ("dnn", 1280), ("tcn", 777), ("e2e_quartznet", 1001),
+                                          ("e2e_dnn", 999)])       # (windows at odd ring offsets through the REF64x101 front end)
 def test_stream_rings_match_oracle_interpreters(torch_cuda, golden_frontend, mt, chunk_len):
     """Multi-stream mode (nww_stream_*): every stream of a StreamBank must behave like its own
     reference interpreter (oracle/interp.py restates nanointerpreter.py:735-814) fed the same
