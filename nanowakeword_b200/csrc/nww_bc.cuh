@@ -208,6 +208,11 @@ bc_dw_kernel(const float* __restrict__ in, const float* __restrict__ w, float* _
              long long n, int C, int H, int W, int sh, int sw) {
     const int Ho = (H - 1) / sh + 1, Wo = (W - 1) / sw + 1, c4n = C / 4;
     const long long total = n * Ho * Wo * c4n;
+    // the filter taps, transposed to [tap][C] in shared memory: a thread's four channels of a tap are ONE 128-bit load
+    // (thirty-six scalar weight loads per output quad made the kernel load-instruction bound)
+    __shared__ __align__(16) float ws[9 * 256];
+    for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) ws[i] = __ldg(w + (i % C) * 9 + i / C);
+    __syncthreads();
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         const int c4 = (int)(t % c4n);
         const long long pix = t / c4n;
@@ -223,10 +228,11 @@ bc_dw_kernel(const float* __restrict__ in, const float* __restrict__ w, float* _
                 if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
                 const float4 v = __ldg(reinterpret_cast<const float4*>(src + ((long long)yy * W + xx) * C));
                 const int tap = r * 3 + q;
-                s.x = fmaf(v.x, __ldg(w + (4 * c4 + 0) * 9 + tap), s.x);
-                s.y = fmaf(v.y, __ldg(w + (4 * c4 + 1) * 9 + tap), s.y);
-                s.z = fmaf(v.z, __ldg(w + (4 * c4 + 2) * 9 + tap), s.z);
-                s.w = fmaf(v.w, __ldg(w + (4 * c4 + 3) * 9 + tap), s.w);
+                const float4 wt = *reinterpret_cast<const float4*>(ws + tap * C + 4 * c4);
+                s.x = fmaf(v.x, wt.x, s.x);
+                s.y = fmaf(v.y, wt.y, s.y);
+                s.z = fmaf(v.z, wt.z, s.z);
+                s.w = fmaf(v.w, wt.w, s.w);
                 if (r == 1 && q == 1) centre = v;
             }
         reinterpret_cast<float4*>(dwo + pix * C)[c4] = s;
