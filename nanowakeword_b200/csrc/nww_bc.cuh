@@ -289,6 +289,9 @@ bc_block_gemm_kernel(const float* __restrict__ dwo, const float* __restrict__ ct
 //   * 2 x (Cin / 16) x 3 tcgen05.mma (128 x 64 x 16, bf16 split products a_hi w_hi + a_lo w_hi + a_hi w_lo)
 //     accumulate the two products side by side in 128 TMEM columns;
 //   * epilogue: act(pw + b_pw) + (sc + b_sc) straight from TMEM to the channel-last output.
+// GELU / SiLU out of line: one copy of the erf / exp code in the kernel instead of one per unrolled epilogue element
+__device__ __noinline__ float bc_act_slow(float x, int act) { return apply_act(x, act); }
+
 constexpr int kBcuRows = 128, kBcuNC = 64, kBcuNT = 256;
 inline size_t bcu_smem_bytes(int Cin) {
     return (size_t)4 * kBcuRows * Cin * 2 /* A: dw, ctr x hi, lo */ + (size_t)4 * kBcuNC * Cin * 2 /* B chunk */ + 128;
@@ -401,7 +404,8 @@ bc_block_umma_kernel(const float* __restrict__ dwo, const float* __restrict__ ct
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const int n = n0 + 4 * j4 + j;
-                            v[j] = apply_act(pv[4 * j4 + j] + __ldg(bpw + n), act) + (sv[4 * j4 + j] + __ldg(bsc + n));
+                            const float pre = pv[4 * j4 + j] + __ldg(bpw + n);
+                            v[j] = (act == ACT_RELU ? fmaxf(pre, 0.0f) : bc_act_slow(pre, act)) + (sv[4 * j4 + j] + __ldg(bsc + n));
                         }
                         dst[j4] = make_float4(v[0], v[1], v[2], v[3]);
                     }

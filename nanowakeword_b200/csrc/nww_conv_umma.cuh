@@ -67,10 +67,10 @@ inline bool conv_umma_plan(int H, int W, int Cin, int Cout, int pool, ConvUmmaPl
     p->acc_cols = cols;
     p->a_bytes = (size_t)p->planes * 2 * p->kg * p->npos * 16;
     p->b_bytes = (size_t)9 * 2 * p->kg * Cout * 16;
-    p->nbuf = (2 * cols <= 512 && 2 * p->a_bytes + p->b_bytes + Cout * sizeof(float) + 128 <= 226 * 1024) ? 2 : 1;
+    p->nbuf = (2 * cols <= 512 && 2 * p->a_bytes + p->b_bytes + Cout * sizeof(float) + 256 <= 226 * 1024) ? 2 : 1;
     const int tc = p->nbuf * cols;
     p->tmem_cols = tc <= 32 ? 32 : tc <= 64 ? 64 : tc <= 128 ? 128 : tc <= 256 ? 256 : 512;
-    p->smem_bytes = p->nbuf * p->a_bytes + p->b_bytes + Cout * sizeof(float) + 128;
+    p->smem_bytes = p->nbuf * p->a_bytes + p->b_bytes + Cout * sizeof(float) + 256;
     return p->smem_bytes <= 226 * 1024;
 }
 
@@ -127,10 +127,13 @@ inline void conv_umma_pack_weights(const float* w, int Cin, int Cout, std::vecto
 // in [n][H*W][Cin] -> out [n][Ho*Wo][Cout]  (Ho, Wo = H/2, W/2 with pool)
 // FRONT1: `in` is the log-mel [n][Hm][Wm]; w1 [9][16] (tap-major) and b1 [16] are the first layer's folded weights (the
 // arithmetic of bc_init_conv_kernel, FMA for FMA, so both routes give the same activations).
-template <bool FRONT1>
+// ACT: the activation is a template parameter — with a run-time code every one of the ~100 unrolled call sites carried
+// the erf / exp paths too, and the kernel no longer fitted the instruction cache (13 % of the stall samples were
+// instruction fetches).
+template <bool FRONT1, int ACT>
 __global__ void __launch_bounds__(kCuNT, 1)
 conv3x3_umma_kernel(const float* __restrict__ in, const uint4* __restrict__ wq, const float* __restrict__ bias,
-                    float* __restrict__ out, long long n_windows, ConvUmmaPlan P, int act,
+                    float* __restrict__ out, long long n_windows, ConvUmmaPlan P,
                     const float* __restrict__ w1 = nullptr, const float* __restrict__ b1 = nullptr) {
     NWW_DYN_SMEM(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -142,7 +145,7 @@ conv3x3_umma_kernel(const float* __restrict__ in, const uint4* __restrict__ wq, 
     bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bar) + 7) & ~(uintptr_t)7);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);    // bar[2]: one per accumulator set
     const int n_acc = P.tiles * (P.pool ? 4 : 1);                  // accumulators = (tile, quad) pairs
-    const int n_issuers = n_acc < 4 ? n_acc : 4;                   // lane 0 of warps 0..3 each issue the MMAs of their accumulators
+    const int n_issuers = n_acc < 4 ? n_acc : 4;                   // one lane of the last n_issuers warps each issues the MMAs of its accumulators
     if (tid == 0) {
         mbar_init(bar, (uint32_t)n_issuers);
         mbar_init(bar + 1, (uint32_t)n_issuers);
@@ -231,39 +234,56 @@ conv3x3_umma_kernel(const float* __restrict__ in, const uint4* __restrict__ wq, 
         }
     };
 
-    // one elected lane of warps 0..3: this window's MMAs from the position lists at descriptor da_win into accumulator set tm_off
+    // MMA issue.  One lane of each of the LAST n_issuers warps (the ones with the least epilogue work when a window has few
+    // (tile, chunk) tasks) issues the MMAs of "its" accumulators: with four pooling quads issuer i always owns quad i, without
+    // pooling quad 0, so the nine taps' operand offsets are per-thread constants worked out once — the issue loop is a
+    // single-thread dependent chain (an ELECT + four R2UR + the MMA per product as it is) and was the longest pole of a window
+    // when the descriptors were re-derived per tap (ncu: 57 % of the stall samples at the CTA barrier behind it).
+    const int issuer = warp - (kCuNT / 32 - n_issuers);                // 0 .. n_issuers - 1 for the issuing warps, negative otherwise
+    // A start offset of tap (r, c) for quad q, 16-byte units: a small shared table (registers are what the loader and the
+    // epilogue are short of)
+    uint32_t* a_tab = reinterpret_cast<uint32_t*>(tmem_slot + 2);        // [4 quads][9 taps], behind the barriers / TMEM slot
+    if (tid < 36) {
+        const int quad = tid / 9, tap = tid - quad * 9, dy = quad >> 1, dx = quad & 1;
+        {
+            const int r = tap / 3, c = tap % 3;
+            int plane, s0;
+            if (P.pool) {
+                const int ry = dy + r - 1, cx = dx + c - 1;
+                plane = ((ry & 1) << 1) | (cx & 1);
+                s0 = (1 + (ry >> 1)) * P.P + 1 + (cx >> 1);
+            } else {
+                plane = 0;
+                s0 = r * P.P + c;
+            }
+            a_tab[tid] = (uint32_t)(((size_t)plane * 2 * plane_bytes) / 16 + s0);
+        }
+    }
+    __syncthreads();
+    const uint32_t a_lo_off = plane_bytes / 16, b_lo_off = bop_bytes / 16, b_tap_step = 2 * bop_bytes / 16;
+    const uint32_t a_kh_step = 2 * lbo_a / 16, b_kh_step = 2 * lbo_b / 16;
+    const int n_kh = P.Cin / 16;                                         // 16 channels = 2 K groups per MMA
     auto issue_mmas = [&](uint64_t da_win, uint32_t tm_off, uint64_t* bar_set) {
-        if (lane == 0 && warp < n_issuers) {
+        if (lane == 0 && issuer >= 0) {
             tc_fence_after();
-            for (int acc = warp; acc < n_acc; acc += n_issuers) {
-                const int t = acc / quads, quad = acc - t * quads;
-                {
-                    const int dy = quad >> 1, dx = quad & 1;
-                    const uint32_t d_tmem = tmem_base + tm_off + (uint32_t)((t * quads + quad) * P.Cout);
-                    bool first = true;
-                    for (int r = 0; r < 3; ++r)
-                        for (int c = 0; c < 3; ++c) {
-                            int plane, s0;
-                            if (P.pool) {
-                                const int ry = dy + r - 1, cx = dx + c - 1;
-                                plane = ((ry & 1) << 1) | (cx & 1);
-                                s0 = t * 128 + (1 + (ry >> 1)) * P.P + 1 + (cx >> 1);
-                            } else {
-                                plane = 0;
-                                s0 = t * 128 + r * P.P + c;
-                            }
-                            const uint64_t a_hi = da_win + (uint64_t)(((size_t)plane * 2 * plane_bytes) / 16 + s0);
-                            const uint64_t a_lo = a_hi + (uint64_t)(plane_bytes / 16);
-                            const uint64_t b_hi = db_base + (uint64_t)(((size_t)(r * 3 + c) * 2 * bop_bytes) / 16);
-                            const uint64_t b_lo = b_hi + (uint64_t)(bop_bytes / 16);
-                            for (int kh = 0; kh < P.Cin / 16; ++kh) {          // 16 channels = 2 K groups per MMA
-                                const uint64_t ao = (uint64_t)(2 * kh * lbo_a / 16), bo = (uint64_t)(2 * kh * lbo_b / 16);
-                                umma_bf16(d_tmem, a_hi + ao, b_hi + bo, idesc, first ? 0u : 1u);
-                                umma_bf16(d_tmem, a_lo + ao, b_hi + bo, idesc, 1);
-                                umma_bf16(d_tmem, a_hi + ao, b_lo + bo, idesc, 1);
-                                first = false;
-                            }
-                        }
+            for (int acc = issuer; acc < n_acc; acc += n_issuers) {
+                const int t = acc / quads;
+                const uint32_t d_tmem = tmem_base + tm_off + (uint32_t)(acc * P.Cout);
+                const uint64_t a_t = da_win + (uint64_t)(t * 128);
+                const uint32_t* a_tap = a_tab + (quads == 4 ? (acc & 3) : 0) * 9;
+                uint32_t accumulate = 0u;
+                uint32_t a_off[9];
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) a_off[tap] = a_tap[tap];          // nine independent shared loads up front
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    uint64_t a_hi = a_t + a_off[tap], b_hi = db_base + (uint64_t)(tap * b_tap_step);
+                    for (int kh = 0; kh < n_kh; ++kh, a_hi += a_kh_step, b_hi += b_kh_step) {
+                        umma_bf16(d_tmem, a_hi, b_hi, idesc, accumulate);
+                        umma_bf16(d_tmem, a_hi + a_lo_off, b_hi, idesc, 1);
+                        umma_bf16(d_tmem, a_hi, b_hi + b_lo_off, idesc, 1);
+                        accumulate = 1u;
+                    }
                 }
             }
             umma_commit(bar_set);
@@ -294,11 +314,11 @@ conv3x3_umma_kernel(const float* __restrict__ in, const uint4* __restrict__ wq, 
 #pragma unroll
                     for (int o = 0; o < 16; ++o) {
                         const float b = bias_s[ch * 16 + o];
-                        float x0 = apply_act(__uint_as_float(r[0][o]) + b, act);
+                        float x0 = apply_act(__uint_as_float(r[0][o]) + b, ACT);
                         if (P.pool) {
-                            x0 = fmaxf(x0, apply_act(__uint_as_float(r[1][o]) + b, act));
-                            x0 = fmaxf(x0, apply_act(__uint_as_float(r[2][o]) + b, act));
-                            x0 = fmaxf(x0, apply_act(__uint_as_float(r[3][o]) + b, act));
+                            x0 = fmaxf(x0, apply_act(__uint_as_float(r[1][o]) + b, ACT));
+                            x0 = fmaxf(x0, apply_act(__uint_as_float(r[2][o]) + b, ACT));
+                            x0 = fmaxf(x0, apply_act(__uint_as_float(r[3][o]) + b, ACT));
                         }
                         v[o] = x0;
                     }
@@ -362,8 +382,8 @@ conv3x3_umma_kernel(const float* __restrict__ in, const uint4* __restrict__ wq, 
             uint32_t h[8], l[8];
 #pragma unroll
             for (int o = 0; o < 8; ++o) {
-                const float best = fmaxf(fmaxf(apply_act(acc[o][0], act), apply_act(acc[o][1], act)),
-                                         fmaxf(apply_act(acc[o][2], act), apply_act(acc[o][3], act)));
+                const float best = fmaxf(fmaxf(apply_act(acc[o][0], ACT), apply_act(acc[o][1], ACT)),
+                                         fmaxf(apply_act(acc[o][2], ACT), apply_act(acc[o][3], ACT)));
                 h[o] = float_to_bf16_bits(best);
                 l[o] = float_to_bf16_bits(best - bf16_bits_to_float(h[o]));
             }
@@ -413,6 +433,18 @@ conv3x3_umma_kernel(const float* __restrict__ in, const uint4* __restrict__ wq, 
         tc_fence_after();
         tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
     }
+}
+
+// host: pick the instantiation for a run-time activation code and launch it
+template <bool FRONT1>
+inline cudaError_t conv3x3_umma_launch(int act, int grid, cudaStream_t st, const float* in, const uint4* wq, const float* bias, float* out,
+                                       long long n, const ConvUmmaPlan& P, const float* w1 = nullptr, const float* b1 = nullptr) {
+    auto k = act == ACT_RELU ? conv3x3_umma_kernel<FRONT1, ACT_RELU> : act == ACT_GELU ? conv3x3_umma_kernel<FRONT1, ACT_GELU>
+                                                                                          : conv3x3_umma_kernel<FRONT1, ACT_SILU>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes);
+    if (e != cudaSuccess) return e;
+    k<<<grid, kCuNT, P.smem_bytes, st>>>(in, wq, bias, out, n, P, w1, b1);
+    return cudaGetLastError();
 }
 
 // AdaptiveAvgPool2d((1, OW)) in its deployed AvgPool2d form (_export/onnx.py:139-147) on channel-last input:

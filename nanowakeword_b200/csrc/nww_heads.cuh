@@ -600,9 +600,7 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
             if (hw.e2e_plan[1].f1_hm) {
                 // conv1 inside conv2's loader: the (16, 32, 50) activations never exist in HBM
                 const ConvUmmaPlan& P = hw.e2e_plan[1];
-                NWW_HCUDA(set_smem(conv3x3_umma_kernel<true>, P.smem_bytes));
-                conv3x3_umma_kernel<true><<<grid, kCuNT, P.smem_bytes, st>>>(mel, hw.e2e_wq[1], hw.e2e_conv[1].b, a2, n, P, act,
-                                                                              hw.e2e_conv[0].w, hw.e2e_conv[0].b);
+                NWW_HCUDA(conv3x3_umma_launch<true>(act, grid, st, mel, hw.e2e_wq[1], hw.e2e_conv[1].b, a2, n, P, hw.e2e_conv[0].w, hw.e2e_conv[0].b));
                 if ((rc = done())) return rc;
             } else {
                 bc_init_conv_kernel<<<ew_grid(n * 2 * 32 * 50, sm_count), 256, 0, st>>>(mel, hw.e2e_conv[0].w, hw.e2e_conv[0].b, a1, n, 64, 101, 16, act);
@@ -610,9 +608,7 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
             }
             for (int j = hw.e2e_plan[1].f1_hm ? 2 : 1; j <= 2; ++j) {
                 const ConvUmmaPlan& P = hw.e2e_plan[j];
-                NWW_HCUDA(set_smem(conv3x3_umma_kernel<false>, P.smem_bytes));
-                conv3x3_umma_kernel<false><<<grid, kCuNT, P.smem_bytes, st>>>(
-                    j == 1 ? a1 : a2, hw.e2e_wq[j], hw.e2e_conv[j].b, j == 1 ? a2 : a3, n, P, act);
+                NWW_HCUDA(conv3x3_umma_launch<false>(act, grid, st, j == 1 ? a1 : a2, hw.e2e_wq[j], hw.e2e_conv[j].b, j == 1 ? a2 : a3, n, P));
                 if ((rc = done())) return rc;
             }
             avgpool_row_nhwc_kernel<25, 4><<<ew_grid(n * 16, sm_count), 256, 0, st>>>(a3, feat, n, 64, 16);
@@ -840,9 +836,7 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
                 // third conv on tcgen05 (nww_conv_umma.cuh), then the (c, h) -> feature repack
                 float* a3 = take((size_t)S0 * In0);
                 const ConvUmmaPlan& P = hw.crnn_plan3;
-                NWW_HCUDA(set_smem(conv3x3_umma_kernel<false>, P.smem_bytes));
-                conv3x3_umma_kernel<false><<<(int)std::min<long long>(n, sm_count), kCuNT, P.smem_bytes, st>>>(
-                    conv2_nhwc, hw.crnn_wq3, hw.crnn_conv[2].b, a3, n, P, act);
+                NWW_HCUDA(conv3x3_umma_launch<false>(act, (int)std::min<long long>(n, sm_count), st, conv2_nhwc, hw.crnn_wq3, hw.crnn_conv[2].b, a3, n, P));
                 if ((rc = done())) return rc;
                 seq_pack_nhwc_kernel<<<ew_grid(n * S0 * In0, sm_count), 256, 0, st>>>(a3, seq_direct, n, hw.crnn_ch[2], 5, 12);
                 if ((rc = done())) return rc;

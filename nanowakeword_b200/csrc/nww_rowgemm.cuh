@@ -497,6 +497,11 @@ template <bool COHERENT> __device__ __forceinline__ float4 kc_ld(const float4* p
     return __ldg(p);
 }
 
+// GELU / SiLU of four values, out of line: one copy of the erf / exp code per kernel instead of one per unrolled call site
+__device__ __noinline__ float4 kc_act4(float4 o, int act) {
+    return make_float4(apply_act(o.x, act), apply_act(o.y, act), apply_act(o.z, act), apply_act(o.w, act));
+}
+
 // mbarrier / ring bookkeeping that lives across tiles (and, in the fused kernel, across layers)
 struct KcState { uint32_t c_slot = 0, c_par = 0, p_slot = 0, done_phase = 0, g = 0; };
 
@@ -671,8 +676,10 @@ __device__ __forceinline__ void rowgemm_kc_run(const float* __restrict__ A, cons
                         }
                         if (!VIEWS) {
                             if (act) { o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f); }
+                        } else if (act == 1) {                         // ReLU: kept apart so that the unrolled loop does not carry
+                            o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f);   // eight copies of erf / exp
                         } else if (act) {
-                            o.x = apply_act(o.x, act - 1); o.y = apply_act(o.y, act - 1); o.z = apply_act(o.z, act - 1); o.w = apply_act(o.w, act - 1);
+                            o = kc_act4(o, act - 1);
                         }
                         dst[j4] = o;
                     }
@@ -940,9 +947,14 @@ rawcnn_conv1_px_kernel(const float* __restrict__ bf, const float* __restrict__ w
                 }
             }
         float4* dst = reinterpret_cast<float4*>(o1 + ((w * (H + 2) + oh + 1) * (long long)(Wo + 2) + ow + 1) * CO);
+        if (act == ACT_RELU) {
 #pragma unroll
-        for (int q = 0; q < Q4; ++q)
-            dst[q] = make_float4(apply_act(acc[q].x, act), apply_act(acc[q].y, act), apply_act(acc[q].z, act), apply_act(acc[q].w, act));
+            for (int q = 0; q < Q4; ++q)
+                dst[q] = make_float4(fmaxf(acc[q].x, 0.0f), fmaxf(acc[q].y, 0.0f), fmaxf(acc[q].z, 0.0f), fmaxf(acc[q].w, 0.0f));
+        } else {
+#pragma unroll
+            for (int q = 0; q < Q4; ++q) dst[q] = kc_act4(acc[q], act);
+        }
     }
 }
 

@@ -20,6 +20,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline __attribute__((always_inline))
+#define __noinline__ __attribute__((noinline))
 #define __restrict__ __restrict
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
