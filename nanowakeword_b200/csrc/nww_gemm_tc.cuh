@@ -62,6 +62,11 @@ struct GemmTcArgs {
     int m_pad;              // rows per split slab of `partial`
 };
 
+// ReLU inline, GELU / SiLU out of line: the epilogue below is unrolled over up to 128 columns, and 256 inlined three-way
+// activation switches made this the largest kernel of the library (20 k instructions)
+__device__ __noinline__ float tc_act_slow(float x, int act) { return apply_act(x, act); }
+__device__ __forceinline__ float tc_act(float x, int act) { return act == ACT_RELU ? fmaxf(x, 0.0f) : tc_act_slow(x, act); }
+
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
                    const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo, GemmTcArgs a) {
@@ -179,11 +184,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_cons
                 const float rstd = 1.0f / sqrtf(var / (float)N + 1e-5f);
 #pragma unroll
                 for (int n = 0; n < kTcMaxN; ++n)
-                    if (n < N) v[n] = apply_act((v[n] - mu) * rstd * __ldg(a.ln_g + n) + __ldg(a.ln_b + n), a.act);
+                    if (n < N) v[n] = tc_act((v[n] - mu) * rstd * __ldg(a.ln_g + n) + __ldg(a.ln_b + n), a.act);
             } else if (a.post == POST_ACT) {
 #pragma unroll
                 for (int n = 0; n < kTcMaxN; ++n)
-                    if (n < N) v[n] = apply_act(v[n], a.act);
+                    if (n < N) v[n] = tc_act(v[n], a.act);
             }
             float4* dst = reinterpret_cast<float4*>(a.out + (size_t)m * N);
 #pragma unroll
