@@ -318,7 +318,7 @@ bc_block_umma_kernel(const float* __restrict__ dwo, const float* __restrict__ ct
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t a_addr = smem_u32(a_s), b_addr = smem_u32(b_s);
+    const uint64_t da0 = umma_desc_noswz(smem_u32(a_s), kBcuRows * 16, 128), db0 = umma_desc_noswz(smem_u32(b_s), kBcuNC * 16, 128);
     const uint32_t idesc = umma_idesc_bf16(128, kBcuNC);
     const int kg_n = Cin / 8;                            // 16-byte K groups
     const int n_chunks = Cout / kBcuNC;
@@ -367,19 +367,16 @@ bc_block_umma_kernel(const float* __restrict__ dwo, const float* __restrict__ ct
             __syncthreads();
             if (tid == 0) {
                 tc_fence_after();
+                // (descriptors = two kernel-constant bases + offsets in 16-byte units: the issuing thread is a single dependent
+                // chain on the tile's critical path, so nothing is re-encoded per MMA)
                 for (int gemm = 0; gemm < 2; ++gemm) {                  // 0: pointwise (A = dw), 1: shortcut (A = ctr)
                     const uint32_t d_tmem = tmem_base + (uint32_t)(gemm * kBcuNC);
-                    const uint32_t ah = a_addr + (uint32_t)((2 * gemm) * a_op), al = ah + (uint32_t)a_op;
-                    const uint32_t bh = b_addr + (uint32_t)((2 * gemm) * b_op), bl = bh + (uint32_t)b_op;
-                    for (int ks = 0; ks < Cin / 16; ++ks) {             // one MMA = 16 channels = 2 K groups
-                        const uint32_t ao = (uint32_t)(2 * ks * kBcuRows * 16), bo = (uint32_t)(2 * ks * kBcuNC * 16);
-                        const uint64_t dah = umma_desc_noswz(ah + ao, kBcuRows * 16, 128);
-                        const uint64_t dal = umma_desc_noswz(al + ao, kBcuRows * 16, 128);
-                        const uint64_t dbh = umma_desc_noswz(bh + bo, kBcuNC * 16, 128);
-                        const uint64_t dbl = umma_desc_noswz(bl + bo, kBcuNC * 16, 128);
+                    uint64_t dah = da0 + (uint64_t)(((2 * gemm) * a_op) >> 4), dbh = db0 + (uint64_t)(((2 * gemm) * b_op) >> 4);
+                    const uint64_t a_lo = (uint64_t)(a_op >> 4), b_lo = (uint64_t)(b_op >> 4);
+                    for (int ks = 0; ks < Cin / 16; ++ks, dah += 2 * kBcuRows, dbh += 2 * kBcuNC) {   // one MMA = 16 channels = 2 K groups
                         umma_bf16(d_tmem, dah, dbh, idesc, ks != 0);
-                        umma_bf16(d_tmem, dal, dbh, idesc, 1);
-                        umma_bf16(d_tmem, dah, dbl, idesc, 1);
+                        umma_bf16(d_tmem, dah + a_lo, dbh, idesc, 1);
+                        umma_bf16(d_tmem, dah, dbh + b_lo, idesc, 1);
                     }
                 }
                 umma_commit(bar);
