@@ -448,7 +448,7 @@ inline int launch_quartznet_blocks(const HeadWeights& hw, const float* x, int pi
         const int n_slice = B.N > 256 && B.N % 256 == 0 ? 256 : B.N;
         const KcLaunch kl = rowgemm_kc_launch(rows, n_slice, sm_count);
         for (int n_off = 0; n_off < B.N; n_off += n_slice) {
-            rowgemm_kc_umma_kernel<false><<<kl.grid, kKcNT, kl.smem, st>>>(
+            rowgemm_kc_umma_kernel<false><<<kl.grid, kKcBlock, kl.smem, st>>>(
                 a, kc_plain(rows, B.K), kc_one_seg(B.K), B.K, B.wq, B.b, B.has_res ? nullptr : x, y, kc_plain(rows, B.N), rows, n_slice, n_slice, 1,
                 kl.ring, KcView{0, 0, 0, 0, 0, 0}, 0, n_off, B.N);
             if ((rc = done())) return rc;
@@ -494,7 +494,7 @@ inline int launch_raw_frontend(const HeadWeights& hw, int sm_count, WindowSource
         }
         const long long rows = n * L.t_out;
         const KcLaunch kl = rowgemm_kc_launch(rows, L.Npad, sm_count);
-        rowgemm_kc_umma_kernel<true><<<kl.grid, kKcNT, kl.smem, st>>>(
+        rowgemm_kc_umma_kernel<true><<<kl.grid, kKcBlock, kl.smem, st>>>(
             in, kc_seq(L.t_out, L.in_len, (long long)L.stride * L.cin, 0), kc_one_seg(L.k * L.cin), L.K, L.wq, L.b, nullptr, out,
             kc_seq(L.t_out, out_len, L.cout, out_pad), rows, L.Npad, L.cout, 1, kl.ring);
         if ((rc = done())) return rc;
@@ -552,7 +552,7 @@ inline int launch_raw_cnn(const HeadWeights& hw, int act, int sm_count, WindowSo
         const KcView av{rpw, (long long)Hp * Wp * L.cin, (long long)L.s * L.cin, 0, L.Wout, (long long)L.s * Wp * L.cin};
         const KcView ov{rpw, (long long)Hp2 * Wp2 * L.cout, L.cout, 0, L.Wout, (long long)Wp2 * L.cout};
         const KcLaunch kl = rowgemm_kc_launch(rows, L.Npad, sm_count);
-        rowgemm_kc_umma_kernel<true><<<kl.grid, kKcNT, kl.smem, st>>>(
+        rowgemm_kc_umma_kernel<true><<<kl.grid, kKcBlock, kl.smem, st>>>(
             img, av, KcSegs{3 * L.cin, (long long)Wp * L.cin, 9 * L.cin}, L.K, L.wq, L.b, nullptr,
             out + (last ? 0 : (size_t)(Wp2 + 1) * L.cout), ov, rows, L.Npad, L.cout, act + 1, kl.ring);
         if ((rc = done())) return rc;
@@ -663,12 +663,12 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
             NWW_HCUDA(set_smem(tcn_rows_fused_kernel, smem));
             NWW_HCUDA(cudaFuncSetAttribute(tcn_rows_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             int per_sm = 0;
-            NWW_HCUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tcn_rows_fused_kernel, kKcNT, smem));
+            NWW_HCUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tcn_rows_fused_kernel, kKcBlock, smem));
             if (per_sm >= 1) {
                 const long long tiles0 = (n * hw.tcn_row[0].n_pos + kKcRows - 1) / kKcRows;
                 const int grid = (int)std::min<long long>(std::max<long long>(tiles0, 1), (long long)sm_count * std::min(per_sm, 2));
                 void* args[] = {(void*)&FP};
-                NWW_HCUDA(cudaLaunchCooperativeKernel((const void*)tcn_rows_fused_kernel, dim3(grid), dim3(kKcNT), args, smem, st));
+                NWW_HCUDA(cudaLaunchCooperativeKernel((const void*)tcn_rows_fused_kernel, dim3(grid), dim3(kKcBlock), args, smem, st));
                 return done();
             }
             p -= (size_t)hw.tcn_rows_pw * (size_t)n;        // no co-residency: fall through to one launch per layer
@@ -694,7 +694,7 @@ inline int launch_head_stage_a(const HeadWeights& hw, const FrontendTables<doubl
                 const float* A = (L.a_in_mel ? mel : act) + L.a_off;
                 float* O = (L.o_in_feat ? feat : act) + L.o_off;
                 const KcLaunch kl = rowgemm_kc_launch(rows, L.N, sm_count);
-                rowgemm_kc_umma_kernel<true><<<kl.grid, kKcNT, kl.smem, st>>>(
+                rowgemm_kc_umma_kernel<true><<<kl.grid, kKcBlock, kl.smem, st>>>(
                     A, kc_seq(L.n_pos, a_ws, L.a_row_stride, 0), kc_one_seg(L.k_valid), L.K, L.wq, L.bias,
                     L.has_res ? act + L.r_off : nullptr, O, kc_seq(L.n_pos, o_ws, L.N, 0), rows, L.N, L.N, L.act, kl.ring,
                     kc_seq(L.n_pos, hw.tcn_rows_pw, L.r_row_stride, 0), L.pre_relu);

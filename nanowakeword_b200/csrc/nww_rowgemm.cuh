@@ -412,6 +412,10 @@ rowgemm_umma_kernel(const float* __restrict__ A, long long a_row_mul, long long 
 // [64 nc, +64) across all chunks; one epilogue per tile.
 // ---------------------------------------------------------------------------------------
 constexpr int kKcRows = 128, kKcNT = 256, kKcKC = 64, kKcNC = 64, kKcRing = 4;
+// kKcNT threads convert operands and run the epilogue; ONE MORE WARP issues the weight copies and the MMAs (its lane 0): the
+// issuer waits for weights to land and for MMAs to free ring slots, and as warp 0 it held up its own share of the next chunk's
+// conversion — and with it every CTA barrier.
+constexpr int kKcBlock = kKcNT + 32, kKcIssuer = kKcNT;
 constexpr int kKcABuf = 2 * (kKcKC / 8) * kKcRows * 16;           // hi | lo of one chunk: 32 KB
 constexpr int kKcSub = 2 * (kKcKC / 8) * kKcNC * 16;              // one weight sub-block: 16 KB
 constexpr int kKcKoff = 256;                                       // K groups (of 8 columns) whose offsets are tabulated: K <= 2048
@@ -529,7 +533,7 @@ __device__ __forceinline__ void rowgemm_kc_run(const float* __restrict__ A, cons
     const bool tab = VIEWS && K / 8 <= kKcKoff;
     if (tab) {
         __syncthreads();                                               // (fused kernel) the previous layer's last conversion has read the table
-        for (int g8 = tid; g8 < K / 8; g8 += kKcNT) {
+        for (int g8 = tid; g8 < K / 8; g8 += kKcBlock) {
             const int k8 = 8 * g8, seg = k8 / sg.seg_len;
             koff[g8] = k8 < sg.k_valid ? seg * sg.seg_stride + (k8 - seg * sg.seg_len) : -1;
         }
@@ -545,7 +549,7 @@ __device__ __forceinline__ void rowgemm_kc_run(const float* __restrict__ A, cons
             p_slot = (int)p_slot + 1 == ring ? 0 : p_slot + 1;
             ++p_pos;
         };
-        if (tid == 0)
+        if (tid == kKcIssuer)
             for (int i = 0; i < ring && p_pos < total; ++i) produce();
         if (VIEWS) {
             __syncthreads();                                           // the previous tile's last conversion has read row_at
@@ -560,6 +564,7 @@ __device__ __forceinline__ void rowgemm_kc_run(const float* __restrict__ A, cons
             // conversion, so a thread has 2 * kPer 128-bit loads in flight instead of 2 (the operand producer was
             // latency-bound on L2: profiles/r02_rowgemm_tcn_before.txt, long-scoreboard 57 % of the samples)
             constexpr int kPer = kKcRows * (kKcKC / 8) / kKcNT;
+            if (tid < kKcNT) {
             float4 v0[kPer], v1[kPer];
             int k8s[kPer];
 #pragma unroll
@@ -614,10 +619,11 @@ __device__ __forceinline__ void rowgemm_kc_run(const float* __restrict__ A, cons
                 *reinterpret_cast<uint4*>(ab + i * 16) = hv;
                 *reinterpret_cast<uint4*>(ab + kKcABuf / 2 + i * 16) = lv;
             }
+            }
             fence_proxy_async();
             tc_fence_before();
             __syncthreads();
-            if (tid == 0) {
+            if (tid == kKcIssuer) {
                 tc_fence_after();
                 const uint64_t da_h = da_buf0 + (uint64_t)((buf * (uint32_t)kKcABuf) >> 4), da_l = da_h + (uint64_t)((kKcABuf / 2) >> 4);
                 for (int nc = 0; nc < n_nc; ++nc) {
@@ -644,14 +650,14 @@ __device__ __forceinline__ void rowgemm_kc_run(const float* __restrict__ A, cons
                 umma_commit(bar_afree + buf);
             }
         }
-        if (tid == 0) {
+        if (tid == kKcIssuer) {
             umma_commit(bar_done);
             mbar_wait_one(bar_empty + prev_slot, prev_par);
         }
         mbar_wait(bar_done, done_phase);
         done_phase ^= 1u;
         tc_fence_after();
-        {
+        if (tid < kKcNT) {
             const int q = warp & 3, hcol = warp >> 2;
             const long long r = r0 + q * 32 + lane;
             const long long o_at = r < rows ? (VIEWS ? ov.at(r) : r * (long long)n_pitch) + n_off : 0;
@@ -692,7 +698,7 @@ __device__ __forceinline__ void rowgemm_kc_run(const float* __restrict__ A, cons
 }
 
 template <bool VIEWS>
-__global__ void __launch_bounds__(kKcNT, 2)
+__global__ void __launch_bounds__(kKcBlock, 2)
 rowgemm_kc_umma_kernel(const float* __restrict__ A, KcView av, KcSegs sg, int K, const uint4* __restrict__ wq,
                        const float* __restrict__ bias, const float* __restrict__ res, float* __restrict__ out, KcView ov, long long rows,
                        int N, int n_valid, int act, int ring,
@@ -785,7 +791,7 @@ tcn_rows_fused_kernel(const __grid_constant__ TcnFusedParams P) {
         // the cone's n_tail frames of every stream, time-major, where the batch front end would have written them
         float* tile = reinterpret_cast<float*>(a_s) + (size_t)warp * (kMelTailMax * (SMel::F + 1));
         const int nw = kKcNT / 32;
-        for (long long w = (long long)blockIdx.x * nw + warp; w < P.n; w += (long long)gridDim.x * nw) {
+        for (long long w = (long long)blockIdx.x * nw + warp; warp < nw && w < P.n; w += (long long)gridDim.x * nw) {
             const long long s = P.ring.stream(w);
             const int head = smel_slot(P.ring.count[s] / SMel::HOP - 3 + 1);
             const float* src = P.ring.ring + s * SMel::STREAM_FLOATS + head + P.t0;

@@ -25,7 +25,7 @@ static double run_case(const char* name, long long n_win, KcView av, KcSegs sg, 
     if (with_res) { res.resize((size_t)rows * N); for (auto& v : res) v = nd(rng); }
     std::vector<uint16_t> wq;
     rowgemm_kc_pack(W.data(), K, N, &wq);
-    cudasim::launch(dim3(grid), dim3(kKcNT), rowgemm_kc_smem_bytes(), [&] {
+    cudasim::launch(dim3(grid), dim3(kKcBlock), rowgemm_kc_smem_bytes(), [&] {
         rowgemm_kc_umma_kernel<true>(A.data(), av, sg, K, reinterpret_cast<const uint4*>(wq.data()), bias.data(), with_res ? res.data() : nullptr,
                                out.data(), ov, rows, N, n_valid, act, N <= 128 ? 2 : kKcRing);
     });
@@ -79,7 +79,7 @@ int main() {
         for (auto& v : res) v = nd(rng);
         std::vector<uint16_t> wq;
         rowgemm_kc_pack(W.data(), K, N, &wq);
-        cudasim::launch(dim3(2), dim3(kKcNT), rowgemm_kc_smem_bytes(), [&] {
+        cudasim::launch(dim3(2), dim3(kKcBlock), rowgemm_kc_smem_bytes(), [&] {
             rowgemm_kc_umma_kernel<false>(A.data(), kc_plain(rows, K), kc_one_seg(K), K, reinterpret_cast<const uint4*>(wq.data()), bias.data(),
                                           res.data(), out.data(), kc_plain(rows, N), rows, N, N, 1, kKcRing);
         });
