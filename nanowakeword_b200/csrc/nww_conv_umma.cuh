@@ -15,6 +15,14 @@
 //   * weights arrive pre-split from the engine: [tap][hi|lo][K group][Cout][8 ic] bf16;
 //   * per 128-row tile: (quads) x 9 taps x (Cin / 16) x 3 split products of tcgen05.mma 128 x Cout x 16, FP32
 //     accumulation in TMEM; epilogue = bias, activation, (max over the four quads), channel-last FP32 store.
+//
+// Schedule (round 2).  Where two sets of position lists and two sets of accumulators fit (conv3 of both models) the
+// windows are software-pipelined: iteration i issues MMAs(i), then runs epilogue(i - 1) and the loads / conversions of
+// window i + 1 under them; one CTA barrier per window.  The E2E conv2 (one set: 147 KB of position lists, all 512
+// TMEM columns) instead takes its input from the log-mel and computes the FIRST layer — Conv2d(1, 16) + act + pool —
+// inside the loader (FRONT1), so that layer's activations never exist in HBM.  The activation is a template parameter
+// (the run-time form put an erf / exp / branch triple at ~100 unrolled call sites and pushed the kernel out of the
+// instruction cache); MMAs are issued by one lane of each of the last warps from tap offsets tabulated once.
 #pragma once
 
 #include <string.h>
