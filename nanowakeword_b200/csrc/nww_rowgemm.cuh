@@ -410,6 +410,9 @@ rowgemm_umma_kernel(const float* __restrict__ A, long long a_row_mul, long long 
 // weights stream from L2 in 16 KB sub-blocks (chunk, 64 columns, hi | lo) through a ring of four slots filled by
 // cp.async.bulk, 4 K steps x 3 products of tcgen05.mma 128 x 64 x 16 per sub-block accumulate into TMEM columns
 // [64 nc, +64) across all chunks; one epilogue per tile.
+// Round 2: the operand producer reads 8 rows x 128 contiguous bytes per warp instruction with the K-group offsets of a
+// row tabulated once per launch; a ninth warp issues the weight copies and the MMAs; layers of up to 256 columns run two
+// CTAs per SM, wider ones as 256-column slices (n_off / n_pitch) of the same launch shape.
 // ---------------------------------------------------------------------------------------
 constexpr int kKcRows = 128, kKcNT = 256, kKcKC = 64, kKcNC = 64, kKcRing = 4;
 // kKcNT threads convert operands and run the epilogue; ONE MORE WARP issues the weight copies and the MMAs (its lane 0): the
