@@ -114,6 +114,11 @@ __device__ __noinline__ void bc_stage_conv(const float* __restrict__ melp, const
 #pragma unroll 1
     for (int T = tid; T < D::H1 * D::W1 * (D::C0 / 8); T += D::NT) {
         const int pix = T >> 2, g = T & 3;
+        // (g is the same for every task of a thread, and left alone the compiler keeps all 72 weights of the group in registers
+        // across the loop — and then spills the accumulators around every task, reloads that miss the small L1 this kernel
+        // leaves.  Laundering the pointer keeps the weight loads, 18 cheap shared-memory broadcasts per task, inside the loop.)
+        const float* wsl = ws;
+        asm volatile("" : "+l"(wsl));
         const int y = pix / D::W1, xx = pix - y * D::W1;
         float in[4][4];
 #pragma unroll
@@ -135,8 +140,8 @@ __device__ __noinline__ void bc_stage_conv(const float* __restrict__ melp, const
         for (int r = 0; r < 3; ++r)
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const float4 wa = *reinterpret_cast<const float4*>(ws + (r * 3 + c) * D::C0 + g * 8);
-                const float4 wb = *reinterpret_cast<const float4*>(ws + (r * 3 + c) * D::C0 + g * 8 + 4);
+                const float4 wa = *reinterpret_cast<const float4*>(wsl + (r * 3 + c) * D::C0 + g * 8);
+                const float4 wb = *reinterpret_cast<const float4*>(wsl + (r * 3 + c) * D::C0 + g * 8 + 4);
                 const float2 wv[4] = {make_float2(wa.x, wa.y), make_float2(wa.z, wa.w), make_float2(wb.x, wb.y), make_float2(wb.z, wb.w)};
                 const float2 p00 = make_float2(in[r][c], in[r][c]), p01 = make_float2(in[r][c + 1], in[r][c + 1]);
                 const float2 p10 = make_float2(in[r + 1][c], in[r + 1][c]), p11 = make_float2(in[r + 1][c + 1], in[r + 1][c + 1]);
